@@ -1,0 +1,191 @@
+/* sahara_b200.h — C ABI of the B200-native search path of sahara.
+ *
+ * The reference (seqan/sahara) has no FFI: the seam this library fills is the set of library calls made
+ * by `runSearch` in /root/reference/src/sahara/search.cpp (all file:line below are relative to
+ * /root/reference/).  A maintainer swaps those calls for the entry points declared here; INTEGRATION.md
+ * shows the patch.  Everything is plain C: pointers and sizes, no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success and non-zero on failure; sb200_last_error() returns the
+ *     message of the last failure on the calling thread (the reference throws error_fmt instead,
+ *     src/sahara/utils/error_fmt.h:11-22).
+ *   - host memory passed in stays owned by the caller; arrays returned through `**out` parameters are
+ *     allocated by the library and released with sb200_free().
+ *   - a context owns one GPU.  There is no CPU fallback: without a usable CUDA device
+ *     sb200_create() fails.
+ *   - ranks: 0 = '$' delimiter, 1..4 = A,C,G,T, 5 = N (only when sigma == 6).
+ */
+#ifndef SAHARA_B200_H
+#define SAHARA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_ABI_VERSION 1
+
+typedef struct sb200_ctx sb200_ctx;
+
+/* ---- library / context -------------------------------------------------------------------------- */
+
+int sb200_abi_version(void);
+const char* sb200_last_error(void);
+/* number of CUDA devices visible; fails when the driver is not usable */
+int sb200_device_count(int* count);
+/* one context per GPU (the reference is a single-threaded CPU program and has no equivalent) */
+int sb200_create(int device, sb200_ctx** out);
+int sb200_destroy(sb200_ctx* ctx);
+/* launch all subsequent work on this cudaStream_t (NULL = the context's own stream) */
+int sb200_set_stream(sb200_ctx* ctx, void* cuda_stream);
+/* block until all work queued by this context has finished */
+int sb200_synchronize(sb200_ctx* ctx);
+
+/* ---- index ---------------------------------------------------------------------------------------
+ * In-memory image of fmc::BiFMIndex<Sigma, fmc::string::InterleavedBitvector16> exactly as
+ * `archive(index)` stores it (src/sahara/index.cpp:96-100, read back at src/sahara/search.cpp:162-169):
+ * per 64 BWT rows one block of Sigma u16 in-superblock counters followed by Sigma one-hot u64 bitplanes
+ * (10*Sigma bytes, unpadded); one superblock row of Sigma u64 every 65536 rows. */
+typedef struct sb200_index_view {
+    uint64_t sigma;              /* 5 (d_dna4) or 6 (d_dna5), src/sahara/search.cpp:284-287 */
+    uint64_t n_rows;             /* text length including one delimiter per sequence */
+    uint64_t n_blocks;           /* n_rows / 64 + 1 */
+    const void* bwt_blocks;      /* n_blocks * 10*sigma bytes */
+    const uint64_t* bwt_super;   /* ceil(n_blocks / 1024) * sigma */
+    const void* bwtrev_blocks;   /* same for the BWT of the reversed text */
+    const uint64_t* bwtrev_super;
+    const uint64_t* C;           /* sigma + 1 entries */
+    const uint64_t* ssa;         /* sampled suffix array: (seqId << bits_for_position) | seqPos, row order */
+    uint64_t n_ssa;
+    const uint64_t* mark_bits;   /* n_rows / 64 + 1 words, bit r set <=> row r is sampled */
+    uint64_t sampling_rate;      /* 16 in the reference, src/sahara/index.cpp:87 */
+    uint64_t bits_for_position;
+} sb200_index_view;
+
+/* replaces `archive(index)` into an fmc::BiFMIndex (src/sahara/search.cpp:162-169): copies the image to
+ * the GPU and re-lays it into the device layout; verifies the image and fails with
+ * "index layout not understood: ..." on any inconsistency. */
+int sb200_index_upload(sb200_ctx* ctx, const sb200_index_view* view);
+
+/* replaces `fmc::BiFMIndex<Sigma, InterleavedBitvector16>{ref, samplingRate, threads}`
+ * (src/sahara/index.cpp:87): builds the index on the GPU from the concatenated ranks of all sequences
+ * (no delimiters; seq_lens[n_seqs] gives the lengths). */
+int sb200_index_build(sb200_ctx* ctx, const uint8_t* seq_ranks, const uint64_t* seq_lens, uint64_t n_seqs,
+                      uint32_t sigma, uint32_t sampling_rate);
+
+/* same, for a text that already lives on the GPU (device pointer to concatenated ranks) */
+int sb200_index_build_device(sb200_ctx* ctx, const uint8_t* d_seq_ranks, const uint64_t* seq_lens, uint64_t n_seqs,
+                             uint32_t sigma, uint32_t sampling_rate);
+
+/* copies the index back in the reference image (for `archive(index)` when writing X.idx,
+ * src/sahara/index.cpp:96-100).  All arrays of *out are library-allocated: release with
+ * sb200_index_view_free(). */
+int sb200_index_download(sb200_ctx* ctx, sb200_index_view* out);
+void sb200_index_view_free(sb200_index_view* view);
+
+typedef struct sb200_index_info {
+    uint64_t sigma, n_rows, n_ssa, sampling_rate, bits_for_position;
+    uint64_t device_sampling_rate; /* sampling rate of the device-side suffix array (<= sampling_rate) */
+    uint64_t device_bytes;         /* HBM used by the index */
+    uint64_t C[8];
+} sb200_index_info;
+int sb200_index_info_get(sb200_ctx* ctx, sb200_index_info* out);
+
+/* re-samples the device suffix array to a denser rate (16, 8, 4, 2 or 1) by walking the LF mapping once;
+ * results of locate are unchanged, LF steps per located row shrink. */
+int sb200_index_densify(sb200_ctx* ctx, uint32_t device_sampling_rate);
+
+/* builds the q-gram jump table: the cursor of every string of `q` symbols over A,C,G,T, used to skip
+ * the first error-free steps of a search (q = 0 removes it). */
+int sb200_index_build_qgram(sb200_ctx* ctx, uint32_t q);
+
+/* ---- search scheme ---------------------------------------------------------------------------------
+ * expanded scheme, one entry per query character: pi/l/u are [n_searches][len] row-major — the
+ * `Scheme` handed to search_ng24::search (src/sahara/search.cpp:222-231).  edit != 0 selects
+ * search<true> (Levenshtein), 0 selects search<false> (Hamming; apply limitToHamming beforehand as
+ * src/sahara/search.cpp:226 does). */
+int sb200_set_scheme(sb200_ctx* ctx, uint32_t n_searches, uint32_t len, const uint16_t* pi, const uint8_t* l,
+                     const uint8_t* u, int edit);
+
+/* ---- search + locate ------------------------------------------------------------------------------- */
+
+/* mirrors std::tuple<size_t, fmc::LeftBiFMIndexCursor, size_t> (src/sahara/search.cpp:214-220) */
+typedef struct sb200_cursor {
+    uint64_t query_id, lb, len, errors;
+} sb200_cursor;
+
+/* mirrors the result tuple (queryId, seqId, seqPos+offset, e) (src/sahara/search.cpp:244-250) */
+typedef struct sb200_hit {
+    uint64_t query_id, seq_id, pos, errors;
+} sb200_hit;
+
+/* replaces fmc::search_ng24::search<Edit>(index, queries, scheme, res_cb) (src/sahara/search.cpp:227-231).
+ * queries: n_queries * len ranks, dense, in the reference's order ([2i] = read i, [2i+1] = its reverse
+ * complement).  Returns every reported cursor (the multiset the reference's callback receives), sorted
+ * by (query_id, lb, len, errors). */
+int sb200_search_cursors(sb200_ctx* ctx, const uint8_t* queries, uint64_t n_queries, uint32_t len,
+                         sb200_cursor** cursors, uint64_t* n_cursors);
+
+/* replaces the LocateLinear loop (src/sahara/search.cpp:244-250).  Hits come back sorted by
+ * (query_id, seq_id, pos, errors); multiplicities are preserved. */
+int sb200_locate(sb200_ctx* ctx, const sb200_cursor* cursors, uint64_t n_cursors, sb200_hit** hits,
+                 uint64_t* n_hits);
+
+/* search + locate in one call with everything kept on the GPU in between — the call `sahara search` makes */
+int sb200_search(sb200_ctx* ctx, const uint8_t* queries, uint64_t n_queries, uint32_t len, sb200_hit** hits,
+                 uint64_t* n_hits);
+
+/* same pipeline with the queries already in HBM (d_queries = device pointer) and the hits left on the
+ * GPU; returns only the counts.  Used to time the kernels without PCIe transfers. */
+int sb200_search_device(sb200_ctx* ctx, const uint8_t* d_queries, uint64_t n_queries, uint32_t len,
+                        uint64_t* n_cursors, uint64_t* n_hits);
+/* copies the hits of the last sb200_search_device call to the host */
+int sb200_fetch_hits(sb200_ctx* ctx, sb200_hit** hits, uint64_t* n_hits);
+
+void sb200_free(void* p);
+
+/* ---- rank / occ probe (kernel 1) -------------------------------------------------------------------
+ * all_ranks at BWT rows: out[i*sigma + c] = number of symbols c in bwt[0, positions[i]).
+ * which: 0 = bwt, 1 = bwtRev.  Parity hook for String::all_ranks of InterleavedBitvector16. */
+int sb200_rank_probe(sb200_ctx* ctx, int which, const uint64_t* positions, uint64_t n, uint64_t* out);
+
+/* micro-benchmark of the same device function: n_chains independent chains of `iters` dependent probes
+ * at pseudo-random rows (seeded); returns elapsed milliseconds and a checksum of the ranks. */
+int sb200_rank_bench(sb200_ctx* ctx, int which, uint64_t n_chains, uint32_t iters, uint64_t seed, float* ms,
+                     uint64_t* checksum);
+
+/* ---- counters -------------------------------------------------------------------------------------- */
+typedef struct sb200_counters {
+    uint64_t nodes;        /* cursor extensions executed by the search kernel */
+    uint64_t rank_ops;     /* BWT rows probed (2 per extension) */
+    uint64_t cursors;      /* cursors reported */
+    uint64_t lf_steps;     /* LF steps walked by the locate kernel */
+    uint64_t hits;         /* located positions */
+    uint64_t kernel_launches; /* kernels launched by this context */
+    float ms_search, ms_locate, ms_sort, ms_h2d, ms_d2h; /* last call, CUDA events */
+} sb200_counters;
+int sb200_get_counters(sb200_ctx* ctx, sb200_counters* out);
+int sb200_reset_counters(sb200_ctx* ctx);
+
+/* ---- synthetic workload ---------------------------------------------
+ * Deterministic counter-based generators, bit-identical to sahara_b200/synth.py.
+ * genome: n_bases ranks in 1..4 written to d_out (device) or out (host). */
+int sb200_synth_genome_device(sb200_ctx* ctx, uint64_t n_bases, uint64_t seed, uint8_t* d_out);
+/* reads: n_reads * 2 queries of length len (read, reverse complement) sampled from the device-resident
+ * genome with up to k errors (substitutions only when edit == 0), 10 % random reads. */
+int sb200_synth_reads_device(sb200_ctx* ctx, const uint8_t* d_genome, uint64_t n_bases, uint64_t n_reads,
+                             uint32_t len, uint32_t k, int edit, uint64_t seed, uint64_t first_read,
+                             uint8_t* d_out);
+
+/* raw device memory helpers for callers that have no CUDA runtime of their own */
+int sb200_device_alloc(sb200_ctx* ctx, uint64_t bytes, void** d_ptr);
+int sb200_device_free(sb200_ctx* ctx, void* d_ptr);
+int sb200_copy_to_host(sb200_ctx* ctx, void* dst, const void* d_src, uint64_t bytes);
+int sb200_copy_to_device(sb200_ctx* ctx, void* d_dst, const void* src, uint64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAHARA_B200_H */
