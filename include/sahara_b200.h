@@ -146,6 +146,10 @@ int sb200_fetch_hits(sb200_ctx* ctx, sb200_hit** hits, uint64_t* n_hits);
 
 void sb200_free(void* p);
 
+/* page-locked host memory for query batches (makes the host->device copy of sb200_search a single DMA);
+ * released with sb200_free. */
+int sb200_host_alloc(uint64_t bytes, void** out);
+
 /* ---- rank / occ probe (kernel 1) -------------------------------------------------------------------
  * all_ranks at BWT rows: out[i*sigma + c] = number of symbols c in bwt[0, positions[i]).
  * which: 0 = bwt, 1 = bwtRev.  Parity hook for String::all_ranks of InterleavedBitvector16. */

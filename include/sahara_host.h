@@ -1,0 +1,57 @@
+/* sahara_host.h — C entry points of the host-side helpers (no CUDA inside): search-scheme generators,
+ * index file reader/writer, FASTA + alphabet conversion.  They mirror the non-kernel calls `sahara search`
+ * makes around the hot path (file:line relative to /root/reference/):
+ *   generator lookup + expand + limitToHamming      src/sahara/search.cpp:174-212, 226
+ *   archive(sigma); archive(index)                   src/sahara/search.cpp:162-169, src/sahara/index.cpp:96-100
+ *   fasta reader, char->rank, reverse complement     src/sahara/search.cpp:115-124
+ * Used by the C++ CLI directly (headers in sahara_b200/host/) and by the Python tests through ctypes.
+ * All functions return 0 on success; sbh_last_error() holds the message otherwise. */
+#ifndef SAHARA_HOST_H
+#define SAHARA_HOST_H
+#include <stddef.h>
+#include <stdint.h>
+#include "sahara_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* sbh_last_error(void);
+
+/* ---- search schemes ---- */
+/* comma separated list of generator names */
+const char* sbh_scheme_names(void);
+/* generates scheme `name` for minK..maxK errors, expands it to `len` characters (len == 0: not expanded,
+ * one entry per part), optionally applies limitToHamming.  Outputs are library-allocated
+ * [n_searches][n_entries] tables released with sbh_free. */
+int sbh_scheme_generate(const char* name, int minK, int maxK, uint32_t len, int limit_to_hamming, uint32_t* n_searches,
+                        uint32_t* n_entries, uint16_t** pi, uint8_t** l, uint8_t** u);
+/* same from a Columba-format text ("{pi} {L} {U}" per line, 0-based) */
+int sbh_scheme_from_columba(const char* text, uint32_t len, int limit_to_hamming, uint32_t* n_searches, uint32_t* n_entries,
+                            uint16_t** pi, uint8_t** l, uint8_t** u);
+/* checks on an unexpanded scheme given as tables [n_searches][parts] */
+int sbh_scheme_check(uint32_t n_searches, uint32_t parts, const uint16_t* pi, const uint8_t* l, const uint8_t* u, int minK, int maxK,
+                     int* valid, int* complete, int* non_redundant);
+/* node counts of an expanded scheme (printed by `sahara search`, src/sahara/search.cpp:197-198) */
+int sbh_scheme_node_count(uint32_t n_searches, uint32_t len, const uint16_t* pi, const uint8_t* l, const uint8_t* u, int edit,
+                          uint64_t sigma, uint64_t ref_len, double* node_count, double* weighted_node_count);
+
+/* ---- index file ---- */
+int sbh_idx_peek_sigma(const char* path, uint64_t* sigma);
+/* loads X.idx; arrays of *out are owned by the returned handle (release with sbh_idx_free) */
+int sbh_idx_load(const char* path, sb200_index_view* out, void** handle);
+void sbh_idx_free(void* handle);
+int sbh_idx_save(const char* path, const sb200_index_view* view);
+
+/* ---- FASTA / alphabet ---- */
+/* reads all records, converts to ranks (sigma 5: d_dna4, 6: d_dna5); concatenated ranks + lengths.
+ * with_revcomp != 0: every record is followed by its reverse complement (the query order of
+ * src/sahara/search.cpp:121-123).  Invalid characters fail with the reference's message. */
+int sbh_fasta_load_ranks(const char* path, uint64_t sigma, int with_revcomp, uint8_t** ranks, uint64_t** lens, uint64_t* n_seqs);
+int sbh_revcomp_ranks(const uint8_t* in, uint64_t n, uint8_t* out);
+
+void sbh_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,295 @@
+"""Python mirror of the reference-facing interface of the hot path.
+
+Names follow /root/reference/src/sahara/search.cpp: a `SearchScheme` is what
+`fmc::search_scheme::generator::all[name].generator(minK, maxK, 0, 0)` + `expand(scheme, len)` (+
+`limitToHamming`) produce (search.cpp:174-212, 226); `Context.search` is
+`fmc::search_ng24::search<Edit>` followed by the `LocateLinear` loop (search.cpp:227-250).
+Every call goes through the C ABI (include/sahara_b200.h); nothing is computed in Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from ._native import check, check_host, cuda, host
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class SearchScheme:
+    """Tables pi/l/u of shape [n_searches, n_entries] (n_entries = parts, or query length once expanded)."""
+
+    def __init__(self, pi, l, u):
+        self.pi = np.ascontiguousarray(pi, dtype=np.uint16)
+        self.l = np.ascontiguousarray(l, dtype=np.uint8)
+        self.u = np.ascontiguousarray(u, dtype=np.uint8)
+        assert self.pi.shape == self.l.shape == self.u.shape and self.pi.ndim == 2
+
+    @property
+    def n_searches(self):
+        return self.pi.shape[0]
+
+    @property
+    def n_entries(self):
+        return self.pi.shape[1]
+
+    @staticmethod
+    def names():
+        return host.sbh_scheme_names().decode().split(",")
+
+    @staticmethod
+    def _take(ns, ne, ppi, pl, pu):
+        S, E = ns.value, ne.value
+        try:
+            pi = np.ctypeslib.as_array(C.cast(ppi, N.u16p), shape=(S * E,)).copy().reshape(S, E)
+            l = np.ctypeslib.as_array(C.cast(pl, N.u8p), shape=(S * E,)).copy().reshape(S, E)
+            u = np.ctypeslib.as_array(C.cast(pu, N.u8p), shape=(S * E,)).copy().reshape(S, E)
+        finally:
+            for p in (ppi, pl, pu):
+                host.sbh_free(p)
+        return SearchScheme(pi, l, u)
+
+    @staticmethod
+    def generate(name, min_k, max_k, length=0, limit_to_hamming=False):
+        ns, ne = C.c_uint32(), C.c_uint32()
+        ppi, pl, pu = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check_host(host.sbh_scheme_generate(name.encode(), min_k, max_k, length, int(limit_to_hamming), C.byref(ns), C.byref(ne),
+                                            C.byref(ppi), C.byref(pl), C.byref(pu)))
+        return SearchScheme._take(ns, ne, ppi, pl, pu)
+
+    @staticmethod
+    def from_columba(text, length=0, limit_to_hamming=False):
+        ns, ne = C.c_uint32(), C.c_uint32()
+        ppi, pl, pu = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check_host(host.sbh_scheme_from_columba(text.encode(), length, int(limit_to_hamming), C.byref(ns), C.byref(ne),
+                                                C.byref(ppi), C.byref(pl), C.byref(pu)))
+        return SearchScheme._take(ns, ne, ppi, pl, pu)
+
+    def to_columba(self):
+        rows = []
+        for j in range(self.n_searches):
+            rows.append(" ".join("{" + ",".join(str(int(x)) for x in t[j]) + "}" for t in (self.pi, self.l, self.u)))
+        return "\n".join(rows) + "\n"
+
+    def check(self, min_k, max_k):
+        v, c, n = C.c_int(), C.c_int(), C.c_int()
+        check_host(host.sbh_scheme_check(self.n_searches, self.n_entries, _ptr(self.pi), _ptr(self.l), _ptr(self.u), min_k, max_k,
+                                         C.byref(v), C.byref(c), C.byref(n)))
+        return bool(v.value), bool(c.value), bool(n.value)
+
+    def node_count(self, edit, sigma, ref_len):
+        a, b = C.c_double(), C.c_double()
+        check_host(host.sbh_scheme_node_count(self.n_searches, self.n_entries, _ptr(self.pi), _ptr(self.l), _ptr(self.u), int(edit),
+                                              sigma, ref_len, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+def load_fasta_ranks(path, sigma=6, with_revcomp=False):
+    """FASTA -> list of uint8 rank arrays (0='$', 1..4=ACGT, 5=N)."""
+    pr, pl, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    check_host(host.sbh_fasta_load_ranks(str(path).encode(), sigma, int(with_revcomp), C.byref(pr), C.byref(pl), C.byref(n)))
+    try:
+        lens = np.ctypeslib.as_array(C.cast(pl, N.u64p), shape=(max(1, n.value),))[: n.value].copy()
+        total = int(lens.sum())
+        ranks = np.ctypeslib.as_array(C.cast(pr, N.u8p), shape=(max(1, total),))[:total].copy()
+    finally:
+        host.sbh_free(pr)
+        host.sbh_free(pl)
+    out, o = [], 0
+    for ln in lens:
+        out.append(ranks[o:o + int(ln)])
+        o += int(ln)
+    return out
+
+
+def revcomp_ranks(r):
+    r = np.ascontiguousarray(r, dtype=np.uint8)
+    out = np.empty_like(r)
+    check_host(host.sbh_revcomp_ranks(_ptr(r), r.size, _ptr(out)))
+    return out
+
+
+class Context:
+    """One GPU: index + scheme + work buffers (sb200_ctx)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(cuda.sb200_create(device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            cuda.sb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- index ----
+    def load_index(self, path):
+        view, handle = N.IndexView(), C.c_void_p()
+        check_host(host.sbh_idx_load(str(path).encode(), C.byref(view), C.byref(handle)))
+        try:
+            check(cuda.sb200_index_upload(self._h, C.byref(view)))
+        finally:
+            host.sbh_idx_free(handle)
+
+    def upload_view(self, view):
+        check(cuda.sb200_index_upload(self._h, C.byref(view)))
+
+    def build_index(self, seqs, sigma=6, sampling_rate=16):
+        seqs = [np.ascontiguousarray(s, dtype=np.uint8) for s in seqs]
+        lens = np.array([s.size for s in seqs], dtype=np.uint64)
+        cat = np.concatenate(seqs) if seqs else np.zeros(0, np.uint8)
+        cat = np.ascontiguousarray(cat)
+        check(cuda.sb200_index_build(self._h, _ptr(cat), _ptr(lens), len(seqs), sigma, sampling_rate))
+
+    def build_index_device(self, d_ptr, lens, sigma=6, sampling_rate=16):
+        lens = np.ascontiguousarray(lens, dtype=np.uint64)
+        check(cuda.sb200_index_build_device(self._h, C.c_void_p(d_ptr), _ptr(lens), lens.size, sigma, sampling_rate))
+
+    def download_view(self):
+        view = N.IndexView()
+        check(cuda.sb200_index_download(self._h, C.byref(view)))
+        return view
+
+    def free_view(self, view):
+        cuda.sb200_index_view_free(C.byref(view))
+
+    def save_index(self, path):
+        view = self.download_view()
+        try:
+            check_host(host.sbh_idx_save(str(path).encode(), C.byref(view)))
+        finally:
+            self.free_view(view)
+
+    def info(self):
+        i = N.IndexInfo()
+        check(cuda.sb200_index_info_get(self._h, C.byref(i)))
+        return {k: (list(getattr(i, k)) if k == "C" else getattr(i, k)) for k, _ in N.IndexInfo._fields_}
+
+    def densify(self, rate):
+        check(cuda.sb200_index_densify(self._h, rate))
+
+    def build_qgram(self, q):
+        check(cuda.sb200_index_build_qgram(self._h, q))
+
+    # ---- scheme ----
+    def set_scheme(self, scheme, edit):
+        check(cuda.sb200_set_scheme(self._h, scheme.n_searches, scheme.n_entries, _ptr(scheme.pi), _ptr(scheme.l), _ptr(scheme.u),
+                                    int(edit)))
+
+    # ---- search ----
+    @staticmethod
+    def _take4(p, n):
+        try:
+            if n.value == 0:
+                return np.zeros((0, 4), dtype=np.uint64)
+            return np.ctypeslib.as_array(C.cast(p, N.u64p), shape=(n.value * 4,)).copy().reshape(-1, 4)
+        finally:
+            cuda.sb200_free(p)
+
+    @staticmethod
+    def _queries(q):
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        if q.ndim != 2:
+            raise ValueError("queries must be a dense [n_queries, length] array of ranks")
+        return q
+
+    def search(self, queries):
+        """-> uint64 [n_hits, 4] = (queryId, seqId, pos, errors), sorted."""
+        q = self._queries(queries)
+        p, n = C.c_void_p(), C.c_uint64()
+        check(cuda.sb200_search(self._h, _ptr(q), q.shape[0], q.shape[1], C.byref(p), C.byref(n)))
+        return self._take4(p, n)
+
+    def search_cursors(self, queries):
+        """-> uint64 [n, 4] = (queryId, lb, len, errors), sorted."""
+        q = self._queries(queries)
+        p, n = C.c_void_p(), C.c_uint64()
+        check(cuda.sb200_search_cursors(self._h, _ptr(q), q.shape[0], q.shape[1], C.byref(p), C.byref(n)))
+        return self._take4(p, n)
+
+    def locate(self, cursors):
+        cur = np.ascontiguousarray(cursors, dtype=np.uint64).reshape(-1, 4)
+        p, n = C.c_void_p(), C.c_uint64()
+        check(cuda.sb200_locate(self._h, _ptr(cur), cur.shape[0], C.byref(p), C.byref(n)))
+        return self._take4(p, n)
+
+    def search_device(self, d_queries, n_queries, length, locate=True):
+        nc, nh = C.c_uint64(), C.c_uint64()
+        check(cuda.sb200_search_device(self._h, C.c_void_p(d_queries), n_queries, length, C.byref(nc),
+                                       C.byref(nh) if locate else None))
+        return nc.value, nh.value
+
+    def fetch_hits(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        check(cuda.sb200_fetch_hits(self._h, C.byref(p), C.byref(n)))
+        return self._take4(p, n)
+
+    # ---- rank ----
+    def rank_probe(self, which, positions):
+        pos = np.ascontiguousarray(positions, dtype=np.uint64)
+        sigma = self.info()["sigma"]
+        out = np.zeros((pos.size, sigma), dtype=np.uint64)
+        check(cuda.sb200_rank_probe(self._h, which, _ptr(pos), pos.size, _ptr(out)))
+        return out
+
+    def rank_bench(self, which, n_chains, iters, seed=1):
+        ms, cs = C.c_float(), C.c_uint64()
+        check(cuda.sb200_rank_bench(self._h, which, n_chains, iters, seed, C.byref(ms), C.byref(cs)))
+        return ms.value, cs.value
+
+    # ---- misc ----
+    def counters(self):
+        c = N.Counters()
+        check(cuda.sb200_get_counters(self._h, C.byref(c)))
+        return {k: getattr(c, k) for k, _ in N.Counters._fields_}
+
+    def reset_counters(self):
+        check(cuda.sb200_reset_counters(self._h))
+
+    def set_stream(self, stream_ptr):
+        check(cuda.sb200_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def synchronize(self):
+        check(cuda.sb200_synchronize(self._h))
+
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        check(cuda.sb200_device_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, d_ptr):
+        check(cuda.sb200_device_free(self._h, C.c_void_p(d_ptr)))
+
+    def to_host(self, d_ptr, nbytes):
+        out = np.empty(nbytes, dtype=np.uint8)
+        check(cuda.sb200_copy_to_host(self._h, _ptr(out), C.c_void_p(d_ptr), nbytes))
+        return out
+
+    def to_device(self, d_ptr, arr):
+        arr = np.ascontiguousarray(arr)
+        check(cuda.sb200_copy_to_device(self._h, C.c_void_p(d_ptr), _ptr(arr), arr.nbytes))
+
+    def synth_genome(self, n_bases, seed):
+        d = self.device_alloc(n_bases + 64)
+        check(cuda.sb200_synth_genome_device(self._h, n_bases, seed, C.c_void_p(d)))
+        return d
+
+    def synth_reads(self, d_genome, n_bases, n_reads, length, k, edit, seed, first_read=0, d_out=None):
+        if d_out is None:
+            d_out = self.device_alloc(2 * n_reads * length)
+        check(cuda.sb200_synth_reads_device(self._h, C.c_void_p(d_genome), n_bases, n_reads, length, k, int(edit), seed, first_read,
+                                            C.c_void_p(d_out)))
+        return d_out

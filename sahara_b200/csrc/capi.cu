@@ -1228,6 +1228,10 @@ void sb200_free(void* p) {
     if (!g_pinned.free(p)) std::free(p);
 }
 
+int sb200_host_alloc(uint64_t bytes, void** out) {
+    return guard([&] { *out = g_pinned.alloc(bytes); });
+}
+
 int sb200_rank_probe(sb200_ctx* c, int which, const uint64_t* positions, uint64_t n, uint64_t* out) {
     return guard([&] {
         use(c);
