@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the sahara_b200 hot path.
+
+Metric (BASELINE.json): queries/s for 150 bp reads, k = 2 edit distance, on a synthetic human-sized genome
+(configs[3]: 3.1 Gbp, query-sharded over 1/2/4/8 B200).  One "query" = one read searched on both strands
+(SURVEY.md §8d).  A step = search + locate + sort of one batch of reads against the replicated index.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--genome BP] [--reads-per-step R]
+
+`value`  : whole-job reads/s with the queries already in HBM and the hits left in HBM (device timed).
+`e2e`    : the same through sb200_search() with pinned HOST buffers: H2D of the queries and D2H of the
+           hits (32 B per hit, the reference's tuple) inside the timed region.
+`roofline`: the search kernel; algorithmic bytes = search nodes x 2 rank-ops x 64 B over
+           its CUDA-event duration, against the measured HBM bandwidth of MEASURED_PEAKS.json.
+`cpu_baseline`: the CPU oracle (restatement of fmc::search_ng24 + LocateLinear, "port") on the host cores,
+           on a bounded sample of the same reads.
+`--impl reference` times only that CPU path (the real sahara cannot be built here: its search lives in
+fmindex-collection, fetched at configure time).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genome", type=int, default=3_100_000_000)
+    ap.add_argument("--reads-per-step", type=int, default=1_000_000)
+    ap.add_argument("--len", type=int, default=150)
+    ap.add_argument("--errors", type=int, default=2)
+    ap.add_argument("--metric", default="lev", choices=["lev", "ham"])
+    ap.add_argument("--generator", default="h2-k2")
+    ap.add_argument("--qgram", type=int, default=-1, help="q-gram jump table length (-1 = auto, 0 = off)")
+    ap.add_argument("--device-sa-rate", type=int, default=0, help="densify the device suffix array (0 = keep 16)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs"""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu = gpu
+        self.rows = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """per-launch DRAM bytes of the search kernel from the committed ncu capture, if any"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    edit = a.metric == "lev"
+
+    if a.impl == "reference" and rank != 0:
+        return 0  # the CPU arm runs on rank 0 only
+
+    import torch
+    import torch.distributed as dist
+    import sahara_b200 as sb
+
+    use_dist = world > 1 and a.impl == "b200"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sahara_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if use_dist:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    ctx = sb.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    R, m, k = a.reads_per_step, a.len, a.errors
+    n_batches = a.steps + a.warmup
+    t0 = time.time()
+    d_genome = ctx.synth_genome(a.genome, 42)
+    ctx.build_index_device(d_genome, [a.genome], 6, 16)
+    t_build = time.time() - t0
+    info = ctx.info()
+    scheme = sb.SearchScheme.generate(a.generator, 0, k, m, limit_to_hamming=not edit)
+    ctx.set_scheme(scheme, edit)
+
+    # distinct reads for every step and rank
+    def batch_first_read(b):
+        return (rank * n_batches + b) * R
+
+    workload = (f"synthetic {a.genome / 1e9:.2f} Gbp random-DNA genome (seed 42), {R} x {m} bp reads per step per GPU "
+                f"(seed 43, 90% sampled with <= {k} errors, 10% random, both strands), k={k} "
+                f"{'edit' if edit else 'Hamming'} distance, generator {a.generator}")
+    config = {"workload": workload, "genome_bp": a.genome, "reads_per_step_per_gpu": R, "read_len": m, "errors": k,
+              "distance": "edit" if edit else "hamming", "generator": a.generator, "index_rows": info["n_rows"],
+              "index_build_s": round(t_build, 2), "parallelism": f"query-sharded x{world}, index replicated",
+              "l2_policy": "inputs larger than L2: index %.1f GB, a fresh 300 MB read batch every step" % (info["device_bytes"] / 1e9)}
+
+    # ---------------- CPU arm / CPU baseline (rank 0) ----------------
+    def cpu_baseline(sample_reads, steps, warm):
+        import oracle as O
+        view = ctx.download_view()
+        try:
+            oix = O.OracleIndex.from_view(view)
+        finally:
+            ctx.free_view(view)
+        threads = O.max_threads()
+        d_q = ctx.synth_reads(d_genome, a.genome, sample_reads * (steps + warm), m, k, edit, 43, batch_first_read(0))
+        q = ctx.to_host(d_q, 2 * sample_reads * (steps + warm) * m).reshape(-1, m)
+        ctx.device_free(d_q)
+        times = []
+        hits_total = 0
+        for s in range(steps + warm):
+            qs = q[2 * sample_reads * s: 2 * sample_reads * (s + 1)]
+            t = time.perf_counter()
+            cur = oix.search(qs, scheme, edit, threads)
+            hits = oix.locate(cur, threads)
+            dt = time.perf_counter() - t
+            if s >= warm:
+                times.append(dt)
+                hits_total += hits.shape[0]
+        # one-thread run, faithful to the single-threaded reference, on a smaller slice
+        n1 = max(1, sample_reads // 8)
+        t = time.perf_counter()
+        cur1 = oix.search(q[: 2 * n1], scheme, edit, 1)
+        oix.locate(cur1, 1)
+        dt1 = time.perf_counter() - t
+        return {"oix": oix, "threads": threads, "times": times, "reads": sample_reads, "one_thread_reads_s": n1 / dt1,
+                "first_batch": q[: 2 * sample_reads], "hits": hits_total}
+
+    if a.impl == "reference":
+        sample = a.cpu_sample or 20_000
+        res = cpu_baseline(sample, a.steps, a.warmup)
+        total_t = sum(res["times"])
+        value = sample * a.steps / total_t
+        line = {"impl": "reference", "metric": "queries/s (150bp, k=2 edit)", "value": round(value, 1), "unit": "reads/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1e3 * total_t / a.steps, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": dict(config, reads_per_step_per_gpu=sample),
+                "cpu_baseline": {"value": round(value, 1), "unit": "reads/s", "cores": res["threads"], "kind": "port",
+                                 "sample": f"{sample} reads per step (both strands), CPU oracle search+locate, "
+                                           f"{res['threads']} OpenMP threads; 1 thread: {res['one_thread_reads_s']:.0f} reads/s"},
+                "e2e": {"value": round(value, 1), "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ---------------- GPU arm ----------------
+    qauto = a.qgram
+    if qauto < 0:
+        qauto = 0
+    if a.device_sa_rate:
+        ctx.densify(a.device_sa_rate)
+    if qauto:
+        ctx.build_qgram(qauto)
+
+    d_batches = [ctx.synth_reads(d_genome, a.genome, R, m, k, edit, 43, batch_first_read(b)) for b in range(n_batches)]
+
+    def barrier():
+        if use_dist:
+            t = torch.zeros(1, device="cuda")
+            dist.all_reduce(t)
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if not use_dist:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if not use_dist:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident timing (`value`) ----
+    for b in range(a.warmup):
+        ctx.search_device(d_batches[b], 2 * R, m)
+    ctx.reset_counters()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ms_search = ms_locate = ms_sort = 0.0
+    hits_total = cursors_total = 0
+    for b in range(a.warmup, n_batches):
+        nc, nh = ctx.search_device(d_batches[b], 2 * R, m)
+        c = ctx.counters()
+        ms_search += c["ms_search"]
+        ms_locate += c["ms_locate"]
+        ms_sort += c["ms_sort"]
+        hits_total += nh
+        cursors_total += nc
+    e1.record(stream)
+    barrier()
+    dev_ms = allmax(e0.elapsed_time(e1))
+    clocks = sampler.finish()
+    ct = ctx.counters()
+    launches = int(ct["kernel_launches"])
+    value = world * R * a.steps / (dev_ms * 1e-3)
+
+    # ---- end-to-end timing through the host-buffer C-ABI call ----
+    import ctypes as C
+    from sahara_b200._native import check, cuda
+    host_batches = []
+    for b in range(n_batches):  # queries go device -> pinned host once, outside the timed region
+        t = torch.empty(2 * R * m, dtype=torch.uint8, pin_memory=True)
+        check(cuda.sb200_copy_to_host(ctx._h, C.c_void_p(t.data_ptr()), C.c_void_p(d_batches[b]), 2 * R * m))
+        host_batches.append(t)
+
+    def e2e_step(t):
+        p, n = C.c_void_p(), C.c_uint64()
+        check(cuda.sb200_search(ctx._h, C.c_void_p(t.data_ptr()), 2 * R, m, C.byref(p), C.byref(n)))
+        first = 0
+        if n.value:
+            first = C.cast(p, C.POINTER(C.c_uint64))[0]  # touch the result on the host
+        cuda.sb200_free(p)
+        return n.value, first
+
+    for b in range(a.warmup):
+        e2e_step(host_batches[b])
+    barrier()
+    t_start = time.perf_counter()
+    e2e_hits = 0
+    for b in range(a.warmup, n_batches):
+        nh, _ = e2e_step(host_batches[b])
+        e2e_hits += nh
+    barrier()
+    e2e_s = allmax(time.perf_counter() - t_start)
+    e2e_value = world * R * a.steps / e2e_s
+    h2d = 2 * R * m
+    d2h = int(32 * e2e_hits / a.steps)
+
+    # ---- roofline of the search kernel ----
+    peak, peak_src = measured_peak()
+    nodes = ct["nodes"]  # extensions executed over the K timed steps (q-gram off => identical to the oracle's count)
+    alg_bytes_per_launch = nodes * 128 / a.steps
+    ms_per_launch = ms_search / a.steps
+    achieved = alg_bytes_per_launch / (ms_per_launch * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    roofline = {"bound": "hbm", "kernel": "sb200::search_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes_per_launch),
+                "nodes_per_launch": int(nodes / a.steps), "rank_ops_per_s": round(2 * nodes / (ms_search * 1e-3), 1),
+                "ms_per_launch": round(ms_per_launch, 3),
+                "phase_ms_per_step": {"search": round(ms_search / a.steps, 3), "locate": round(ms_locate / a.steps, 3),
+                                      "sort": round(ms_sort / a.steps, 3)},
+                "qgram": qauto, "lf_steps_per_step": int(ct["lf_steps"] / a.steps)}
+
+    line = {"metric": "queries/s (150bp, k=2 edit)", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": round(dev_ms / a.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 1), "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(1e3 * e2e_s / a.steps, 3)},
+            "gpu_launches": launches, "roofline": roofline,
+            "hits_per_step": int(hits_total / a.steps), "cursors_per_step": int(cursors_total / a.steps)}
+
+    if rank == 0 and not a.no_cpu_baseline:
+        sample = a.cpu_sample or 20_000
+        res = cpu_baseline(sample, 1, 0)
+        cpu_v = sample / res["times"][0]
+        # parity of the sample through the C ABI against the oracle (checker, not the measured path)
+        oix = res["oix"]
+        cur = oix.search(res["first_batch"], scheme, edit, res["threads"])
+        import oracle as O
+        want = O.sort_rows(oix.locate(cur, res["threads"]))
+        got = ctx.search(res["first_batch"])
+        line["parity_sample_ok"] = bool(np.array_equal(got, want))
+        line["cpu_baseline"] = {"value": round(cpu_v, 1), "unit": "reads/s", "cores": res["threads"], "kind": "port",
+                                "sample": f"first {sample} reads of rank 0's first batch (both strands), CPU oracle search+locate, "
+                                          f"{res['threads']} OpenMP threads",
+                                "one_thread_value": round(res["one_thread_reads_s"], 1)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

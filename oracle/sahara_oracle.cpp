@@ -340,6 +340,54 @@ static std::unique_ptr<Index<S>> load_index(FILE* f) {
     return idx;
 }
 
+
+// In-memory image of the index in the on-disk packing (same fields as the file; mirror of the product's
+// sb200_index_view, declared here so that the oracle stays self-contained).
+struct OrcIndexView {
+    u64 sigma, n_rows, n_blocks;
+    void const* bwt_blocks;
+    u64 const* bwt_super;
+    void const* bwtrev_blocks;
+    u64 const* bwtrev_super;
+    u64 const* C;
+    u64 const* ssa;
+    u64 n_ssa;
+    u64 const* mark_bits;
+    u64 sampling_rate, bits_for_position;
+};
+
+template <int S>
+static std::unique_ptr<Index<S>> index_from_view(OrcIndexView const& v) {
+    auto idx = std::make_unique<Index<S>>();
+    idx->sigma = S;
+    auto fill = [&](OccTable<S>& t, void const* blocks, u64 const* super) {
+        t.n = v.n_rows;
+        t.blocks.resize(v.n_blocks);
+        u8 const* p = static_cast<u8 const*>(blocks);
+#if defined(_OPENMP)
+#pragma omp parallel for schedule(static)
+#endif
+        for (u64 b = 0; b < v.n_blocks; ++b) {
+            std::memcpy(t.blocks[b].cnt, p + b * 10 * S, 2 * S);
+            std::memcpy(t.blocks[b].bits, p + b * 10 * S + 2 * S, 8 * S);
+        }
+        u64 ns = (v.n_blocks + 1023) / 1024;
+        t.superBlocks.resize(ns);
+        for (u64 i = 0; i < ns; ++i) std::memcpy(t.superBlocks[i].data(), super + i * S, 8 * S);
+    };
+    fill(idx->bwt, v.bwt_blocks, v.bwt_super);
+    fill(idx->bwtRev, v.bwtrev_blocks, v.bwtrev_super);
+    std::memcpy(idx->C.data(), v.C, 8 * (S + 1));
+    idx->ssa.assign(v.ssa, v.ssa + v.n_ssa);
+    idx->marks.n = v.n_rows;
+    idx->marks.bits.assign(v.mark_bits, v.mark_bits + (v.n_rows / 64 + 1));
+    idx->marks.finalize();
+    idx->samplingRate = v.sampling_rate;
+    idx->bitsForPosition = v.bits_for_position;
+    if (idx->marks.ones() != v.n_ssa) throw std::runtime_error("index layout not understood: marked rows != samples");
+    return idx;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Bidirectional cursor: (lb, lbRev, len); extendLeft uses bwt, extendRight bwtRev.
 // ---------------------------------------------------------------------------------------------
@@ -601,6 +649,15 @@ int orc_index_build(u8 const* seqs, u64 const* lens, u64 nSeqs, int sigma, u64 s
         if (sigma == 5) *out = static_cast<IndexBase*>(build_index<5>(seqs, lens, nSeqs, samplingRate).release());
         else if (sigma == 6) *out = static_cast<IndexBase*>(build_index<6>(seqs, lens, nSeqs, samplingRate).release());
         else throw std::runtime_error("unknown index with " + std::to_string(sigma) + " letters");
+    });
+}
+
+int orc_index_from_view(void const* view, void** out) {
+    return guard([&] {
+        auto const& v = *static_cast<OrcIndexView const*>(view);
+        if (v.sigma == 5) *out = static_cast<IndexBase*>(index_from_view<5>(v).release());
+        else if (v.sigma == 6) *out = static_cast<IndexBase*>(index_from_view<6>(v).release());
+        else throw std::runtime_error("unknown index with " + std::to_string(v.sigma) + " letters");
     });
 }
 

@@ -13,6 +13,7 @@ _lib.orc_last_error.restype = C.c_char_p
 _lib.orc_max_threads.restype = C.c_int
 _lib.orc_index_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]
 _lib.orc_index_free.argtypes = [C.c_void_p]
+_lib.orc_index_from_view.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
 _lib.orc_index_save.argtypes = [C.c_void_p, C.c_char_p]
 _lib.orc_index_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
 _lib.orc_index_info.argtypes = [C.c_void_p, C.c_void_p]
@@ -58,6 +59,13 @@ class OracleIndex:
         cat = np.ascontiguousarray(np.concatenate(seqs)) if seqs else np.zeros(1, np.uint8)
         h = C.c_void_p()
         _check(_lib.orc_index_build(_ptr(cat), _ptr(lens), len(seqs), sigma, sampling_rate, C.byref(h)))
+        return OracleIndex(h)
+
+    @staticmethod
+    def from_view(view):
+        """view: ctypes structure with the layout of sb200_index_view (arrays are copied)"""
+        h = C.c_void_p()
+        _check(_lib.orc_index_from_view(C.byref(view), C.byref(h)))
         return OracleIndex(h)
 
     @staticmethod
