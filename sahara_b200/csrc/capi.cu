@@ -563,11 +563,13 @@ void launch_search_k(sb200_ctx* c, const SearchParams& P, unsigned grid, size_t 
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         kern<<<grid, 256, smem, c->stream>>>(P);
     };
+    // worst-case stack depth of the pair/chain traversal (search.cuh): D(k) = 2, D(e) = F(e) - 1 + D(e + 1)
+    // with F(e) <= 9 (k - e) + 2 frames pushed per iteration
     if (k == 0) go(std::integral_constant<int, 4>{});
-    else if (k == 1) go(std::integral_constant<int, 12>{});
-    else if (k == 2) go(std::integral_constant<int, 22>{});
-    else if (k == 3) go(std::integral_constant<int, 32>{});
-    else if (k == 4) go(std::integral_constant<int, 42>{});
+    else if (k == 1) go(std::integral_constant<int, 16>{});
+    else if (k == 2) go(std::integral_constant<int, 36>{});
+    else if (k == 3) go(std::integral_constant<int, 64>{});
+    else if (k == 4) go(std::integral_constant<int, 96>{});
     else throw Error("search schemes with more than 4 errors are not supported by the GPU kernel yet");
     launch_check(c);
 }
@@ -618,9 +620,11 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         P.counters = c->d_counters.get<unsigned long long>();
         P.qgram = ix.qgram_q ? ix.qgram.get<uint4>() : nullptr;
         P.qgram_q = ix.qgram_q;
+        if (const char* dbg = std::getenv("SB200_DEBUG")) P.debug_flags = static_cast<uint32_t>(std::atoi(dbg));
         launch_search(c, P);
         CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->d_counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (std::getenv("SB200_DEBUG")) fprintf(stderr, "[sb200 debug] max stack depth %llu overflow %llu\n", c->h_counters[5], c->h_counters[3]);
         if (c->h_counters[3]) throw Error("internal error: search stack overflow");
         n_cursors = c->h_counters[1];
         if (n_cursors <= c->cursor_cap) break;

@@ -17,7 +17,23 @@
 // 4 bits per row instead of the reference's 8: a 3.1 Gbp index is 2 x 1.55 GB.
 #pragma once
 #include <cstdint>
+#if defined(SB200_HOST_EMU)
+// Host emulation of the device code (tests/host_emu): the kernel bodies are compiled with g++ and run as a
+// single thread so that the traversal logic can be checked against the oracle without a GPU.
+#include <cstring>
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __align__(n) alignas(n)
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+static inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = v; return o; }
+static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; if (v > o) *p = v; return o; }
+#else
 #include <cuda_runtime.h>
+#endif
 
 namespace sb200 {
 
@@ -44,6 +60,25 @@ struct U32x8 {
 };
 
 // one 256-bit load = one memory request (LDG.E.ENL2.256 on sm_100a)
+#if defined(SB200_HOST_EMU)
+__device__ __forceinline__ OccBlk load_blk(const OccBlk* p) { return *p; }
+__device__ __forceinline__ OccSup load_sup(const OccSup* p) { return *p; }
+#elif defined(SB200_NO_LD256)
+__device__ __forceinline__ OccBlk load_blk(const OccBlk* p) {
+    const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p);
+    ulonglong2 a = __ldg(q), b = __ldg(q + 1);
+    OccBlk r;
+    r.p0 = a.x; r.p1 = a.y; r.p2 = b.x; r.ctr = b.y;
+    return r;
+}
+__device__ __forceinline__ OccSup load_sup(const OccSup* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    OccSup r;
+    r.c[0] = a.x; r.c[1] = a.y; r.c[2] = a.z; r.c[3] = a.w; r.c[4] = b.x; r.c[5] = b.y; r.c[6] = b.z; r.c[7] = b.w;
+    return r;
+}
+#else
 __device__ __forceinline__ OccBlk load_blk(const OccBlk* p) {
     OccBlk r;
     asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.p0), "=l"(r.p1), "=l"(r.p2), "=l"(r.ctr) : "l"(p));
@@ -57,6 +92,7 @@ __device__ __forceinline__ OccSup load_sup(const OccSup* p) {
                  : "l"(p));
     return r;
 }
+#endif
 
 // occurrences of rank s (1..5) among the first `o` rows of the block (o in 0..63)
 __device__ __forceinline__ uint32_t blk_count(const OccBlk& b, uint32_t o, int s) {

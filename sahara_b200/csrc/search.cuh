@@ -16,6 +16,7 @@
 // The order in which cursors are reported differs from the reference's recursion order; the reported
 // multiset is identical (the reference does not depend on order, src/sahara/search.cpp:218-220).
 #pragma once
+#include <cstdio>
 #include "layout.cuh"
 
 namespace sb200 {
@@ -46,185 +47,230 @@ struct SearchParams {
     // optional q-gram jump table (cursor after the first qgram_q characters of a search)
     const uint4* qgram;  // [4^q] (lb, lbRev, len, 0)
     uint32_t qgram_q;
+    uint32_t debug_flags;  // 1: no pair frames, 2: no insertion chains (diagnostics only)
 };
 
-template <int SIGMA, bool EDIT, int STACK>
-__global__ void __launch_bounds__(256) search_kernel(const SearchParams P) {
-    extern __shared__ uint32_t s_steps[];
-    for (uint32_t i = threadIdx.x; i < P.n_searches * P.len; i += blockDim.x) s_steps[i] = P.steps[i];
-    __syncthreads();
+// Frames and states.  A stack frame is a cursor plus one search state (step, e, LInfo, RInfo), or — flag
+// PAIR — the two states a mismatching symbol produces on the same child cursor: the deletion
+// (step, e, side = D) and the substitution (step + 1, e, side = S).  Both extend the same cursor, so one
+// probe of the occurrence table serves both.  Likewise the insertion child of a state keeps the cursor
+// of its parent: it is processed in the same iteration ("insertion chain") from the ranks already in
+// registers.  Every state is expanded exactly like the corresponding call of the reference recursion,
+// so the reported multiset is unchanged; only the number of memory probes shrinks.
+constexpr uint32_t META_PAIR = 1u << 18;
 
+// body of one (persistent) thread; s_steps = the packed scheme table (shared memory on the device)
+template <int SIGMA, bool EDIT, int STACK>
+__device__ __forceinline__ void search_thread(const SearchParams& P, const uint32_t* s_steps) {
     uint4 stack[STACK];
     int sp = 0;
-    uint32_t lb = 0, lbRev = 0, len = 0, meta = 0;
-    bool have = false;
     const uint8_t* q = nullptr;
     const uint32_t* tbl = nullptr;
     uint32_t qid = 0;
     uint32_t nodes = 0;
     bool overflow = false;
+    int maxsp = 0;
     const uint32_t total_items = P.n_queries * P.n_searches;
     const uint32_t qlen = P.len;
 
+    auto emit = [&](uint32_t lb, uint32_t len, uint32_t e) {
+        uint32_t idx = static_cast<uint32_t>(atomicAdd(&P.counters[1], 1ull));
+#if defined(SB200_TRACE)
+        if (P.debug_flags & 4u) printf("EMIT q=%u lb=%u len=%u e=%u idx=%u\n", qid, lb, len, e, idx);
+#endif
+        if (idx < P.out_cap) P.out[idx] = make_uint4(qid, lb, len, e);
+    };
+
     while (true) {
-        if (!have) {
-            if (sp > 0) {
-                uint4 f = stack[--sp];
-                lb = f.x; lbRev = f.y; len = f.z; meta = f.w;
-            } else {
-                uint32_t w = static_cast<uint32_t>(atomicAdd(&P.counters[0], 1ull));
-                if (w >= total_items) break;
-                qid = w / P.n_searches;
-                tbl = s_steps + (w % P.n_searches) * qlen;
-                q = P.queries + static_cast<uint64_t>(qid) * qlen;
-                lb = 0; lbRev = 0; len = P.n_rows; meta = 0;
-                uint32_t st0 = tbl[0];
-                if (((st0 >> 16) & 0xf) > 1) continue;  // neither a match nor a mismatch allowed at step 0
-                // q-gram jump: skip the leading steps that allow no error
-                if (P.qgram_q) {
-                    uint32_t qq = P.qgram_q;
-                    bool ok = qq <= qlen;
-                    uint32_t code = 0;
-                    bool right0 = (st0 >> 24) & 1;
-                    for (uint32_t i = 0; ok && i < qq; ++i) {
-                        uint32_t st = tbl[i];
-                        ok = ((st >> 20) & 0xf) == 0;  // u == 0 (then l == 0 as well)
-                        uint32_t c = q[st & 0xffff];
-                        ok = ok && c >= 1 && c <= 4;
-                        ok = ok && (((st >> 24) & 1) == right0);
-                        // table is keyed by the string in text order
-                        if (right0) code = (code << 2) | (c - 1);
-                        else code |= (c - 1) << (2 * i);
+        uint32_t lb, lbRev, len, meta;
+        maxsp = sp > maxsp ? sp : maxsp;
+        if (sp > 0) {
+            uint4 f = stack[--sp];
+            lb = f.x; lbRev = f.y; len = f.z; meta = f.w;
+        } else {
+            uint32_t w = static_cast<uint32_t>(atomicAdd(&P.counters[0], 1ull));
+            if (w >= total_items) break;
+            qid = w / P.n_searches;
+            tbl = s_steps + (w % P.n_searches) * qlen;
+            q = P.queries + static_cast<uint64_t>(qid) * qlen;
+            lb = 0; lbRev = 0; len = P.n_rows; meta = 0;
+            uint32_t st0 = tbl[0];
+            if (((st0 >> 16) & 0xfu) > 1) continue;  // neither a match nor a mismatch allowed at step 0
+            if (P.qgram_q) {  // q-gram jump: skip the leading steps that allow no error
+                uint32_t qq = P.qgram_q;
+                bool ok = qq <= qlen;
+                uint32_t code = 0;
+                bool right0 = (st0 >> 24) & 1u;
+                for (uint32_t i = 0; ok && i < qq; ++i) {
+                    uint32_t st = tbl[i];
+                    uint32_t c = q[st & 0xffffu];
+                    ok = ((st >> 20) & 0xfu) == 0 && c >= 1 && c <= 4 && (((st >> 24) & 1u) == right0);
+                    // the table is keyed by the string in text order, first symbol most significant
+                    if (right0) code = (code << 2) | (c - 1);
+                    else code |= (c - 1) << (2 * i);
+                }
+                if (ok) {
+                    uint4 g = P.qgram[code];
+                    if (g.z == 0) continue;
+                    lb = g.x; lbRev = g.y; len = g.z;
+                    if (qq == qlen) {
+                        emit(lb, len, 0);
+                        continue;
                     }
-                    if (ok) {
-                        uint4 g = P.qgram[code];
-                        if (g.z == 0) continue;
-                        lb = g.x; lbRev = g.y; len = g.z;
-                        uint32_t L = INFO_M, R = INFO_M;
-                        if (qq == qlen) {
-                            uint32_t idx = static_cast<uint32_t>(atomicAdd(&P.counters[1], 1ull));
-                            if (idx < P.out_cap) P.out[idx] = make_uint4(qid, lb, len, 0);
-                            continue;
-                        }
-                        uint32_t st = tbl[qq];
-                        if (((st >> 16) & 0xf) > 1) continue;
-                        meta = pack_meta(qq, 0, L, R);
-                    }
+                    if (((tbl[qq] >> 16) & 0xfu) > 1) continue;
+                    meta = pack_meta(qq, 0, INFO_M, INFO_M);
                 }
             }
         }
-        have = false;
 
-        // ---- one cursor extension ---------------------------------------------------------------
-        const uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
-        const uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
-        const uint32_t st = tbl[step];
-        const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
-        const bool right = (st >> 24) & 1u;
-        const uint32_t c = q[st & 0xffffu];
-        const bool matchOK = l <= e && e <= u;
-        const bool mmOK = l <= e + 1 && e + 1 <= u;
-        const uint32_t T = right ? Rinfo : Linfo;
-
+        // ---- one probe of the occurrence table for this cursor ------------------------------------
+        uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
+        uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
+        const bool pair = (meta & META_PAIR) != 0;
+        const bool right = (tbl[step] >> 24) & 1u;
         const OccTable& tab = right ? P.bwtRev : P.bwt;
         const uint32_t lo = right ? lbRev : lb;
         const uint32_t hi = lo + len;
-        const bool sameBlk = (lo >> kBlkShift) == (hi >> kBlkShift);
         OccBlk b1 = load_blk(tab.blk + (lo >> kBlkShift));
         OccSup s1 = load_sup(tab.sup + (lo >> kSupShift));
         OccBlk b2 = b1;
         OccSup s2 = s1;
-        if (!sameBlk) {
+        if ((lo >> kBlkShift) != (hi >> kBlkShift)) {
             b2 = load_blk(tab.blk + (hi >> kBlkShift));
             if ((lo >> kSupShift) != (hi >> kSupShift)) s2 = load_sup(tab.sup + (hi >> kSupShift));
         }
-        ++nodes;
-
-        uint32_t r1[SIGMA], cnt[SIGMA];
+        // child cursors per symbol: (klb[s], klbRev[s], cnt[s]).  The probed side continues at C[s] + rank(lo, s),
+        // the other side moves by the number of smaller symbols inside the interval.
+        uint32_t klb[SIGMA], klbRev[SIGMA], cnt[SIGMA];
         {
+            uint32_t own[SIGMA];
             uint32_t sum1 = 0, sumc = 0;
 #pragma unroll
             for (int s = 1; s < SIGMA; ++s) {
                 uint32_t a = s1.c[s] + blk_ctr(b1, s) + blk_count(b1, lo & 63u, s);
                 uint32_t b = s2.c[s] + blk_ctr(b2, s) + blk_count(b2, hi & 63u, s);
-                r1[s] = a;
+                own[s] = P.C[s] + a;
                 cnt[s] = b - a;
                 sum1 += a;
                 sumc += b - a;
             }
-            r1[0] = lo - sum1;
+            own[0] = lo - sum1;  // C[0] == 0
             cnt[0] = len - sumc;
-        }
-
-        // pending child kept in registers
-        uint32_t plb = 0, plbRev = 0, plen = 0, pmeta = 0;
-        bool phave = false;
-
-        auto offer = [&](uint32_t nlb, uint32_t nlbRev, uint32_t nlen, uint32_t nstep, uint32_t ne, uint32_t nL,
-                         uint32_t nR) {
-            if (nlen == 0) return;
-            if (nstep == qlen) {
-                if (!EDIT || (((nL | nR) & 1u) == 0)) {  // both ends M or I
-                    uint32_t idx = static_cast<uint32_t>(atomicAdd(&P.counters[1], 1ull));
-                    if (idx < P.out_cap) P.out[idx] = make_uint4(qid, nlb, nlen, ne);
-                }
-                return;
-            }
-            uint32_t st2 = tbl[nstep];
-            uint32_t l2 = (st2 >> 16) & 0xfu, u2 = (st2 >> 20) & 0xfu;
-            if (!(ne <= u2 && l2 <= ne + 1)) return;  // neither match nor mismatch possible there
-            if (phave) {
-                if (sp < STACK) stack[sp++] = make_uint4(plb, plbRev, plen, pmeta);
-                else overflow = true;
-            }
-            plb = nlb; plbRev = nlbRev; plen = nlen; pmeta = pack_meta(nstep, ne, nL, nR);
-            phave = true;
-        };
-
-        // child cursor for symbol s
-        uint32_t smaller = 0;  // occurrences of symbols < s inside the interval
-        uint32_t mLb = 0, mLbRev = 0, mLen = 0;
-        const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
-        const bool insOK = EDIT && (T == INFO_M || T == INFO_I);
-        // match first
-        {
-            uint32_t sm = 0;
+            uint32_t other = right ? lb : lbRev;  // interval start on the side that is not probed
 #pragma unroll
             for (int s = 0; s < SIGMA; ++s) {
-                if (static_cast<uint32_t>(s) == c) {
-                    uint32_t own = P.C[s] + r1[s];
-                    mLb = right ? lb + sm : own;
-                    mLbRev = right ? own : lbRev + sm;
-                    mLen = cnt[s];
-                }
-                sm += cnt[s];
+                klb[s] = right ? other : own[s];
+                klbRev[s] = right ? own[s] : other;
+                other += cnt[s];
             }
         }
-        if (matchOK) {
-            offer(mLb, mLbRev, mLen, step + 1, e, right ? Linfo : INFO_M, right ? INFO_M : Rinfo);
-        }
-        if (mmOK) {
-            smaller = cnt[0];
+
+        // ---- expand every state that lives on this cursor ------------------------------------------
+        bool second = false;  // second half of a pair already taken
+        while (true) {
+            ++nodes;
+#if defined(SB200_TRACE)
+            if (P.debug_flags & 4u)
+                printf("STATE q=%u lb=%u lbRev=%u len=%u step=%u e=%u L=%u R=%u pair=%d second=%d right=%d cnt=%u,%u,%u,%u,%u,%u\n", qid, lb,
+                       lbRev, len, step, e, Linfo, Rinfo, (int)pair, (int)second, (int)right, cnt[0], cnt[1], cnt[2], cnt[3], cnt[4],
+                       SIGMA > 5 ? cnt[SIGMA - 1] : 0u);
+#endif
+            const uint32_t st = tbl[step];
+            const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
+            const uint32_t c = q[st & 0xffffu];
+            const bool last = step + 1 == qlen;
+            const uint32_t stn = last ? 0u : tbl[step + 1];
+            const uint32_t lnext = (stn >> 16) & 0xfu;
+            const bool sameDirNext = !last && (((stn >> 24) & 1u) == static_cast<uint32_t>(right));
+            const bool matchOK = l <= e && e <= u;
+            const bool mmOK = l <= e + 1 && e + 1 <= u;
+            const uint32_t T = right ? Rinfo : Linfo;
+            const uint32_t O = right ? Linfo : Rinfo;  // info of the other end
+            const bool otherEndOK = !EDIT || (O & 1u) == 0;  // M or I
+            // metas of the possible children: the moving side gets the new info
+            const uint32_t keepL = right ? Linfo : 0u, keepR = right ? 0u : Rinfo;
+            const uint32_t sideShift = right ? 16u : 14u;
+            const uint32_t metaBase = (keepL << 14) | (keepR << 16);
+            const uint32_t mM = metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift);
+            const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift);
+            const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift);
+            const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift);
+            // match
+            {
+                uint32_t mc = 0, nlb = 0, nlbRev = 0;
 #pragma unroll
-            for (int s = 1; s < SIGMA; ++s) {
-                if (static_cast<uint32_t>(s) != c && cnt[s] != 0) {
-                    uint32_t own = P.C[s] + r1[s];
-                    uint32_t nlb = right ? lb + smaller : own;
-                    uint32_t nlbRev = right ? own : lbRev + smaller;
-                    if (delOK) offer(nlb, nlbRev, cnt[s], step, e + 1, right ? Linfo : INFO_D, right ? INFO_D : Rinfo);
-                    offer(nlb, nlbRev, cnt[s], step + 1, e + 1, right ? Linfo : INFO_S, right ? INFO_S : Rinfo);
+                for (int s = 0; s < SIGMA; ++s)
+                    if (static_cast<uint32_t>(s) == c) { mc = cnt[s]; nlb = klb[s]; nlbRev = klbRev[s]; }
+                const bool alive = matchOK && mc != 0;
+                if (alive && last) {
+                    if (otherEndOK) emit(nlb, mc, e);
+                } else if (alive && lnext <= e + 1) {
+                    if (sp < STACK) stack[sp] = make_uint4(nlb, nlbRev, mc, mM);
+                    else overflow = true;
+                    ++sp;
                 }
-                smaller += cnt[s];
             }
-            if (insOK) offer(lb, lbRev, len, step + 1, e + 1, right ? Linfo : INFO_I, right ? INFO_I : Rinfo);
-        }
-        if (phave) {
-            lb = plb; lbRev = plbRev; len = plen; meta = pmeta;
-            have = true;
+            if (mmOK) {
+                const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
+                const bool subAlive = !last && lnext <= e + 2;
+                const bool asPair = delOK && subAlive && sameDirNext && !(P.debug_flags & 1u);
+#pragma unroll
+                for (int s = 1; s < SIGMA; ++s) {
+                    const bool live = static_cast<uint32_t>(s) != c && cnt[s] != 0;
+                    const uint32_t nlb = klb[s], nlbRev = klbRev[s];
+                    if (live && (asPair || delOK)) {
+                        if (sp < STACK) stack[sp] = make_uint4(nlb, nlbRev, cnt[s], asPair ? (mD | META_PAIR) : mD);
+                        else overflow = true;
+                        ++sp;
+                    }
+                    if (live && !asPair && subAlive) {
+                        if (sp < STACK) stack[sp] = make_uint4(nlb, nlbRev, cnt[s], mS);
+                        else overflow = true;
+                        ++sp;
+                    }
+                    if (!EDIT && live && last) emit(nlb, cnt[s], e + 1);
+                }
+            }
+            // next state on the same cursor
+            if (pair) {
+                if (second) break;
+                second = true;
+                // second half of the pair: the substitution (step + 1, e, side = S)
+                step += 1;
+                if (right) Rinfo = INFO_S; else Linfo = INFO_S;
+                continue;
+            }
+            const bool insOK = EDIT && mmOK && (T == INFO_M || T == INFO_I);
+            if (!insOK) break;
+            if (last) {
+                if (otherEndOK) emit(lb, len, e + 1);
+                break;
+            }
+            if (lnext > e + 2) break;  // dead at the next step
+            if (!sameDirNext || (P.debug_flags & 2u)) {  // direction changes: needs a probe of the other table
+                if (sp < STACK) stack[sp] = make_uint4(lb, lbRev, len, mI);
+                else overflow = true;
+                ++sp;
+                break;
+            }
+            step += 1;
+            e += 1;
+            if (right) Rinfo = INFO_I; else Linfo = INFO_I;
         }
     }
     if (nodes) atomicAdd(&P.counters[2], static_cast<unsigned long long>(nodes));
     if (overflow) atomicExch(&P.counters[3], 1ull);
+    atomicMax(&P.counters[5], static_cast<unsigned long long>(maxsp));
 }
+
+#if !defined(SB200_HOST_EMU)
+template <int SIGMA, bool EDIT, int STACK>
+__global__ void __launch_bounds__(256) search_kernel(const SearchParams P) {
+    extern __shared__ uint32_t s_steps[];
+    for (uint32_t i = threadIdx.x; i < P.n_searches * P.len; i += blockDim.x) s_steps[i] = P.steps[i];
+    __syncthreads();
+    search_thread<SIGMA, EDIT, STACK>(P, s_steps);
+}
+#endif
 
 }  // namespace sb200

@@ -1,0 +1,52 @@
+"""ctypes wrapper of the host emulation of the CUDA search kernel (tests/host_emu/search_emu.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libsearch_emu.so")
+SRC = os.path.join(HERE, "search_emu.cpp")
+
+
+def _build():
+    deps = [SRC] + [os.path.join(HERE, "..", "..", "sahara_b200", "csrc", f) for f in ("search.cuh", "layout.cuh")]
+    if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
+        return
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=undefined",
+                           "-fno-sanitize-recover=undefined", SRC, "-o", SO])
+
+
+_build()
+_lib = C.CDLL(SO)
+_lib.emu_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
+                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                            C.POINTER(C.c_uint64)]
+_lib.emu_free.argtypes = [C.c_void_p]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def search(oracle_index, queries, scheme, edit, debug_flags=0):
+    """runs the kernel body on the host over the oracle index's BWTs -> (sorted cursors uint64 [n,4], nodes)"""
+    info = oracle_index.info()
+    bwt = np.ascontiguousarray(oracle_index.bwt(0))
+    rev = np.ascontiguousarray(oracle_index.bwt(1))
+    Carr = np.array(info["C"], dtype=np.uint64)
+    q = np.ascontiguousarray(queries, dtype=np.uint8)
+    out, n, nodes = C.c_void_p(), C.c_uint64(), C.c_uint64()
+    rc = _lib.emu_search(_p(bwt), _p(rev), info["n_rows"], info["sigma"], _p(Carr), _p(q), q.shape[0], q.shape[1], scheme.n_searches,
+                         _p(scheme.pi), _p(scheme.l), _p(scheme.u), int(edit), debug_flags, C.byref(out), C.byref(n), C.byref(nodes))
+    if rc != 0:
+        raise RuntimeError(f"emu_search failed with code {rc}")
+    try:
+        a = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint32)), shape=(max(1, n.value) * 4,))[: n.value * 4].copy()
+    finally:
+        _lib.emu_free(out)
+    a = a.reshape(-1, 4).astype(np.uint64)
+    if a.shape[0]:
+        a = a[np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))]
+    return a, nodes.value

@@ -1,0 +1,104 @@
+// search_emu.cpp — host emulation of the CUDA search kernel (test infrastructure).
+// Compiles sahara_b200/csrc/search.cuh with g++ (SB200_HOST_EMU) and runs the per-thread body as a single
+// thread over a device-layout index built on the host from BWT symbols.  Lets the `-m "not gpu"` tests
+// compare the real kernel source with the oracle.
+#define SB200_HOST_EMU 1
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../sahara_b200/csrc/search.cuh"
+
+using namespace sb200;
+
+namespace {
+struct HostOcc {
+    std::vector<OccBlk> blk;
+    std::vector<OccSup> sup;
+    void build(const uint8_t* bwt, uint64_t n) {
+        uint64_t nb = n / 64 + 1, ns = nb / 64 + 1;
+        blk.assign(nb + 1, OccBlk{0, 0, 0, 0});
+        sup.assign(ns + 1, OccSup{});
+        uint32_t abs[8] = {0}, rel[8] = {0};
+        for (uint64_t b = 0; b < nb; ++b) {
+            if (b % 64 == 0) {
+                for (int c = 0; c < 8; ++c) { sup[b / 64].c[c] = abs[c]; rel[c] = 0; }
+            }
+            OccBlk& o = blk[b];
+            for (int s = 1; s < 6; ++s) o.ctr |= uint64_t(rel[s] & 0xfff) << (12 * (s - 1));
+            for (uint64_t r = b * 64; r < (b + 1) * 64 && r < n; ++r) {
+                uint32_t c = bwt[r];
+                o.p0 |= uint64_t(c & 1) << (r & 63);
+                o.p1 |= uint64_t((c >> 1) & 1) << (r & 63);
+                o.p2 |= uint64_t((c >> 2) & 1) << (r & 63);
+                abs[c]++; rel[c]++;
+            }
+        }
+    }
+};
+}  // namespace
+
+extern "C" {
+
+// bwt / bwtRev: symbols per row; C: sigma+1 entries; scheme tables as for sb200_set_scheme.
+// out: library-allocated (qid, lb, len, e) u32 quadruples, release with emu_free.
+int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int sigma, const uint64_t* C, const uint8_t* queries,
+               uint64_t n_queries, uint32_t len, uint32_t n_searches, const uint16_t* pi, const uint8_t* l, const uint8_t* u, int edit,
+               uint32_t debug_flags, uint32_t** out, uint64_t* n_out, uint64_t* nodes) {
+    HostOcc a, b;
+    a.build(bwt, n_rows);
+    b.build(bwtRev, n_rows);
+    std::vector<uint32_t> steps(size_t(n_searches) * len);
+    uint32_t kmax = 0;
+    for (uint32_t j = 0; j < n_searches; ++j)
+        for (uint32_t i = 0; i < len; ++i) {
+            size_t k = size_t(j) * len + i;
+            bool right = (i == 0) ? (len < 2 || pi[k] < pi[k + 1]) : (pi[k - 1] < pi[k]);
+            steps[k] = pack_step(pi[k], l[k], u[k], right);
+            if (u[k] > kmax) kmax = u[k];
+        }
+    if (kmax > 4) return 2;
+    uint64_t cap = 1 << 16;
+    std::vector<uint4> buf;
+    unsigned long long counters[8];
+    while (true) {
+        buf.assign(cap + 1, uint4{0, 0, 0, 0});
+        std::memset(counters, 0, sizeof counters);
+        SearchParams P{};
+        P.bwt = OccTable{a.blk.data(), a.sup.data()};
+        P.bwtRev = OccTable{b.blk.data(), b.sup.data()};
+        for (int i = 0; i < 8; ++i) P.C[i] = static_cast<uint32_t>(i <= sigma ? C[i] : n_rows);
+        P.n_rows = static_cast<uint32_t>(n_rows);
+        P.queries = queries;
+        P.n_queries = static_cast<uint32_t>(n_queries);
+        P.len = len;
+        P.n_searches = n_searches;
+        P.steps = steps.data();
+        P.out = buf.data();
+        P.out_cap = static_cast<uint32_t>(cap);
+        P.counters = counters;
+        P.qgram = nullptr;
+        P.qgram_q = 0;
+        P.debug_flags = debug_flags;
+        if (sigma == 6) {
+            if (edit) search_thread<6, true, 96>(P, steps.data());
+            else search_thread<6, false, 96>(P, steps.data());
+        } else if (sigma == 5) {
+            if (edit) search_thread<5, true, 96>(P, steps.data());
+            else search_thread<5, false, 96>(P, steps.data());
+        } else return 3;
+        if (counters[3]) return 4;  // stack overflow
+        if (counters[1] <= cap) break;
+        cap = counters[1];
+    }
+    uint64_t n = counters[1];
+    *out = static_cast<uint32_t*>(std::malloc(std::max<uint64_t>(1, n) * 16));
+    std::memcpy(*out, buf.data(), n * 16);
+    *n_out = n;
+    if (nodes) *nodes = counters[2];
+    return 0;
+}
+
+void emu_free(void* p) { std::free(p); }
+}
