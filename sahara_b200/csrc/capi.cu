@@ -162,9 +162,9 @@ struct sb200_ctx {
     uint32_t n_searches{}, qlen{}, kmax{};
     bool edit{}, have_scheme{};
     // work buffers
-    DevBuf d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
+    DevBuf d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
     uint64_t cursor_cap{};
-    uint64_t last_cursors{}, last_hits{};
+    uint64_t last_cursors{}, last_real_cursors{}, last_hits{};
     bool hits_in_second{};  // which of the double buffers holds the sorted hits
     unsigned long long* h_counters{};  // pinned, 8 entries
     sb200_counters ct{};
@@ -575,11 +575,13 @@ void launch_search_k(sb200_ctx* c, const SearchParams& P, unsigned grid, size_t 
 }
 
 void launch_search(sb200_ctx* c, const SearchParams& P) {
-    size_t smem = size_t(P.n_searches) * P.len * 4;
-    if (smem > 200 * 1024) throw Error("search scheme table does not fit shared memory");
-    unsigned grid = static_cast<unsigned>(c->sms) * 4;
-    uint64_t items = uint64_t(P.n_queries) * P.n_searches;
-    unsigned need = grid_for(items);
+    // shared memory: scheme table + one staged packed query per thread
+    size_t smem = (size_t(P.n_searches) * P.len + size_t(packed_words(P.len)) * 256) * 4;
+    if (smem > 100 * 1024) throw Error("search scheme table and staged queries do not fit shared memory (query too long)");
+    unsigned per_sm = 4;
+    if (const char* e = std::getenv("SB200_BLOCKS_PER_SM")) per_sm = static_cast<unsigned>(std::max(1, std::atoi(e)));
+    unsigned grid = static_cast<unsigned>(c->sms) * per_sm;
+    unsigned need = grid_for((uint64_t(P.n_queries) + kQueryBatch - 1) / kQueryBatch);
     if (need < grid) grid = std::max(1u, need);
     with_sigma(c->idx.sigma, [&](auto S) {
         if (c->edit) launch_search_k<S(), true>(c, P, grid, smem);
@@ -601,6 +603,10 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
     if (c->cursor_cap < n_queries * 16) c->cursor_cap = std::max<uint64_t>(1 << 20, n_queries * 16);
     c->d_counters.reserve(8 * sizeof(unsigned long long));
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    const uint32_t W = packed_words(len);
+    c->d_packed.reserve(n_queries * W * 4);
+    pack_queries_kernel<<<grid_for(n_queries * W), 256, 0, c->stream>>>(d_queries, n_queries, len, c->d_packed.get<uint32_t>());
+    launch_check(c);
     uint64_t n_cursors = 0;
     while (true) {
         c->d_cursors.reserve((c->cursor_cap + 1) * sizeof(uint4));
@@ -611,6 +617,7 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         for (int i = 0; i < 8; ++i) P.C[i] = ix.C[i];
         P.n_rows = static_cast<uint32_t>(ix.n_rows);
         P.queries = d_queries;
+        P.packed = c->d_packed.get<uint32_t>();
         P.n_queries = static_cast<uint32_t>(n_queries);
         P.len = len;
         P.n_searches = c->n_searches;
@@ -637,8 +644,9 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
     c->ct.ms_locate = c->ct.ms_sort = 0;
     c->ct.nodes += c->h_counters[2];
     c->ct.rank_ops += 2 * c->h_counters[2];
-    c->ct.cursors += n_cursors;
-    c->last_cursors = n_cursors;
+    c->ct.cursors += c->h_counters[6];
+    c->last_cursors = n_cursors;  // reserved output slots; unused ones are empty entries (qid 0xffffffff, len 0)
+    c->last_real_cursors = c->h_counters[6];
     c->last_hits = 0;
 }
 
@@ -814,7 +822,7 @@ int sb200_destroy(sb200_ctx* c) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         c->idx.release();
-        for (DevBuf* b : {&c->d_steps, &c->d_queries, &c->d_cursors, &c->d_counters, &c->d_offsets, &c->d_keys[0], &c->d_keys[1],
+        for (DevBuf* b : {&c->d_steps, &c->d_packed, &c->d_queries, &c->d_cursors, &c->d_counters, &c->d_offsets, &c->d_keys[0], &c->d_keys[1],
                           &c->d_qids[0], &c->d_qids[1], &c->d_tmp, &c->d_scratch})
             b->release();
         for (auto& ev : c->ev) cudaEventDestroy(ev);
@@ -1160,7 +1168,7 @@ int sb200_search_device(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queri
     return guard([&] {
         use(c);
         run_pipeline(c, d_queries, n_queries, len, n_hits != nullptr);
-        if (n_cursors) *n_cursors = c->last_cursors;
+        if (n_cursors) *n_cursors = c->last_real_cursors;
         if (n_hits) *n_hits = c->last_hits;
     });
 }
@@ -1191,6 +1199,9 @@ int sb200_search_cursors(sb200_ctx* c, const uint8_t* queries, uint64_t n_querie
         std::vector<uint4> tmp(n);
         CUDA_TRY(cudaMemcpyAsync(tmp.data(), c->d_cursors.p, n * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
+        tmp.erase(std::remove_if(tmp.begin(), tmp.end(), [](uint4 const& a) { return a.x == kInvalidQid; }), tmp.end());
+        if (tmp.size() != c->last_real_cursors) throw Error("internal error: cursor count mismatch");
+        n = tmp.size();
         std::sort(tmp.begin(), tmp.end(), [](uint4 const& a, uint4 const& b) {
             if (a.x != b.x) return a.x < b.x;
             if (a.y != b.y) return a.y < b.y;

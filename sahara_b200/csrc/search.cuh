@@ -38,11 +38,13 @@ struct SearchParams {
     uint32_t C[8];
     uint32_t n_rows;
     const uint8_t* queries;  // [n_queries][len] ranks
+    const uint32_t* packed;  // [n_queries][packed_words(len)] 4-bit packed copies of the queries
     uint32_t n_queries, len, n_searches;
     const uint32_t* steps;   // [n_searches][len] packed
     uint4* out;              // (qid, lb, len, e)
     uint32_t out_cap;
-    // counters: [0] next work item, [1] cursors reported, [2] nodes, [3] stack overflow flag
+    // counters: [0] next query, [1] output slots reserved, [2] nodes, [3] stack overflow flag, [5] max stack depth,
+    //           [6] cursors reported
     unsigned long long* counters;
     // optional q-gram jump table (cursor after the first qgram_q characters of a search)
     const uint4* qgram;  // [4^q] (lb, lbRev, len, 0)
@@ -58,44 +60,79 @@ struct SearchParams {
 // registers.  Every state is expanded exactly like the corresponding call of the reference recursion,
 // so the reported multiset is unchanged; only the number of memory probes shrinks.
 constexpr uint32_t META_PAIR = 1u << 18;
+constexpr uint32_t kEmitChunk = 16;       // output slots a thread reserves per atomic
+constexpr uint32_t kQueryBatch = 2;       // queries a thread takes per atomic
+constexpr uint32_t kInvalidQid = 0xffffffffu;
 
-// body of one (persistent) thread; s_steps = the packed scheme table (shared memory on the device)
+// queries packed 8 symbols per word (4 bits each) by pack_queries_kernel
+__host__ __device__ inline uint32_t packed_words(uint32_t len) { return (len + 7) / 8; }
+
+#if !defined(SB200_HOST_EMU)
+__global__ void pack_queries_kernel(const uint8_t* q, uint64_t n_queries, uint32_t len, uint32_t* out) {
+    uint32_t W = packed_words(len);
+    uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n_queries * W) return;
+    uint64_t qi = i / W;
+    uint32_t w = static_cast<uint32_t>(i % W);
+    const uint8_t* src = q + qi * len + w * 8;
+    uint32_t v = 0;
+    for (uint32_t k = 0; k < 8 && w * 8 + k < len; ++k) v |= static_cast<uint32_t>(src[k] & 0xfu) << (4 * k);
+    out[i] = v;
+}
+#endif
+
+// body of one (persistent) thread.
+//   s_steps: the packed scheme table (shared memory on the device)
+//   s_query: this thread's staging area for the packed query, element w at s_query[w * qstride]
 template <int SIGMA, bool EDIT, int STACK>
-__device__ __forceinline__ void search_thread(const SearchParams& P, const uint32_t* s_steps) {
+__device__ __forceinline__ void search_thread(const SearchParams& P, const uint32_t* s_steps, uint32_t* s_query, uint32_t qstride) {
     uint4 stack[STACK];
     int sp = 0;
-    const uint8_t* q = nullptr;
     const uint32_t* tbl = nullptr;
-    uint32_t qid = 0;
-    uint32_t nodes = 0;
+    uint32_t qid = 0, qid_end = 0, next_search = P.n_searches;  // forces the first fetch
+    uint32_t nodes = 0, emitted = 0;
+    uint32_t out_pos = 0, out_end = 0;
     bool overflow = false;
     int maxsp = 0;
-    const uint32_t total_items = P.n_queries * P.n_searches;
     const uint32_t qlen = P.len;
+    const uint32_t W = packed_words(qlen);
+
+    auto qsym = [&](uint32_t pos) -> uint32_t { return (s_query[(pos >> 3) * qstride] >> ((pos & 7u) * 4u)) & 0xfu; };
 
     auto emit = [&](uint32_t lb, uint32_t len, uint32_t e) {
-        uint32_t idx = static_cast<uint32_t>(atomicAdd(&P.counters[1], 1ull));
+        if (out_pos == out_end) {
+            out_pos = static_cast<uint32_t>(atomicAdd(&P.counters[1], static_cast<unsigned long long>(kEmitChunk)));
+            out_end = out_pos + kEmitChunk;
+        }
 #if defined(SB200_TRACE)
-        if (P.debug_flags & 4u) printf("EMIT q=%u lb=%u len=%u e=%u idx=%u\n", qid, lb, len, e, idx);
+        if (P.debug_flags & 4u) printf("EMIT q=%u lb=%u len=%u e=%u\n", qid, lb, len, e);
 #endif
-        if (idx < P.out_cap) P.out[idx] = make_uint4(qid, lb, len, e);
+        if (out_pos < P.out_cap) P.out[out_pos] = make_uint4(qid, lb, len, e);
+        ++out_pos;
+        ++emitted;
     };
 
+    bool done = false;
     while (true) {
-        uint32_t lb, lbRev, len, meta;
-        maxsp = sp > maxsp ? sp : maxsp;
-        if (sp > 0) {
-            uint4 f = stack[--sp];
-            lb = f.x; lbRev = f.y; len = f.z; meta = f.w;
-        } else {
-            uint32_t w = static_cast<uint32_t>(atomicAdd(&P.counters[0], 1ull));
-            if (w >= total_items) break;
-            qid = w / P.n_searches;
-            tbl = s_steps + (w % P.n_searches) * qlen;
-            q = P.queries + static_cast<uint64_t>(qid) * qlen;
-            lb = 0; lbRev = 0; len = P.n_rows; meta = 0;
+        // ---- make sure there is a frame: next search of the current query, next query, next batch ----
+        while (sp == 0) {
+            if (next_search == P.n_searches) {
+                next_search = 0;
+                ++qid;
+                if (qid >= qid_end) {
+                    unsigned long long w = atomicAdd(&P.counters[0], static_cast<unsigned long long>(kQueryBatch));
+                    if (w >= P.n_queries) { done = true; break; }
+                    qid = static_cast<uint32_t>(w);
+                    qid_end = qid + kQueryBatch < P.n_queries ? qid + kQueryBatch : P.n_queries;
+                }
+                const uint32_t* src = P.packed + static_cast<uint64_t>(qid) * W;
+                for (uint32_t w = 0; w < W; ++w) s_query[w * qstride] = src[w];
+            }
+            tbl = s_steps + next_search * qlen;
+            ++next_search;
             uint32_t st0 = tbl[0];
             if (((st0 >> 16) & 0xfu) > 1) continue;  // neither a match nor a mismatch allowed at step 0
+            uint4 root = make_uint4(0, 0, P.n_rows, 0);
             if (P.qgram_q) {  // q-gram jump: skip the leading steps that allow no error
                 uint32_t qq = P.qgram_q;
                 bool ok = qq <= qlen;
@@ -103,7 +140,7 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
                 bool right0 = (st0 >> 24) & 1u;
                 for (uint32_t i = 0; ok && i < qq; ++i) {
                     uint32_t st = tbl[i];
-                    uint32_t c = q[st & 0xffffu];
+                    uint32_t c = qsym(st & 0xffffu);
                     ok = ((st >> 20) & 0xfu) == 0 && c >= 1 && c <= 4 && (((st >> 24) & 1u) == right0);
                     // the table is keyed by the string in text order, first symbol most significant
                     if (right0) code = (code << 2) | (c - 1);
@@ -112,15 +149,23 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
                 if (ok) {
                     uint4 g = P.qgram[code];
                     if (g.z == 0) continue;
-                    lb = g.x; lbRev = g.y; len = g.z;
                     if (qq == qlen) {
-                        emit(lb, len, 0);
+                        emit(g.x, g.z, 0);
                         continue;
                     }
                     if (((tbl[qq] >> 16) & 0xfu) > 1) continue;
-                    meta = pack_meta(qq, 0, INFO_M, INFO_M);
+                    root = make_uint4(g.x, g.y, g.z, pack_meta(qq, 0, INFO_M, INFO_M));
                 }
             }
+            stack[0] = root;
+            sp = 1;
+        }
+        if (done) break;
+        maxsp = sp > maxsp ? sp : maxsp;
+        uint32_t lb, lbRev, len, meta;
+        {
+            uint4 f = stack[--sp];
+            lb = f.x; lbRev = f.y; len = f.z; meta = f.w;
         }
 
         // ---- one probe of the occurrence table for this cursor ------------------------------------
@@ -177,11 +222,12 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
 #endif
             const uint32_t st = tbl[step];
             const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
-            const uint32_t c = q[st & 0xffffu];
+            const uint32_t c = qsym(st & 0xffffu);
             const bool last = step + 1 == qlen;
             const uint32_t stn = last ? 0u : tbl[step + 1];
             const uint32_t lnext = (stn >> 16) & 0xfu;
-            const bool sameDirNext = !last && (((stn >> 24) & 1u) == static_cast<uint32_t>(right));
+            const bool rightNext = (stn >> 24) & 1u;
+            const bool sameDirNext = !last && (rightNext == right);
             const bool matchOK = l <= e && e <= u;
             const bool mmOK = l <= e + 1 && e + 1 <= u;
             const uint32_t T = right ? Rinfo : Linfo;
@@ -227,7 +273,7 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
                         if (sp < STACK) stack[sp] = make_uint4(nlb, nlbRev, cnt[s], mS);
                         else overflow = true;
                         ++sp;
-                    }
+                        }
                     if (!EDIT && live && last) emit(nlb, cnt[s], e + 1);
                 }
             }
@@ -258,18 +304,24 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
             if (right) Rinfo = INFO_I; else Linfo = INFO_I;
         }
     }
+    // unused slots of the last reserved chunk become empty entries (len 0: they locate to nothing)
+    for (; out_pos < out_end; ++out_pos)
+        if (out_pos < P.out_cap) P.out[out_pos] = make_uint4(kInvalidQid, 0, 0, 0);
     if (nodes) atomicAdd(&P.counters[2], static_cast<unsigned long long>(nodes));
     if (overflow) atomicExch(&P.counters[3], 1ull);
     atomicMax(&P.counters[5], static_cast<unsigned long long>(maxsp));
+    if (emitted) atomicAdd(&P.counters[6], static_cast<unsigned long long>(emitted));
 }
 
 #if !defined(SB200_HOST_EMU)
 template <int SIGMA, bool EDIT, int STACK>
-__global__ void __launch_bounds__(256) search_kernel(const SearchParams P) {
+__global__ void __launch_bounds__(256, 4) search_kernel(const SearchParams P) {
     extern __shared__ uint32_t s_steps[];
-    for (uint32_t i = threadIdx.x; i < P.n_searches * P.len; i += blockDim.x) s_steps[i] = P.steps[i];
+    const uint32_t n_steps = P.n_searches * P.len;
+    for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) s_steps[i] = P.steps[i];
     __syncthreads();
-    search_thread<SIGMA, EDIT, STACK>(P, s_steps);
+    // word w of this thread's query lives at s_query[w * blockDim.x]: every lane stays in its own bank
+    search_thread<SIGMA, EDIT, STACK>(P, s_steps, s_steps + n_steps + threadIdx.x, blockDim.x);
 }
 #endif
 

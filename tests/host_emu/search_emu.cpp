@@ -59,6 +59,10 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
             if (u[k] > kmax) kmax = u[k];
         }
     if (kmax > 4) return 2;
+    uint32_t W = packed_words(len);
+    std::vector<uint32_t> packed(size_t(n_queries) * W, 0), stage(W + 1, 0);
+    for (uint64_t qi = 0; qi < n_queries; ++qi)
+        for (uint32_t i = 0; i < len; ++i) packed[qi * W + i / 8] |= uint32_t(queries[qi * len + i] & 0xf) << (4 * (i % 8));
     uint64_t cap = 1 << 16;
     std::vector<uint4> buf;
     unsigned long long counters[8];
@@ -71,6 +75,7 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
         for (int i = 0; i < 8; ++i) P.C[i] = static_cast<uint32_t>(i <= sigma ? C[i] : n_rows);
         P.n_rows = static_cast<uint32_t>(n_rows);
         P.queries = queries;
+        P.packed = packed.data();
         P.n_queries = static_cast<uint32_t>(n_queries);
         P.len = len;
         P.n_searches = n_searches;
@@ -82,19 +87,21 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
         P.qgram_q = 0;
         P.debug_flags = debug_flags;
         if (sigma == 6) {
-            if (edit) search_thread<6, true, 96>(P, steps.data());
-            else search_thread<6, false, 96>(P, steps.data());
+            if (edit) search_thread<6, true, 96>(P, steps.data(), stage.data(), 1);
+            else search_thread<6, false, 96>(P, steps.data(), stage.data(), 1);
         } else if (sigma == 5) {
-            if (edit) search_thread<5, true, 96>(P, steps.data());
-            else search_thread<5, false, 96>(P, steps.data());
+            if (edit) search_thread<5, true, 96>(P, steps.data(), stage.data(), 1);
+            else search_thread<5, false, 96>(P, steps.data(), stage.data(), 1);
         } else return 3;
         if (counters[3]) return 4;  // stack overflow
         if (counters[1] <= cap) break;
         cap = counters[1];
     }
-    uint64_t n = counters[1];
-    *out = static_cast<uint32_t*>(std::malloc(std::max<uint64_t>(1, n) * 16));
-    std::memcpy(*out, buf.data(), n * 16);
+    uint64_t slots = counters[1], n = 0;
+    *out = static_cast<uint32_t*>(std::malloc(std::max<uint64_t>(1, slots) * 16));
+    for (uint64_t i = 0; i < slots; ++i)
+        if (buf[i].x != kInvalidQid) std::memcpy(*out + 4 * n++, &buf[i], 16);
+    if (n != counters[6]) return 5;
     *n_out = n;
     if (nodes) *nodes = counters[2];
     return 0;
