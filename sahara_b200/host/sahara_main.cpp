@@ -1,1 +1,390 @@
-int main() { return 0; }
+// sahara_main.cpp — `sahara index` and `sahara search` on the B200 path.
+//
+// Drop-in for the two sub-commands of the reference that surround the hot path
+//   /root/reference/src/sahara/index.cpp:20-121   (sahara index <fasta> [--ignore_unknown] [--dna4])
+//   /root/reference/src/sahara/search.cpp:23-291  (sahara search -q Q -i X.idx [-o OUT] [-g GEN] [-e K]
+//                                                  [--no-reverse] [-m all] [-d ham|lev] [--limit_queries N])
+// Same flags, same index file, same "queryId seqId pos" output lines, same statistics block.  The
+// library calls the reference makes into fmindex-collection are replaced by the C ABI of
+// include/sahara_b200.h.  Queries are sharded over the visible GPUs (--gpus N,
+// index replicated); hit lists are concatenated on the host in query order.
+//
+// Not implemented on the GPU path (fails with a clear message): -m besthits, --max_hits > 0,
+// --dynamic_generator (SURVEY.md §8f "next" rows).
+#include <chrono>
+#include <cinttypes>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <iterator>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/sahara_b200.h"
+#include "alphabet.hpp"
+#include "fasta.hpp"
+#include "idxfile.hpp"
+#include "scheme.hpp"
+
+namespace {
+
+struct StopWatch {  // /root/reference/src/sahara/utils/StopWatch.h:8-29
+    std::chrono::steady_clock::time_point start{std::chrono::steady_clock::now()};
+    double reset() {
+        auto now = std::chrono::steady_clock::now();
+        double d = std::chrono::duration<double>(now - start).count();
+        start = now;
+        return d;
+    }
+};
+
+[[noreturn]] void fail(std::string const& msg) { throw std::runtime_error(msg); }
+
+void check(int rc) {
+    if (rc != 0) fail(sb200_last_error());
+}
+
+struct Args {
+    std::vector<std::string> pos;
+    std::vector<std::pair<std::string, std::string>> opts;
+    bool has(std::string const& k) const {
+        for (auto const& [a, b] : opts)
+            if (a == k) return true;
+        return false;
+    }
+    std::string get(std::string const& k, std::string const& def = "") const {
+        for (auto const& [a, b] : opts)
+            if (a == k) return b;
+        return def;
+    }
+};
+
+// flags that take a value
+bool takesValue(std::string const& f) {
+    static char const* v[] = {"-q", "--query", "-i", "--index", "-o", "--output", "-g", "--generator", "-e", "--errors", "-m",
+                              "--search_mode", "-d", "--distance-metric", "--max_hits", "--limit_queries", "--gpus", "--scheme-file",
+                              "--batch", "--device-sa-rate", "--qgram"};
+    for (auto s : v)
+        if (f == s) return true;
+    return false;
+}
+
+std::string canonical(std::string const& f) {
+    if (f == "-q") return "--query";
+    if (f == "-i") return "--index";
+    if (f == "-o") return "--output";
+    if (f == "-g") return "--generator";
+    if (f == "-e") return "--errors";
+    if (f == "-m") return "--search_mode";
+    if (f == "-d") return "--distance-metric";
+    return f;
+}
+
+Args parse(int argc, char** argv, int first) {
+    Args a;
+    for (int i = first; i < argc; ++i) {
+        std::string s = argv[i];
+        if (s.size() > 1 && s[0] == '-') {
+            if (takesValue(s)) {
+                if (i + 1 >= argc) fail("option " + s + " needs a value");
+                a.opts.emplace_back(canonical(s), argv[++i]);
+            } else {
+                a.opts.emplace_back(canonical(s), "1");
+            }
+        } else {
+            a.pos.push_back(s);
+        }
+    }
+    return a;
+}
+
+void printTiming(std::vector<std::pair<std::string, double>> const& timing, double* total) {
+    printf("stats:\n");
+    *total = 0;
+    for (auto const& [key, t] : timing) {
+        printf("  %-20s %10.2fs\n", (key + " time:").c_str(), t);
+        *total += t;
+    }
+    printf("  total time:          %10.2fs\n", *total);
+}
+
+int gpuCount() {
+    int n = 0;
+    check(sb200_device_count(&n));
+    if (n == 0) fail("sahara_b200 needs a CUDA device and has no CPU fallback");
+    return n;
+}
+
+// ---- sahara index ---------------------------------------------------------------------------------
+template <typename Alphabet>
+void createIndex(Args const& a) {
+    if (a.pos.empty()) fail("usage: sahara index <fasta> [--ignore_unknown] [--dna4]");
+    std::string path = a.pos[0];
+    bool ignoreUnknown = a.has("--ignore_unknown"), dna4 = a.has("--dna4");
+    constexpr size_t Sigma = Alphabet::size();
+    printf("constructing an index for %s\n", path.c_str());
+    std::vector<std::pair<std::string, double>> timing;
+    StopWatch sw;
+
+    std::vector<uint8_t> all;
+    std::vector<uint64_t> lens;
+    size_t totalSize = 0, count = 0;
+    sahara::fasta::read(path, [&](sahara::fasta::Record& rec) {
+        ++count;
+        totalSize += rec.seq.size();
+        auto r = sahara::convert_char_to_rank<Alphabet>(rec.seq);
+        if (ignoreUnknown) {
+            for (auto& v : r) {
+                if (sahara::verify_rank(v)) continue;
+                v = dna4 ? static_cast<uint8_t>(Alphabet::char_to_rank('A') + rand() % 4) : Alphabet::char_to_rank('N');
+            }
+        }
+        if (auto pos = sahara::verify_rank(r); pos) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "ref '%s' (%zu) has invalid character '%c' (0x%02x) at position %zu", rec.id.c_str(), count,
+                     rec.seq[*pos], static_cast<unsigned>(static_cast<uint8_t>(rec.seq[*pos])), *pos);
+            fail(buf);
+        }
+        for (auto v : r)
+            if (v == 0) fail("ref '" + rec.id + "' contains the delimiter character '$'");
+        all.insert(all.end(), r.begin(), r.end());
+        lens.push_back(r.size());
+    });
+    if (lens.empty()) fail("reference file " + path + " was empty - abort\n");
+    printf("config:\n  file: %s\n  sigma: %zu\n  references: %zu\n  totalSize: %zu\n", path.c_str(), Sigma, lens.size(), totalSize);
+    timing.emplace_back("ld queries", sw.reset());
+
+    gpuCount();
+    sb200_ctx* ctx = nullptr;
+    check(sb200_create(0, &ctx));
+    check(sb200_index_build(ctx, all.data(), lens.data(), lens.size(), static_cast<uint32_t>(Sigma), /*samplingRate*/ 16));
+    timing.emplace_back("index creation", sw.reset());
+
+    std::string indexPath = path + (dna4 ? ".dna4.idx" : ".idx");
+    sb200_index_view view{};
+    check(sb200_index_download(ctx, &view));
+    sahara::saveIndexFile(indexPath, view);
+    sb200_index_view_free(&view);
+    sb200_destroy(ctx);
+    timing.emplace_back("saving to disk", sw.reset());
+    double total;
+    printTiming(timing, &total);
+}
+
+// ---- sahara search --------------------------------------------------------------------------------
+template <typename Alphabet>
+void runSearch(Args const& a) {
+    namespace ss = sahara::scheme;
+    constexpr size_t Sigma = Alphabet::size();
+    std::string queryPath = a.get("--query"), indexPath = a.get("--index"), outPath = a.get("--output", "sahara-output.txt");
+    std::string generator = a.get("--generator", "h2-k2"), mode = a.get("--search_mode", "all"), metric = a.get("--distance-metric", "lev");
+    size_t k = std::stoul(a.get("--errors", "0"));
+    bool noReverse = a.has("--no-reverse");
+    long maxHits = std::stol(a.get("--max_hits", "0"));
+    size_t limitQueries = std::stoul(a.get("--limit_queries", "0"));
+    if (mode != "all" && mode != "besthits") fail("unknown search mode \"" + mode + "\"");
+    if (metric != "ham" && metric != "lev") fail("unknown distance metric \"" + metric + "\"");
+    if (mode == "besthits") fail("search mode besthits is not available on the GPU path yet");
+    if (maxHits != 0) fail("--max_hits is not available on the GPU path yet");
+    if (a.has("--dynamic_generator")) fail("--dynamic_generator is not available on the GPU path yet");
+    bool edit = metric == "lev";
+
+    std::vector<std::pair<std::string, double>> timing;
+    StopWatch sw;
+
+    // load fasta file: queries[2i] = read i, queries[2i+1] = its reverse complement (search.cpp:115-124)
+    std::vector<uint8_t> queries;
+    size_t nQueries = 0, qlen = 0, count = 0;
+    sahara::fasta::read(queryPath, [&](sahara::fasta::Record& rec) {
+        ++count;
+        auto r = sahara::convert_char_to_rank<Alphabet>(rec.seq);
+        if (auto pos = sahara::verify_rank(r); pos) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "query '%s' (%zu) has invalid character at position %zu '%c'(%x)", rec.id.c_str(), nQueries + 1, *pos,
+                     rec.seq[*pos], static_cast<unsigned>(static_cast<uint8_t>(rec.seq[*pos])));
+            fail(buf);
+        }
+        if (nQueries == 0) qlen = r.size();
+        if (r.size() != qlen)
+            fail("query '" + rec.id + "' has length " + std::to_string(r.size()) + ", the search scheme is expanded for the length of the first query (" +
+                 std::to_string(qlen) + ")");
+        queries.insert(queries.end(), r.begin(), r.end());
+        ++nQueries;
+        if (!noReverse) {
+            auto rc = sahara::reverse_complement_rank<Alphabet>(r);
+            queries.insert(queries.end(), rc.begin(), rc.end());
+            ++nQueries;
+        }
+    });
+    if (limitQueries) {
+        nQueries = std::min(limitQueries, nQueries);
+        queries.resize(nQueries * qlen);
+    }
+    if (nQueries == 0) fail("query file " + queryPath + " was empty - abort\n");
+    timing.emplace_back("ld queries", sw.reset());
+
+    printf("config:\n  query:               %s\n  index:               %s\n  generator:           %s\n  dynamic expansion:   %s\n"
+           "  allowed errors:      %zu\n  reverse complements: %s\n  search mode:         %s\n  max hits:            %ld\n"
+           "  output path:         %s\n",
+           queryPath.c_str(), indexPath.c_str(), generator.c_str(), "false", k, noReverse ? "false" : "true", mode.c_str(), maxHits,
+           outPath.c_str());
+    {
+        size_t fwd = nQueries / (noReverse ? 1 : 2);
+        printf("fwd queries: %zu\nbwd queries: %zu\n", fwd, nQueries - fwd);
+    }
+    if (!std::filesystem::exists(indexPath)) fail("no valid index path at " + indexPath);
+
+    int nGpus = gpuCount();
+    if (a.has("--gpus")) nGpus = std::min(nGpus, std::max(1, std::stoi(a.get("--gpus"))));
+    nGpus = static_cast<int>(std::min<size_t>(nGpus, (nQueries + 1) / 2));
+    auto image = sahara::loadIndexFile(indexPath);
+    auto view = image.view();
+    std::vector<sb200_ctx*> ctxs(nGpus, nullptr);
+    for (int g = 0; g < nGpus; ++g) {
+        check(sb200_create(g, &ctxs[g]));
+        check(sb200_index_upload(ctxs[g], &view));
+        if (a.has("--device-sa-rate")) check(sb200_index_densify(ctxs[g], std::stoul(a.get("--device-sa-rate"))));
+        if (a.has("--qgram")) check(sb200_index_build_qgram(ctxs[g], std::stoul(a.get("--qgram"))));
+    }
+    timing.emplace_back("ld index", sw.reset());
+
+    // search scheme (search.cpp:174-212, 226)
+    ss::Scheme scheme;
+    if (a.has("--scheme-file")) {
+        std::ifstream in(a.get("--scheme-file"));
+        if (!in) fail("cannot open scheme file " + a.get("--scheme-file"));
+        std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        scheme = ss::fromColumba(text);
+        if (!ss::isComplete(scheme, 0, k)) fail("the scheme in " + a.get("--scheme-file") + " is not complete for " + std::to_string(k) + " errors");
+    } else {
+        scheme = ss::generator::generate(generator, 0, static_cast<int>(k));
+    }
+    scheme = ss::expand(scheme, qlen);
+    if (edit) {
+        printf("node count: %.0Lf\n", ss::nodeCount<true>(scheme, Sigma));
+        printf("weighted node count: %.2Lf\n", ss::weightedNodeCount<true>(scheme, Sigma, image.n_rows));
+    } else {
+        printf("node count: %.0Lf\n", ss::nodeCount<false>(scheme, Sigma));
+        printf("weighted node count: %.2Lf\n", ss::weightedNodeCount<false>(scheme, Sigma, image.n_rows));
+        scheme = ss::limitToHamming(scheme);
+    }
+    std::vector<uint16_t> pi;
+    std::vector<uint8_t> lo, up;
+    for (auto const& s : scheme)
+        for (size_t i = 0; i < s.pi.size(); ++i) {
+            pi.push_back(static_cast<uint16_t>(s.pi[i]));
+            lo.push_back(static_cast<uint8_t>(s.l[i]));
+            up.push_back(static_cast<uint8_t>(s.u[i]));
+        }
+    for (auto* c : ctxs)
+        check(sb200_set_scheme(c, static_cast<uint32_t>(scheme.size()), static_cast<uint32_t>(qlen), pi.data(), lo.data(), up.data(), edit));
+    timing.emplace_back("searchScheme", sw.reset());
+
+    // search + locate: contiguous shards of reads per GPU, batches inside a shard
+    size_t batch = std::stoul(a.get("--batch", "2000000"));
+    batch += batch & 1;  // keep both strands of a read together
+    std::vector<std::vector<sb200_hit>> results(nGpus);
+    std::vector<std::string> errors(nGpus);
+    std::vector<double> msSearch(nGpus, 0), msLocate(nGpus, 0);
+    size_t perGpu = ((nQueries / (noReverse ? 1 : 2) + nGpus - 1) / nGpus) * (noReverse ? 1 : 2);
+    std::vector<std::thread> threads;
+    for (int g = 0; g < nGpus; ++g) {
+        threads.emplace_back([&, g] {
+            size_t q0 = std::min(nQueries, perGpu * g), q1 = std::min(nQueries, perGpu * (g + 1));
+            for (size_t b = q0; b < q1; b += batch) {
+                size_t n = std::min(batch, q1 - b);
+                sb200_hit* hits = nullptr;
+                uint64_t nHits = 0;
+                if (sb200_search(ctxs[g], queries.data() + b * qlen, n, static_cast<uint32_t>(qlen), &hits, &nHits) != 0) {
+                    errors[g] = sb200_last_error();
+                    return;
+                }
+                size_t old = results[g].size();
+                results[g].resize(old + nHits);
+                for (uint64_t i = 0; i < nHits; ++i) {
+                    results[g][old + i] = hits[i];
+                    results[g][old + i].query_id += b;  // batch-local -> global query id
+                }
+                sb200_free(hits);
+                sb200_counters ct{};
+                sb200_get_counters(ctxs[g], &ct);
+                msSearch[g] += ct.ms_search;
+                msLocate[g] += ct.ms_locate + ct.ms_sort;
+            }
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (auto const& e : errors)
+        if (!e.empty()) fail(e);
+    double total = sw.reset();
+    double sMax = 0, lMax = 0;
+    for (int g = 0; g < nGpus; ++g) {
+        sMax = std::max(sMax, msSearch[g] * 1e-3);
+        lMax = std::max(lMax, msLocate[g] * 1e-3);
+    }
+    // split the wall time of the fused phase in the proportion of the device timers
+    double frac = (sMax + lMax) > 0 ? sMax / (sMax + lMax) : 1.0;
+    timing.emplace_back("search", total * frac);
+    timing.emplace_back("locate", total * (1 - frac));
+
+    size_t nHitsTotal = 0;
+    {
+        FILE* ofs = fopen(outPath.c_str(), "w");
+        if (!ofs) fail("cannot open " + outPath + " for writing");
+        std::vector<char> buf(1 << 22);
+        setvbuf(ofs, buf.data(), _IOFBF, buf.size());
+        for (int g = 0; g < nGpus; ++g) {
+            for (auto const& h : results[g]) fprintf(ofs, "%" PRIu64 " %" PRIu64 " %" PRIu64 "\n", h.query_id, h.seq_id, h.pos);
+            nHitsTotal += results[g].size();
+        }
+        fclose(ofs);
+    }
+    timing.emplace_back("result", sw.reset());
+    double totalTime;
+    printTiming(timing, &totalTime);
+    printf("  queries per second:  %10.0fq/s\n", nQueries / totalTime);
+    printf("  number of hits:      %10zu\n", nHitsTotal);
+    printf("  gpus:                %10d\n", nGpus);
+    for (auto* c : ctxs) sb200_destroy(c);
+}
+
+void usage() {
+    printf("sahara (B200 path)\n"
+           "  sahara index <fasta> [--ignore_unknown] [--dna4]\n"
+           "  sahara search -q <fasta> -i <index> [-o <out>] [-g <generator>] [-e <errors>] [--no-reverse]\n"
+           "                [-m all] [-d ham|lev] [--limit_queries <n>] [--gpus <n>] [--scheme-file <columba.txt>]\n"
+           "                [--batch <queries per call>] [--device-sa-rate <16|8|4|2|1>] [--qgram <q>]\n");
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    try {
+        if (argc < 2 || std::string(argv[1]) == "--help" || std::string(argv[1]) == "-h") {
+            usage();
+            return argc < 2 ? 1 : 0;
+        }
+        std::string cmd = argv[1];
+        Args a = parse(argc, argv, 2);
+        if (cmd == "index") {
+            if (a.has("--dna4")) createIndex<sahara::d_dna4>(a);
+            else createIndex<sahara::d_dna5>(a);
+        } else if (cmd == "search") {
+            if (!a.has("--query") || !a.has("--index")) fail("sahara search needs --query and --index");
+            uint64_t sigma = sahara::peekSigma(a.get("--index"));  // search.cpp:278-290
+            if (sigma == 5) runSearch<sahara::d_dna4>(a);
+            else if (sigma == 6) runSearch<sahara::d_dna5>(a);
+            else fail("unknown index with " + std::to_string(sigma) + " letters");
+        } else {
+            fail("unknown command \"" + cmd + "\"");
+        }
+    } catch (std::exception const& e) {
+        fprintf(stderr, "%s\n", e.what());  // clice prints the message and exits 1 (main.cpp:13)
+        return 1;
+    }
+    return 0;
+}

@@ -123,3 +123,124 @@ def test_qgram_jump_table_keeps_results(sb, ctx, cases, qlen):
         ctx.set_scheme(sch, edit)
         assert np.array_equal(ctx.search_cursors(q), O.sort_rows(ix.search(q, sch, edit)))
     ctx.build_qgram(0)
+
+
+def test_edge_cases(sb, ctx, cases):
+    rng, seqs, ix, path = cases[("multi", 6)]
+    ctx.load_index(path)
+    m = 20
+    sch = sb.SearchScheme.generate("h2-k2", 0, 2, m)
+    ctx.set_scheme(sch, True)
+    with pytest.raises(sb.SaharaError, match="empty"):
+        ctx.search(np.zeros((0, m), np.uint8))
+    with pytest.raises(sb.SaharaError, match="does not match the expanded search scheme"):
+        ctx.search(np.ones((4, m + 1), np.uint8))  # ragged / wrong length
+    with pytest.raises(sb.SaharaError, match="invalid character"):
+        ctx.search(np.full((2, m), 9, np.uint8))
+    # queries made of N, of '$', and reads spanning a sequence boundary never crash and match the oracle
+    q = np.stack([np.full(m, 5, np.uint8), np.full(m, 1, np.uint8), np.concatenate([seqs[0][-10:], seqs[1], seqs[2][:9]])[:m],
+                  np.concatenate([seqs[4][-8:], [0], seqs[5][:11]]).astype(np.uint8)])
+    want = O.sort_rows(ix.locate(ix.search(q, sch, True)))
+    assert np.array_equal(ctx.search(q), want)
+    # a single query, an odd number of queries
+    for n in (1, 3):
+        qq = W.sample_reads(rng, seqs, 2, m, 2, True)[:n]
+        assert np.array_equal(ctx.search(qq), O.sort_rows(ix.locate(ix.search(qq, sch, True))))
+
+
+def test_k4_and_long_reads(sb, ctx, cases):
+    rng, seqs, ix, path = cases[("repeats", 6)]
+    ctx.load_index(path)
+    for m, k, n in ((250, 3, 60), (64, 4, 40), (301, 2, 20)):
+        q = W.sample_reads(rng, seqs, n, m, k, True)
+        sch = sb.SearchScheme.generate("h2-k2", 0, k, m)
+        ctx.set_scheme(sch, True)
+        assert np.array_equal(ctx.search(q), O.sort_rows(ix.locate(ix.search(q, sch, True))))
+
+
+def test_synthetic_generators_match_numpy_mirror(sb, ctx):
+    from sahara_b200 import synth
+    n = 20000
+    d = ctx.synth_genome(n, 42)
+    g = ctx.to_host(d, n)
+    assert np.array_equal(g, synth.genome(n, 42))
+    for edit, k in ((True, 2), (False, 3)):
+        dq = ctx.synth_reads(d, n, 64, 50, k, edit, 43, first_read=7)
+        got = ctx.to_host(dq, 2 * 64 * 50).reshape(-1, 50)
+        assert np.array_equal(got, synth.reads(g, 64, 50, k, edit, 43, first_read=7))
+        ctx.device_free(dq)
+    ctx.device_free(d)
+
+
+def test_device_pipeline_and_properties_at_scale(sb, ctx):
+    """20 Mbp synthetic genome built on the GPU; properties that need no oracle run:
+    every sampled read is found at an edit distance not above the number of planted errors, the hit list is
+    sorted, and Hamming hits are a subset of edit hits."""
+    n, R, m, k = 20_000_000, 20000, 100, 2
+    d = ctx.synth_genome(n, 42)
+    ctx.build_index_device(d, [n], 6, 16)
+    dq = ctx.synth_reads(d, n, R, m, k, True, 43)
+    sch = sb.SearchScheme.generate("h2-k2", 0, k, m)
+    ctx.set_scheme(sch, True)
+    nc, nh = ctx.search_device(dq, 2 * R, m)
+    hits = ctx.fetch_hits()
+    assert hits.shape[0] == nh and nh >= nc > 0
+    order = np.lexsort((hits[:, 3], hits[:, 2], hits[:, 1], hits[:, 0]))
+    assert np.array_equal(order, np.arange(nh))
+    found = np.zeros(R, bool)
+    found[(hits[:, 0] // 2).astype(np.int64)] = True
+    assert found.mean() > 0.88  # 90 % of the reads are sampled from the genome, 10 % are random
+    sch_h = sb.SearchScheme.generate("h2-k2", 0, k, m, limit_to_hamming=True)
+    ctx.set_scheme(sch_h, False)
+    ctx.search_device(dq, 2 * R, m)
+    ham = ctx.fetch_hits()
+    edit_set = set(map(tuple, hits[:, :3].tolist()))
+    assert all(tuple(h) in edit_set for h in ham[:2000, :3].tolist())
+    # oracle on a slice of the same reads, through the downloaded index image
+    view = ctx.download_view()
+    try:
+        oix = O.OracleIndex.from_view(view)
+    finally:
+        ctx.free_view(view)
+    q = ctx.to_host(dq, 2 * 500 * m).reshape(-1, m)
+    ctx.set_scheme(sch, True)
+    assert np.array_equal(ctx.search(q), O.sort_rows(oix.locate(oix.search(q, sch, True))))
+    ctx.device_free(dq)
+    ctx.device_free(d)
+
+
+def test_cli_index_and_search_roundtrip(sb, cases, tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "sahara_b200", "sahara")
+    rng, seqs, ix, path = cases[("multi", 6)]
+    fa = os.path.join(tmp_path, "ref.fa")
+    with open(fa, "w") as f:
+        for i, s in enumerate(seqs):
+            f.write(f">seq{i}\n")
+            txt = "".join("$ACGTN"[c] for c in s)
+            for o in range(0, len(txt), 80):
+                f.write(txt[o:o + 80] + "\n")
+    subprocess.check_call([exe, "index", fa], stdout=subprocess.DEVNULL)
+    assert open(fa + ".idx", "rb").read() == open(path, "rb").read()  # same file as the oracle's builder
+    m, k = 36, 2
+    q = W.sample_reads(rng, seqs, 150, m, k, True)
+    qa = os.path.join(tmp_path, "reads.fa")
+    with open(qa, "w") as f:
+        for i in range(0, q.shape[0], 2):
+            f.write(f">r{i // 2}\n" + "".join("$ACGTN"[c] for c in q[i]) + "\n")
+    out = os.path.join(tmp_path, "out.txt")
+    for extra, edit in (([], True), (["-d", "ham"], False)):
+        res = subprocess.run([exe, "search", "-q", qa, "-i", fa + ".idx", "-e", str(k), "-o", out, "--batch", "100"] + extra,
+                             capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        assert "queries per second" in res.stdout and "number of hits" in res.stdout
+        got = sorted(tuple(int(x) for x in line.split()) for line in open(out))
+        sch = sb.SearchScheme.generate("h2-k2", 0, k, m, limit_to_hamming=not edit)
+        want = sorted((int(a), int(b), int(c)) for a, b, c, d in ix.locate(ix.search(q, sch, edit)))
+        assert got == want
+    # error behaviour of the reference CLI: message + exit code 1
+    res = subprocess.run([exe, "search", "-q", qa, "-i", os.path.join(tmp_path, "missing.idx")], capture_output=True, text=True)
+    assert res.returncode == 1 and "no valid index path" in res.stderr
+    res = subprocess.run([exe, "search", "-q", qa, "-i", fa + ".idx", "-g", "nope"], capture_output=True, text=True)
+    assert res.returncode == 1 and "unknown search scheme generetaror" in res.stderr

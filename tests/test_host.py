@@ -1,0 +1,127 @@
+"""CPU tests of the host layer and of the C-ABI library surface (no compute without a GPU)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as O
+import workloads as W
+import sahara_b200 as sb
+from sahara_b200 import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared(header, prefix):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(" + prefix + r"_[a-z0-9_]+)\s*\(", text)))
+
+
+def exported(lib):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "sahara_b200", lib)], text=True)
+    return set(line.split()[-1] for line in out.splitlines() if " T " in line)
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    names = declared("sahara_b200.h", "sb200")
+    assert len(names) >= 30
+    exp = exported("libsahara_b200.so")
+    assert [n for n in names if n not in exp] == []
+    assert sorted(N.SB200_SYMBOLS) == names  # the ctypes table binds exactly the header
+    assert N.cuda.sb200_abi_version() == 1
+
+
+def test_host_library_exports_every_declared_symbol():
+    names = declared("sahara_host.h", "sbh")
+    exp = exported("libsahara_host.so")
+    assert [n for n in names if n not in exp] == []
+    assert sorted(N.SBH_SYMBOLS) == names
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(sb.SaharaError, match="no CPU fallback|CUDA"):
+        sb.Context(0)
+
+
+def test_product_does_not_touch_the_oracle():
+    bad = []
+    for base, _, files in os.walk(os.path.join(ROOT, "sahara_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(base, f), errors="replace").read()
+                if re.search(r"(import oracle|from oracle|libsahara_oracle|orc_[a-z_]+\()", text):
+                    bad.append(f)
+    assert bad == []
+
+
+def test_fasta_alphabet_and_revcomp(tmp_path):
+    p = os.path.join(tmp_path, "q.fa")
+    with open(p, "w") as f:
+        f.write(">r1 first\nACGT\nacgtn\n>r2\nTTTTU\r\n\n>r3\nN\n")
+    r = sb.load_fasta_ranks(p, sigma=6)
+    assert [x.tolist() for x in r] == [[1, 2, 3, 4, 1, 2, 3, 4, 5], [4, 4, 4, 4, 4], [5]]
+    both = sb.load_fasta_ranks(p, sigma=6, with_revcomp=True)
+    assert both[1].tolist() == [5, 1, 2, 3, 4, 1, 2, 3, 4] and both[3].tolist() == [1, 1, 1, 1, 1]
+    assert sb.revcomp_ranks(np.array([1, 2, 5, 0, 4], np.uint8)).tolist() == [1, 0, 5, 3, 4]
+    with pytest.raises(sb.SaharaError, match="invalid character at position 8"):
+        sb.load_fasta_ranks(p, sigma=5)  # N is not in d_dna4
+    with open(p, "w") as f:
+        f.write(">x\nACGTXA\n")
+    with pytest.raises(sb.SaharaError, match=r"query 'x' \(1\) has invalid character at position 4 'X'\(58\)"):
+        sb.load_fasta_ranks(p, sigma=6)
+
+
+def test_index_file_reader_agrees_with_oracle_and_rejects_garbage(tmp_path):
+    rng = np.random.default_rng(3)
+    seqs = [W.random_genome(rng, 5000, with_n=True), W.random_genome(rng, 100)]
+    ix = O.OracleIndex.build(seqs, 6, 16)
+    path = os.path.join(tmp_path, "a.idx")
+    ix.save(path)
+    sigma = C.c_uint64()
+    N.check_host(N.host.sbh_idx_peek_sigma(path.encode(), C.byref(sigma)))
+    assert sigma.value == 6
+    view, handle = N.IndexView(), C.c_void_p()
+    N.check_host(N.host.sbh_idx_load(path.encode(), C.byref(view), C.byref(handle)))
+    info = ix.info()
+    assert (view.sigma, view.n_rows, view.n_ssa, view.sampling_rate, view.bits_for_position) == (
+        6, info["n_rows"], info["n_ssa"], 16, info["bits_for_position"])
+    out = os.path.join(tmp_path, "b.idx")
+    N.check_host(N.host.sbh_idx_save(out.encode(), C.byref(view)))
+    N.host.sbh_idx_free(handle)
+    data = open(path, "rb").read()
+    assert open(out, "rb").read() == data
+    # the oracle ingests the same in-memory image
+    view2, handle2 = N.IndexView(), C.c_void_p()
+    N.check_host(N.host.sbh_idx_load(path.encode(), C.byref(view2), C.byref(handle2)))
+    again = O.OracleIndex.from_view(view2)
+    N.host.sbh_idx_free(handle2)
+    assert np.array_equal(again.bwt(0), ix.bwt(0)) and np.array_equal(again.bwt(1), ix.bwt(1))
+    for bad, msg in [(data[:-9], "unexpected end of file|not understood"), (data + b"x", "trailing bytes"),
+                     ((7).to_bytes(8, "little") + data[8:], "unknown index with 7 letters"),
+                     (data[:8] + (5).to_bytes(8, "little") + data[16:], "not understood")]:
+        p = os.path.join(tmp_path, "bad.idx")
+        open(p, "wb").write(bad)
+        v, h = N.IndexView(), C.c_void_p()
+        assert N.host.sbh_idx_load(p.encode(), C.byref(v), C.byref(h)) != 0
+        assert re.search(msg, N.host.sbh_last_error().decode())
+        with pytest.raises(O.OracleError):
+            O.OracleIndex.load(p)
+    assert N.host.sbh_idx_load(b"/nonexistent.idx", C.byref(view), C.byref(handle)) != 0
+    assert "no valid index path" in N.host.sbh_last_error().decode()
+
+
+def test_synth_mirror_is_deterministic():
+    from sahara_b200 import synth
+    g = synth.genome(5000, 42)
+    assert g.min() >= 1 and g.max() <= 4 and abs(np.bincount(g)[1:] / 5000 - 0.25).max() < 0.03
+    r = synth.reads(g, 20, 50, 2, True, 43)
+    assert r.shape == (40, 50) and np.array_equal(r[1], (5 - r[0])[::-1])
+    assert np.array_equal(r, synth.reads(g, 20, 50, 2, True, 43))
+    assert np.array_equal(synth.reads(g, 5, 50, 2, True, 43, first_read=10), r[20:30])

@@ -1,0 +1,51 @@
+"""The CUDA search kernel source (sahara_b200/csrc/search.cuh) compiled for the host with g++ + UBSan and run
+as a single thread against the oracle: checks the traversal logic (pair frames, insertion chains, chunked
+output, query staging) without a GPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as O
+import workloads as W
+import sahara_b200 as sb
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu"))
+import emu  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def indexes():
+    rng = np.random.default_rng(77)
+    out = {}
+    out["repeats"] = (rng, [W.repetitive_genome(rng, 20000), W.repetitive_genome(rng, 3000)], 6)
+    out["multi"] = (rng, [W.random_genome(rng, int(n), with_n=True) for n in (9000, 1, 17, 64, 4096, 33)], 6)
+    out["dna4"] = (rng, [W.random_genome(rng, 15000)], 5)
+    return {k: (r, s, O.OracleIndex.build(s, sig, 16)) for k, (r, s, sig) in out.items()}
+
+
+@pytest.mark.parametrize("key", ["repeats", "multi", "dna4"])
+@pytest.mark.parametrize("edit,k", [(False, 0), (False, 2), (False, 3), (True, 1), (True, 2), (True, 3), (True, 4)])
+def test_kernel_source_matches_oracle(indexes, key, edit, k):
+    rng, seqs, ix = indexes[key]
+    m = 40
+    q = W.sample_reads(rng, seqs, 60 if k < 4 else 12, m, k, edit)
+    for gen in ("h2-k2", "pigeon_opt"):
+        sch = sb.SearchScheme.generate(gen, 0, k, m, limit_to_hamming=not edit)
+        before = int(ix.counters[0])
+        want = O.sort_rows(ix.search(q, sch, edit))
+        nodes_oracle = int(ix.counters[0]) - before
+        got, nodes = emu.search(ix, q, sch, edit)
+        assert got.shape == want.shape and np.array_equal(got, want)
+        assert nodes == nodes_oracle  # every state the kernel expands is one extension of the reference recursion
+
+
+def test_debug_variants_agree(indexes):
+    rng, seqs, ix = indexes["repeats"]
+    q = W.sample_reads(rng, seqs, 40, 36, 2, True)
+    sch = sb.SearchScheme.generate("h2-k2", 0, 2, 36)
+    want = O.sort_rows(ix.search(q, sch, True))
+    for flags in (1, 2, 3):  # no pair frames / no insertion chains / neither
+        got, _ = emu.search(ix, q, sch, True, flags)
+        assert np.array_equal(got, want)

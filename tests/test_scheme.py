@@ -1,0 +1,83 @@
+"""CPU tests of the host-side search-scheme module (sahara_b200/host/scheme.hpp through libsahara_host.so)."""
+import numpy as np
+import pytest
+
+import sahara_b200 as sb
+
+ALL = ["backtracking", "optimum", "01*0", "01*0_opt", "pigeon", "pigeon_opt", "suffix", "h2-k1", "h2-k2", "h2-k3", "kianfar",
+       "kucherov-k1", "kucherov-k2"]
+
+
+def test_names_match_reference_list():
+    # the subset of /root/reference/src/sahara/search_scheme.cpp:192 implemented so far
+    assert sorted(sb.SearchScheme.names()) == sorted(ALL)
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 4])
+def test_generators_are_valid_and_complete(name, k):
+    s = sb.SearchScheme.generate(name, 0, k)
+    valid, complete, _ = s.check(0, k)
+    assert valid and complete
+
+
+def test_known_tables():
+    s = sb.SearchScheme.generate("optimum", 0, 2)  # SeqAn optimum_search_scheme<0,2>, 0-based parts
+    assert s.pi.tolist() == [[0, 1, 2, 3], [2, 1, 0, 3], [3, 2, 1, 0]]
+    assert s.l.tolist() == [[0, 0, 1, 1], [0, 0, 0, 0], [0, 0, 0, 2]]
+    assert s.u.tolist() == [[0, 0, 2, 2], [0, 1, 1, 2], [0, 1, 2, 2]]
+    assert s.check(0, 2) == (True, True, True)
+    assert sb.SearchScheme.generate("h2-k2", 0, 2).pi.tolist() == s.pi.tolist()  # default generator of sahara search
+
+
+def test_incomplete_scheme_is_detected():
+    s = sb.SearchScheme(np.array([[0, 1]], np.uint16), np.array([[0, 0]], np.uint8), np.array([[0, 1]], np.uint8))
+    assert s.check(0, 1) == (True, False, False)
+    bad = sb.SearchScheme(np.array([[0, 2, 1]], np.uint16), np.zeros((1, 3), np.uint8), np.ones((1, 3), np.uint8))
+    assert bad.check(0, 1)[0] is False  # not connected
+
+
+@pytest.mark.parametrize("length", [4, 5, 31, 100, 150, 151])
+def test_expand(length):
+    s = sb.SearchScheme.generate("h2-k2", 0, 2)
+    e = sb.SearchScheme.generate("h2-k2", 0, 2, length)
+    P = s.n_entries
+    counts = [length // P + (1 if i < length % P else 0) for i in range(P)]
+    starts = np.cumsum([0] + counts)
+    for j in range(s.n_searches):
+        assert sorted(e.pi[j].tolist()) == list(range(length))
+        o = 0
+        for i in range(P):
+            part = int(s.pi[j][i])
+            seg = e.pi[j][o:o + counts[part]].tolist()
+            right = (s.pi[j][0] < s.pi[j][1]) if i == 0 else (s.pi[j][i - 1] < s.pi[j][i])
+            rng_ = list(range(int(starts[part]), int(starts[part + 1])))
+            assert seg == (rng_ if right else rng_[::-1])
+            assert set(e.u[j][o:o + counts[part]].tolist()) == {int(s.u[j][i])}
+            assert e.l[j][o + counts[part] - 1] == s.l[j][i]
+            prev = int(s.l[j][i - 1]) if i else 0
+            assert all(x == prev for x in e.l[j][o:o + counts[part] - 1].tolist())
+            o += counts[part]
+
+
+def test_limit_to_hamming_and_columba_roundtrip():
+    e = sb.SearchScheme.generate("pigeon", 0, 3, 40)
+    h = sb.SearchScheme.generate("pigeon", 0, 3, 40, limit_to_hamming=True)
+    assert np.array_equal(h.u, np.minimum(e.u, np.arange(1, 41, dtype=np.uint8)[None, :]))
+    s = sb.SearchScheme.generate("kianfar", 0, 2)
+    back = sb.SearchScheme.from_columba(s.to_columba())
+    assert np.array_equal(back.pi, s.pi) and np.array_equal(back.l, s.l) and np.array_equal(back.u, s.u)
+
+
+def test_unknown_generator_message():
+    with pytest.raises(sb.SaharaError, match="unknown search scheme generetaror"):
+        sb.SearchScheme.generate("nope", 0, 1)
+
+
+def test_node_counts_are_monotone_in_k():
+    prev = 0
+    for k in range(4):
+        s = sb.SearchScheme.generate("h2-k2", 0, k, 100)
+        nc, wnc = s.node_count(True, 6, 3_100_000_000)
+        assert nc >= prev and wnc <= nc
+        prev = nc
