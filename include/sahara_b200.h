@@ -97,6 +97,11 @@ int sb200_index_info_get(sb200_ctx* ctx, sb200_index_info* out);
  * results of locate are unchanged, LF steps per located row shrink. */
 int sb200_index_densify(sb200_ctx* ctx, uint32_t device_sampling_rate);
 
+/* in-text verification: builds the complete suffix array, its inverse and the packed text on the device
+ * (about 17 bytes per row) so that cursors holding a single row are extended by reading the text instead of
+ * probing the occurrence tables.  Results are unchanged.  enable = 0 releases the tables. */
+int sb200_index_enable_text(sb200_ctx* ctx, int enable);
+
 /* builds the q-gram jump table: the cursor of every string of `q` symbols over A,C,G,T, used to skip
  * the first error-free steps of a search (q = 0 removes it). */
 int sb200_index_build_qgram(sb200_ctx* ctx, uint32_t q);

@@ -181,6 +181,10 @@ class Context:
     def densify(self, rate):
         check(cuda.sb200_index_densify(self._h, rate))
 
+    def enable_text(self, enable=True):
+        """in-text verification for cursors that hold a single row (results unchanged)"""
+        check(cuda.sb200_index_enable_text(self._h, int(enable)))
+
     def build_qgram(self, q):
         check(cuda.sb200_index_build_qgram(self._h, q))
 

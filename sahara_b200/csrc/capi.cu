@@ -138,16 +138,20 @@ struct DeviceIndex {
     uint64_t n_ref_ssa{};
     DevBuf qgram;
     uint32_t qgram_q{};
+    DevBuf sa32, isa32, text4;  // in-text verification tables
+    bool text_mode{};
     OccTable bwt() const { return OccTable{bwt_blk.get<OccBlk>(), bwt_sup.get<OccSup>()}; }
     OccTable rev() const { return OccTable{rev_blk.get<OccBlk>(), rev_sup.get<OccSup>()}; }
     uint64_t bytes() const {
         return bwt_blk.cap + bwt_sup.cap + rev_blk.cap + rev_sup.cap + marks.cap + ssa.cap + ref_mark_words.cap + ref_ssa.cap +
-               qgram.cap;
+               qgram.cap + sa32.cap + isa32.cap + text4.cap;
     }
     void release() {
-        for (DevBuf* b : {&bwt_blk, &bwt_sup, &rev_blk, &rev_sup, &d_C, &marks, &ssa, &ref_mark_words, &ref_ssa, &qgram}) b->release();
+        for (DevBuf* b : {&bwt_blk, &bwt_sup, &rev_blk, &rev_sup, &d_C, &marks, &ssa, &ref_mark_words, &ref_ssa, &qgram, &sa32, &isa32, &text4})
+            b->release();
         loaded = false;
         qgram_q = 0;
+        text_mode = false;
     }
 };
 
@@ -627,6 +631,9 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         P.counters = c->d_counters.get<unsigned long long>();
         P.qgram = ix.qgram_q ? ix.qgram.get<uint4>() : nullptr;
         P.qgram_q = ix.qgram_q;
+        P.sa32 = ix.text_mode ? ix.sa32.get<uint32_t>() : nullptr;
+        P.isa32 = ix.text_mode ? ix.isa32.get<uint32_t>() : nullptr;
+        P.text4 = ix.text_mode ? ix.text4.get<uint32_t>() : nullptr;
         if (const char* dbg = std::getenv("SB200_DEBUG")) P.debug_flags = static_cast<uint32_t>(std::atoi(dbg));
         launch_search(c, P);
         CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->d_counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
@@ -1023,9 +1030,68 @@ void sb200_index_view_free(sb200_index_view* v) {
     std::memset(v, 0, sizeof(*v));
 }
 
+static void densify_index(sb200_ctx* c, uint32_t rate);
+
 int sb200_index_densify(sb200_ctx* c, uint32_t rate) {
     return guard([&] {
         use(c);
+        densify_index(c, rate);
+    });
+}
+
+int sb200_index_enable_text(sb200_ctx* c, int enable) {
+    return guard([&] {
+        use(c);
+        auto& ix = c->idx;
+        if (!ix.loaded) throw Error("no index loaded");
+        if (!enable) {
+            for (DevBuf* b : {&ix.sa32, &ix.isa32, &ix.text4}) b->release();
+            ix.text_mode = false;
+            return;
+        }
+        if (ix.text_mode) return;
+        densify_index(c, 1);  // complete suffix array as (seqId, pos)
+        uint64_t n = ix.n_rows;
+        // sequence starts from the delimiter rows: rows [0, C[1]) are the suffixes that start with a delimiter,
+        // their value is (seqId, length of that sequence)
+        uint64_t n_seqs = ix.C64[1];
+        if (n_seqs == 0) throw Error("index has no delimiter");
+        std::vector<uint64_t> vals(n_seqs), start(n_seqs + 1, 0), lens(n_seqs, 0);
+        CUDA_TRY(cudaMemcpyAsync(vals.data(), ix.ssa.p, n_seqs * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        uint64_t mask = (uint64_t{1} << ix.bits_for_position) - 1;
+        for (uint64_t v : vals) {
+            uint64_t sid = v >> ix.bits_for_position;
+            if (sid >= n_seqs) throw Error("index layout not understood: sequence id of a delimiter row out of range");
+            lens[sid] = v & mask;
+        }
+        for (uint64_t i = 0; i < n_seqs; ++i) start[i + 1] = start[i] + lens[i] + 1;
+        if (start[n_seqs] != n) throw Error("index layout not understood: sequence lengths do not add up to the text length");
+        DevBuf d_start;
+        d_start.reserve((n_seqs + 1) * 8);
+        CUDA_TRY(cudaMemcpyAsync(d_start.p, start.data(), (n_seqs + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        ix.sa32.reserve(n * 4);
+        ix.isa32.reserve(n * 4);
+        uint64_t n_words = n / 8 + 2;
+        ix.text4.reserve(n_words * 4);
+        CUDA_TRY(cudaMemsetAsync(ix.text4.p, 0, n_words * 4, c->stream));
+        sa32_kernel<<<grid_for(n), 256, 0, c->stream>>>(ix.ssa.get<uint64_t>(), d_start.get<uint64_t>(), n,
+                                                         static_cast<uint32_t>(ix.bits_for_position), ix.sa32.get<uint32_t>(),
+                                                         ix.isa32.get<uint32_t>());
+        launch_check(c);
+        with_sigma(ix.sigma, [&](auto S) {
+            text4_kernel<S()><<<grid_for(n), 256, 0, c->stream>>>(ix.bwt(), ix.sa32.get<uint32_t>(), n, ix.text4.get<uint32_t>());
+            return 0;
+        });
+        launch_check(c);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        d_start.release();
+        ix.text_mode = true;
+    });
+}
+
+static void densify_index(sb200_ctx* c, uint32_t rate) {
+    {
         auto& ix = c->idx;
         if (!ix.loaded) throw Error("no index loaded");
         if (rate == 0 || (rate & (rate - 1)) || rate > ix.device_rate) throw Error("device sampling rate must be a power of two not above the current rate");
@@ -1091,7 +1157,7 @@ int sb200_index_densify(sb200_ctx* c, uint32_t rate) {
         new_words.release();
         row_value.release();
         ix.device_rate = rate;
-    });
+    }
 }
 
 int sb200_index_build_qgram(sb200_ctx* c, uint32_t q) {
@@ -1136,7 +1202,7 @@ int sb200_set_scheme(sb200_ctx* c, uint32_t n_searches, uint32_t len, const uint
     return guard([&] {
         use(c);
         if (n_searches == 0 || len == 0) throw Error("empty search scheme");
-        if (len > 1023) throw Error("queries longer than 1023 characters are not supported");
+        if (len > 1000) throw Error("queries longer than 1000 characters are not supported");
         std::vector<uint32_t> steps(size_t(n_searches) * len);
         uint32_t kmax = 0;
         for (uint32_t j = 0; j < n_searches; ++j) {

@@ -200,6 +200,28 @@ __global__ void __launch_bounds__(256) rank_bench_kernel(OccTable t, uint32_t n_
     if ((threadIdx.x & 31) == 0) atomicAdd(checksum, acc);
 }
 
+// ---- in-text verification tables -------------------------------------------------------------------
+// sa32[row] = global text position of the suffix (start of its sequence + in-sequence position)
+__global__ void sa32_kernel(const uint64_t* full_ssa, const uint64_t* seq_start, uint64_t n, uint32_t bits, uint32_t* sa32, uint32_t* isa32) {
+    uint64_t r = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (r >= n) return;
+    uint64_t v = full_ssa[r];
+    uint32_t p = static_cast<uint32_t>(seq_start[v >> bits] + (v & ((uint64_t{1} << bits) - 1)));
+    sa32[r] = p;
+    isa32[p] = static_cast<uint32_t>(r);
+}
+// T[SA[r] - 1] = bwt[r] (cyclic): scatter the symbols into the zero-initialised packed text
+template <int SIGMA>
+__global__ void text4_kernel(OccTable bwt, const uint32_t* sa32, uint64_t n, uint32_t* text4) {
+    uint64_t r = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (r >= n) return;
+    uint32_t p = sa32[r];
+    p = p == 0 ? static_cast<uint32_t>(n - 1) : p - 1;
+    OccBlk b = bwt.blk[r >> kBlkShift];
+    uint32_t c = static_cast<uint32_t>(blk_symbol(b, static_cast<uint32_t>(r & 63u)));
+    if (c) atomicOr(&text4[p >> 3], c << ((p & 7u) * 4u));
+}
+
 // ---- q-gram jump table ------------------------------------------------------------------------------
 // level t (strings of t symbols over A,C,G,T, first symbol most significant) from level t-1 by one
 // extendRight: cursor(parent + c).

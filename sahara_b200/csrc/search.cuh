@@ -50,6 +50,10 @@ struct SearchParams {
     const uint4* qgram;  // [4^q] (lb, lbRev, len, 0)
     uint32_t qgram_q;
     uint32_t debug_flags;  // 1: no pair frames, 2: no insertion chains (diagnostics only)
+    // in-text verification (nullptr = off): suffix array, its inverse, and the text packed 8 symbols per word
+    const uint32_t* sa32;
+    const uint32_t* isa32;
+    const uint32_t* text4;
 };
 
 // Frames and states.  A stack frame is a cursor plus one search state (step, e, LInfo, RInfo), or — flag
@@ -60,6 +64,14 @@ struct SearchParams {
 // registers.  Every state is expanded exactly like the corresponding call of the reference recursion,
 // so the reported multiset is unchanged; only the number of memory probes shrinks.
 constexpr uint32_t META_PAIR = 1u << 18;
+// In-text verification.  Once a cursor holds a single row its occurrence T[a, b) is unique, and whether a
+// child cursor is empty is decided by one text symbol (T[a-1] or T[b]) instead of two rank probes.  Frames
+// flagged META_TEXT carry (a, b) in place of (lb, lbRev); the expansion of the states is unchanged, so the
+// reported multiset is unchanged.  FM-mode metas carry the number of text symbols consumed so far (tlen,
+// bits 20..29) so that b = a + tlen when the frame switches; a = SA[lb], and the reported cursor of a text
+// frame is lb = ISA[a], len = 1.
+constexpr uint32_t META_TEXT = 1u << 19;
+constexpr uint32_t META_TLEN_SHIFT = 20;
 constexpr uint32_t kEmitChunk = 16;       // output slots a thread reserves per atomic
 constexpr uint32_t kQueryBatch = 2;       // queries a thread takes per atomic
 constexpr uint32_t kInvalidQid = 0xffffffffu;
@@ -75,8 +87,8 @@ __global__ void pack_queries_kernel(const uint8_t* q, uint64_t n_queries, uint32
     uint64_t qi = i / W;
     uint32_t w = static_cast<uint32_t>(i % W);
     const uint8_t* src = q + qi * len + w * 8;
-    uint32_t v = 0;
-    for (uint32_t k = 0; k < 8 && w * 8 + k < len; ++k) v |= static_cast<uint32_t>(src[k] & 0xfu) << (4 * k);
+    uint32_t v = 0xffffffffu;  // unused nibbles stay 0xF (never a valid symbol)
+    for (uint32_t k = 0; k < 8 && w * 8 + k < len; ++k) v = (v & ~(0xfu << (4 * k))) | (static_cast<uint32_t>(src[k] & 0xfu) << (4 * k));
     out[i] = v;
 }
 #endif
@@ -93,13 +105,16 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
     uint32_t nodes = 0, emitted = 0;
     uint32_t out_pos = 0, out_end = 0;
     bool overflow = false;
+    bool textOK = false;  // in-text verification allowed for the current query
     int maxsp = 0;
     const uint32_t qlen = P.len;
     const uint32_t W = packed_words(qlen);
 
     auto qsym = [&](uint32_t pos) -> uint32_t { return (s_query[(pos >> 3) * qstride] >> ((pos & 7u) * 4u)) & 0xfu; };
 
+    bool textFrame = false;  // the frame being expanded is in text mode
     auto emit = [&](uint32_t lb, uint32_t len, uint32_t e) {
+        if (textFrame) lb = P.isa32[lb];  // (a, b) -> the row of the suffix starting at a; len is 1
         if (out_pos == out_end) {
             out_pos = static_cast<uint32_t>(atomicAdd(&P.counters[1], static_cast<unsigned long long>(kEmitChunk)));
             out_end = out_pos + kEmitChunk;
@@ -126,7 +141,13 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
                     qid_end = qid + kQueryBatch < P.n_queries ? qid + kQueryBatch : P.n_queries;
                 }
                 const uint32_t* src = P.packed + static_cast<uint64_t>(qid) * W;
-                for (uint32_t w = 0; w < W; ++w) s_query[w * qstride] = src[w];
+                bool delim = false;
+                for (uint32_t w = 0; w < W; ++w) {
+                    uint32_t v = src[w];
+                    s_query[w * qstride] = v;
+                    delim = delim || (((v - 0x11111111u) & ~v & 0x88888888u) != 0);  // some nibble is 0
+                }
+                textOK = P.sa32 != nullptr && !delim;
             }
             tbl = s_steps + next_search * qlen;
             ++next_search;
@@ -150,11 +171,12 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
                     uint4 g = P.qgram[code];
                     if (g.z == 0) continue;
                     if (qq == qlen) {
+                        textFrame = false;
                         emit(g.x, g.z, 0);
                         continue;
                     }
                     if (((tbl[qq] >> 16) & 0xfu) > 1) continue;
-                    root = make_uint4(g.x, g.y, g.z, pack_meta(qq, 0, INFO_M, INFO_M));
+                    root = make_uint4(g.x, g.y, g.z, pack_meta(qq, 0, INFO_M, INFO_M) | (qq << META_TLEN_SHIFT));
                 }
             }
             stack[0] = root;
@@ -168,26 +190,47 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
             lb = f.x; lbRev = f.y; len = f.z; meta = f.w;
         }
 
-        // ---- one probe of the occurrence table for this cursor ------------------------------------
+        // ---- one probe for this cursor: occurrence table (FM mode) or one text symbol (text mode) -------
         uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
         uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
         const bool pair = (meta & META_PAIR) != 0;
         const bool right = (tbl[step] >> 24) & 1u;
-        const OccTable& tab = right ? P.bwtRev : P.bwt;
-        const uint32_t lo = right ? lbRev : lb;
-        const uint32_t hi = lo + len;
-        OccBlk b1 = load_blk(tab.blk + (lo >> kBlkShift));
-        OccSup s1 = load_sup(tab.sup + (lo >> kSupShift));
-        OccBlk b2 = b1;
-        OccSup s2 = s1;
-        if ((lo >> kBlkShift) != (hi >> kBlkShift)) {
-            b2 = load_blk(tab.blk + (hi >> kBlkShift));
-            if ((lo >> kSupShift) != (hi >> kSupShift)) s2 = load_sup(tab.sup + (hi >> kSupShift));
+        const uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
+        textFrame = (meta & META_TEXT) != 0;
+        if (!textFrame && textOK && len == 1) {  // unique occurrence: switch to the text
+            uint32_t a = P.sa32[lb];
+            lb = a;
+            lbRev = a + tlen;
+            textFrame = true;
         }
-        // child cursors per symbol: (klb[s], klbRev[s], cnt[s]).  The probed side continues at C[s] + rank(lo, s),
-        // the other side moves by the number of smaller symbols inside the interval.
+        // child cursors per symbol: (klb[s], klbRev[s], cnt[s])
         uint32_t klb[SIGMA], klbRev[SIGMA], cnt[SIGMA];
-        {
+        if (textFrame) {
+            // lb = a, lbRev = b.  Left extension reads T[a-1] (the delimiter before position 0), right T[b].
+            const uint32_t pos = right ? lbRev : lb - 1;
+            uint32_t t = 0;
+            if (right || lb != 0) t = (P.text4[pos >> 3] >> ((pos & 7u) * 4u)) & 0xfu;
+            const uint32_t na = right ? lb : lb - 1, nb = right ? lbRev + 1 : lbRev;
+#pragma unroll
+            for (int s = 0; s < SIGMA; ++s) {
+                klb[s] = na;
+                klbRev[s] = nb;
+                cnt[s] = (s != 0 && static_cast<uint32_t>(s) == t) ? 1u : 0u;
+            }
+        } else {
+            const OccTable& tab = right ? P.bwtRev : P.bwt;
+            const uint32_t lo = right ? lbRev : lb;
+            const uint32_t hi = lo + len;
+            OccBlk b1 = load_blk(tab.blk + (lo >> kBlkShift));
+            OccSup s1 = load_sup(tab.sup + (lo >> kSupShift));
+            OccBlk b2 = b1;
+            OccSup s2 = s1;
+            if ((lo >> kBlkShift) != (hi >> kBlkShift)) {
+                b2 = load_blk(tab.blk + (hi >> kBlkShift));
+                if ((lo >> kSupShift) != (hi >> kSupShift)) s2 = load_sup(tab.sup + (hi >> kSupShift));
+            }
+            // The probed side continues at C[s] + rank(lo, s), the other side moves by the number of smaller
+            // symbols inside the interval.
             uint32_t own[SIGMA];
             uint32_t sum1 = 0, sumc = 0;
 #pragma unroll
@@ -209,6 +252,9 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
                 other += cnt[s];
             }
         }
+        // flags every child inherits: text mode, and the text length of children that consume a text symbol
+        const uint32_t inheritSame = (textFrame ? META_TEXT : 0u) | (tlen << META_TLEN_SHIFT);
+        const uint32_t inheritNext = (textFrame ? META_TEXT : 0u) | ((tlen + 1) << META_TLEN_SHIFT);
 
         // ---- expand every state that lives on this cursor ------------------------------------------
         bool second = false;  // second half of a pair already taken
@@ -237,10 +283,10 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
             const uint32_t keepL = right ? Linfo : 0u, keepR = right ? 0u : Rinfo;
             const uint32_t sideShift = right ? 16u : 14u;
             const uint32_t metaBase = (keepL << 14) | (keepR << 16);
-            const uint32_t mM = metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift);
-            const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift);
-            const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift);
-            const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift);
+            const uint32_t mM = metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift) | inheritNext;
+            const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift) | inheritNext;
+            const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift) | inheritNext;
+            const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift) | inheritSame;
             // match
             {
                 uint32_t mc = 0, nlb = 0, nlbRev = 0;

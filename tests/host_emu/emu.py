@@ -21,8 +21,8 @@ def _build():
 _build()
 _lib = C.CDLL(SO)
 _lib.emu_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
-                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
-                            C.POINTER(C.c_uint64)]
+                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
 _lib.emu_free.argtypes = [C.c_void_p]
 
 
@@ -30,8 +30,19 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def search(oracle_index, queries, scheme, edit, debug_flags=0):
-    """runs the kernel body on the host over the oracle index's BWTs -> (sorted cursors uint64 [n,4], nodes)"""
+def text_tables(oracle_index, seqs):
+    """suffix array (global text positions) and the delimited text, for the in-text verification mode"""
+    n = oracle_index.info()["n_rows"]
+    starts = np.cumsum([0] + [len(s) + 1 for s in seqs])
+    loc = oracle_index.locate_rows(np.arange(n, dtype=np.uint64))
+    sa = (starts[loc[:, 0].astype(np.int64)] + loc[:, 1].astype(np.int64)).astype(np.uint32)
+    text = np.concatenate([np.concatenate([np.asarray(s, np.uint8), np.zeros(1, np.uint8)]) for s in seqs])
+    return np.ascontiguousarray(sa), np.ascontiguousarray(text)
+
+
+def search(oracle_index, queries, scheme, edit, debug_flags=0, text=None):
+    """runs the kernel body on the host over the oracle index's BWTs -> (sorted cursors uint64 [n,4], nodes).
+    text = (sa32, text symbols) from text_tables() enables the in-text verification mode."""
     info = oracle_index.info()
     bwt = np.ascontiguousarray(oracle_index.bwt(0))
     rev = np.ascontiguousarray(oracle_index.bwt(1))
@@ -39,7 +50,8 @@ def search(oracle_index, queries, scheme, edit, debug_flags=0):
     q = np.ascontiguousarray(queries, dtype=np.uint8)
     out, n, nodes = C.c_void_p(), C.c_uint64(), C.c_uint64()
     rc = _lib.emu_search(_p(bwt), _p(rev), info["n_rows"], info["sigma"], _p(Carr), _p(q), q.shape[0], q.shape[1], scheme.n_searches,
-                         _p(scheme.pi), _p(scheme.l), _p(scheme.u), int(edit), debug_flags, C.byref(out), C.byref(n), C.byref(nodes))
+                         _p(scheme.pi), _p(scheme.l), _p(scheme.u), int(edit), debug_flags,
+                         _p(text[0]) if text else None, _p(text[1]) if text else None, C.byref(out), C.byref(n), C.byref(nodes))
     if rc != 0:
         raise RuntimeError(f"emu_search failed with code {rc}")
     try:

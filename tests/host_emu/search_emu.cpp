@@ -45,7 +45,7 @@ extern "C" {
 // out: library-allocated (qid, lb, len, e) u32 quadruples, release with emu_free.
 int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int sigma, const uint64_t* C, const uint8_t* queries,
                uint64_t n_queries, uint32_t len, uint32_t n_searches, const uint16_t* pi, const uint8_t* l, const uint8_t* u, int edit,
-               uint32_t debug_flags, uint32_t** out, uint64_t* n_out, uint64_t* nodes) {
+               uint32_t debug_flags, const uint32_t* sa32, const uint8_t* text, uint32_t** out, uint64_t* n_out, uint64_t* nodes) {
     HostOcc a, b;
     a.build(bwt, n_rows);
     b.build(bwtRev, n_rows);
@@ -59,10 +59,21 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
             if (u[k] > kmax) kmax = u[k];
         }
     if (kmax > 4) return 2;
+    // optional in-text verification tables
+    std::vector<uint32_t> isa, text4;
+    if (sa32 && text) {
+        isa.assign(n_rows, 0);
+        for (uint64_t r = 0; r < n_rows; ++r) isa[sa32[r]] = static_cast<uint32_t>(r);
+        text4.assign(n_rows / 8 + 2, 0);
+        for (uint64_t i = 0; i < n_rows; ++i) text4[i / 8] |= uint32_t(text[i] & 0xf) << (4 * (i % 8));
+    }
     uint32_t W = packed_words(len);
-    std::vector<uint32_t> packed(size_t(n_queries) * W, 0), stage(W + 1, 0);
+    std::vector<uint32_t> packed(size_t(n_queries) * W, 0xffffffffu), stage(W + 1, 0);
     for (uint64_t qi = 0; qi < n_queries; ++qi)
-        for (uint32_t i = 0; i < len; ++i) packed[qi * W + i / 8] |= uint32_t(queries[qi * len + i] & 0xf) << (4 * (i % 8));
+        for (uint32_t i = 0; i < len; ++i) {
+            uint32_t& w = packed[qi * W + i / 8];
+            w = (w & ~(0xfu << (4 * (i % 8)))) | (uint32_t(queries[qi * len + i] & 0xf) << (4 * (i % 8)));
+        }
     uint64_t cap = 1 << 16;
     std::vector<uint4> buf;
     unsigned long long counters[8];
@@ -86,6 +97,9 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
         P.qgram = nullptr;
         P.qgram_q = 0;
         P.debug_flags = debug_flags;
+        P.sa32 = isa.empty() ? nullptr : sa32;
+        P.isa32 = isa.empty() ? nullptr : isa.data();
+        P.text4 = isa.empty() ? nullptr : text4.data();
         if (sigma == 6) {
             if (edit) search_thread<6, true, 96>(P, steps.data(), stage.data(), 1);
             else search_thread<6, false, 96>(P, steps.data(), stage.data(), 1);

@@ -245,3 +245,21 @@ def test_cli_index_and_search_roundtrip(sb, cases, tmp_path):
     assert res.returncode == 1 and "no valid index path" in res.stderr
     res = subprocess.run([exe, "search", "-q", qa, "-i", fa + ".idx", "-g", "nope"], capture_output=True, text=True)
     assert res.returncode == 1 and "unknown search scheme generetaror" in res.stderr
+
+
+@pytest.mark.parametrize("key", [("random", 6), ("multi", 6), ("repeats", 6), ("random", 5)])
+def test_text_mode_keeps_results(sb, ctx, cases, key):
+    rng, seqs, ix, path = cases[key]
+    ctx.load_index(path)
+    ctx.enable_text(True)
+    m = 44
+    for edit, k in ((False, 2), (True, 1), (True, 2), (True, 3)):
+        q = W.sample_reads(rng, seqs, 200, m, k, edit)
+        q[3, 5] = 0  # a query that contains the delimiter stays on the FM path
+        for gen in ("h2-k2", "pigeon_opt"):
+            sch = sb.SearchScheme.generate(gen, 0, k, m, limit_to_hamming=not edit)
+            ctx.set_scheme(sch, edit)
+            want_cur = O.sort_rows(ix.search(q, sch, edit))
+            assert np.array_equal(ctx.search_cursors(q), want_cur)
+            assert np.array_equal(ctx.search(q), O.sort_rows(ix.locate(want_cur)))
+    ctx.enable_text(False)

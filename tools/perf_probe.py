@@ -17,6 +17,7 @@ ap.add_argument("--edit", type=int, default=1)
 ap.add_argument("--gen", default="h2-k2")
 ap.add_argument("--qgram", type=int, default=0)
 ap.add_argument("--densify", type=int, default=0)
+ap.add_argument("--text", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--rank-bench", type=int, default=1)
 a = ap.parse_args()
@@ -33,6 +34,8 @@ if a.rank_bench:
         print(f"rank_bench chains={chains} {ms:.3f} ms  {ops / ms / 1e6:.2f} Gops/s  {ops * 64 / ms / 1e6:.1f} GB/s(64B/op)", flush=True)
 if a.densify:
     t = time.time(); ctx.densify(a.densify); print("densify s", round(time.time() - t, 2), flush=True)
+if a.text:
+    t = time.time(); ctx.enable_text(True); print("enable_text s", round(time.time() - t, 2), ctx.info()["device_bytes"] / 1e9, "GB", flush=True)
 if a.qgram:
     t = time.time(); ctx.build_qgram(a.qgram); print("qgram s", round(time.time() - t, 2), flush=True)
 sch = sb.SearchScheme.generate(a.gen, 0, a.k, a.len, limit_to_hamming=not a.edit)
