@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--generator", default="h2-k2")
     ap.add_argument("--qgram", type=int, default=-1, help="q-gram jump table length (-1 = auto, 0 = off)")
     ap.add_argument("--device-sa-rate", type=int, default=0, help="densify the device suffix array (0 = keep 16)")
+    ap.add_argument("--text", type=int, default=1, help="in-text verification of unique cursors (1 = on)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -216,6 +217,8 @@ def main():
         qauto = 0
     if a.device_sa_rate:
         ctx.densify(a.device_sa_rate)
+    if a.text:
+        ctx.enable_text(True)
     if qauto:
         ctx.build_qgram(qauto)
 
@@ -314,7 +317,7 @@ def main():
                 "ms_per_launch": round(ms_per_launch, 3),
                 "phase_ms_per_step": {"search": round(ms_search / a.steps, 3), "locate": round(ms_locate / a.steps, 3),
                                       "sort": round(ms_sort / a.steps, 3)},
-                "qgram": qauto, "lf_steps_per_step": int(ct["lf_steps"] / a.steps)}
+                "qgram": qauto, "text_mode": bool(a.text), "lf_steps_per_step": int(ct["lf_steps"] / a.steps)}
 
     line = {"metric": "queries/s (150bp, k=2 edit)", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": round(dev_ms / a.steps, 3), "higher_is_better": True, "scaling": "weak",

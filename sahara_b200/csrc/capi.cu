@@ -166,11 +166,11 @@ struct sb200_ctx {
     uint32_t n_searches{}, qlen{}, kmax{};
     bool edit{}, have_scheme{};
     // work buffers
-    DevBuf d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
-    uint64_t cursor_cap{};
+    DevBuf d_seeds, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
+    uint64_t cursor_cap{}, seed_cap{};
     uint64_t last_cursors{}, last_real_cursors{}, last_hits{};
     bool hits_in_second{};  // which of the double buffers holds the sorted hits
-    unsigned long long* h_counters{};  // pinned, 8 entries
+    unsigned long long* h_counters{};  // pinned, CT_COUNT entries
     sb200_counters ct{};
     cudaEvent_t ev[8]{};
     int sms{};
@@ -559,39 +559,54 @@ void build_index_device(sb200_ctx* c, const uint8_t* d_src, const uint64_t* seq_
 
 // ---- search pipeline ---------------------------------------------------------------------------------
 
-template <int SIGMA, bool EDIT>
-void launch_search_k(sb200_ctx* c, const SearchParams& P, unsigned grid, size_t smem) {
-    uint32_t k = c->kmax;
-    auto go = [&](auto STACK) {
-        auto kern = search_kernel<SIGMA, EDIT, STACK()>;
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        kern<<<grid, 256, smem, c->stream>>>(P);
-    };
-    // worst-case stack depth of the pair/chain traversal (search.cuh): D(k) = 2, D(e) = F(e) - 1 + D(e + 1)
-    // with F(e) <= 9 (k - e) + 2 frames pushed per iteration
-    if (k == 0) go(std::integral_constant<int, 4>{});
-    else if (k == 1) go(std::integral_constant<int, 16>{});
-    else if (k == 2) go(std::integral_constant<int, 36>{});
-    else if (k == 3) go(std::integral_constant<int, 64>{});
-    else if (k == 4) go(std::integral_constant<int, 96>{});
+// worst-case stack depth of the pair/chain traversal (search.cuh): D(k) = 2, D(e) = F(e) - 1 + D(e + 1) with
+// F(e) <= 9 (k - e) + 2 frames pushed per iteration
+template <typename F>
+void with_stack(uint32_t k, F&& f) {
+    if (k == 0) f(std::integral_constant<int, 4>{});
+    else if (k == 1) f(std::integral_constant<int, 16>{});
+    else if (k == 2) f(std::integral_constant<int, 36>{});
+    else if (k == 3) f(std::integral_constant<int, 64>{});
+    else if (k == 4) f(std::integral_constant<int, 96>{});
     else throw Error("search schemes with more than 4 errors are not supported by the GPU kernel yet");
-    launch_check(c);
+}
+
+unsigned blocks_per_sm(const char* env, unsigned def) {
+    if (const char* e = std::getenv(env)) return static_cast<unsigned>(std::max(1, std::atoi(e)));
+    return def;
 }
 
 void launch_search(sb200_ctx* c, const SearchParams& P) {
     // shared memory: scheme table + one staged packed query per thread
     size_t smem = (size_t(P.n_searches) * P.len + size_t(packed_words(P.len)) * 256) * 4;
     if (smem > 100 * 1024) throw Error("search scheme table and staged queries do not fit shared memory (query too long)");
-    unsigned per_sm = 4;
-    if (const char* e = std::getenv("SB200_BLOCKS_PER_SM")) per_sm = static_cast<unsigned>(std::max(1, std::atoi(e)));
-    unsigned grid = static_cast<unsigned>(c->sms) * per_sm;
+    unsigned grid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_BLOCKS_PER_SM", 4);
     unsigned need = grid_for((uint64_t(P.n_queries) + kQueryBatch - 1) / kQueryBatch);
     if (need < grid) grid = std::max(1u, need);
     with_sigma(c->idx.sigma, [&](auto S) {
-        if (c->edit) launch_search_k<S(), true>(c, P, grid, smem);
-        else launch_search_k<S(), false>(c, P, grid, smem);
+        with_stack(c->kmax, [&](auto STACK) {
+            auto go = [&](auto kern) {
+                if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                kern<<<grid, 256, smem, c->stream>>>(P);
+            };
+            if (c->edit) go(fm_kernel<S(), true, STACK()>);
+            else go(fm_kernel<S(), false, STACK()>);
+        });
         return 0;
     });
+    launch_check(c);
+    if (P.sa32) {  // in-text verification of the seeds (reads the seed count from device memory: no host sync)
+        unsigned tgrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_TEXT_BLOCKS_PER_SM", 6);
+        with_stack(c->kmax, [&](auto STACK) {
+            auto go = [&](auto kern) {
+                if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                kern<<<tgrid, 256, smem, c->stream>>>(P);
+            };
+            if (c->edit) go(text_kernel<true, STACK()>);
+            else go(text_kernel<false, STACK()>);
+        });
+        launch_check(c);
+    }
 }
 
 // kernel 2 on device-resident queries; cursors stay in c->d_cursors
@@ -605,7 +620,8 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
     if (n_queries * uint64_t(c->n_searches) >= (1ull << 32)) throw Error("too many (query, search) pairs for one call; split the batch");
 
     if (c->cursor_cap < n_queries * 16) c->cursor_cap = std::max<uint64_t>(1 << 20, n_queries * 16);
-    c->d_counters.reserve(8 * sizeof(unsigned long long));
+    if (c->seed_cap < n_queries * 4) c->seed_cap = std::max<uint64_t>(1 << 20, n_queries * 4);
+    c->d_counters.reserve(CT_COUNT * sizeof(unsigned long long));
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     const uint32_t W = packed_words(len);
     c->d_packed.reserve(n_queries * W * 4);
@@ -614,14 +630,16 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
     uint64_t n_cursors = 0;
     while (true) {
         c->d_cursors.reserve((c->cursor_cap + 1) * sizeof(uint4));
-        CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
+        if (ix.text_mode) c->d_seeds.reserve((c->seed_cap + 1) * sizeof(uint4));
+        CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, CT_COUNT * sizeof(unsigned long long), c->stream));
         SearchParams P{};
         P.bwt = ix.bwt();
         P.bwtRev = ix.rev();
         for (int i = 0; i < 8; ++i) P.C[i] = ix.C[i];
         P.n_rows = static_cast<uint32_t>(ix.n_rows);
-        P.queries = d_queries;
         P.packed = c->d_packed.get<uint32_t>();
+        P.seeds = c->d_seeds.get<uint4>();
+        P.seed_cap = static_cast<uint32_t>(std::min<uint64_t>(c->seed_cap, 0xfffffffeull));
         P.n_queries = static_cast<uint32_t>(n_queries);
         P.len = len;
         P.n_searches = c->n_searches;
@@ -636,24 +654,35 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         P.text4 = ix.text_mode ? ix.text4.get<uint32_t>() : nullptr;
         if (const char* dbg = std::getenv("SB200_DEBUG")) P.debug_flags = static_cast<uint32_t>(std::atoi(dbg));
         launch_search(c, P);
-        CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->d_counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->d_counters.p, CT_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        if (std::getenv("SB200_DEBUG")) fprintf(stderr, "[sb200 debug] max stack depth %llu overflow %llu\n", c->h_counters[5], c->h_counters[3]);
-        if (c->h_counters[3]) throw Error("internal error: search stack overflow");
-        n_cursors = c->h_counters[1];
-        if (n_cursors <= c->cursor_cap) break;
-        if (n_cursors >= 0xfffffffeull) throw Error("more than 2^32 cursors in one call; split the batch");
-        c->cursor_cap = n_cursors + n_cursors / 4;  // rerun with a buffer that fits
+        if (std::getenv("SB200_DEBUG"))
+            fprintf(stderr, "[sb200 debug] max stack depth %llu overflow %llu seeds %llu\n", c->h_counters[CT_MAX_SP], c->h_counters[CT_OVERFLOW],
+                    c->h_counters[CT_SEEDS]);
+        if (c->h_counters[CT_OVERFLOW]) throw Error("internal error: search stack overflow");
+        n_cursors = c->h_counters[CT_OUT_SLOTS];
+        uint64_t n_seed_slots = c->h_counters[CT_SEED_SLOTS];
+        if (n_cursors >= 0xfffffffeull || n_seed_slots >= 0xfffffffeull) throw Error("more than 2^32 cursors in one call; split the batch");
+        bool fits = true;
+        if (n_seed_slots > c->seed_cap) {  // the text kernel saw a truncated seed list: rerun with a buffer that fits
+            c->seed_cap = n_seed_slots + n_seed_slots / 4;
+            fits = false;
+        }
+        if (n_cursors > c->cursor_cap) {
+            c->cursor_cap = n_cursors + n_cursors / 4;
+            fits = false;
+        }
+        if (fits) break;
     }
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     CUDA_TRY(cudaEventSynchronize(c->ev[1]));
     CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_search, c->ev[0], c->ev[1]));
     c->ct.ms_locate = c->ct.ms_sort = 0;
-    c->ct.nodes += c->h_counters[2];
-    c->ct.rank_ops += 2 * c->h_counters[2];
-    c->ct.cursors += c->h_counters[6];
+    c->ct.nodes += c->h_counters[CT_NODES];
+    c->ct.rank_ops += 2 * c->h_counters[CT_NODES];
+    c->ct.cursors += c->h_counters[CT_CURSORS];
     c->last_cursors = n_cursors;  // reserved output slots; unused ones are empty entries (qid 0xffffffff, len 0)
-    c->last_real_cursors = c->h_counters[6];
+    c->last_real_cursors = c->h_counters[CT_CURSORS];
     c->last_hits = 0;
 }
 
@@ -662,8 +691,8 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
 void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
     auto& ix = c->idx;
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-    c->d_counters.reserve(8 * sizeof(unsigned long long));
-    CUDA_TRY(cudaMemsetAsync(c->d_counters.get<unsigned long long>() + 4, 0, sizeof(unsigned long long), c->stream));
+    c->d_counters.reserve(CT_COUNT * sizeof(unsigned long long));
+    CUDA_TRY(cudaMemsetAsync(c->d_counters.get<unsigned long long>() + CT_LF_STEPS, 0, sizeof(unsigned long long), c->stream));
     uint64_t total_rows = 0;
     if (n_cursors > 0) {
         c->d_offsets.reserve((n_cursors + 1) * 8);
@@ -723,9 +752,9 @@ void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
         c->ct.kernel_launches += 2 * ((key_bits + 7) / 8 + 1) + 2 * ((qid_bits + 7) / 8 + 1);
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->d_counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->d_counters.p, CT_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    c->ct.lf_steps += c->h_counters[4];
+    c->ct.lf_steps += c->h_counters[CT_LF_STEPS];
     c->ct.hits += total_rows;
     c->last_hits = total_rows;
     CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_locate, c->ev[1], c->ev[2]));
@@ -815,7 +844,7 @@ int sb200_create(int device, sb200_ctx** out) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
         c->stream = c->own_stream;
         for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
-        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counters), 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counters), CT_COUNT * sizeof(unsigned long long), cudaHostAllocDefault));
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, device));
         c->sms = prop.multiProcessorCount;
@@ -829,7 +858,7 @@ int sb200_destroy(sb200_ctx* c) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         c->idx.release();
-        for (DevBuf* b : {&c->d_steps, &c->d_packed, &c->d_queries, &c->d_cursors, &c->d_counters, &c->d_offsets, &c->d_keys[0], &c->d_keys[1],
+        for (DevBuf* b : {&c->d_steps, &c->d_seeds, &c->d_packed, &c->d_queries, &c->d_cursors, &c->d_counters, &c->d_offsets, &c->d_keys[0], &c->d_keys[1],
                           &c->d_qids[0], &c->d_qids[1], &c->d_tmp, &c->d_scratch})
             b->release();
         for (auto& ev : c->ev) cudaEventDestroy(ev);
@@ -1344,8 +1373,8 @@ int sb200_rank_bench(sb200_ctx* c, int which, uint64_t n_chains, uint32_t iters,
         use(c);
         auto& ix = c->idx;
         if (!ix.loaded) throw Error("no index loaded");
-        c->d_counters.reserve(8 * sizeof(unsigned long long));
-        CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
+        c->d_counters.reserve(CT_COUNT * sizeof(unsigned long long));
+        CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, CT_COUNT * sizeof(unsigned long long), c->stream));
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         with_sigma(ix.sigma, [&](auto S) {
             rank_bench_kernel<S()><<<grid_for(n_chains), 256, 0, c->stream>>>(which ? ix.rev() : ix.bwt(), static_cast<uint32_t>(ix.n_rows),

@@ -1,20 +1,29 @@
 // search.cuh — kernel 2: search-scheme backtracking over the bidirectional FM-index.
 //
 // Replaces fmc::search_ng24::search<Edit>(index, queries, scheme, delegate) as called at
-// /root/reference/src/sahara/search.cpp:227-231 (semantics: SURVEY.md §9.4).  One CUDA thread owns one
-// (query, search) pair at a time and walks its search tree depth first with an explicit stack; threads
-// are persistent and pull the next pair from a global counter when their stack runs empty.
+// /root/reference/src/sahara/search.cpp:227-231 (semantics: SURVEY.md §9.4).
 //
-// Per loop iteration every lane performs exactly ONE cursor extension (= the two row probes lb and
-// lb+len of one BWT), so warps stay converged at node granularity.  Children are generated in the
-// order  match, (deletion, substitution) per symbol, insertion;  the last live child stays in registers
-// and becomes the next node, the others are pushed.  Because the match child is generated first it is
-// resumed only after all error children of the same node are finished, which bounds the stack by
-// 9 * maxErrors frames (Sigma = 6): on the current path only nodes left through an error edge keep
-// siblings on the stack, and a path has at most maxErrors error edges.
+// Two persistent-thread kernels share one state machine:
 //
-// The order in which cursors are reported differs from the reference's recursion order; the reported
-// multiset is identical (the reference does not depend on order, src/sahara/search.cpp:218-220).
+//   fm_kernel    walks the search trees while a cursor still covers several suffix-array rows.  One thread owns
+//                one query at a time and explores each search depth first with an explicit stack.  One loop
+//                iteration = ONE probe of one BWT (the rows lb and lb+len; a single 32-byte request when they
+//                share a block) from which the child cursors of all symbols are derived; then every search
+//                state that lives on this cursor is expanded.
+//   text_kernel  takes over as soon as a cursor holds a single row ("seed"): its occurrence T[a, b) is unique,
+//                so whether a child cursor is empty is decided by one text symbol (T[a-1] or T[b]) instead of
+//                two rank probes (in-text verification).  The reported cursor is lb = ISA[a], len = 1.
+//
+// States.  A frame is a cursor plus a search state (step, e, LInfo, RInfo) — LInfo/RInfo = last operation at the
+// left/right end of the match, as in the reference recursion.  The deletion (step, e+1, D) and the substitution
+// (step+1, e+1, S) of a mismatching symbol share the child cursor: one PAIR frame.  The insertion child keeps the
+// cursor of its parent and is expanded in the same iteration (insertion chain).  Every state is expanded exactly
+// like the corresponding call of the reference, so the reported multiset of (query, cursor, errors) is the
+// reference's; only the order differs (the reference does not depend on it, search.cpp:218-220).  The number of
+// expanded states equals the number of cursor extensions of the reference ("nodes").
+//
+// Children are pushed match first, so the error subtrees of a node finish before its match child resumes: a
+// path keeps siblings only at the nodes it left through an error edge, which bounds the stack (capi.cu).
 #pragma once
 #include <cstdio>
 #include "layout.cuh"
@@ -28,55 +37,53 @@ __host__ __device__ inline uint32_t pack_step(uint32_t pi, uint32_t l, uint32_t 
 
 enum : uint32_t { INFO_M = 0, INFO_S = 1, INFO_I = 2, INFO_D = 3 };
 
-// node meta: step (10 bits) | e << 10 (4 bits) | LInfo << 14 | RInfo << 16
-__device__ __forceinline__ uint32_t pack_meta(uint32_t step, uint32_t e, uint32_t L, uint32_t R) {
+// frame meta: step (10 bits) | e << 10 (4 bits) | LInfo << 14 | RInfo << 16 | PAIR << 18 | tlen << 20 (10 bits)
+// tlen = number of text symbols the match covers so far (matches, substitutions, deletions)
+__host__ __device__ inline uint32_t pack_meta(uint32_t step, uint32_t e, uint32_t L, uint32_t R) {
     return step | (e << 10) | (L << 14) | (R << 16);
 }
+constexpr uint32_t META_PAIR = 1u << 18;
+constexpr uint32_t META_TLEN_SHIFT = 20;
+constexpr uint32_t kEmitChunk = 16;   // output slots a thread reserves per atomic
+constexpr uint32_t kQueryBatch = 2;   // queries a thread takes per atomic
+constexpr uint32_t kInvalidQid = 0xffffffffu;
+
+// counters (unsigned long long each)
+enum : int {
+    CT_NEXT_QUERY = 0,   // work distribution of fm_kernel
+    CT_OUT_SLOTS = 1,    // cursor output slots reserved
+    CT_NODES = 2,        // states expanded
+    CT_OVERFLOW = 3,     // stack overflow flag
+    CT_LF_STEPS = 4,     // (locate kernel)
+    CT_MAX_SP = 5,       // deepest stack seen
+    CT_CURSORS = 6,      // cursors reported
+    CT_SEED_SLOTS = 7,   // seed slots reserved by fm_kernel
+    CT_NEXT_SEED = 8,    // work distribution of text_kernel
+    CT_SEEDS = 9,        // seeds produced
+    CT_COUNT = 16
+};
 
 struct SearchParams {
     OccTable bwt, bwtRev;
     uint32_t C[8];
     uint32_t n_rows;
-    const uint8_t* queries;  // [n_queries][len] ranks
-    const uint32_t* packed;  // [n_queries][packed_words(len)] 4-bit packed copies of the queries
+    const uint32_t* packed;  // [n_queries][packed_words(len)] queries, 8 symbols per word
     uint32_t n_queries, len, n_searches;
     const uint32_t* steps;   // [n_searches][len] packed
     uint4* out;              // (qid, lb, len, e)
     uint32_t out_cap;
-    // counters: [0] next query, [1] output slots reserved, [2] nodes, [3] stack overflow flag, [5] max stack depth,
-    //           [6] cursors reported
     unsigned long long* counters;
-    // optional q-gram jump table (cursor after the first qgram_q characters of a search)
-    const uint4* qgram;  // [4^q] (lb, lbRev, len, 0)
+    const uint4* qgram;      // optional q-gram jump table [4^q] (lb, lbRev, len, 0)
     uint32_t qgram_q;
-    uint32_t debug_flags;  // 1: no pair frames, 2: no insertion chains (diagnostics only)
-    // in-text verification (nullptr = off): suffix array, its inverse, and the text packed 8 symbols per word
+    uint32_t debug_flags;    // 1: no pair frames, 2: no insertion chains in fm_kernel (diagnostics only)
+    // in-text verification (nullptr = off): suffix array, its inverse, the text packed 8 symbols per word
     const uint32_t* sa32;
     const uint32_t* isa32;
     const uint32_t* text4;
+    uint4* seeds;            // (qid, lb, search, meta) handed from fm_kernel to text_kernel
+    uint32_t seed_cap;
 };
 
-// Frames and states.  A stack frame is a cursor plus one search state (step, e, LInfo, RInfo), or — flag
-// PAIR — the two states a mismatching symbol produces on the same child cursor: the deletion
-// (step, e, side = D) and the substitution (step + 1, e, side = S).  Both extend the same cursor, so one
-// probe of the occurrence table serves both.  Likewise the insertion child of a state keeps the cursor
-// of its parent: it is processed in the same iteration ("insertion chain") from the ranks already in
-// registers.  Every state is expanded exactly like the corresponding call of the reference recursion,
-// so the reported multiset is unchanged; only the number of memory probes shrinks.
-constexpr uint32_t META_PAIR = 1u << 18;
-// In-text verification.  Once a cursor holds a single row its occurrence T[a, b) is unique, and whether a
-// child cursor is empty is decided by one text symbol (T[a-1] or T[b]) instead of two rank probes.  Frames
-// flagged META_TEXT carry (a, b) in place of (lb, lbRev); the expansion of the states is unchanged, so the
-// reported multiset is unchanged.  FM-mode metas carry the number of text symbols consumed so far (tlen,
-// bits 20..29) so that b = a + tlen when the frame switches; a = SA[lb], and the reported cursor of a text
-// frame is lb = ISA[a], len = 1.
-constexpr uint32_t META_TEXT = 1u << 19;
-constexpr uint32_t META_TLEN_SHIFT = 20;
-constexpr uint32_t kEmitChunk = 16;       // output slots a thread reserves per atomic
-constexpr uint32_t kQueryBatch = 2;       // queries a thread takes per atomic
-constexpr uint32_t kInvalidQid = 0xffffffffu;
-
-// queries packed 8 symbols per word (4 bits each) by pack_queries_kernel
 __host__ __device__ inline uint32_t packed_words(uint32_t len) { return (len + 7) / 8; }
 
 #if !defined(SB200_HOST_EMU)
@@ -93,38 +100,69 @@ __global__ void pack_queries_kernel(const uint8_t* q, uint64_t n_queries, uint32
 }
 #endif
 
-// body of one (persistent) thread.
-//   s_steps: the packed scheme table (shared memory on the device)
-//   s_query: this thread's staging area for the packed query, element w at s_query[w * qstride]
+// chunked append to a global array: one atomic per kEmitChunk entries
+struct ChunkWriter {
+    uint32_t pos{0}, end{0};
+    __device__ __forceinline__ void put(uint4* buf, uint32_t cap, unsigned long long* counter, uint4 v) {
+        if (pos == end) {
+            pos = static_cast<uint32_t>(atomicAdd(counter, static_cast<unsigned long long>(kEmitChunk)));
+            end = pos + kEmitChunk;
+        }
+        if (pos < cap) buf[pos] = v;
+        ++pos;
+    }
+    // unused slots of the last chunk become empty entries
+    __device__ __forceinline__ void finish(uint4* buf, uint32_t cap) {
+        for (; pos < end; ++pos)
+            if (pos < cap) buf[pos] = make_uint4(kInvalidQid, 0, 0, 0);
+    }
+};
+
+// copies the packed query into this thread's staging words; returns true when it contains the delimiter
+__device__ __forceinline__ bool stage_query(const SearchParams& P, uint32_t qid, uint32_t W, uint32_t* s_query, uint32_t qstride) {
+    const uint32_t* src = P.packed + static_cast<uint64_t>(qid) * W;
+    bool delim = false;
+    for (uint32_t w = 0; w < W; ++w) {
+        uint32_t v = src[w];
+        s_query[w * qstride] = v;
+        delim = delim || (((v - 0x11111111u) & ~v & 0x88888888u) != 0);  // some nibble is 0
+    }
+    return delim;
+}
+
+// ================================================================================================
+// fm_kernel body.  s_steps: scheme table (shared memory); s_query: this thread's staged query, word w at
+// s_query[w * qstride].
+// ================================================================================================
 template <int SIGMA, bool EDIT, int STACK>
-__device__ __forceinline__ void search_thread(const SearchParams& P, const uint32_t* s_steps, uint32_t* s_query, uint32_t qstride) {
+__device__ __forceinline__ void fm_thread(const SearchParams& P, const uint32_t* s_steps, uint32_t* s_query, uint32_t qstride) {
     uint4 stack[STACK];
     int sp = 0;
     const uint32_t* tbl = nullptr;
     uint32_t qid = 0, qid_end = 0, next_search = P.n_searches;  // forces the first fetch
-    uint32_t nodes = 0, emitted = 0;
-    uint32_t out_pos = 0, out_end = 0;
+    uint32_t nodes = 0, emitted = 0, seeded = 0;
+    ChunkWriter outW, seedW;
     bool overflow = false;
-    bool textOK = false;  // in-text verification allowed for the current query
+    bool toText = false;  // unique cursors of the current query are handed to text_kernel
     int maxsp = 0;
     const uint32_t qlen = P.len;
     const uint32_t W = packed_words(qlen);
 
     auto qsym = [&](uint32_t pos) -> uint32_t { return (s_query[(pos >> 3) * qstride] >> ((pos & 7u) * 4u)) & 0xfu; };
-
-    bool textFrame = false;  // the frame being expanded is in text mode
     auto emit = [&](uint32_t lb, uint32_t len, uint32_t e) {
-        if (textFrame) lb = P.isa32[lb];  // (a, b) -> the row of the suffix starting at a; len is 1
-        if (out_pos == out_end) {
-            out_pos = static_cast<uint32_t>(atomicAdd(&P.counters[1], static_cast<unsigned long long>(kEmitChunk)));
-            out_end = out_pos + kEmitChunk;
-        }
-#if defined(SB200_TRACE)
-        if (P.debug_flags & 4u) printf("EMIT q=%u lb=%u len=%u e=%u\n", qid, lb, len, e);
-#endif
-        if (out_pos < P.out_cap) P.out[out_pos] = make_uint4(qid, lb, len, e);
-        ++out_pos;
+        outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], make_uint4(qid, lb, len, e));
         ++emitted;
+    };
+    // a child frame: unique cursors go to the text kernel, the others on the stack
+    auto push = [&](uint32_t nlb, uint32_t nlbRev, uint32_t nlen, uint32_t m) {
+        if (toText && nlen == 1) {
+            seedW.put(P.seeds, P.seed_cap, &P.counters[CT_SEED_SLOTS], make_uint4(qid, nlb, next_search - 1, m));
+            ++seeded;
+        } else {
+            if (sp < STACK) stack[sp] = make_uint4(nlb, nlbRev, nlen, m);
+            else overflow = true;
+            ++sp;
+        }
     };
 
     bool done = false;
@@ -135,19 +173,13 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
                 next_search = 0;
                 ++qid;
                 if (qid >= qid_end) {
-                    unsigned long long w = atomicAdd(&P.counters[0], static_cast<unsigned long long>(kQueryBatch));
+                    unsigned long long w = atomicAdd(&P.counters[CT_NEXT_QUERY], static_cast<unsigned long long>(kQueryBatch));
                     if (w >= P.n_queries) { done = true; break; }
                     qid = static_cast<uint32_t>(w);
                     qid_end = qid + kQueryBatch < P.n_queries ? qid + kQueryBatch : P.n_queries;
                 }
-                const uint32_t* src = P.packed + static_cast<uint64_t>(qid) * W;
-                bool delim = false;
-                for (uint32_t w = 0; w < W; ++w) {
-                    uint32_t v = src[w];
-                    s_query[w * qstride] = v;
-                    delim = delim || (((v - 0x11111111u) & ~v & 0x88888888u) != 0);  // some nibble is 0
-                }
-                textOK = P.sa32 != nullptr && !delim;
+                bool delim = stage_query(P, qid, W, s_query, qstride);
+                toText = P.sa32 != nullptr && !delim;  // a query with the delimiter stays on the FM path
             }
             tbl = s_steps + next_search * qlen;
             ++next_search;
@@ -171,7 +203,6 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
                     uint4 g = P.qgram[code];
                     if (g.z == 0) continue;
                     if (qq == qlen) {
-                        textFrame = false;
                         emit(g.x, g.z, 0);
                         continue;
                     }
@@ -179,8 +210,7 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
                     root = make_uint4(g.x, g.y, g.z, pack_meta(qq, 0, INFO_M, INFO_M) | (qq << META_TLEN_SHIFT));
                 }
             }
-            stack[0] = root;
-            sp = 1;
+            push(root.x, root.y, root.z, root.w);
         }
         if (done) break;
         maxsp = sp > maxsp ? sp : maxsp;
@@ -190,34 +220,17 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
             lb = f.x; lbRev = f.y; len = f.z; meta = f.w;
         }
 
-        // ---- one probe for this cursor: occurrence table (FM mode) or one text symbol (text mode) -------
+        // ---- one probe of the occurrence table for this cursor ------------------------------------
         uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
         uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
         const bool pair = (meta & META_PAIR) != 0;
-        const bool right = (tbl[step] >> 24) & 1u;
         const uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
-        textFrame = (meta & META_TEXT) != 0;
-        if (!textFrame && textOK && len == 1) {  // unique occurrence: switch to the text
-            uint32_t a = P.sa32[lb];
-            lb = a;
-            lbRev = a + tlen;
-            textFrame = true;
-        }
-        // child cursors per symbol: (klb[s], klbRev[s], cnt[s])
+        const bool right = (tbl[step] >> 24) & 1u;
+        // child cursors per symbol: (klb[s], klbRev[s], cnt[s]).  The probed side continues at C[s] + rank(lo, s),
+        // the other side moves by the number of smaller symbols inside the interval.  (The selection by `right`
+        // is done once here, outside the state loop.)
         uint32_t klb[SIGMA], klbRev[SIGMA], cnt[SIGMA];
-        if (textFrame) {
-            // lb = a, lbRev = b.  Left extension reads T[a-1] (the delimiter before position 0), right T[b].
-            const uint32_t pos = right ? lbRev : lb - 1;
-            uint32_t t = 0;
-            if (right || lb != 0) t = (P.text4[pos >> 3] >> ((pos & 7u) * 4u)) & 0xfu;
-            const uint32_t na = right ? lb : lb - 1, nb = right ? lbRev + 1 : lbRev;
-#pragma unroll
-            for (int s = 0; s < SIGMA; ++s) {
-                klb[s] = na;
-                klbRev[s] = nb;
-                cnt[s] = (s != 0 && static_cast<uint32_t>(s) == t) ? 1u : 0u;
-            }
-        } else {
+        {
             const OccTable& tab = right ? P.bwtRev : P.bwt;
             const uint32_t lo = right ? lbRev : lb;
             const uint32_t hi = lo + len;
@@ -229,8 +242,6 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
                 b2 = load_blk(tab.blk + (hi >> kBlkShift));
                 if ((lo >> kSupShift) != (hi >> kSupShift)) s2 = load_sup(tab.sup + (hi >> kSupShift));
             }
-            // The probed side continues at C[s] + rank(lo, s), the other side moves by the number of smaller
-            // symbols inside the interval.
             uint32_t own[SIGMA];
             uint32_t sum1 = 0, sumc = 0;
 #pragma unroll
@@ -252,9 +263,7 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
                 other += cnt[s];
             }
         }
-        // flags every child inherits: text mode, and the text length of children that consume a text symbol
-        const uint32_t inheritSame = (textFrame ? META_TEXT : 0u) | (tlen << META_TLEN_SHIFT);
-        const uint32_t inheritNext = (textFrame ? META_TEXT : 0u) | ((tlen + 1) << META_TLEN_SHIFT);
+        const uint32_t tlenSame = tlen << META_TLEN_SHIFT, tlenNext = (tlen + 1) << META_TLEN_SHIFT;
 
         // ---- expand every state that lives on this cursor ------------------------------------------
         bool second = false;  // second half of a pair already taken
@@ -262,9 +271,8 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
             ++nodes;
 #if defined(SB200_TRACE)
             if (P.debug_flags & 4u)
-                printf("STATE q=%u lb=%u lbRev=%u len=%u step=%u e=%u L=%u R=%u pair=%d second=%d right=%d cnt=%u,%u,%u,%u,%u,%u\n", qid, lb,
-                       lbRev, len, step, e, Linfo, Rinfo, (int)pair, (int)second, (int)right, cnt[0], cnt[1], cnt[2], cnt[3], cnt[4],
-                       SIGMA > 5 ? cnt[SIGMA - 1] : 0u);
+                printf("STATE q=%u lb=%u lbRev=%u len=%u step=%u e=%u L=%u R=%u pair=%d second=%d right=%d\n", qid, lb, lbRev, len, step, e,
+                       Linfo, Rinfo, (int)pair, (int)second, (int)right);
 #endif
             const uint32_t st = tbl[step];
             const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
@@ -277,16 +285,16 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
             const bool matchOK = l <= e && e <= u;
             const bool mmOK = l <= e + 1 && e + 1 <= u;
             const uint32_t T = right ? Rinfo : Linfo;
-            const uint32_t O = right ? Linfo : Rinfo;  // info of the other end
-            const bool otherEndOK = !EDIT || (O & 1u) == 0;  // M or I
+            const uint32_t O = right ? Linfo : Rinfo;          // info of the other end
+            const bool otherEndOK = !EDIT || (O & 1u) == 0;    // M or I
             // metas of the possible children: the moving side gets the new info
             const uint32_t keepL = right ? Linfo : 0u, keepR = right ? 0u : Rinfo;
             const uint32_t sideShift = right ? 16u : 14u;
             const uint32_t metaBase = (keepL << 14) | (keepR << 16);
-            const uint32_t mM = metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift) | inheritNext;
-            const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift) | inheritNext;
-            const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift) | inheritNext;
-            const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift) | inheritSame;
+            const uint32_t mM = metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift) | tlenNext;
+            const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift) | tlenNext;
+            const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift) | tlenNext;
+            const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift) | tlenSame;
             // match
             {
                 uint32_t mc = 0, nlb = 0, nlbRev = 0;
@@ -297,9 +305,7 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
                 if (alive && last) {
                     if (otherEndOK) emit(nlb, mc, e);
                 } else if (alive && lnext <= e + 1) {
-                    if (sp < STACK) stack[sp] = make_uint4(nlb, nlbRev, mc, mM);
-                    else overflow = true;
-                    ++sp;
+                    push(nlb, nlbRev, mc, mM);
                 }
             }
             if (mmOK) {
@@ -310,16 +316,8 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
                 for (int s = 1; s < SIGMA; ++s) {
                     const bool live = static_cast<uint32_t>(s) != c && cnt[s] != 0;
                     const uint32_t nlb = klb[s], nlbRev = klbRev[s];
-                    if (live && (asPair || delOK)) {
-                        if (sp < STACK) stack[sp] = make_uint4(nlb, nlbRev, cnt[s], asPair ? (mD | META_PAIR) : mD);
-                        else overflow = true;
-                        ++sp;
-                    }
-                    if (live && !asPair && subAlive) {
-                        if (sp < STACK) stack[sp] = make_uint4(nlb, nlbRev, cnt[s], mS);
-                        else overflow = true;
-                        ++sp;
-                        }
+                    if (live && (asPair || delOK)) push(nlb, nlbRev, cnt[s], asPair ? (mD | META_PAIR) : mD);
+                    if (live && !asPair && subAlive) push(nlb, nlbRev, cnt[s], mS);
                     if (!EDIT && live && last) emit(nlb, cnt[s], e + 1);
                 }
             }
@@ -340,9 +338,7 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
             }
             if (lnext > e + 2) break;  // dead at the next step
             if (!sameDirNext || (P.debug_flags & 2u)) {  // direction changes: needs a probe of the other table
-                if (sp < STACK) stack[sp] = make_uint4(lb, lbRev, len, mI);
-                else overflow = true;
-                ++sp;
+                push(lb, lbRev, len, mI);
                 break;
             }
             step += 1;
@@ -350,24 +346,167 @@ __device__ __forceinline__ void search_thread(const SearchParams& P, const uint3
             if (right) Rinfo = INFO_I; else Linfo = INFO_I;
         }
     }
-    // unused slots of the last reserved chunk become empty entries (len 0: they locate to nothing)
-    for (; out_pos < out_end; ++out_pos)
-        if (out_pos < P.out_cap) P.out[out_pos] = make_uint4(kInvalidQid, 0, 0, 0);
-    if (nodes) atomicAdd(&P.counters[2], static_cast<unsigned long long>(nodes));
-    if (overflow) atomicExch(&P.counters[3], 1ull);
-    atomicMax(&P.counters[5], static_cast<unsigned long long>(maxsp));
-    if (emitted) atomicAdd(&P.counters[6], static_cast<unsigned long long>(emitted));
+    outW.finish(P.out, P.out_cap);
+    seedW.finish(P.seeds, P.seed_cap);
+    if (nodes) atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(nodes));
+    if (overflow) atomicExch(&P.counters[CT_OVERFLOW], 1ull);
+    atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxsp));
+    if (emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(emitted));
+    if (seeded) atomicAdd(&P.counters[CT_SEEDS], static_cast<unsigned long long>(seeded));
+}
+
+// ================================================================================================
+// text_kernel body: in-text verification of the seeds.  A frame is (a, meta) with the same meta layout; the
+// occurrence is T[a, a + tlen).
+// ================================================================================================
+template <bool EDIT, int STACK>
+__device__ __forceinline__ void text_thread(const SearchParams& P, const uint32_t* s_steps, uint32_t* s_query, uint32_t qstride) {
+    uint2 stack[STACK];
+    int sp = 0;
+    const uint32_t* tbl = nullptr;
+    uint32_t qid = kInvalidQid;
+    uint32_t nodes = 0, emitted = 0;
+    ChunkWriter outW;
+    bool overflow = false;
+    int maxsp = 0;
+    const uint32_t qlen = P.len;
+    const uint32_t W = packed_words(qlen);
+    const unsigned long long slots = P.counters[CT_SEED_SLOTS];
+    const uint32_t n_slots = static_cast<uint32_t>(slots < P.seed_cap ? slots : P.seed_cap);
+
+    auto qsym = [&](uint32_t pos) -> uint32_t { return (s_query[(pos >> 3) * qstride] >> ((pos & 7u) * 4u)) & 0xfu; };
+    auto emit = [&](uint32_t a, uint32_t e) {
+        outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], make_uint4(qid, P.isa32[a], 1, e));
+        ++emitted;
+    };
+    auto push = [&](uint32_t a, uint32_t m) {
+        if (sp < STACK) stack[sp] = make_uint2(a, m);
+        else overflow = true;
+        ++sp;
+    };
+
+    while (true) {
+        if (sp == 0) {
+            uint32_t i = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_SEED], 1ull));
+            if (i >= n_slots) break;
+            uint4 seed = P.seeds[i];
+            if (seed.x == kInvalidQid) continue;
+            if (seed.x != qid) {
+                qid = seed.x;
+                stage_query(P, qid, W, s_query, qstride);
+            }
+            tbl = s_steps + seed.z * qlen;
+            push(P.sa32[seed.y], seed.w);  // a = SA[lb]; the meta already carries tlen = b - a
+        }
+        maxsp = sp > maxsp ? sp : maxsp;
+        const uint2 f = stack[--sp];
+        const uint32_t a = f.x, meta = f.y;
+        uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
+        uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
+        const bool pair = (meta & META_PAIR) != 0;
+        const uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
+        const uint32_t b = a + tlen;
+        const bool rightFrame = (tbl[step] >> 24) & 1u;  // the end the frame's own error (D / S) sits on
+        // the text symbols left and right of the occurrence (the delimiter before position 0)
+        uint32_t tL = 0;
+        if (a != 0) tL = (P.text4[(a - 1) >> 3] >> (((a - 1) & 7u) * 4u)) & 0xfu;
+        const uint32_t tR = (P.text4[b >> 3] >> ((b & 7u) * 4u)) & 0xfu;
+
+        bool second = false;
+        while (true) {
+            ++nodes;
+#if defined(SB200_TRACE)
+            if (P.debug_flags & 4u)
+                printf("TSTATE q=%u a=%u tlen=%u step=%u e=%u L=%u R=%u pair=%d second=%d\n", qid, a, tlen, step, e, Linfo, Rinfo, (int)pair,
+                       (int)second);
+#endif
+            const uint32_t st = tbl[step];
+            const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
+            const bool right = (st >> 24) & 1u;
+            const uint32_t c = qsym(st & 0xffffu);
+            const bool last = step + 1 == qlen;
+            const uint32_t stn = last ? 0u : tbl[step + 1];
+            const uint32_t lnext = (stn >> 16) & 0xfu;
+            const bool sameDirNext = !last && ((((stn >> 24) & 1u) != 0) == right);
+            const bool matchOK = l <= e && e <= u;
+            const bool mmOK = l <= e + 1 && e + 1 <= u;
+            const uint32_t T = right ? Rinfo : Linfo;
+            const uint32_t O = right ? Linfo : Rinfo;
+            const bool otherEndOK = !EDIT || (O & 1u) == 0;
+            const uint32_t t = right ? tR : tL;    // the only symbol whose child cursor is not empty
+            const uint32_t na = right ? a : a - 1;  // child occurrence T[na, na + tlen + 1)
+            const uint32_t keepL = right ? Linfo : 0u, keepR = right ? 0u : Rinfo;
+            const uint32_t sideShift = right ? 16u : 14u;
+            const uint32_t metaBase = (keepL << 14) | (keepR << 16) | ((tlen + 1) << META_TLEN_SHIFT);
+            if (t != 0) {
+                if (t == c) {
+                    if (matchOK) {
+                        if (last) {
+                            if (otherEndOK) emit(na, e);
+                        } else if (lnext <= e + 1) {
+                            push(na, metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift));
+                        }
+                    }
+                } else if (mmOK) {
+                    const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
+                    const bool subAlive = !last && lnext <= e + 2;
+                    const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift);
+                    const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift);
+                    // a pair only when both halves extend the same end: then the substitution half has T = S and
+                    // no insertion chain of its own (as in fm_kernel)
+                    if (delOK && subAlive && sameDirNext) push(na, mD | META_PAIR);
+                    else {
+                        if (delOK) push(na, mD);
+                        if (subAlive) push(na, mS);
+                    }
+                    if (!EDIT && last) emit(na, e + 1);
+                }
+            }
+            // next state on the same cursor
+            if (pair) {
+                if (second) break;
+                second = true;
+                step += 1;  // the substitution half: (step + 1, e), S at the end both halves extend
+                if (rightFrame) Rinfo = INFO_S; else Linfo = INFO_S;
+                continue;
+            }
+            const bool insOK = EDIT && mmOK && (T == INFO_M || T == INFO_I);
+            if (!insOK) break;
+            if (last) {
+                if (otherEndOK) emit(a, e + 1);
+                break;
+            }
+            if (lnext > e + 2) break;
+            step += 1;
+            e += 1;
+            if (right) Rinfo = INFO_I; else Linfo = INFO_I;
+        }
+    }
+    outW.finish(P.out, P.out_cap);
+    if (nodes) atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(nodes));
+    if (overflow) atomicExch(&P.counters[CT_OVERFLOW], 1ull);
+    atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxsp));
+    if (emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(emitted));
 }
 
 #if !defined(SB200_HOST_EMU)
 template <int SIGMA, bool EDIT, int STACK>
-__global__ void __launch_bounds__(256, 4) search_kernel(const SearchParams P) {
+__global__ void __launch_bounds__(256, 4) fm_kernel(const SearchParams P) {
     extern __shared__ uint32_t s_steps[];
     const uint32_t n_steps = P.n_searches * P.len;
     for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) s_steps[i] = P.steps[i];
     __syncthreads();
     // word w of this thread's query lives at s_query[w * blockDim.x]: every lane stays in its own bank
-    search_thread<SIGMA, EDIT, STACK>(P, s_steps, s_steps + n_steps + threadIdx.x, blockDim.x);
+    fm_thread<SIGMA, EDIT, STACK>(P, s_steps, s_steps + n_steps + threadIdx.x, blockDim.x);
+}
+
+template <bool EDIT, int STACK>
+__global__ void __launch_bounds__(256) text_kernel(const SearchParams P) {
+    extern __shared__ uint32_t s_steps[];
+    const uint32_t n_steps = P.n_searches * P.len;
+    for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) s_steps[i] = P.steps[i];
+    __syncthreads();
+    text_thread<EDIT, STACK>(P, s_steps, s_steps + n_steps + threadIdx.x, blockDim.x);
 }
 #endif
 

@@ -74,19 +74,21 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
             uint32_t& w = packed[qi * W + i / 8];
             w = (w & ~(0xfu << (4 * (i % 8)))) | (uint32_t(queries[qi * len + i] & 0xf) << (4 * (i % 8)));
         }
-    uint64_t cap = 1 << 16;
-    std::vector<uint4> buf;
-    unsigned long long counters[8];
+    uint64_t cap = 1 << 16, seed_cap = 1 << 16;
+    std::vector<uint4> buf, seeds;
+    unsigned long long counters[CT_COUNT];
     while (true) {
         buf.assign(cap + 1, uint4{0, 0, 0, 0});
+        seeds.assign(seed_cap + 1, uint4{0, 0, 0, 0});
         std::memset(counters, 0, sizeof counters);
         SearchParams P{};
         P.bwt = OccTable{a.blk.data(), a.sup.data()};
         P.bwtRev = OccTable{b.blk.data(), b.sup.data()};
         for (int i = 0; i < 8; ++i) P.C[i] = static_cast<uint32_t>(i <= sigma ? C[i] : n_rows);
         P.n_rows = static_cast<uint32_t>(n_rows);
-        P.queries = queries;
         P.packed = packed.data();
+        P.seeds = seeds.data();
+        P.seed_cap = static_cast<uint32_t>(seed_cap);
         P.n_queries = static_cast<uint32_t>(n_queries);
         P.len = len;
         P.n_searches = n_searches;
@@ -101,23 +103,31 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
         P.isa32 = isa.empty() ? nullptr : isa.data();
         P.text4 = isa.empty() ? nullptr : text4.data();
         if (sigma == 6) {
-            if (edit) search_thread<6, true, 96>(P, steps.data(), stage.data(), 1);
-            else search_thread<6, false, 96>(P, steps.data(), stage.data(), 1);
+            if (edit) fm_thread<6, true, 96>(P, steps.data(), stage.data(), 1);
+            else fm_thread<6, false, 96>(P, steps.data(), stage.data(), 1);
         } else if (sigma == 5) {
-            if (edit) search_thread<5, true, 96>(P, steps.data(), stage.data(), 1);
-            else search_thread<5, false, 96>(P, steps.data(), stage.data(), 1);
+            if (edit) fm_thread<5, true, 96>(P, steps.data(), stage.data(), 1);
+            else fm_thread<5, false, 96>(P, steps.data(), stage.data(), 1);
         } else return 3;
-        if (counters[3]) return 4;  // stack overflow
-        if (counters[1] <= cap) break;
-        cap = counters[1];
+        if (counters[CT_SEED_SLOTS] > seed_cap) {
+            seed_cap = counters[CT_SEED_SLOTS];
+            continue;
+        }
+        if (P.sa32) {  // second kernel: in-text verification of the seeds
+            if (edit) text_thread<true, 96>(P, steps.data(), stage.data(), 1);
+            else text_thread<false, 96>(P, steps.data(), stage.data(), 1);
+        }
+        if (counters[CT_OVERFLOW]) return 4;  // stack overflow
+        if (counters[CT_OUT_SLOTS] <= cap) break;
+        cap = counters[CT_OUT_SLOTS];
     }
-    uint64_t slots = counters[1], n = 0;
+    uint64_t slots = counters[CT_OUT_SLOTS], n = 0;
     *out = static_cast<uint32_t*>(std::malloc(std::max<uint64_t>(1, slots) * 16));
     for (uint64_t i = 0; i < slots; ++i)
         if (buf[i].x != kInvalidQid) std::memcpy(*out + 4 * n++, &buf[i], 16);
-    if (n != counters[6]) return 5;
+    if (n != counters[CT_CURSORS]) return 5;
     *n_out = n;
-    if (nodes) *nodes = counters[2];
+    if (nodes) *nodes = counters[CT_NODES];
     return 0;
 }
 

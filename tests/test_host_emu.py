@@ -22,27 +22,33 @@ def indexes():
     out["repeats"] = (rng, [W.repetitive_genome(rng, 20000), W.repetitive_genome(rng, 3000)], 6)
     out["multi"] = (rng, [W.random_genome(rng, int(n), with_n=True) for n in (9000, 1, 17, 64, 4096, 33)], 6)
     out["dna4"] = (rng, [W.random_genome(rng, 15000)], 5)
-    return {k: (r, s, O.OracleIndex.build(s, sig, 16)) for k, (r, s, sig) in out.items()}
+    res = {}
+    for k, (r, s, sig) in out.items():
+        ix = O.OracleIndex.build(s, sig, 16)
+        res[k] = (r, s, ix, emu.text_tables(ix, s))
+    return res
 
 
 @pytest.mark.parametrize("key", ["repeats", "multi", "dna4"])
 @pytest.mark.parametrize("edit,k", [(False, 0), (False, 2), (False, 3), (True, 1), (True, 2), (True, 3), (True, 4)])
 def test_kernel_source_matches_oracle(indexes, key, edit, k):
-    rng, seqs, ix = indexes[key]
+    rng, seqs, ix, tt = indexes[key]
     m = 40
     q = W.sample_reads(rng, seqs, 60 if k < 4 else 12, m, k, edit)
-    for gen in ("h2-k2", "pigeon_opt"):
+    q[3, 9] = 0  # one query with the delimiter (never verified in the text)
+    for gen in ("h2-k2", "pigeon_opt", "01*0"):
         sch = sb.SearchScheme.generate(gen, 0, k, m, limit_to_hamming=not edit)
         before = int(ix.counters[0])
         want = O.sort_rows(ix.search(q, sch, edit))
         nodes_oracle = int(ix.counters[0]) - before
-        got, nodes = emu.search(ix, q, sch, edit)
-        assert got.shape == want.shape and np.array_equal(got, want)
-        assert nodes == nodes_oracle  # every state the kernel expands is one extension of the reference recursion
+        for text in (None, tt):  # fm_kernel alone, fm_kernel + text_kernel
+            got, nodes = emu.search(ix, q, sch, edit, 0, text)
+            assert got.shape == want.shape and np.array_equal(got, want)
+            assert nodes == nodes_oracle  # every state the kernels expand is one extension of the reference recursion
 
 
 def test_debug_variants_agree(indexes):
-    rng, seqs, ix = indexes["repeats"]
+    rng, seqs, ix, tt = indexes["repeats"]
     q = W.sample_reads(rng, seqs, 40, 36, 2, True)
     sch = sb.SearchScheme.generate("h2-k2", 0, 2, 36)
     want = O.sort_rows(ix.search(q, sch, True))
