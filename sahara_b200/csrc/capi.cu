@@ -162,7 +162,7 @@ struct sb200_ctx {
     cudaStream_t own_stream{}, stream{};
     DeviceIndex idx;
     // scheme
-    DevBuf d_steps;
+    DevBuf d_steps, d_runs;
     uint32_t n_searches{}, qlen{}, kmax{};
     bool edit{}, have_scheme{};
     // work buffers
@@ -578,7 +578,7 @@ unsigned blocks_per_sm(const char* env, unsigned def) {
 
 void launch_search(sb200_ctx* c, const SearchParams& P) {
     // shared memory: scheme table + one staged packed query per thread
-    size_t smem = (size_t(P.n_searches) * P.len + size_t(packed_words(P.len)) * 256) * 4;
+    size_t smem = (size_t(P.n_searches) * P.len + (size_t(P.n_searches) * P.len * kRunE + 3) / 4 + size_t(packed_words(P.len)) * 256) * 4;
     if (smem > 100 * 1024) throw Error("search scheme table and staged queries do not fit shared memory (query too long)");
     unsigned grid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_BLOCKS_PER_SM", 4);
     unsigned need = grid_for((uint64_t(P.n_queries) + kQueryBatch - 1) / kQueryBatch);
@@ -644,6 +644,7 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         P.len = len;
         P.n_searches = c->n_searches;
         P.steps = c->d_steps.get<uint32_t>();
+        P.runs = c->d_runs.get<uint8_t>();
         P.out = c->d_cursors.get<uint4>();
         P.out_cap = static_cast<uint32_t>(std::min<uint64_t>(c->cursor_cap, 0xfffffffeull));
         P.counters = c->d_counters.get<unsigned long long>();
@@ -858,7 +859,7 @@ int sb200_destroy(sb200_ctx* c) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         c->idx.release();
-        for (DevBuf* b : {&c->d_steps, &c->d_seeds, &c->d_packed, &c->d_queries, &c->d_cursors, &c->d_counters, &c->d_offsets, &c->d_keys[0], &c->d_keys[1],
+        for (DevBuf* b : {&c->d_steps, &c->d_runs, &c->d_seeds, &c->d_packed, &c->d_queries, &c->d_cursors, &c->d_counters, &c->d_offsets, &c->d_keys[0], &c->d_keys[1],
                           &c->d_qids[0], &c->d_qids[1], &c->d_tmp, &c->d_scratch})
             b->release();
         for (auto& ev : c->ev) cudaEventDestroy(ev);
@@ -1250,6 +1251,10 @@ int sb200_set_scheme(sb200_ctx* c, uint32_t n_searches, uint32_t len, const uint
         if (kmax > 4) throw Error("search schemes with more than 4 errors are not supported by the GPU kernel yet");
         c->d_steps.reserve(steps.size() * 4);
         CUDA_TRY(cudaMemcpyAsync(c->d_steps.p, steps.data(), steps.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        std::vector<uint8_t> runs(steps.size() * kRunE + 4, 0);
+        build_runs(n_searches, len, steps.data(), runs.data());
+        c->d_runs.reserve(runs.size());
+        CUDA_TRY(cudaMemcpyAsync(c->d_runs.p, runs.data(), runs.size(), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->n_searches = n_searches;
         c->qlen = len;

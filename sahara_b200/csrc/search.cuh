@@ -47,6 +47,31 @@ constexpr uint32_t META_TLEN_SHIFT = 20;
 constexpr uint32_t kEmitChunk = 16;   // output slots a thread reserves per atomic
 constexpr uint32_t kQueryBatch = 2;   // queries a thread takes per atomic
 constexpr uint32_t kInvalidQid = 0xffffffffu;
+constexpr uint32_t kRunE = 5;         // error levels 0..4 in the run table
+
+// Match-only runs.  At (step, e) with u[step] == e and l[step] <= e only a match is possible (no error may be
+// added) — in the text kernel such steps are compared symbol by symbol without touching the stack.  run(step, e)
+// = number of consecutive such steps that extend the same end over consecutive query positions.
+inline void build_runs(uint32_t n_searches, uint32_t len, const uint32_t* steps, uint8_t* runs) {
+    for (uint32_t j = 0; j < n_searches; ++j)
+        for (uint32_t e = 0; e < kRunE; ++e)
+            for (uint32_t i = len; i-- > 0;) {
+                const uint32_t st = steps[j * len + i];
+                const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu, right = (st >> 24) & 1u, pi = st & 0xffffu;
+                uint32_t r = 0;
+                if (u == e && l <= e) {
+                    r = 1;
+                    if (i + 1 < len) {
+                        const uint32_t sn = steps[j * len + i + 1];
+                        const uint32_t pn = sn & 0xffffu;
+                        bool consecutive = ((sn >> 24) & 1u) == right && (right ? pn == pi + 1 : pn + 1 == pi);
+                        if (consecutive) r += runs[((j * len) + i + 1) * kRunE + e];
+                    }
+                    if (r > 255) r = 255;
+                }
+                runs[((j * len) + i) * kRunE + e] = static_cast<uint8_t>(r);
+            }
+}
 
 // counters (unsigned long long each)
 enum : int {
@@ -70,6 +95,7 @@ struct SearchParams {
     const uint32_t* packed;  // [n_queries][packed_words(len)] queries, 8 symbols per word
     uint32_t n_queries, len, n_searches;
     const uint32_t* steps;   // [n_searches][len] packed
+    const uint8_t* runs;     // [n_searches][len][kRunE]: length of the match-only run that starts at (step, e)
     uint4* out;              // (qid, lb, len, e)
     uint32_t out_cap;
     unsigned long long* counters;
@@ -360,10 +386,12 @@ __device__ __forceinline__ void fm_thread(const SearchParams& P, const uint32_t*
 // occurrence is T[a, a + tlen).
 // ================================================================================================
 template <bool EDIT, int STACK>
-__device__ __forceinline__ void text_thread(const SearchParams& P, const uint32_t* s_steps, uint32_t* s_query, uint32_t qstride) {
+__device__ __forceinline__ void text_thread(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, uint32_t* s_query,
+                                            uint32_t qstride) {
     uint2 stack[STACK];
     int sp = 0;
     const uint32_t* tbl = nullptr;
+    const uint8_t* runs = nullptr;
     uint32_t qid = kInvalidQid;
     uint32_t nodes = 0, emitted = 0;
     ChunkWriter outW;
@@ -396,15 +424,63 @@ __device__ __forceinline__ void text_thread(const SearchParams& P, const uint32_
                 stage_query(P, qid, W, s_query, qstride);
             }
             tbl = s_steps + seed.z * qlen;
+            runs = s_runs + seed.z * qlen * kRunE;
             push(P.sa32[seed.y], seed.w);  // a = SA[lb]; the meta already carries tlen = b - a
         }
         maxsp = sp > maxsp ? sp : maxsp;
         const uint2 f = stack[--sp];
-        const uint32_t a = f.x, meta = f.y;
+        uint32_t a = f.x;
+        const uint32_t meta = f.y;
         uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
         uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
         const bool pair = (meta & META_PAIR) != 0;
-        const uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
+        uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
+
+        // ---- match-only run: compare query and text symbol by symbol, no stack traffic ---------------
+        bool dead = false;
+        if (!pair) {
+            uint32_t R = runs[step * kRunE + e];
+            while (R != 0) {
+                const uint32_t st = tbl[step];
+                const bool right = (st >> 24) & 1u;
+                const uint32_t p0 = st & 0xffffu;
+                uint32_t r = 0;
+                if (right) {
+                    const uint32_t t0 = a + tlen;
+                    for (; r < R; ++r) {
+                        const uint32_t pos = t0 + r;
+                        const uint32_t t = (P.text4[pos >> 3] >> ((pos & 7u) * 4u)) & 0xfu;
+                        if (t != qsym(p0 + r)) break;
+                    }
+                } else {
+                    for (; r < R; ++r) {
+                        if (a < r + 1) break;  // the delimiter before position 0
+                        const uint32_t pos = a - 1 - r;
+                        const uint32_t t = (P.text4[pos >> 3] >> ((pos & 7u) * 4u)) & 0xfu;
+                        if (t != qsym(p0 - r)) break;
+                    }
+                }
+                if (r < R) {  // a symbol differs: the state at step + r has no child
+                    nodes += r + 1;
+                    dead = true;
+                    break;
+                }
+                nodes += R;
+                step += R;
+                tlen += R;
+                if (right) Rinfo = INFO_M;
+                else { Linfo = INFO_M; a -= R; }
+                if (step == qlen) {  // the last step matched
+                    const uint32_t O = right ? Linfo : Rinfo;
+                    if (!EDIT || (O & 1u) == 0) emit(a, e);
+                    dead = true;
+                    break;
+                }
+                if (((tbl[step] >> 16) & 0xfu) > e + 1) { dead = true; break; }  // dead at the next step
+                R = runs[step * kRunE + e];
+            }
+        }
+        if (dead) continue;
         const uint32_t b = a + tlen;
         const bool rightFrame = (tbl[step] >> 24) & 1u;  // the end the frame's own error (D / S) sits on
         // the text symbols left and right of the occurrence (the delimiter before position 0)
@@ -504,9 +580,12 @@ template <bool EDIT, int STACK>
 __global__ void __launch_bounds__(256) text_kernel(const SearchParams P) {
     extern __shared__ uint32_t s_steps[];
     const uint32_t n_steps = P.n_searches * P.len;
+    const uint32_t n_run_words = (n_steps * kRunE + 3) / 4;
+    uint32_t* s_runs = s_steps + n_steps;
     for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) s_steps[i] = P.steps[i];
+    for (uint32_t i = threadIdx.x; i < n_run_words; i += blockDim.x) s_runs[i] = reinterpret_cast<const uint32_t*>(P.runs)[i];
     __syncthreads();
-    text_thread<EDIT, STACK>(P, s_steps, s_steps + n_steps + threadIdx.x, blockDim.x);
+    text_thread<EDIT, STACK>(P, s_steps, reinterpret_cast<const uint8_t*>(s_runs), s_runs + n_run_words + threadIdx.x, blockDim.x);
 }
 #endif
 

@@ -59,6 +59,8 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
             if (u[k] > kmax) kmax = u[k];
         }
     if (kmax > 4) return 2;
+    std::vector<uint8_t> runs(steps.size() * kRunE + 4, 0);
+    build_runs(n_searches, len, steps.data(), runs.data());
     // optional in-text verification tables
     std::vector<uint32_t> isa, text4;
     if (sa32 && text) {
@@ -93,6 +95,7 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
         P.len = len;
         P.n_searches = n_searches;
         P.steps = steps.data();
+        P.runs = runs.data();
         P.out = buf.data();
         P.out_cap = static_cast<uint32_t>(cap);
         P.counters = counters;
@@ -114,8 +117,8 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
             continue;
         }
         if (P.sa32) {  // second kernel: in-text verification of the seeds
-            if (edit) text_thread<true, 96>(P, steps.data(), stage.data(), 1);
-            else text_thread<false, 96>(P, steps.data(), stage.data(), 1);
+            if (edit) text_thread<true, 96>(P, steps.data(), runs.data(), stage.data(), 1);
+            else text_thread<false, 96>(P, steps.data(), runs.data(), stage.data(), 1);
         }
         if (counters[CT_OVERFLOW]) return 4;  // stack overflow
         if (counters[CT_OUT_SLOTS] <= cap) break;
