@@ -381,6 +381,22 @@ __device__ __forceinline__ void fm_thread(const SearchParams& P, const uint32_t*
     if (seeded) atomicAdd(&P.counters[CT_SEEDS], static_cast<unsigned long long>(seeded));
 }
 
+__device__ __forceinline__ uint32_t nib_mask(uint32_t n) { return n >= 8u ? 0xffffffffu : ((1u << (4u * n)) - 1u); }
+#if defined(SB200_HOST_EMU)
+static inline uint32_t ctz32(uint32_t x) { return static_cast<uint32_t>(__builtin_ctz(x)); }
+static inline uint32_t clz32(uint32_t x) { return static_cast<uint32_t>(__builtin_clz(x)); }
+static inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return sh ? (lo >> sh) | (hi << (32u - sh)) : lo; }
+#else
+__device__ __forceinline__ uint32_t ctz32(uint32_t x) { return static_cast<uint32_t>(__ffs(static_cast<int>(x)) - 1); }
+__device__ __forceinline__ uint32_t clz32(uint32_t x) { return static_cast<uint32_t>(__clz(static_cast<int>(x))); }
+__device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+#endif
+// the 8 text symbols that start at position pos (symbol i in nibble i); text4 is padded by two words
+__device__ __forceinline__ uint32_t text8(const uint32_t* text4, uint32_t pos) {
+    const uint32_t w = pos >> 3;
+    return funnel_r(text4[w], text4[w + 1], (pos & 7u) * 4u);
+}
+
 // ================================================================================================
 // text_kernel body: in-text verification of the seeds.  A frame is (a, meta) with the same meta layout; the
 // occurrence is T[a, a + tlen).
@@ -403,6 +419,13 @@ __device__ __forceinline__ void text_thread(const SearchParams& P, const uint32_
     const uint32_t n_slots = static_cast<uint32_t>(slots < P.seed_cap ? slots : P.seed_cap);
 
     auto qsym = [&](uint32_t pos) -> uint32_t { return (s_query[(pos >> 3) * qstride] >> ((pos & 7u) * 4u)) & 0xfu; };
+    // the 8 query symbols that start at position pos; positions behind the query read as 0xF
+    auto query8 = [&](uint32_t pos) -> uint32_t {
+        const uint32_t w = pos >> 3;
+        const uint32_t lo = s_query[w * qstride];
+        const uint32_t hi = w + 1 < W ? s_query[(w + 1) * qstride] : 0xffffffffu;
+        return funnel_r(lo, hi, (pos & 7u) * 4u);
+    };
     auto emit = [&](uint32_t a, uint32_t e) {
         outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], make_uint4(qid, P.isa32[a], 1, e));
         ++emitted;
@@ -444,20 +467,24 @@ __device__ __forceinline__ void text_thread(const SearchParams& P, const uint32_
                 const uint32_t st = tbl[step];
                 const bool right = (st >> 24) & 1u;
                 const uint32_t p0 = st & 0xffffu;
+                // compare up to 8 symbols per round on the packed words (4 bits per symbol)
                 uint32_t r = 0;
                 if (right) {
-                    const uint32_t t0 = a + tlen;
-                    for (; r < R; ++r) {
-                        const uint32_t pos = t0 + r;
-                        const uint32_t t = (P.text4[pos >> 3] >> ((pos & 7u) * 4u)) & 0xfu;
-                        if (t != qsym(p0 + r)) break;
+                    while (r < R) {
+                        const uint32_t n = R - r < 8u ? R - r : 8u;
+                        const uint32_t x = (text8(P.text4, a + tlen + r) ^ query8(p0 + r)) & nib_mask(n);
+                        if (x != 0) { r += (ctz32(x) >> 2); break; }
+                        r += n;
                     }
                 } else {
-                    for (; r < R; ++r) {
+                    while (r < R) {
                         if (a < r + 1) break;  // the delimiter before position 0
-                        const uint32_t pos = a - 1 - r;
-                        const uint32_t t = (P.text4[pos >> 3] >> ((pos & 7u) * 4u)) & 0xfu;
-                        if (t != qsym(p0 - r)) break;
+                        const uint32_t endT = a - 1 - r, endQ = p0 - r;  // compare the symbols ending here, downwards
+                        uint32_t n = R - r < 8u ? R - r : 8u;
+                        if (n > endT + 1) n = endT + 1;
+                        const uint32_t x = (text8(P.text4, endT + 1 - n) ^ query8(endQ + 1 - n)) & nib_mask(n);
+                        if (x != 0) { r += n - 1 - ((31u - clz32(x)) >> 2); break; }
+                        r += n;
                     }
                 }
                 if (r < R) {  // a symbol differs: the state at step + r has no child
