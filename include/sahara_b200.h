@@ -174,6 +174,8 @@ typedef struct sb200_counters {
     uint64_t hits;         /* located positions */
     uint64_t kernel_launches; /* kernels launched by this context */
     float ms_search, ms_locate, ms_sort, ms_h2d, ms_d2h; /* last call, CUDA events */
+    float ms_fm, ms_text;     /* last call: the two search kernels (fm_kernel, text_kernel) */
+    uint64_t nodes_text;      /* extensions verified in the text instead of the occurrence tables (subset of nodes) */
 } sb200_counters;
 int sb200_get_counters(sb200_ctx* ctx, sb200_counters* out);
 int sb200_reset_counters(sb200_ctx* ctx);

@@ -50,7 +50,7 @@ class Counters(C.Structure):
         ("nodes", C.c_uint64), ("rank_ops", C.c_uint64), ("cursors", C.c_uint64), ("lf_steps", C.c_uint64),
         ("hits", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("ms_search", C.c_float), ("ms_locate", C.c_float), ("ms_sort", C.c_float), ("ms_h2d", C.c_float),
-        ("ms_d2h", C.c_float),
+        ("ms_d2h", C.c_float), ("ms_fm", C.c_float), ("ms_text", C.c_float), ("nodes_text", C.c_uint64),
     ]
 
 

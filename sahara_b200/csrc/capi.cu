@@ -5,6 +5,7 @@
 #include "../../include/sahara_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -169,11 +170,17 @@ struct sb200_ctx {
     DevBuf d_seeds, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
     uint64_t cursor_cap{}, seed_cap{};
     uint64_t last_cursors{}, last_real_cursors{}, last_hits{};
+    uint64_t nodes_text{};
+    float ms_fm{}, ms_text{};
     bool hits_in_second{};  // which of the double buffers holds the sorted hits
     unsigned long long* h_counters{};  // pinned, CT_COUNT entries
     sb200_counters ct{};
-    cudaEvent_t ev[8]{};
+    cudaEvent_t ev[12]{};
     int sms{};
+    // pipelined host-buffer search: copy streams, double buffers
+    cudaStream_t s_in{}, s_out{};
+    DevBuf d_qchunk[2], d_hitchunk[2];
+    cudaEvent_t ev_in[2]{}, ev_free_q[2]{}, ev_expanded[2]{}, ev_out[2]{};
 };
 
 namespace {
@@ -583,6 +590,7 @@ void launch_search(sb200_ctx* c, const SearchParams& P) {
     unsigned grid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_BLOCKS_PER_SM", 4);
     unsigned need = grid_for((uint64_t(P.n_queries) + kQueryBatch - 1) / kQueryBatch);
     if (need < grid) grid = std::max(1u, need);
+    CUDA_TRY(cudaEventRecord(c->ev[8], c->stream));
     with_sigma(c->idx.sigma, [&](auto S) {
         with_stack(c->kmax, [&](auto STACK) {
             auto go = [&](auto kern) {
@@ -595,6 +603,7 @@ void launch_search(sb200_ctx* c, const SearchParams& P) {
         return 0;
     });
     launch_check(c);
+    CUDA_TRY(cudaEventRecord(c->ev[9], c->stream));
     if (P.sa32) {  // in-text verification of the seeds (reads the seed count from device memory: no host sync)
         unsigned tgrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_TEXT_BLOCKS_PER_SM", 6);
         with_stack(c->kmax, [&](auto STACK) {
@@ -607,6 +616,7 @@ void launch_search(sb200_ctx* c, const SearchParams& P) {
         });
         launch_check(c);
     }
+    CUDA_TRY(cudaEventRecord(c->ev[10], c->stream));
 }
 
 // kernel 2 on device-resident queries; cursors stay in c->d_cursors
@@ -625,13 +635,16 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     const uint32_t W = packed_words(len);
     c->d_packed.reserve(n_queries * W * 4);
-    pack_queries_kernel<<<grid_for(n_queries * W), 256, 0, c->stream>>>(d_queries, n_queries, len, c->d_packed.get<uint32_t>());
+    CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, CT_COUNT * sizeof(unsigned long long), c->stream));
+    pack_queries_kernel<<<grid_for(n_queries * W), 256, 0, c->stream>>>(d_queries, n_queries, len, ix.sigma, c->d_packed.get<uint32_t>(),
+                                                                        c->d_counters.get<unsigned long long>());
     launch_check(c);
     uint64_t n_cursors = 0;
     while (true) {
         c->d_cursors.reserve((c->cursor_cap + 1) * sizeof(uint4));
         if (ix.text_mode) c->d_seeds.reserve((c->seed_cap + 1) * sizeof(uint4));
-        CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, CT_COUNT * sizeof(unsigned long long), c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, CT_BAD_QUERY * sizeof(unsigned long long), c->stream));  // keeps CT_BAD_QUERY
+        CUDA_TRY(cudaMemsetAsync(c->d_counters.get<unsigned long long>() + CT_NODES_TEXT, 0, sizeof(unsigned long long), c->stream));
         SearchParams P{};
         P.bwt = ix.bwt();
         P.bwtRev = ix.rev();
@@ -660,6 +673,10 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         if (std::getenv("SB200_DEBUG"))
             fprintf(stderr, "[sb200 debug] max stack depth %llu overflow %llu seeds %llu\n", c->h_counters[CT_MAX_SP], c->h_counters[CT_OVERFLOW],
                     c->h_counters[CT_SEEDS]);
+        if (c->h_counters[CT_BAD_QUERY]) {
+            uint64_t off = c->h_counters[CT_BAD_QUERY] - 1;
+            throw Error("query has invalid character at offset " + std::to_string(off % len) + " of query " + std::to_string(off / len));
+        }
         if (c->h_counters[CT_OVERFLOW]) throw Error("internal error: search stack overflow");
         n_cursors = c->h_counters[CT_OUT_SLOTS];
         uint64_t n_seed_slots = c->h_counters[CT_SEED_SLOTS];
@@ -678,9 +695,12 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     CUDA_TRY(cudaEventSynchronize(c->ev[1]));
     CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_search, c->ev[0], c->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&c->ms_fm, c->ev[8], c->ev[9]));
+    CUDA_TRY(cudaEventElapsedTime(&c->ms_text, c->ev[9], c->ev[10]));
     c->ct.ms_locate = c->ct.ms_sort = 0;
     c->ct.nodes += c->h_counters[CT_NODES];
-    c->ct.rank_ops += 2 * c->h_counters[CT_NODES];
+    c->nodes_text += c->h_counters[CT_NODES_TEXT];
+    c->ct.rank_ops += 2 * (c->h_counters[CT_NODES] - c->h_counters[CT_NODES_TEXT]);
     c->ct.cursors += c->h_counters[CT_CURSORS];
     c->last_cursors = n_cursors;  // reserved output slots; unused ones are empty entries (qid 0xffffffff, len 0)
     c->last_real_cursors = c->h_counters[CT_CURSORS];
@@ -775,7 +795,7 @@ void fetch_hits(sb200_ctx* c, sb200_hit** hits, uint64_t* n_hits) {
         // expand to the reference tuple on the device, then one pinned copy
         c->d_scratch.reserve(n * sizeof(sb200_hit));
         expand_hits_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->d_keys[0].get<uint64_t>(), c->d_qids[0].get<uint32_t>(), n,
-                                                               static_cast<uint32_t>(ix.bits_for_position),
+                                                               static_cast<uint32_t>(ix.bits_for_position), 0,
                                                                c->d_scratch.get<uint64_t>());
         launch_check(c);
         CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
@@ -801,7 +821,6 @@ void check_queries_host(const uint8_t* q, uint64_t n, uint32_t sigma) {
 const uint8_t* stage_queries(sb200_ctx* c, const uint8_t* queries, uint64_t n_queries, uint32_t len) {
     if (!c->idx.loaded) throw Error("no index loaded");
     if (!queries || n_queries == 0) throw Error("query file was empty - abort");
-    check_queries_host(queries, n_queries * len, c->idx.sigma);
     c->d_queries.reserve(n_queries * len);
     CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->d_queries.p, queries, n_queries * len, cudaMemcpyHostToDevice, c->stream));
@@ -845,6 +864,14 @@ int sb200_create(int device, sb200_ctx** out) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
         c->stream = c->own_stream;
         for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_free_q[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_expanded[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+        }
         CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counters), CT_COUNT * sizeof(unsigned long long), cudaHostAllocDefault));
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -863,6 +890,16 @@ int sb200_destroy(sb200_ctx* c) {
                           &c->d_qids[0], &c->d_qids[1], &c->d_tmp, &c->d_scratch})
             b->release();
         for (auto& ev : c->ev) cudaEventDestroy(ev);
+        for (int i = 0; i < 2; ++i) {
+            c->d_qchunk[i].release();
+            c->d_hitchunk[i].release();
+            cudaEventDestroy(c->ev_in[i]);
+            cudaEventDestroy(c->ev_free_q[i]);
+            cudaEventDestroy(c->ev_expanded[i]);
+            cudaEventDestroy(c->ev_out[i]);
+        }
+        cudaStreamDestroy(c->s_in);
+        cudaStreamDestroy(c->s_out);
         cudaFreeHost(c->h_counters);
         cudaStreamDestroy(c->own_stream);
         delete c;
@@ -1280,13 +1317,88 @@ int sb200_fetch_hits(sb200_ctx* c, sb200_hit** hits, uint64_t* n_hits) {
     });
 }
 
+// search + locate from host buffers, pipelined: the batch is cut into chunks of reads; the host->device copy of
+// chunk i+1 and the device->host copy of the hits of chunk i-1 run on their own streams while chunk i computes.
+// Chunks are contiguous query ranges, so concatenating their sorted hit lists keeps the global order.
 int sb200_search(sb200_ctx* c, const uint8_t* queries, uint64_t n_queries, uint32_t len, sb200_hit** hits, uint64_t* n_hits) {
     return guard([&] {
         use(c);
-        const uint8_t* dq = stage_queries(c, queries, n_queries, len);
-        run_pipeline(c, dq, n_queries, len, true);
-        CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_h2d, c->ev[6], c->ev[7]));
-        fetch_hits(c, hits, n_hits);
+        auto& ix = c->idx;
+        if (!ix.loaded) throw Error("no index loaded");
+        if (!queries || n_queries == 0) throw Error("query file was empty - abort");
+        uint64_t chunk = 500000;
+        if (const char* e = std::getenv("SB200_CHUNK")) chunk = std::max<uint64_t>(2, std::strtoull(e, nullptr, 10));
+        chunk += chunk & 1;  // both strands of a read stay together
+        const uint64_t n_chunks = (n_queries + chunk - 1) / chunk;
+        for (int i = 0; i < 2; ++i) c->d_qchunk[i].reserve(std::min(chunk, n_queries) * len);
+        // wait until earlier work on the caller's stream is done before the copy streams touch the buffers
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        auto copy_in = [&](uint64_t k) {
+            const uint64_t q0 = k * chunk, n = std::min(chunk, n_queries - q0);
+            const int b = static_cast<int>(k & 1);
+            if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->ev_free_q[b], 0));  // chunk k-2 no longer reads this buffer
+            CUDA_TRY(cudaMemcpyAsync(c->d_qchunk[b].p, queries + q0 * len, n * len, cudaMemcpyHostToDevice, c->s_in));
+            CUDA_TRY(cudaEventRecord(c->ev_in[b], c->s_in));
+        };
+        sb200_hit* out = nullptr;
+        uint64_t out_cap = 0, total = 0;
+        auto t0 = std::chrono::steady_clock::now();
+        copy_in(0);
+        float ms_search = 0, ms_locate = 0, ms_sort = 0;
+        try {
+            for (uint64_t k = 0; k < n_chunks; ++k) {
+                const uint64_t q0 = k * chunk, n = std::min(chunk, n_queries - q0);
+                const int b = static_cast<int>(k & 1);
+                if (k + 1 < n_chunks) copy_in(k + 1);
+                CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
+                run_pipeline(c, c->d_qchunk[b].get<uint8_t>(), n, len, true);  // search + locate + sort of this chunk
+                CUDA_TRY(cudaEventRecord(c->ev_free_q[b], c->stream));
+                ms_search += c->ct.ms_search;
+                ms_locate += c->ct.ms_locate;
+                ms_sort += c->ct.ms_sort;
+                const uint64_t nh = c->last_hits;
+                // output buffer: sized from the first chunk, grown (rarely) when the estimate was too small
+                if (total + nh > out_cap) {
+                    uint64_t want = k == 0 ? nh * n_chunks + nh / 4 + 1024 : (total + nh) * 2;
+                    sb200_hit* bigger = static_cast<sb200_hit*>(g_pinned.alloc(std::max<uint64_t>(1, want) * sizeof(sb200_hit)));
+                    if (out) {
+                        CUDA_TRY(cudaStreamSynchronize(c->s_out));  // copies into the old buffer must have landed
+                        std::memcpy(bigger, out, total * sizeof(sb200_hit));
+                        g_pinned.free(out);
+                    }
+                    out = bigger;
+                    out_cap = want;
+                }
+                if (nh) {
+                    if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_out[b], 0));  // hits of chunk k-2 have left this buffer
+                    c->d_hitchunk[b].reserve(nh * sizeof(sb200_hit));
+                    expand_hits_kernel<<<grid_for(nh), 256, 0, c->stream>>>(c->d_keys[0].get<uint64_t>(), c->d_qids[0].get<uint32_t>(), nh,
+                                                                            static_cast<uint32_t>(ix.bits_for_position), q0,
+                                                                            c->d_hitchunk[b].get<uint64_t>());
+                    launch_check(c);
+                    CUDA_TRY(cudaEventRecord(c->ev_expanded[b], c->stream));
+                    CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->ev_expanded[b], 0));
+                    CUDA_TRY(cudaMemcpyAsync(out + total, c->d_hitchunk[b].p, nh * sizeof(sb200_hit), cudaMemcpyDeviceToHost, c->s_out));
+                }
+                CUDA_TRY(cudaEventRecord(c->ev_out[b], c->s_out));
+                total += nh;
+            }
+            CUDA_TRY(cudaStreamSynchronize(c->s_out));
+            CUDA_TRY(cudaStreamSynchronize(c->s_in));
+        } catch (...) {
+            cudaStreamSynchronize(c->s_out);
+            cudaStreamSynchronize(c->s_in);
+            if (out) g_pinned.free(out);
+            throw;
+        }
+        if (!out) out = static_cast<sb200_hit*>(g_pinned.alloc(sizeof(sb200_hit)));
+        c->ct.ms_search = ms_search;
+        c->ct.ms_locate = ms_locate;
+        c->ct.ms_sort = ms_sort;
+        c->ct.ms_h2d = c->ct.ms_d2h = 0;  // overlapped with the kernels
+        (void)t0;
+        *hits = out;
+        *n_hits = total;
     });
 }
 
@@ -1401,12 +1513,16 @@ int sb200_get_counters(sb200_ctx* c, sb200_counters* out) {
     return guard([&] {
         if (!c) throw Error("null context");
         *out = c->ct;
+        out->ms_fm = c->ms_fm;
+        out->ms_text = c->ms_text;
+        out->nodes_text = c->nodes_text;
     });
 }
 int sb200_reset_counters(sb200_ctx* c) {
     return guard([&] {
         if (!c) throw Error("null context");
         c->ct = sb200_counters{};
+        c->nodes_text = 0;
     });
 }
 

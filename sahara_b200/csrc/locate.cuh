@@ -114,13 +114,14 @@ struct BitFlag {
 };
 
 // sorted (key, qid) pairs -> the reference's result tuple (queryId, seqId, pos, errors), 4 x u64
-__global__ void expand_hits_kernel(const uint64_t* keys, const uint32_t* qids, uint64_t n, uint32_t bits, uint64_t* out) {
+__global__ void expand_hits_kernel(const uint64_t* keys, const uint32_t* qids, uint64_t n, uint32_t bits, uint64_t first_query,
+                                   uint64_t* out) {
     uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (i >= n) return;
     uint64_t k = keys[i];
     uint64_t v = k >> 4;
     ulonglong4 h;
-    h.x = qids[i];
+    h.x = first_query + qids[i];
     h.y = v >> bits;
     h.z = v & ((uint64_t{1} << bits) - 1);
     h.w = k & 15u;

@@ -85,6 +85,8 @@ enum : int {
     CT_SEED_SLOTS = 7,   // seed slots reserved by fm_kernel
     CT_NEXT_SEED = 8,    // work distribution of text_kernel
     CT_SEEDS = 9,        // seeds produced
+    CT_BAD_QUERY = 10,   // 1 + offset of a query symbol outside the alphabet (0 = none)
+    CT_NODES_TEXT = 11,  // states expanded by text_kernel (subset of CT_NODES)
     CT_COUNT = 16
 };
 
@@ -113,7 +115,9 @@ struct SearchParams {
 __host__ __device__ inline uint32_t packed_words(uint32_t len) { return (len + 7) / 8; }
 
 #if !defined(SB200_HOST_EMU)
-__global__ void pack_queries_kernel(const uint8_t* q, uint64_t n_queries, uint32_t len, uint32_t* out) {
+// packs the queries 8 symbols per word and verifies them (verify_rank of /root/reference/src/sahara/search.cpp:118-120)
+__global__ void pack_queries_kernel(const uint8_t* q, uint64_t n_queries, uint32_t len, uint32_t sigma, uint32_t* out,
+                                    unsigned long long* counters) {
     uint32_t W = packed_words(len);
     uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (i >= n_queries * W) return;
@@ -121,7 +125,10 @@ __global__ void pack_queries_kernel(const uint8_t* q, uint64_t n_queries, uint32
     uint32_t w = static_cast<uint32_t>(i % W);
     const uint8_t* src = q + qi * len + w * 8;
     uint32_t v = 0xffffffffu;  // unused nibbles stay 0xF (never a valid symbol)
-    for (uint32_t k = 0; k < 8 && w * 8 + k < len; ++k) v = (v & ~(0xfu << (4 * k))) | (static_cast<uint32_t>(src[k] & 0xfu) << (4 * k));
+    for (uint32_t k = 0; k < 8 && w * 8 + k < len; ++k) {
+        if (src[k] >= sigma) atomicMax(&counters[CT_BAD_QUERY], static_cast<unsigned long long>(qi * len + w * 8 + k + 1));
+        v = (v & ~(0xfu << (4 * k))) | (static_cast<uint32_t>(src[k] & 0xfu) << (4 * k));
+    }
     out[i] = v;
 }
 #endif
@@ -587,6 +594,7 @@ __device__ __forceinline__ void text_thread(const SearchParams& P, const uint32_
     }
     outW.finish(P.out, P.out_cap);
     if (nodes) atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(nodes));
+    if (nodes) atomicAdd(&P.counters[CT_NODES_TEXT], static_cast<unsigned long long>(nodes));
     if (overflow) atomicExch(&P.counters[CT_OVERFLOW], 1ull);
     atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxsp));
     if (emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(emitted));
