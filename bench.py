@@ -213,8 +213,9 @@ def main():
 
     # ---------------- GPU arm ----------------
     qauto = a.qgram
-    if qauto < 0:
-        qauto = 0
+    if qauto < 0:  # auto: leave ~3 levels below the expected depth at which cursors become unique
+        import math
+        qauto = max(0, min(12, int(math.log(max(4, info["n_rows"]), 4)) - 3))
     if a.device_sa_rate:
         ctx.densify(a.device_sa_rate)
     if a.text:

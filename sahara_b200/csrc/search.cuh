@@ -404,6 +404,8 @@ __device__ __forceinline__ uint32_t text8(const uint32_t* text4, uint32_t pos) {
     return funnel_r(text4[w], text4[w + 1], (pos & 7u) * 4u);
 }
 
+constexpr uint32_t kSeedClaim = 1;  // seeds a thread takes per atomic (larger claims lose more to the tail than they save)
+
 // ================================================================================================
 // text_kernel body: in-text verification of the seeds.  A frame is (a, meta) with the same meta layout; the
 // occurrence is T[a, a + tlen).
@@ -443,11 +445,15 @@ __device__ __forceinline__ void text_thread(const SearchParams& P, const uint32_
         ++sp;
     };
 
+    uint32_t seed_i = 0, seed_end = 0;  // claimed range of seeds (consecutive seeds mostly share their query)
     while (true) {
         if (sp == 0) {
-            uint32_t i = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_SEED], 1ull));
-            if (i >= n_slots) break;
-            uint4 seed = P.seeds[i];
+            if (seed_i == seed_end) {
+                seed_i = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_SEED], static_cast<unsigned long long>(kSeedClaim)));
+                if (seed_i >= n_slots) break;
+                seed_end = seed_i + kSeedClaim < n_slots ? seed_i + kSeedClaim : n_slots;
+            }
+            uint4 seed = P.seeds[seed_i++];
             if (seed.x == kInvalidQid) continue;
             if (seed.x != qid) {
                 qid = seed.x;

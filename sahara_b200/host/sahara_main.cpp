@@ -248,7 +248,13 @@ void runSearch(Args const& a) {
         check(sb200_create(g, &ctxs[g]));
         check(sb200_index_upload(ctxs[g], &view));
         if (a.has("--device-sa-rate")) check(sb200_index_densify(ctxs[g], std::stoul(a.get("--device-sa-rate"))));
-        if (a.has("--qgram")) check(sb200_index_build_qgram(ctxs[g], std::stoul(a.get("--qgram"))));
+        // in-text verification (17 more bytes per row on the device) and the q-gram jump table are on by default
+        if (!a.has("--no-text")) check(sb200_index_enable_text(ctxs[g], 1));
+        unsigned q = 0;
+        for (uint64_t n = image.n_rows; n >= 4 && q < 15; n /= 4) ++q;  // floor(log4(rows))
+        q = q > 3 ? std::min(12u, q - 3) : 0;
+        if (a.has("--qgram")) q = static_cast<unsigned>(std::stoul(a.get("--qgram")));
+        check(sb200_index_build_qgram(ctxs[g], q));
     }
     timing.emplace_back("ld index", sw.reset());
 
@@ -357,7 +363,7 @@ void usage() {
            "  sahara index <fasta> [--ignore_unknown] [--dna4]\n"
            "  sahara search -q <fasta> -i <index> [-o <out>] [-g <generator>] [-e <errors>] [--no-reverse]\n"
            "                [-m all] [-d ham|lev] [--limit_queries <n>] [--gpus <n>] [--scheme-file <columba.txt>]\n"
-           "                [--batch <queries per call>] [--device-sa-rate <16|8|4|2|1>] [--qgram <q>]\n");
+           "                [--batch <queries per call>] [--device-sa-rate <16|8|4|2|1>] [--qgram <q>] [--no-text]\n");
 }
 
 }  // namespace

@@ -263,3 +263,22 @@ def test_text_mode_keeps_results(sb, ctx, cases, key):
             assert np.array_equal(ctx.search_cursors(q), want_cur)
             assert np.array_equal(ctx.search(q), O.sort_rows(ix.locate(want_cur)))
     ctx.enable_text(False)
+
+
+def test_pipelined_host_search_with_small_chunks(sb, ctx, cases, monkeypatch):
+    """sb200_search cuts the batch into chunks that overlap copies and kernels; tiny chunks exercise the
+    double buffering, the growth of the pinned result buffer and the global query ids."""
+    rng, seqs, ix, path = cases[("repeats", 6)]
+    ctx.load_index(path)
+    ctx.enable_text(True)
+    ctx.build_qgram(5)
+    m, k = 40, 2
+    q = W.sample_reads(rng, seqs, 333, m, k, True)
+    sch = sb.SearchScheme.generate("h2-k2", 0, k, m)
+    ctx.set_scheme(sch, True)
+    want = O.sort_rows(ix.locate(ix.search(q, sch, True)))
+    for chunk in ("7", "64", "100000"):
+        monkeypatch.setenv("SB200_CHUNK", chunk)
+        assert np.array_equal(ctx.search(q), want)
+    ctx.build_qgram(0)
+    ctx.enable_text(False)
