@@ -9,8 +9,12 @@
 // include/sahara_b200.h.  Queries are sharded over the visible GPUs (--gpus N,
 // index replicated); hit lists are concatenated on the host in query order.
 //
-// Not implemented on the GPU path (fails with a clear message): -m besthits, --max_hits > 0,
-// --dynamic_generator (SURVEY.md §8f "next" rows).
+// -m besthits follows fmc::search_ng21::search_best (search.cpp:233-240): per query the strata of exactly
+// 0, 1, ..., k errors are searched in turn (schemes generator(j, j)) and the first stratum with a hit ends the
+// query; as in the reference this mode always uses edit distance.
+// Not implemented on the GPU path (fails with a clear message): --max_hits > 0 (its result depends on the
+// reference's recursion order) and --dynamic_generator (SURVEY.md §8f "next" rows).
+#include <algorithm>
 #include <chrono>
 #include <cinttypes>
 #include <cstdio>
@@ -188,10 +192,10 @@ void runSearch(Args const& a) {
     size_t limitQueries = std::stoul(a.get("--limit_queries", "0"));
     if (mode != "all" && mode != "besthits") fail("unknown search mode \"" + mode + "\"");
     if (metric != "ham" && metric != "lev") fail("unknown distance metric \"" + metric + "\"");
-    if (mode == "besthits") fail("search mode besthits is not available on the GPU path yet");
+    const bool bestHits = mode == "besthits";
     if (maxHits != 0) fail("--max_hits is not available on the GPU path yet");
     if (a.has("--dynamic_generator")) fail("--dynamic_generator is not available on the GPU path yet");
-    bool edit = metric == "lev";
+    bool edit = metric == "lev" || bestHits;  // search_best has no Hamming variant (search.cpp:239)
 
     std::vector<std::pair<std::string, double>> timing;
     StopWatch sw;
@@ -258,36 +262,50 @@ void runSearch(Args const& a) {
     }
     timing.emplace_back("ld index", sw.reset());
 
-    // search scheme (search.cpp:174-212, 226)
-    ss::Scheme scheme;
-    if (a.has("--scheme-file")) {
-        std::ifstream in(a.get("--scheme-file"));
-        if (!in) fail("cannot open scheme file " + a.get("--scheme-file"));
-        std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
-        scheme = ss::fromColumba(text);
-        if (!ss::isComplete(scheme, 0, k)) fail("the scheme in " + a.get("--scheme-file") + " is not complete for " + std::to_string(k) + " errors");
-    } else {
-        scheme = ss::generator::generate(generator, 0, static_cast<int>(k));
-    }
-    scheme = ss::expand(scheme, qlen);
-    if (edit) {
-        printf("node count: %.0Lf\n", ss::nodeCount<true>(scheme, Sigma));
-        printf("weighted node count: %.2Lf\n", ss::weightedNodeCount<true>(scheme, Sigma, image.n_rows));
-    } else {
-        printf("node count: %.0Lf\n", ss::nodeCount<false>(scheme, Sigma));
-        printf("weighted node count: %.2Lf\n", ss::weightedNodeCount<false>(scheme, Sigma, image.n_rows));
-        scheme = ss::limitToHamming(scheme);
-    }
-    std::vector<uint16_t> pi;
-    std::vector<uint8_t> lo, up;
-    for (auto const& s : scheme)
-        for (size_t i = 0; i < s.pi.size(); ++i) {
-            pi.push_back(static_cast<uint16_t>(s.pi[i]));
-            lo.push_back(static_cast<uint8_t>(s.l[i]));
-            up.push_back(static_cast<uint8_t>(s.u[i]));
+    // search scheme (search.cpp:174-212, 226); besthits: one scheme per stratum of exactly j errors (search.cpp:234-237)
+    struct Tables {
+        uint32_t nSearches;
+        std::vector<uint16_t> pi;
+        std::vector<uint8_t> lo, up;
+    };
+    auto loadSearchScheme = [&](int minK, int maxK) {
+        ss::Scheme scheme;
+        if (a.has("--scheme-file")) {
+            std::ifstream in(a.get("--scheme-file"));
+            if (!in) fail("cannot open scheme file " + a.get("--scheme-file"));
+            std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+            scheme = ss::fromColumba(text);
+            if (!ss::isComplete(scheme, minK, maxK))
+                fail("the scheme in " + a.get("--scheme-file") + " is not complete for " + std::to_string(minK) + ".." + std::to_string(maxK) + " errors");
+        } else {
+            scheme = ss::generator::generate(generator, minK, maxK);
         }
-    for (auto* c : ctxs)
-        check(sb200_set_scheme(c, static_cast<uint32_t>(scheme.size()), static_cast<uint32_t>(qlen), pi.data(), lo.data(), up.data(), edit));
+        scheme = ss::expand(scheme, qlen);
+        if (edit) {
+            printf("node count: %.0Lf\n", ss::nodeCount<true>(scheme, Sigma));
+            printf("weighted node count: %.2Lf\n", ss::weightedNodeCount<true>(scheme, Sigma, image.n_rows));
+        } else {
+            printf("node count: %.0Lf\n", ss::nodeCount<false>(scheme, Sigma));
+            printf("weighted node count: %.2Lf\n", ss::weightedNodeCount<false>(scheme, Sigma, image.n_rows));
+            scheme = ss::limitToHamming(scheme);
+        }
+        Tables t;
+        t.nSearches = static_cast<uint32_t>(scheme.size());
+        for (auto const& s : scheme)
+            for (size_t i = 0; i < s.pi.size(); ++i) {
+                t.pi.push_back(static_cast<uint16_t>(s.pi[i]));
+                t.lo.push_back(static_cast<uint8_t>(s.l[i]));
+                t.up.push_back(static_cast<uint8_t>(s.u[i]));
+            }
+        return t;
+    };
+    std::vector<Tables> schemes;
+    if (!bestHits) schemes.push_back(loadSearchScheme(0, static_cast<int>(k)));
+    else
+        for (size_t j = 0; j <= k; ++j) schemes.push_back(loadSearchScheme(static_cast<int>(j), static_cast<int>(j)));
+    auto setScheme = [&](sb200_ctx* c, Tables const& t) {
+        check(sb200_set_scheme(c, t.nSearches, static_cast<uint32_t>(qlen), t.pi.data(), t.lo.data(), t.up.data(), edit));
+    };
     timing.emplace_back("searchScheme", sw.reset());
 
     // search + locate: contiguous shards of reads per GPU, batches inside a shard
@@ -301,25 +319,68 @@ void runSearch(Args const& a) {
     for (int g = 0; g < nGpus; ++g) {
         threads.emplace_back([&, g] {
             size_t q0 = std::min(nQueries, perGpu * g), q1 = std::min(nQueries, perGpu * (g + 1));
-            for (size_t b = q0; b < q1; b += batch) {
-                size_t n = std::min(batch, q1 - b);
-                sb200_hit* hits = nullptr;
-                uint64_t nHits = 0;
-                if (sb200_search(ctxs[g], queries.data() + b * qlen, n, static_cast<uint32_t>(qlen), &hits, &nHits) != 0) {
-                    errors[g] = sb200_last_error();
-                    return;
+            try {
+                auto account = [&] {
+                    sb200_counters ct{};
+                    sb200_get_counters(ctxs[g], &ct);
+                    msSearch[g] += ct.ms_search;
+                    msLocate[g] += ct.ms_locate + ct.ms_sort;
+                };
+                if (!bestHits) {
+                    setScheme(ctxs[g], schemes[0]);
+                    for (size_t b = q0; b < q1; b += batch) {
+                        size_t n = std::min(batch, q1 - b);
+                        sb200_hit* hits = nullptr;
+                        uint64_t nHits = 0;
+                        check(sb200_search(ctxs[g], queries.data() + b * qlen, n, static_cast<uint32_t>(qlen), &hits, &nHits));
+                        size_t old = results[g].size();
+                        results[g].resize(old + nHits);
+                        for (uint64_t i = 0; i < nHits; ++i) {
+                            results[g][old + i] = hits[i];
+                            results[g][old + i].query_id += b;  // batch-local -> global query id
+                        }
+                        sb200_free(hits);
+                        account();
+                    }
+                } else {
+                    // strata of exactly j errors; queries that found a hit leave the pool
+                    std::vector<uint64_t> active(q1 - q0);
+                    for (size_t i = 0; i < active.size(); ++i) active[i] = q0 + i;
+                    std::vector<uint8_t> dense;
+                    for (size_t j = 0; j < schemes.size() && !active.empty(); ++j) {
+                        setScheme(ctxs[g], schemes[j]);
+                        std::vector<uint8_t> found(active.size(), 0);
+                        for (size_t b = 0; b < active.size(); b += batch) {
+                            size_t n = std::min(batch, active.size() - b);
+                            dense.resize(n * qlen);
+                            for (size_t i = 0; i < n; ++i) std::memcpy(dense.data() + i * qlen, queries.data() + active[b + i] * qlen, qlen);
+                            sb200_hit* hits = nullptr;
+                            uint64_t nHits = 0;
+                            check(sb200_search(ctxs[g], dense.data(), n, static_cast<uint32_t>(qlen), &hits, &nHits));
+                            size_t old = results[g].size();
+                            results[g].resize(old + nHits);
+                            for (uint64_t i = 0; i < nHits; ++i) {
+                                found[b + hits[i].query_id] = 1;
+                                results[g][old + i] = hits[i];
+                                results[g][old + i].query_id = active[b + hits[i].query_id];
+                            }
+                            sb200_free(hits);
+                            account();
+                        }
+                        std::vector<uint64_t> rest;
+                        for (size_t i = 0; i < active.size(); ++i)
+                            if (!found[i]) rest.push_back(active[i]);
+                        active.swap(rest);
+                    }
+                    std::sort(results[g].begin(), results[g].end(), [](sb200_hit const& x, sb200_hit const& y) {
+                        if (x.query_id != y.query_id) return x.query_id < y.query_id;
+                        if (x.seq_id != y.seq_id) return x.seq_id < y.seq_id;
+                        if (x.pos != y.pos) return x.pos < y.pos;
+                        return x.errors < y.errors;
+                    });
                 }
-                size_t old = results[g].size();
-                results[g].resize(old + nHits);
-                for (uint64_t i = 0; i < nHits; ++i) {
-                    results[g][old + i] = hits[i];
-                    results[g][old + i].query_id += b;  // batch-local -> global query id
-                }
-                sb200_free(hits);
-                sb200_counters ct{};
-                sb200_get_counters(ctxs[g], &ct);
-                msSearch[g] += ct.ms_search;
-                msLocate[g] += ct.ms_locate + ct.ms_sort;
+            } catch (std::exception const& ex) {
+                errors[g] = ex.what();
             }
         });
     }
@@ -341,12 +402,29 @@ void runSearch(Args const& a) {
     {
         FILE* ofs = fopen(outPath.c_str(), "w");
         if (!ofs) fail("cannot open " + outPath + " for writing");
-        std::vector<char> buf(1 << 22);
-        setvbuf(ofs, buf.data(), _IOFBF, buf.size());
+        // "{queryId} {seqId} {pos}\n" (search.cpp:257-259) formatted by hand into large blocks
+        std::vector<char> buf(1 << 24);
+        size_t used = 0;
+        auto putNum = [&](uint64_t v, char sep) {
+            char tmp[24];
+            int n = 0;
+            do { tmp[n++] = static_cast<char>('0' + v % 10); v /= 10; } while (v);
+            while (n) buf[used++] = tmp[--n];
+            buf[used++] = sep;
+        };
         for (int g = 0; g < nGpus; ++g) {
-            for (auto const& h : results[g]) fprintf(ofs, "%" PRIu64 " %" PRIu64 " %" PRIu64 "\n", h.query_id, h.seq_id, h.pos);
+            for (auto const& h : results[g]) {
+                if (used + 80 > buf.size()) {
+                    fwrite(buf.data(), 1, used, ofs);
+                    used = 0;
+                }
+                putNum(h.query_id, ' ');
+                putNum(h.seq_id, ' ');
+                putNum(h.pos, '\n');
+            }
             nHitsTotal += results[g].size();
         }
+        fwrite(buf.data(), 1, used, ofs);
         fclose(ofs);
     }
     timing.emplace_back("result", sw.reset());

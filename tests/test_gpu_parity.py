@@ -282,3 +282,39 @@ def test_pipelined_host_search_with_small_chunks(sb, ctx, cases, monkeypatch):
         assert np.array_equal(ctx.search(q), want)
     ctx.build_qgram(0)
     ctx.enable_text(False)
+
+
+def test_cli_besthits_follows_search_best(sb, cases, tmp_path):
+    """-m besthits: strata of exactly 0..k errors, the first stratum with a hit ends the query
+    (fmc::search_ng21::search_best as called at /root/reference/src/sahara/search.cpp:233-240)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "sahara_b200", "sahara")
+    rng, seqs, ix, path = cases[("repeats", 6)]
+    m, k = 36, 2
+    q = W.sample_reads(rng, seqs, 120, m, k, True)
+    qa = os.path.join(tmp_path, "reads.fa")
+    with open(qa, "w") as f:
+        for i in range(0, q.shape[0], 2):
+            f.write(f">r{i // 2}\n" + "".join("$ACGTN"[c] for c in q[i]) + "\n")
+    out = os.path.join(tmp_path, "best.txt")
+    res = subprocess.run([exe, "search", "-q", qa, "-i", path, "-e", str(k), "-o", out, "-m", "besthits", "--batch", "50"],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    got = sorted(tuple(int(x) for x in line.split()) for line in open(out))
+    want = []
+    active = list(range(q.shape[0]))
+    for j in range(k + 1):
+        if not active:
+            break
+        sch = sb.SearchScheme.generate("h2-k2", j, j, m)
+        hits = ix.locate(ix.search(q[active], sch, True))
+        found = set()
+        for a, b, c, d in hits:
+            assert int(d) == j
+            found.add(int(a))
+            want.append((active[int(a)], int(b), int(c)))
+        active = [x for i, x in enumerate(active) if i not in found]
+    assert got == sorted(want)
+    res = subprocess.run([exe, "search", "-q", qa, "-i", path, "--max_hits", "3"], capture_output=True, text=True)
+    assert res.returncode == 1 and "max_hits" in res.stderr
