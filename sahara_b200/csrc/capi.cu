@@ -1329,12 +1329,28 @@ int sb200_search(sb200_ctx* c, const uint8_t* queries, uint64_t n_queries, uint3
         uint64_t chunk = 500000;
         if (const char* e = std::getenv("SB200_CHUNK")) chunk = std::max<uint64_t>(2, std::strtoull(e, nullptr, 10));
         chunk += chunk & 1;  // both strands of a read stay together
-        const uint64_t n_chunks = (n_queries + chunk - 1) / chunk;
-        for (int i = 0; i < 2; ++i) c->d_qchunk[i].reserve(std::min(chunk, n_queries) * len);
+        // chunk boundaries: a short first chunk (its copy-in cannot be hidden) and a short last one (its copy-out
+        // cannot be hidden), full chunks in between
+        std::vector<uint64_t> bounds{0};
+        {
+            uint64_t small = std::max<uint64_t>(2, (chunk / 4) & ~uint64_t{1});
+            if (n_queries > 2 * chunk) {
+                bounds.push_back(small);
+                while (bounds.back() + chunk + small < n_queries) bounds.push_back(bounds.back() + chunk);
+                if (n_queries - bounds.back() > small) bounds.push_back(n_queries - small);
+            } else {
+                while (bounds.back() + chunk < n_queries) bounds.push_back(bounds.back() + chunk);
+            }
+            bounds.push_back(n_queries);
+        }
+        const uint64_t n_chunks = bounds.size() - 1;
+        uint64_t max_chunk = 0;
+        for (uint64_t k = 0; k < n_chunks; ++k) max_chunk = std::max(max_chunk, bounds[k + 1] - bounds[k]);
+        for (int i = 0; i < 2; ++i) c->d_qchunk[i].reserve(max_chunk * len);
         // wait until earlier work on the caller's stream is done before the copy streams touch the buffers
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         auto copy_in = [&](uint64_t k) {
-            const uint64_t q0 = k * chunk, n = std::min(chunk, n_queries - q0);
+            const uint64_t q0 = bounds[k], n = bounds[k + 1] - q0;
             const int b = static_cast<int>(k & 1);
             if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->ev_free_q[b], 0));  // chunk k-2 no longer reads this buffer
             CUDA_TRY(cudaMemcpyAsync(c->d_qchunk[b].p, queries + q0 * len, n * len, cudaMemcpyHostToDevice, c->s_in));
@@ -1347,7 +1363,7 @@ int sb200_search(sb200_ctx* c, const uint8_t* queries, uint64_t n_queries, uint3
         float ms_search = 0, ms_locate = 0, ms_sort = 0;
         try {
             for (uint64_t k = 0; k < n_chunks; ++k) {
-                const uint64_t q0 = k * chunk, n = std::min(chunk, n_queries - q0);
+                const uint64_t q0 = bounds[k], n = bounds[k + 1] - q0;
                 const int b = static_cast<int>(k & 1);
                 if (k + 1 < n_chunks) copy_in(k + 1);
                 CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
@@ -1359,7 +1375,8 @@ int sb200_search(sb200_ctx* c, const uint8_t* queries, uint64_t n_queries, uint3
                 const uint64_t nh = c->last_hits;
                 // output buffer: sized from the first chunk, grown (rarely) when the estimate was too small
                 if (total + nh > out_cap) {
-                    uint64_t want = k == 0 ? nh * n_chunks + nh / 4 + 1024 : (total + nh) * 2;
+                    // first estimate: the hit density of the first chunk over the whole batch
+                    uint64_t want = k == 0 ? nh * ((n_queries + n - 1) / n) + nh / 4 + 1024 : (total + nh) * 2;
                     sb200_hit* bigger = static_cast<sb200_hit*>(g_pinned.alloc(std::max<uint64_t>(1, want) * sizeof(sb200_hit)));
                     if (out) {
                         CUDA_TRY(cudaStreamSynchronize(c->s_out));  // copies into the old buffer must have landed
