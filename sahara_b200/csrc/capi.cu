@@ -808,16 +808,6 @@ void fetch_hits(sb200_ctx* c, sb200_hit** hits, uint64_t* n_hits) {
     *n_hits = n;
 }
 
-void check_queries_host(const uint8_t* q, uint64_t n, uint32_t sigma) {
-    // same condition as verify_rank at /root/reference/src/sahara/search.cpp:118-120
-    uint8_t bad = 0;
-    for (uint64_t i = 0; i < n; ++i) bad |= (q[i] >= sigma);
-    if (bad) {
-        for (uint64_t i = 0; i < n; ++i)
-            if (q[i] >= sigma) throw Error("query has invalid character (rank " + std::to_string(q[i]) + ") at offset " + std::to_string(i));
-    }
-}
-
 const uint8_t* stage_queries(sb200_ctx* c, const uint8_t* queries, uint64_t n_queries, uint32_t len) {
     if (!c->idx.loaded) throw Error("no index loaded");
     if (!queries || n_queries == 0) throw Error("query file was empty - abort");
@@ -1367,7 +1357,13 @@ int sb200_search(sb200_ctx* c, const uint8_t* queries, uint64_t n_queries, uint3
                 const int b = static_cast<int>(k & 1);
                 if (k + 1 < n_chunks) copy_in(k + 1);
                 CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
+                auto tc0 = std::chrono::steady_clock::now();
                 run_pipeline(c, c->d_qchunk[b].get<uint8_t>(), n, len, true);  // search + locate + sort of this chunk
+                if (std::getenv("SB200_DEBUG"))
+                    fprintf(stderr, "[sb200 debug] chunk %llu: %llu queries, host wall %.3f ms, device search %.3f locate %.3f sort %.3f ms\n",
+                            (unsigned long long)k, (unsigned long long)n,
+                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count(), c->ct.ms_search,
+                            c->ct.ms_locate, c->ct.ms_sort);
                 CUDA_TRY(cudaEventRecord(c->ev_free_q[b], c->stream));
                 ms_search += c->ct.ms_search;
                 ms_locate += c->ct.ms_locate;
@@ -1409,6 +1405,9 @@ int sb200_search(sb200_ctx* c, const uint8_t* queries, uint64_t n_queries, uint3
             throw;
         }
         if (!out) out = static_cast<sb200_hit*>(g_pinned.alloc(sizeof(sb200_hit)));
+        if (std::getenv("SB200_DEBUG"))
+            fprintf(stderr, "[sb200 debug] sb200_search total host wall %.3f ms\n",
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         c->ct.ms_search = ms_search;
         c->ct.ms_locate = ms_locate;
         c->ct.ms_sort = ms_sort;
