@@ -306,6 +306,30 @@ def main():
     h2d = 2 * R * m
     d2h = int(32 * e2e_hits / a.steps)
 
+    # the compact host-buffer call: reads only (reverse complements made on the device), 16-byte hits
+    def e2e_reads_step(t):
+        p, n = C.c_void_p(), C.c_uint64()
+        check(cuda.sb200_search_reads(ctx._h, C.c_void_p(t.data_ptr()), R, m, 1, C.byref(p), C.byref(n)))
+        if n.value:
+            C.cast(p, C.POINTER(C.c_uint32))[0]
+        cuda.sb200_free(p)
+        return n.value
+
+    fwd_batches = []
+    for b in range(n_batches):  # forward strands = every second query of the batch
+        t = torch.empty(R * m, dtype=torch.uint8, pin_memory=True)
+        t.view(R, m).copy_(host_batches[b].view(R, 2, m)[:, 0, :])
+        fwd_batches.append(t)
+    for b in range(a.warmup):
+        e2e_reads_step(fwd_batches[b])
+    barrier()
+    t_start = time.perf_counter()
+    compact_hits = 0
+    for b in range(a.warmup, n_batches):
+        compact_hits += e2e_reads_step(fwd_batches[b])
+    barrier()
+    e2e_compact_s = allmax(time.perf_counter() - t_start)
+
     # ---- roofline (SURVEY.md §8d accounting: one search node = 2 rank-ops = 128 B, however it is served) ----
     peak, peak_src = measured_peak()
     nodes = ct["nodes"]            # extensions over the K timed steps == the oracle's extension count (tests assert it)
@@ -344,7 +368,11 @@ def main():
             "warmup": a.warmup, "ms_per_step": round(dev_ms / a.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(1e3 * e2e_s / a.steps, 3)},
+                    "ms_per_step": round(1e3 * e2e_s / a.steps, 3), "call": "sb200_search (both strands in, 32-byte hit tuples out)"},
+            "e2e_compact": {"value": round(world * R * a.steps / e2e_compact_s, 1), "unit": "reads/s", "h2d_bytes_per_step": R * m,
+                            "d2h_bytes_per_step": int(16 * compact_hits / a.steps), "ms_per_step": round(1e3 * e2e_compact_s / a.steps, 3),
+                            "hits_match": bool(compact_hits == e2e_hits),
+                            "call": "sb200_search_reads (reads in, reverse complements on the device, 16-byte hits out)"},
             "gpu_launches": launches, "roofline": roofline,
             "hits_per_step": int(hits_total / a.steps), "cursors_per_step": int(cursors_total / a.steps)}
 

@@ -142,6 +142,16 @@ int sb200_locate(sb200_ctx* ctx, const sb200_cursor* cursors, uint64_t n_cursors
 int sb200_search(sb200_ctx* ctx, const uint8_t* queries, uint64_t n_queries, uint32_t len, sb200_hit** hits,
                  uint64_t* n_hits);
 
+/* compact variant for callers that hold only the reads: the reverse complements (src/sahara/search.cpp:121-123,
+ * skipped with --no-reverse) are made on the device and the hits come back as 16-byte records, which halves the
+ * PCIe traffic of sb200_search.  query_id counts queries as the reference does (2i = read i, 2i+1 = its reverse
+ * complement when with_reverse != 0, else i = read i).  Needs bits_for_position <= 32. */
+typedef struct sb200_hit32 {
+    uint32_t query_id, seq_id, pos, errors;
+} sb200_hit32;
+int sb200_search_reads(sb200_ctx* ctx, const uint8_t* reads, uint64_t n_reads, uint32_t len, int with_reverse,
+                       sb200_hit32** hits, uint64_t* n_hits);
+
 /* same pipeline with the queries already in HBM (d_queries = device pointer) and the hits left on the
  * GPU; returns only the counts.  Used to time the kernels without PCIe transfers. */
 int sb200_search_device(sb200_ctx* ctx, const uint8_t* d_queries, uint64_t n_queries, uint32_t len,

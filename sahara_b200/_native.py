@@ -76,6 +76,7 @@ SB200_SYMBOLS = {
     "sb200_search_cursors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p), u64p]),
     "sb200_locate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), u64p]),
     "sb200_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p), u64p]),
+    "sb200_search_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_void_p), u64p]),
     "sb200_search_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, u64p, u64p]),
     "sb200_fetch_hits": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p]),
     "sb200_free": (None, [C.c_void_p]),

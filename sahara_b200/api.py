@@ -217,6 +217,19 @@ class Context:
         check(cuda.sb200_search(self._h, _ptr(q), q.shape[0], q.shape[1], C.byref(p), C.byref(n)))
         return self._take4(p, n)
 
+    def search_reads(self, reads, with_reverse=True):
+        """forward reads only -> uint32 [n_hits, 4] = (queryId, seqId, pos, errors); reverse complements are made on
+        the device, query ids count both strands like the reference (2i, 2i+1)."""
+        r = self._queries(reads)
+        p, n = C.c_void_p(), C.c_uint64()
+        check(cuda.sb200_search_reads(self._h, _ptr(r), r.shape[0], r.shape[1], int(with_reverse), C.byref(p), C.byref(n)))
+        try:
+            if n.value == 0:
+                return np.zeros((0, 4), dtype=np.uint32)
+            return np.ctypeslib.as_array(C.cast(p, N.u32p), shape=(n.value * 4,)).copy().reshape(-1, 4)
+        finally:
+            cuda.sb200_free(p)
+
     def search_cursors(self, queries):
         """-> uint64 [n, 4] = (queryId, lb, len, errors), sorted."""
         q = self._queries(queries)

@@ -818,6 +818,132 @@ const uint8_t* stage_queries(sb200_ctx* c, const uint8_t* queries, uint64_t n_qu
     return c->d_queries.get<uint8_t>();
 }
 
+// search + locate from host buffers, pipelined: the batch is cut into chunks of reads; the host->device copy of
+// chunk i+1 and the device->host copy of the hits of chunk i-1 run on their own streams while chunk i computes.
+// Chunks are contiguous query ranges, so concatenating their sorted hit lists keeps the global order.
+//   make_rc : the host buffer holds only the reads; the reverse complements are made on the device
+//             (queries[2i] = read i, queries[2i+1] = its reverse complement, search.cpp:121-123)
+//   compact : hits are returned as sb200_hit32 (16 bytes) instead of the reference's 32-byte tuple
+void search_host_pipelined(sb200_ctx* c, const uint8_t* src, uint64_t n_items, uint32_t len, bool make_rc, bool compact, void** hits,
+                           uint64_t* n_hits) {
+    auto& ix = c->idx;
+    if (!ix.loaded) throw Error("no index loaded");
+    if (!src || n_items == 0) throw Error("query file was empty - abort");
+    const uint64_t per_item = make_rc ? 2 : 1;  // queries per host item
+    const uint64_t n_queries = n_items * per_item;
+    const size_t hit_bytes = compact ? sizeof(sb200_hit32) : sizeof(sb200_hit);
+    uint64_t chunk = 500000;  // queries per chunk
+    if (const char* e = std::getenv("SB200_CHUNK")) chunk = std::max<uint64_t>(2, std::strtoull(e, nullptr, 10));
+    chunk += chunk & 1;  // both strands of a read stay together
+    // chunk boundaries (in queries): a short first chunk (its copy-in cannot be hidden) and a short last one (its
+    // copy-out cannot be hidden), full chunks in between
+    std::vector<uint64_t> bounds{0};
+    {
+        uint64_t small = std::max<uint64_t>(2, (chunk / 4) & ~uint64_t{1});
+        if (n_queries > 2 * chunk) {
+            bounds.push_back(small);
+            while (bounds.back() + chunk + small < n_queries) bounds.push_back(bounds.back() + chunk);
+            if (n_queries - bounds.back() > small) bounds.push_back(n_queries - small);
+        } else {
+            while (bounds.back() + chunk < n_queries) bounds.push_back(bounds.back() + chunk);
+        }
+        bounds.push_back(n_queries);
+    }
+    const uint64_t n_chunks = bounds.size() - 1;
+    uint64_t max_chunk = 0;
+    for (uint64_t k = 0; k < n_chunks; ++k) max_chunk = std::max(max_chunk, bounds[k + 1] - bounds[k]);
+    for (int i = 0; i < 2; ++i) c->d_qchunk[i].reserve(max_chunk * len);
+    if (make_rc) c->d_queries.reserve(max_chunk * len);
+    // wait until earlier work on the caller's stream is done before the copy streams touch the buffers
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    auto copy_in = [&](uint64_t k) {
+        const uint64_t q0 = bounds[k], n = bounds[k + 1] - q0;
+        const int b = static_cast<int>(k & 1);
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->ev_free_q[b], 0));  // chunk k-2 no longer reads this buffer
+        CUDA_TRY(cudaMemcpyAsync(c->d_qchunk[b].p, src + (q0 / per_item) * len, (n / per_item) * len, cudaMemcpyHostToDevice, c->s_in));
+        CUDA_TRY(cudaEventRecord(c->ev_in[b], c->s_in));
+    };
+    uint8_t* out = nullptr;
+    uint64_t out_cap = 0, total = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    copy_in(0);
+    float ms_search = 0, ms_locate = 0, ms_sort = 0;
+    try {
+        for (uint64_t k = 0; k < n_chunks; ++k) {
+            const uint64_t q0 = bounds[k], n = bounds[k + 1] - q0;
+            const int b = static_cast<int>(k & 1);
+            if (k + 1 < n_chunks) copy_in(k + 1);
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
+            const uint8_t* dq = c->d_qchunk[b].get<uint8_t>();
+            if (make_rc) {
+                revcomp_kernel<<<grid_for(n / 2 * len), 256, 0, c->stream>>>(dq, n / 2, len, c->d_queries.get<uint8_t>());
+                launch_check(c);
+                dq = c->d_queries.get<uint8_t>();
+            }
+            auto tc0 = std::chrono::steady_clock::now();
+            run_pipeline(c, dq, n, len, true);  // search + locate + sort of this chunk
+            if (std::getenv("SB200_DEBUG"))
+                fprintf(stderr, "[sb200 debug] chunk %llu: %llu queries, host wall %.3f ms, device search %.3f locate %.3f sort %.3f ms\n",
+                        (unsigned long long)k, (unsigned long long)n,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count(), c->ct.ms_search,
+                        c->ct.ms_locate, c->ct.ms_sort);
+            CUDA_TRY(cudaEventRecord(c->ev_free_q[b], c->stream));
+            ms_search += c->ct.ms_search;
+            ms_locate += c->ct.ms_locate;
+            ms_sort += c->ct.ms_sort;
+            const uint64_t nh = c->last_hits;
+            // output buffer: sized from the first chunk, grown (rarely) when the estimate was too small
+            if (total + nh > out_cap) {
+                // first estimate: the hit density of the first chunk over the whole batch
+                uint64_t want = k == 0 ? nh * ((n_queries + n - 1) / n) + nh / 4 + 1024 : (total + nh) * 2;
+                uint8_t* bigger = static_cast<uint8_t*>(g_pinned.alloc(std::max<uint64_t>(1, want) * hit_bytes));
+                if (out) {
+                    CUDA_TRY(cudaStreamSynchronize(c->s_out));  // copies into the old buffer must have landed
+                    std::memcpy(bigger, out, total * hit_bytes);
+                    g_pinned.free(out);
+                }
+                out = bigger;
+                out_cap = want;
+            }
+            if (nh) {
+                if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_out[b], 0));  // hits of chunk k-2 have left this buffer
+                c->d_hitchunk[b].reserve(nh * hit_bytes);
+                if (compact)
+                    compact_hits_kernel<<<grid_for(nh), 256, 0, c->stream>>>(c->d_keys[0].get<uint64_t>(), c->d_qids[0].get<uint32_t>(), nh,
+                                                                             static_cast<uint32_t>(ix.bits_for_position),
+                                                                             static_cast<uint32_t>(q0), c->d_hitchunk[b].get<uint4>());
+                else
+                    expand_hits_kernel<<<grid_for(nh), 256, 0, c->stream>>>(c->d_keys[0].get<uint64_t>(), c->d_qids[0].get<uint32_t>(), nh,
+                                                                            static_cast<uint32_t>(ix.bits_for_position), q0,
+                                                                            c->d_hitchunk[b].get<uint64_t>());
+                launch_check(c);
+                CUDA_TRY(cudaEventRecord(c->ev_expanded[b], c->stream));
+                CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->ev_expanded[b], 0));
+                CUDA_TRY(cudaMemcpyAsync(out + total * hit_bytes, c->d_hitchunk[b].p, nh * hit_bytes, cudaMemcpyDeviceToHost, c->s_out));
+            }
+            CUDA_TRY(cudaEventRecord(c->ev_out[b], c->s_out));
+            total += nh;
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->s_out));
+        CUDA_TRY(cudaStreamSynchronize(c->s_in));
+    } catch (...) {
+        cudaStreamSynchronize(c->s_out);
+        cudaStreamSynchronize(c->s_in);
+        if (out) g_pinned.free(out);
+        throw;
+    }
+    if (!out) out = static_cast<uint8_t*>(g_pinned.alloc(hit_bytes));
+    if (std::getenv("SB200_DEBUG"))
+        fprintf(stderr, "[sb200 debug] host-buffer search total host wall %.3f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    c->ct.ms_search = ms_search;
+    c->ct.ms_locate = ms_locate;
+    c->ct.ms_sort = ms_sort;
+    c->ct.ms_h2d = c->ct.ms_d2h = 0;  // overlapped with the kernels
+    *hits = out;
+    *n_hits = total;
+}
+
 }  // namespace
 
 // ======================================================================================================
@@ -1307,114 +1433,24 @@ int sb200_fetch_hits(sb200_ctx* c, sb200_hit** hits, uint64_t* n_hits) {
     });
 }
 
-// search + locate from host buffers, pipelined: the batch is cut into chunks of reads; the host->device copy of
-// chunk i+1 and the device->host copy of the hits of chunk i-1 run on their own streams while chunk i computes.
-// Chunks are contiguous query ranges, so concatenating their sorted hit lists keeps the global order.
+
 int sb200_search(sb200_ctx* c, const uint8_t* queries, uint64_t n_queries, uint32_t len, sb200_hit** hits, uint64_t* n_hits) {
     return guard([&] {
         use(c);
-        auto& ix = c->idx;
-        if (!ix.loaded) throw Error("no index loaded");
-        if (!queries || n_queries == 0) throw Error("query file was empty - abort");
-        uint64_t chunk = 500000;
-        if (const char* e = std::getenv("SB200_CHUNK")) chunk = std::max<uint64_t>(2, std::strtoull(e, nullptr, 10));
-        chunk += chunk & 1;  // both strands of a read stay together
-        // chunk boundaries: a short first chunk (its copy-in cannot be hidden) and a short last one (its copy-out
-        // cannot be hidden), full chunks in between
-        std::vector<uint64_t> bounds{0};
-        {
-            uint64_t small = std::max<uint64_t>(2, (chunk / 4) & ~uint64_t{1});
-            if (n_queries > 2 * chunk) {
-                bounds.push_back(small);
-                while (bounds.back() + chunk + small < n_queries) bounds.push_back(bounds.back() + chunk);
-                if (n_queries - bounds.back() > small) bounds.push_back(n_queries - small);
-            } else {
-                while (bounds.back() + chunk < n_queries) bounds.push_back(bounds.back() + chunk);
-            }
-            bounds.push_back(n_queries);
-        }
-        const uint64_t n_chunks = bounds.size() - 1;
-        uint64_t max_chunk = 0;
-        for (uint64_t k = 0; k < n_chunks; ++k) max_chunk = std::max(max_chunk, bounds[k + 1] - bounds[k]);
-        for (int i = 0; i < 2; ++i) c->d_qchunk[i].reserve(max_chunk * len);
-        // wait until earlier work on the caller's stream is done before the copy streams touch the buffers
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        auto copy_in = [&](uint64_t k) {
-            const uint64_t q0 = bounds[k], n = bounds[k + 1] - q0;
-            const int b = static_cast<int>(k & 1);
-            if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->ev_free_q[b], 0));  // chunk k-2 no longer reads this buffer
-            CUDA_TRY(cudaMemcpyAsync(c->d_qchunk[b].p, queries + q0 * len, n * len, cudaMemcpyHostToDevice, c->s_in));
-            CUDA_TRY(cudaEventRecord(c->ev_in[b], c->s_in));
-        };
-        sb200_hit* out = nullptr;
-        uint64_t out_cap = 0, total = 0;
-        auto t0 = std::chrono::steady_clock::now();
-        copy_in(0);
-        float ms_search = 0, ms_locate = 0, ms_sort = 0;
-        try {
-            for (uint64_t k = 0; k < n_chunks; ++k) {
-                const uint64_t q0 = bounds[k], n = bounds[k + 1] - q0;
-                const int b = static_cast<int>(k & 1);
-                if (k + 1 < n_chunks) copy_in(k + 1);
-                CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
-                auto tc0 = std::chrono::steady_clock::now();
-                run_pipeline(c, c->d_qchunk[b].get<uint8_t>(), n, len, true);  // search + locate + sort of this chunk
-                if (std::getenv("SB200_DEBUG"))
-                    fprintf(stderr, "[sb200 debug] chunk %llu: %llu queries, host wall %.3f ms, device search %.3f locate %.3f sort %.3f ms\n",
-                            (unsigned long long)k, (unsigned long long)n,
-                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count(), c->ct.ms_search,
-                            c->ct.ms_locate, c->ct.ms_sort);
-                CUDA_TRY(cudaEventRecord(c->ev_free_q[b], c->stream));
-                ms_search += c->ct.ms_search;
-                ms_locate += c->ct.ms_locate;
-                ms_sort += c->ct.ms_sort;
-                const uint64_t nh = c->last_hits;
-                // output buffer: sized from the first chunk, grown (rarely) when the estimate was too small
-                if (total + nh > out_cap) {
-                    // first estimate: the hit density of the first chunk over the whole batch
-                    uint64_t want = k == 0 ? nh * ((n_queries + n - 1) / n) + nh / 4 + 1024 : (total + nh) * 2;
-                    sb200_hit* bigger = static_cast<sb200_hit*>(g_pinned.alloc(std::max<uint64_t>(1, want) * sizeof(sb200_hit)));
-                    if (out) {
-                        CUDA_TRY(cudaStreamSynchronize(c->s_out));  // copies into the old buffer must have landed
-                        std::memcpy(bigger, out, total * sizeof(sb200_hit));
-                        g_pinned.free(out);
-                    }
-                    out = bigger;
-                    out_cap = want;
-                }
-                if (nh) {
-                    if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_out[b], 0));  // hits of chunk k-2 have left this buffer
-                    c->d_hitchunk[b].reserve(nh * sizeof(sb200_hit));
-                    expand_hits_kernel<<<grid_for(nh), 256, 0, c->stream>>>(c->d_keys[0].get<uint64_t>(), c->d_qids[0].get<uint32_t>(), nh,
-                                                                            static_cast<uint32_t>(ix.bits_for_position), q0,
-                                                                            c->d_hitchunk[b].get<uint64_t>());
-                    launch_check(c);
-                    CUDA_TRY(cudaEventRecord(c->ev_expanded[b], c->stream));
-                    CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->ev_expanded[b], 0));
-                    CUDA_TRY(cudaMemcpyAsync(out + total, c->d_hitchunk[b].p, nh * sizeof(sb200_hit), cudaMemcpyDeviceToHost, c->s_out));
-                }
-                CUDA_TRY(cudaEventRecord(c->ev_out[b], c->s_out));
-                total += nh;
-            }
-            CUDA_TRY(cudaStreamSynchronize(c->s_out));
-            CUDA_TRY(cudaStreamSynchronize(c->s_in));
-        } catch (...) {
-            cudaStreamSynchronize(c->s_out);
-            cudaStreamSynchronize(c->s_in);
-            if (out) g_pinned.free(out);
-            throw;
-        }
-        if (!out) out = static_cast<sb200_hit*>(g_pinned.alloc(sizeof(sb200_hit)));
-        if (std::getenv("SB200_DEBUG"))
-            fprintf(stderr, "[sb200 debug] sb200_search total host wall %.3f ms\n",
-                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
-        c->ct.ms_search = ms_search;
-        c->ct.ms_locate = ms_locate;
-        c->ct.ms_sort = ms_sort;
-        c->ct.ms_h2d = c->ct.ms_d2h = 0;  // overlapped with the kernels
-        (void)t0;
-        *hits = out;
-        *n_hits = total;
+        void* p = nullptr;
+        search_host_pipelined(c, queries, n_queries, len, false, false, &p, n_hits);
+        *hits = static_cast<sb200_hit*>(p);
+    });
+}
+
+int sb200_search_reads(sb200_ctx* c, const uint8_t* reads, uint64_t n_reads, uint32_t len, int with_reverse, sb200_hit32** hits,
+                       uint64_t* n_hits) {
+    return guard([&] {
+        use(c);
+        if (c->idx.loaded && c->idx.bits_for_position > 32) throw Error("sequences too long for 32-bit positions: use sb200_search");
+        void* p = nullptr;
+        search_host_pipelined(c, reads, n_reads, len, with_reverse != 0, true, &p, n_hits);
+        *hits = static_cast<sb200_hit32*>(p);
     });
 }
 

@@ -318,3 +318,24 @@ def test_cli_besthits_follows_search_best(sb, cases, tmp_path):
     assert got == sorted(want)
     res = subprocess.run([exe, "search", "-q", qa, "-i", path, "--max_hits", "3"], capture_output=True, text=True)
     assert res.returncode == 1 and "max_hits" in res.stderr
+
+
+def test_search_reads_compact_matches_full_call(sb, ctx, cases, monkeypatch):
+    """sb200_search_reads: reads only, reverse complements made on the device, 16-byte hits."""
+    rng, seqs, ix, path = cases[("multi", 6)]
+    ctx.load_index(path)
+    ctx.enable_text(True)
+    m, k = 33, 2
+    q = W.sample_reads(rng, seqs, 211, m, k, True)
+    reads = np.ascontiguousarray(q[0::2])
+    sch = sb.SearchScheme.generate("h2-k2", 0, k, m)
+    ctx.set_scheme(sch, True)
+    want = O.sort_rows(ix.locate(ix.search(q, sch, True)))
+    for chunk in ("10", "500000"):
+        monkeypatch.setenv("SB200_CHUNK", chunk)
+        got = ctx.search_reads(reads)
+        assert got.dtype == np.uint32 and np.array_equal(got.astype(np.uint64), want)
+        fwd_only = ctx.search_reads(reads, with_reverse=False)
+        want_fwd = O.sort_rows(ix.locate(ix.search(reads, sch, True)))
+        assert np.array_equal(fwd_only.astype(np.uint64), want_fwd)
+    ctx.enable_text(False)
