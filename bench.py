@@ -8,8 +8,9 @@ Metric (BASELINE.json): queries/s for 150 bp reads, k = 2 edit distance, on a sy
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--genome BP] [--reads-per-step R]
 
 `value`  : whole-job reads/s with the queries already in HBM and the hits left in HBM (device timed).
-`e2e`    : the same through sb200_search() with pinned HOST buffers: H2D of the queries and D2H of the
-           hits (32 B per hit, the reference's tuple) inside the timed region.
+`e2e`    : the same through sb200_search_reads() with pinned HOST buffers: H2D of the reads (the reverse
+           complements are made on the device) and D2H of the hits (16 B per hit) inside the timed region.
+`e2e_full_tuples`: the same through sb200_search(): both strands from the host, 32-byte hit tuples back.
 `roofline`: the search kernel; algorithmic bytes = search nodes x 2 rank-ops x 64 B over
            its CUDA-event duration, against the measured HBM bandwidth of MEASURED_PEAKS.json.
 `cpu_baseline`: the CPU oracle (restatement of fmc::search_ng24 + LocateLinear, "port") on the host cores,
@@ -367,12 +368,12 @@ def main():
     line = {"metric": "queries/s (150bp, k=2 edit)", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": round(dev_ms / a.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": round(e2e_value, 1), "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(1e3 * e2e_s / a.steps, 3), "call": "sb200_search (both strands in, 32-byte hit tuples out)"},
-            "e2e_compact": {"value": round(world * R * a.steps / e2e_compact_s, 1), "unit": "reads/s", "h2d_bytes_per_step": R * m,
-                            "d2h_bytes_per_step": int(16 * compact_hits / a.steps), "ms_per_step": round(1e3 * e2e_compact_s / a.steps, 3),
-                            "hits_match": bool(compact_hits == e2e_hits),
-                            "call": "sb200_search_reads (reads in, reverse complements on the device, 16-byte hits out)"},
+            "e2e": {"value": round(world * R * a.steps / e2e_compact_s, 1), "unit": "reads/s", "h2d_bytes_per_step": R * m,
+                    "d2h_bytes_per_step": int(16 * compact_hits / a.steps), "ms_per_step": round(1e3 * e2e_compact_s / a.steps, 3),
+                    "call": "sb200_search_reads (reads in, reverse complements on the device, 16-byte hits out)"},
+            "e2e_full_tuples": {"value": round(e2e_value, 1), "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                "ms_per_step": round(1e3 * e2e_s / a.steps, 3), "hits_match": bool(compact_hits == e2e_hits),
+                                "call": "sb200_search (both strands in, 32-byte hit tuples out)"},
             "gpu_launches": launches, "roofline": roofline,
             "hits_per_step": int(hits_total / a.steps), "cursors_per_step": int(cursors_total / a.steps)}
 
@@ -382,11 +383,21 @@ def main():
         cpu_v = sample / res["times"][0]
         # parity of the sample through the C ABI against the oracle (checker, not the measured path)
         oix = res["oix"]
+        nodes_before = int(oix.counters[0])
         cur = oix.search(res["first_batch"], scheme, edit, res["threads"])
+        oracle_nodes = int(oix.counters[0]) - nodes_before
         import oracle as O
         want = O.sort_rows(oix.locate(cur, res["threads"]))
         got = ctx.search(res["first_batch"])
         line["parity_sample_ok"] = bool(np.array_equal(got, want))
+        # the roofline numerator: with the q-gram table off the kernels expand exactly the oracle's extensions
+        ctx.build_qgram(0)
+        ctx.reset_counters()
+        ctx.search_cursors(res["first_batch"])
+        line["nodes_sample"] = {"kernels": int(ctx.counters()["nodes"]), "oracle": oracle_nodes,
+                                "equal": bool(ctx.counters()["nodes"] == oracle_nodes)}
+        if qauto:
+            ctx.build_qgram(qauto)
         line["cpu_baseline"] = {"value": round(cpu_v, 1), "unit": "reads/s", "cores": res["threads"], "kind": "port",
                                 "sample": f"first {sample} reads of rank 0's first batch (both strands), CPU oracle search+locate, "
                                           f"{res['threads']} OpenMP threads",
