@@ -167,7 +167,7 @@ struct sb200_ctx {
     uint32_t n_searches{}, qlen{}, kmax{};
     bool edit{}, have_scheme{};
     // work buffers
-    DevBuf d_seeds, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
+    DevBuf d_seeds, d_spill, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
     uint64_t cursor_cap{}, seed_cap{};
     uint64_t last_cursors{}, last_real_cursors{}, last_hits{};
     uint64_t nodes_text{};
@@ -604,7 +604,26 @@ void launch_search(sb200_ctx* c, const SearchParams& P) {
     });
     launch_check(c);
     CUDA_TRY(cudaEventRecord(c->ev[9], c->stream));
-    if (P.sa32) {  // in-text verification of the seeds (reads the seed count from device memory: no host sync)
+    static const bool use_pool = !(std::getenv("SB200_TEXT_POOL") && std::atoi(std::getenv("SB200_TEXT_POOL")) == 0);
+    if (P.sa32 && use_pool) {  // in-text verification, one frame pool per warp
+        with_stack(c->kmax, [&](auto STACK) {
+            const size_t tables = ((size_t(P.n_searches) * P.len + (size_t(P.n_searches) * P.len * kRunE + 3) / 4) * 4 + 7) & ~size_t{7};
+            const unsigned threads = std::min(kPoolThreads, blocks_per_sm("SB200_POOL_THREADS", kPoolThreads)) & ~31u;
+            const size_t psmem = tables + (threads / 32) * size_t(pool_bytes(P.len));
+            if (psmem > 200 * 1024) throw Error("search scheme table and frame pools do not fit shared memory (query too long)");
+            const unsigned per_sm = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(2048 / threads, (227 * 1024) / (psmem + 1024))));
+            unsigned tgrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_POOL_BLOCKS_PER_SM", per_sm);
+            auto go = [&](auto kern) {
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem)));
+                c->d_spill.reserve(size_t(tgrid) * (threads / 32) * kSpillCap * sizeof(uint4));
+                kern<<<tgrid, threads, psmem, c->stream>>>(P, 2 * (c->kmax + 1), blocks_per_sm("SB200_RUN_ROUNDS", kRunRounds),
+                                                           c->d_spill.get<uint4>());
+            };
+            if (c->edit) go(text_pool_kernel<true, STACK()>);
+            else go(text_pool_kernel<false, STACK()>);
+        });
+        launch_check(c);
+    } else if (P.sa32) {  // in-text verification of the seeds (reads the seed count from device memory: no host sync)
         unsigned tgrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_TEXT_BLOCKS_PER_SM", 6);
         with_stack(c->kmax, [&](auto STACK) {
             auto go = [&](auto kern) {
@@ -832,18 +851,22 @@ void search_host_pipelined(sb200_ctx* c, const uint8_t* src, uint64_t n_items, u
     const uint64_t per_item = make_rc ? 2 : 1;  // queries per host item
     const uint64_t n_queries = n_items * per_item;
     const size_t hit_bytes = compact ? sizeof(sb200_hit32) : sizeof(sb200_hit);
-    uint64_t chunk = 500000;  // queries per chunk
+    // Chunk boundaries (in queries).  Every chunk costs ~0.9 ms of kernel drain (the longest single seed), so few
+    // chunks: a short first one (its copy-in cannot be hidden), a short last one (its copy-out cannot be hidden),
+    // and the rest in pieces of at most `chunk` queries whose copies hide behind the neighbours' kernels.
+    uint64_t chunk = 2000000, edge_div = 8;
     if (const char* e = std::getenv("SB200_CHUNK")) chunk = std::max<uint64_t>(2, std::strtoull(e, nullptr, 10));
+    if (const char* e = std::getenv("SB200_EDGE_DIV")) edge_div = std::max<uint64_t>(2, std::strtoull(e, nullptr, 10));
     chunk += chunk & 1;  // both strands of a read stay together
-    // chunk boundaries (in queries): a short first chunk (its copy-in cannot be hidden) and a short last one (its
-    // copy-out cannot be hidden), full chunks in between
     std::vector<uint64_t> bounds{0};
     {
-        uint64_t small = std::max<uint64_t>(2, (chunk / 4) & ~uint64_t{1});
-        if (n_queries > 2 * chunk) {
-            bounds.push_back(small);
-            while (bounds.back() + chunk + small < n_queries) bounds.push_back(bounds.back() + chunk);
-            if (n_queries - bounds.back() > small) bounds.push_back(n_queries - small);
+        uint64_t edge = std::min(chunk / 2, n_queries / edge_div) & ~uint64_t{1};
+        if (edge >= 16384 && n_queries >= 4 * edge) {
+            const uint64_t middle = n_queries - 2 * edge;
+            const uint64_t pieces = (middle + chunk - 1) / chunk;
+            bounds.push_back(edge);
+            for (uint64_t i = 1; i < pieces; ++i) bounds.push_back(edge + ((middle * i / pieces) & ~uint64_t{1}));
+            bounds.push_back(n_queries - edge);
         } else {
             while (bounds.back() + chunk < n_queries) bounds.push_back(bounds.back() + chunk);
         }
@@ -883,10 +906,11 @@ void search_host_pipelined(sb200_ctx* c, const uint8_t* src, uint64_t n_items, u
             auto tc0 = std::chrono::steady_clock::now();
             run_pipeline(c, dq, n, len, true);  // search + locate + sort of this chunk
             if (std::getenv("SB200_DEBUG"))
-                fprintf(stderr, "[sb200 debug] chunk %llu: %llu queries, host wall %.3f ms, device search %.3f locate %.3f sort %.3f ms\n",
+                fprintf(stderr,
+                        "[sb200 debug] chunk %llu: %llu queries, host wall %.3f ms, device search %.3f (fm %.3f text %.3f) locate %.3f sort %.3f ms\n",
                         (unsigned long long)k, (unsigned long long)n,
-                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count(), c->ct.ms_search,
-                        c->ct.ms_locate, c->ct.ms_sort);
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count(), c->ct.ms_search, c->ms_fm,
+                        c->ms_text, c->ct.ms_locate, c->ct.ms_sort);
             CUDA_TRY(cudaEventRecord(c->ev_free_q[b], c->stream));
             ms_search += c->ct.ms_search;
             ms_locate += c->ct.ms_locate;
@@ -1002,7 +1026,7 @@ int sb200_destroy(sb200_ctx* c) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         c->idx.release();
-        for (DevBuf* b : {&c->d_steps, &c->d_runs, &c->d_seeds, &c->d_packed, &c->d_queries, &c->d_cursors, &c->d_counters, &c->d_offsets, &c->d_keys[0], &c->d_keys[1],
+        for (DevBuf* b : {&c->d_steps, &c->d_runs, &c->d_seeds, &c->d_spill, &c->d_packed, &c->d_queries, &c->d_cursors, &c->d_counters, &c->d_offsets, &c->d_keys[0], &c->d_keys[1],
                           &c->d_qids[0], &c->d_qids[1], &c->d_tmp, &c->d_scratch})
             b->release();
         for (auto& ev : c->ev) cudaEventDestroy(ev);

@@ -606,6 +606,278 @@ __device__ __forceinline__ void text_thread(const SearchParams& P, const uint32_
     if (emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(emitted));
 }
 
+// ================================================================================================
+// text_pool_kernel: the same in-text verification, but the frames of a warp live in ONE pool in shared memory
+// instead of 32 private stacks.  Every trip the warp pops up to 32 frames from the top of the pool, each lane
+// expands one of them (any lane, any seed: the frame names the seed slot whose staged query it needs) and pushes
+// the children back.  Lanes therefore stay busy as long as the warp has frames at all — the private-stack version
+// (text_thread) keeps 6.6 of 32 lanes active because the lanes drift into different phases — and a heavy seed is
+// expanded by many lanes at once, which also shortens the drain at the end of the kernel.
+//   * 32 seeds are fetched at once when the pool runs empty (slot = lane).
+//   * a frame compares at most kRunRounds x 8 symbols of a match-only run per pop, then is pushed back, so one
+//     long run does not hold up the other 31 lanes.
+//   * pops narrow down when the pool is nearly full; with one frame per trip the order is depth first and the
+//     pool cannot grow by more than the private-stack bound (STACK), which is kept as head room.
+// ================================================================================================
+#if defined(SB200_POOL_CAP)
+constexpr uint32_t kPoolCap = SB200_POOL_CAP;      // (tests: tiny pools exercise the spill area and the narrow pops)
+constexpr uint32_t kSpillCap = SB200_SPILL_CAP;
+#else
+constexpr uint32_t kPoolCap = 144;    // frames per warp held in shared memory
+constexpr uint32_t kSpillCap = 1024;  // frames per warp that spill to global memory behind them (rare)
+#endif
+constexpr uint32_t kPoolSlots = 64;   // seeds a warp works on at a time
+constexpr uint32_t kPoolThreads = 320;  // 10 warps per block: three blocks (30 warps) fit the shared memory of an SM at 150 bp
+constexpr uint32_t kRunRounds = 4;    // rounds of 8 symbols per pop
+
+struct TextPool {
+    uint2* frames;         // [kPoolCap] (a, meta): frames 0 .. kPoolCap-1 of the stack
+    uint8_t* slots;        // [kPoolCap] seed slot of the frame
+    uint4* spill;          // [kSpillCap] (a, meta, slot, -): frames kPoolCap .. of the stack, global memory
+    uint32_t* top;         // number of frames in the pool
+    uint32_t* live;        // [kPoolSlots] frames of the slot's seed that are still in the pool or being expanded
+    uint32_t* ctx_qid;     // [kPoolSlots] query id of the seed in the slot
+    uint32_t* ctx_search;  // [kPoolSlots] its search
+    uint32_t* query;       // [kPoolSlots][Wp] staged packed queries
+    uint32_t Wp;           // odd stride (words) between the queries: spreads the slots over the banks
+};
+struct PoolLane {
+    uint32_t nodes{0}, emitted{0};
+    ChunkWriter outW;
+    bool overflow{false};
+};
+__host__ __device__ inline uint32_t pool_query_stride(uint32_t len) { return packed_words(len) | 1u; }
+// bytes of shared memory one warp's pool takes
+__host__ __device__ inline uint32_t pool_bytes(uint32_t len) {
+    return kPoolCap * 8u + ((kPoolCap + 7u) & ~7u) + 8u + 3u * kPoolSlots * 4u + kPoolSlots * pool_query_stride(len) * 4u;
+}
+// How many frames the warp may pop when `top` are present and one frame pushes at most `maxpush` children.
+// Pops only narrow down when even the spill area is nearly full; with one frame per trip the order is depth first
+// and the stack cannot grow by more than the private-stack bound `stack`, which is kept as head room.
+__host__ __device__ inline uint32_t pool_pop_width(uint32_t top, uint32_t maxpush, uint32_t lanes, uint32_t stack) {
+    const uint32_t cap = kPoolCap + kSpillCap - stack;
+    uint32_t n = top < lanes ? top : lanes;
+    const uint32_t room = top < cap ? (cap - top) / (maxpush - 1u) : 0u;
+    if (n > room) n = room ? room : 1u;
+    return n;
+}
+__device__ __forceinline__ void pool_push(const TextPool& pool, uint32_t a, uint32_t meta, uint32_t slot, PoolLane& ls) {
+#if defined(SB200_HOST_EMU)
+    const uint32_t idx = (*pool.top)++;
+#else
+    const uint32_t idx = atomicAdd(pool.top, 1u);
+#endif
+    if (idx < kPoolCap) {
+        pool.frames[idx] = make_uint2(a, meta);
+        pool.slots[idx] = static_cast<uint8_t>(slot);
+    } else if (idx - kPoolCap < kSpillCap) {
+        pool.spill[idx - kPoolCap] = make_uint4(a, meta, slot, 0);
+    } else {
+        ls.overflow = true;
+    }
+}
+// frame idx of the stack -> (a, meta), slot
+__device__ __forceinline__ uint2 pool_get(const TextPool& pool, uint32_t idx, uint32_t& slot) {
+    if (idx < kPoolCap) {
+        slot = pool.slots[idx];
+        return pool.frames[idx];
+    }
+    const uint4 v = pool.spill[idx - kPoolCap];
+    slot = v.z;
+    return make_uint2(v.x, v.y);
+}
+
+// expands one frame exactly like one pop of text_thread; returns the number of frames it pushed
+template <bool EDIT>
+__device__ __forceinline__ uint32_t text_expand(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, const TextPool& pool,
+                                            const uint2 f, const uint32_t slot, PoolLane& ls, const uint32_t run_rounds) {
+    const uint32_t qlen = P.len;
+    const uint32_t W = packed_words(qlen);
+    const uint32_t* q = pool.query + slot * pool.Wp;
+    const uint32_t qid = pool.ctx_qid[slot];
+    const uint32_t sid = pool.ctx_search[slot];
+    const uint32_t* tbl = s_steps + sid * qlen;
+    const uint8_t* runs = s_runs + sid * qlen * kRunE;
+    auto qsym = [&](uint32_t pos) -> uint32_t { return (q[pos >> 3] >> ((pos & 7u) * 4u)) & 0xfu; };
+    auto query8 = [&](uint32_t pos) -> uint32_t {
+        const uint32_t w = pos >> 3;
+        const uint32_t lo = q[w];
+        const uint32_t hi = w + 1 < W ? q[w + 1] : 0xffffffffu;
+        return funnel_r(lo, hi, (pos & 7u) * 4u);
+    };
+    auto emit = [&](uint32_t a, uint32_t e) {
+        ls.outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], make_uint4(qid, P.isa32[a], 1, e));
+        ++ls.emitted;
+    };
+    uint32_t pushed = 0;
+    auto push = [&](uint32_t a, uint32_t m) {
+        pool_push(pool, a, m, slot, ls);
+        ++pushed;
+    };
+
+    uint32_t a = f.x;
+    const uint32_t meta = f.y;
+    uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
+    uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
+    const bool pair = (meta & META_PAIR) != 0;
+    uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
+    uint32_t nodes = 0;
+
+    if (!pair) {
+        uint32_t R = runs[step * kRunE + e];
+        uint32_t budget = run_rounds;
+        while (R != 0) {
+            const uint32_t st = tbl[step];
+            const bool right = (st >> 24) & 1u;
+            const uint32_t p0 = st & 0xffffu;
+            uint32_t r = 0;
+            bool differs = false;
+            // one code path for both directions: a window of n symbols that starts at tpos / qpos
+            while (r < R && budget != 0) {
+                uint32_t n = R - r < 8u ? R - r : 8u;
+                if (!right) {
+                    if (a < r + 1) { differs = true; break; }  // the delimiter before position 0
+                    if (n > a - r) n = a - r;
+                }
+                --budget;
+                const uint32_t tpos = right ? a + tlen + r : a - r - n;
+                const uint32_t qpos = right ? p0 + r : p0 + 1 - r - n;
+                const uint32_t x = (text8(P.text4, tpos) ^ query8(qpos)) & nib_mask(n);
+                if (x != 0) {
+                    r += right ? (ctz32(x) >> 2) : n - 1 - ((31u - clz32(x)) >> 2);
+                    differs = true;
+                    break;
+                }
+                r += n;
+            }
+            if (differs) {  // the state at step + r has no child
+                ls.nodes += nodes + r + 1;
+                return pushed;
+            }
+            nodes += r;
+            step += r;
+            tlen += r;
+            if (r != 0) {
+                if (right) Rinfo = INFO_M;
+                else { Linfo = INFO_M; a -= r; }
+            }
+            if (r < R) {  // out of rounds: the rest of the run waits for the next pop
+                ls.nodes += nodes;
+                push(a, pack_meta(step, e, Linfo, Rinfo) | (tlen << META_TLEN_SHIFT));
+                return pushed;
+            }
+            if (step == qlen) {  // the last step matched
+                const uint32_t O = right ? Linfo : Rinfo;
+                if (!EDIT || (O & 1u) == 0) emit(a, e);
+                ls.nodes += nodes;
+                return pushed;
+            }
+            if (((tbl[step] >> 16) & 0xfu) > e + 1) { ls.nodes += nodes; return pushed; }  // dead at the next step
+            R = runs[step * kRunE + e];
+        }
+    }
+    const uint32_t b = a + tlen;
+    const bool rightFrame = (tbl[step] >> 24) & 1u;
+    uint32_t tL = 0;
+    if (a != 0) tL = (P.text4[(a - 1) >> 3] >> (((a - 1) & 7u) * 4u)) & 0xfu;
+    const uint32_t tR = (P.text4[b >> 3] >> ((b & 7u) * 4u)) & 0xfu;
+
+    bool second = false;
+    while (true) {
+        ++nodes;
+        const uint32_t st = tbl[step];
+        const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
+        const bool right = (st >> 24) & 1u;
+        const uint32_t c = qsym(st & 0xffffu);
+        const bool last = step + 1 == qlen;
+        const uint32_t stn = last ? 0u : tbl[step + 1];
+        const uint32_t lnext = (stn >> 16) & 0xfu;
+        const bool sameDirNext = !last && ((((stn >> 24) & 1u) != 0) == right);
+        const bool matchOK = l <= e && e <= u;
+        const bool mmOK = l <= e + 1 && e + 1 <= u;
+        const uint32_t T = right ? Rinfo : Linfo;
+        const uint32_t O = right ? Linfo : Rinfo;
+        const bool otherEndOK = !EDIT || (O & 1u) == 0;
+        const uint32_t t = right ? tR : tL;
+        const uint32_t na = right ? a : a - 1;
+        const uint32_t keepL = right ? Linfo : 0u, keepR = right ? 0u : Rinfo;
+        const uint32_t sideShift = right ? 16u : 14u;
+        const uint32_t metaBase = (keepL << 14) | (keepR << 16) | ((tlen + 1) << META_TLEN_SHIFT);
+        if (t != 0) {
+            if (t == c) {
+                if (matchOK) {
+                    if (last) {
+                        if (otherEndOK) emit(na, e);
+                    } else if (lnext <= e + 1) {
+                        push(na, metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift));
+                    }
+                }
+            } else if (mmOK) {
+                const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
+                const bool subAlive = !last && lnext <= e + 2;
+                const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift);
+                const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift);
+                if (delOK && subAlive && sameDirNext) push(na, mD | META_PAIR);
+                else {
+                    if (delOK) push(na, mD);
+                    if (subAlive) push(na, mS);
+                }
+                if (!EDIT && last) emit(na, e + 1);
+            }
+        }
+        if (pair) {
+            if (second) break;
+            second = true;
+            step += 1;
+            if (rightFrame) Rinfo = INFO_S; else Linfo = INFO_S;
+            continue;
+        }
+        const bool insOK = EDIT && mmOK && (T == INFO_M || T == INFO_I);
+        if (!insOK) break;
+        if (last) {
+            if (otherEndOK) emit(a, e + 1);
+            break;
+        }
+        if (lnext > e + 2) break;
+        step += 1;
+        e += 1;
+        if (right) Rinfo = INFO_I; else Linfo = INFO_I;
+    }
+    ls.nodes += nodes;
+    return pushed;
+}
+
+// one seed into slot `slot`: stage its query, remember its context, push its root frame
+__device__ __forceinline__ void pool_load_seed(const SearchParams& P, const TextPool& pool, uint32_t slot, const uint4 seed, PoolLane& ls) {
+    const uint32_t W = packed_words(P.len);
+    const uint32_t* src = P.packed + static_cast<uint64_t>(seed.x) * W;
+    uint32_t* dst = pool.query + slot * pool.Wp;
+    for (uint32_t w = 0; w < W; ++w) dst[w] = src[w];
+    pool.ctx_qid[slot] = seed.x;
+    pool.ctx_search[slot] = seed.z;
+    pool.live[slot] = 1;
+    pool_push(pool, P.sa32[seed.y], seed.w, slot, ls);
+}
+
+// the expanded frame is gone, `pushed` frames of the same seed were added
+__device__ __forceinline__ void pool_retire(const TextPool& pool, uint32_t slot, uint32_t pushed) {
+    if (pushed == 1) return;
+#if defined(SB200_HOST_EMU)
+    pool.live[slot] += pushed - 1u;
+#else
+    atomicAdd(&pool.live[slot], pushed - 1u);
+#endif
+}
+
+__device__ __forceinline__ void pool_finish(const SearchParams& P, PoolLane& ls, uint32_t maxtop) {
+    ls.outW.finish(P.out, P.out_cap);
+    if (ls.nodes) atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(ls.nodes));
+    if (ls.nodes) atomicAdd(&P.counters[CT_NODES_TEXT], static_cast<unsigned long long>(ls.nodes));
+    if (ls.overflow) atomicExch(&P.counters[CT_OVERFLOW], 1ull);
+    atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxtop));
+    if (ls.emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(ls.emitted));
+}
+
 #if !defined(SB200_HOST_EMU)
 template <int SIGMA, bool EDIT, int STACK>
 __global__ void __launch_bounds__(256, 4) fm_kernel(const SearchParams P) {
@@ -627,6 +899,84 @@ __global__ void __launch_bounds__(256) text_kernel(const SearchParams P) {
     for (uint32_t i = threadIdx.x; i < n_run_words; i += blockDim.x) s_runs[i] = reinterpret_cast<const uint32_t*>(P.runs)[i];
     __syncthreads();
     text_thread<EDIT, STACK>(P, s_steps, reinterpret_cast<const uint8_t*>(s_runs), s_runs + n_run_words + threadIdx.x, blockDim.x);
+}
+
+template <bool EDIT, int STACK>
+__global__ void __launch_bounds__(kPoolThreads) text_pool_kernel(const SearchParams P, const uint32_t maxpush, const uint32_t run_rounds, uint4* spill) {
+    extern __shared__ uint32_t s_steps[];
+    const uint32_t n_steps = P.n_searches * P.len;
+    const uint32_t n_run_words = (n_steps * kRunE + 3) / 4;
+    uint32_t* s_runs = s_steps + n_steps;
+    for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) s_steps[i] = P.steps[i];
+    for (uint32_t i = threadIdx.x; i < n_run_words; i += blockDim.x) s_runs[i] = reinterpret_cast<const uint32_t*>(P.runs)[i];
+    // this warp's pool (8-byte aligned region behind the tables)
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint8_t* base = reinterpret_cast<uint8_t*>(s_steps) + (((n_steps + n_run_words) * 4u + 7u) & ~7u) + warp * pool_bytes(P.len);
+    TextPool pool;
+    pool.frames = reinterpret_cast<uint2*>(base);
+    pool.slots = base + kPoolCap * 8u;
+    pool.spill = spill + (static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * kSpillCap;
+    uint32_t* words = reinterpret_cast<uint32_t*>(base + kPoolCap * 8u + ((kPoolCap + 7u) & ~7u));
+    pool.top = words;
+    pool.live = words + 2;
+    pool.ctx_qid = words + 2 + kPoolSlots;
+    pool.ctx_search = words + 2 + 2 * kPoolSlots;
+    pool.query = words + 2 + 3 * kPoolSlots;
+    pool.Wp = pool_query_stride(P.len);
+    if (lane == 0) *pool.top = 0;
+    for (uint32_t i = lane; i < kPoolSlots; i += 32u) pool.live[i] = 0;
+    __syncthreads();
+
+    PoolLane ls;
+    const unsigned long long slots = P.counters[CT_SEED_SLOTS];
+    const uint32_t n_slots = static_cast<uint32_t>(slots < P.seed_cap ? slots : P.seed_cap);
+    const uint8_t* runs8 = reinterpret_cast<const uint8_t*>(s_runs);
+    uint32_t maxtop = 0;
+    bool exhausted = false;  // (warp uniform) the seed list has been handed out
+    while (true) {
+        uint32_t top = *pool.top;
+        if (top < 32u && !exhausted) {  // the warp starves: new seeds into every free slot
+            uint32_t my_free[kPoolSlots / 32];
+            uint32_t n_free = 0, my_rank[kPoolSlots / 32];
+#pragma unroll
+            for (uint32_t j = 0; j < kPoolSlots / 32; ++j) {
+                const bool fr = pool.live[j * 32u + lane] == 0;
+                const uint32_t m = __ballot_sync(0xffffffffu, fr);
+                my_free[j] = fr;
+                my_rank[j] = n_free + __popc(m & ((1u << lane) - 1u));
+                n_free += __popc(m);
+            }
+            uint32_t first = 0;
+            if (lane == 0) first = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_SEED], static_cast<unsigned long long>(n_free)));
+            first = __shfl_sync(0xffffffffu, first, 0);
+            exhausted = first + n_free >= n_slots;
+#pragma unroll
+            for (uint32_t j = 0; j < kPoolSlots / 32; ++j) {
+                const uint32_t i = first + my_rank[j];
+                if (my_free[j] && i < n_slots) {
+                    const uint4 seed = P.seeds[i];
+                    if (seed.x != kInvalidQid) pool_load_seed(P, pool, j * 32u + lane, seed, ls);
+                }
+            }
+            __syncwarp();
+            top = *pool.top;
+        }
+        if (top == 0) {
+            if (exhausted) break;
+            continue;  // only padding entries were fetched
+        }
+        maxtop = top > maxtop ? top : maxtop;
+        const uint32_t n = pool_pop_width(top, maxpush, 32u, STACK);
+        uint2 f = make_uint2(0, 0);
+        uint32_t slot = 0;
+        if (lane < n) f = pool_get(pool, top - 1 - lane, slot);
+        __syncwarp();
+        if (lane == 0) *pool.top = top - n;
+        __syncwarp();
+        if (lane < n) pool_retire(pool, slot, text_expand<EDIT>(P, s_steps, runs8, pool, f, slot, ls, run_rounds));
+        __syncwarp();
+    }
+    pool_finish(P, ls, maxtop);
 }
 #endif
 

@@ -6,24 +6,29 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libsearch_emu.so")
 SRC = os.path.join(HERE, "search_emu.cpp")
 
 
-def _build():
+def _load(name, flags):
+    so = os.path.join(HERE, name)
     deps = [SRC] + [os.path.join(HERE, "..", "..", "sahara_b200", "csrc", f) for f in ("search.cuh", "layout.cuh")]
-    if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
-        return
-    subprocess.check_call(["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=undefined",
-                           "-fno-sanitize-recover=undefined", SRC, "-o", SO])
+    if not (os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps)):
+        subprocess.check_call(["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=undefined",
+                               "-fno-sanitize-recover=undefined", *flags, SRC, "-o", so])
+    lib = C.CDLL(so)
+    lib.emu_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                               C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.emu_free.argtypes = [C.c_void_p]
+    return lib
 
 
-_build()
-_lib = C.CDLL(SO)
-_lib.emu_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
-                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
-                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-_lib.emu_free.argtypes = [C.c_void_p]
+_lib = _load("libsearch_emu.so", [])
+# the same source with a 24-frame pool and 120 spill frames: the pooled text kernel then spills all the time and
+# pops narrowly / depth first most of the time (head room = the private-stack bound of 96 frames)
+_lib_small_pool = _load("libsearch_emu_smallpool.so", ["-DSB200_POOL_CAP=24", "-DSB200_SPILL_CAP=120"])
+
+POOL = 8  # debug flag: run the in-text verification with the pooled kernel body (text_pool_kernel)
 
 
 def _p(a):
@@ -40,7 +45,7 @@ def text_tables(oracle_index, seqs):
     return np.ascontiguousarray(sa), np.ascontiguousarray(text)
 
 
-def search(oracle_index, queries, scheme, edit, debug_flags=0, text=None):
+def search(oracle_index, queries, scheme, edit, debug_flags=0, text=None, small_pool=False):
     """runs the kernel body on the host over the oracle index's BWTs -> (sorted cursors uint64 [n,4], nodes).
     text = (sa32, text symbols) from text_tables() enables the in-text verification mode."""
     info = oracle_index.info()
@@ -49,7 +54,8 @@ def search(oracle_index, queries, scheme, edit, debug_flags=0, text=None):
     Carr = np.array(info["C"], dtype=np.uint64)
     q = np.ascontiguousarray(queries, dtype=np.uint8)
     out, n, nodes = C.c_void_p(), C.c_uint64(), C.c_uint64()
-    rc = _lib.emu_search(_p(bwt), _p(rev), info["n_rows"], info["sigma"], _p(Carr), _p(q), q.shape[0], q.shape[1], scheme.n_searches,
+    lib = _lib_small_pool if small_pool else _lib
+    rc = lib.emu_search(_p(bwt), _p(rev), info["n_rows"], info["sigma"], _p(Carr), _p(q), q.shape[0], q.shape[1], scheme.n_searches,
                          _p(scheme.pi), _p(scheme.l), _p(scheme.u), int(edit), debug_flags,
                          _p(text[0]) if text else None, _p(text[1]) if text else None, C.byref(out), C.byref(n), C.byref(nodes))
     if rc != 0:
@@ -57,7 +63,7 @@ def search(oracle_index, queries, scheme, edit, debug_flags=0, text=None):
     try:
         a = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint32)), shape=(max(1, n.value) * 4,))[: n.value * 4].copy()
     finally:
-        _lib.emu_free(out)
+        lib.emu_free(out)
     a = a.reshape(-1, 4).astype(np.uint64)
     if a.shape[0]:
         a = a[np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))]

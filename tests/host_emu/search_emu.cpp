@@ -5,6 +5,7 @@
 #define SB200_HOST_EMU 1
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -37,6 +38,54 @@ struct HostOcc {
         }
     }
 };
+
+// text_pool_kernel as one warp of 32 lanes in lockstep: the pops of a trip all read the pool before any lane
+// expands (what the __syncwarp()s of the kernel guarantee), then the lanes expand one after the other.
+template <bool EDIT>
+void run_text_pool(const SearchParams& P, const uint32_t* steps, const uint8_t* runs, uint32_t kmax) {
+    constexpr uint32_t STACK = 96, LANES = 32;
+    std::vector<uint2> frames(kPoolCap);
+    std::vector<uint8_t> slots(kPoolCap);
+    std::vector<uint4> spill(kSpillCap);
+    std::vector<uint32_t> ctx(3 * kPoolSlots, 0), query(kPoolSlots * pool_query_stride(P.len));
+    uint32_t top = 0;
+    TextPool pool{frames.data(), slots.data(), spill.data(), &top, ctx.data(), ctx.data() + kPoolSlots, ctx.data() + 2 * kPoolSlots,
+                  query.data(), pool_query_stride(P.len)};
+    PoolLane lanes[LANES];
+    const uint32_t maxpush = 2 * (kmax + 1);
+    const unsigned long long slots_total = P.counters[CT_SEED_SLOTS];
+    const uint32_t n_slots = static_cast<uint32_t>(slots_total < P.seed_cap ? slots_total : P.seed_cap);
+    uint32_t maxtop = 0;
+    bool exhausted = false;
+    while (true) {
+        if (top < LANES && !exhausted) {
+            std::vector<uint32_t> free_slots;
+            for (uint32_t sl = 0; sl < kPoolSlots; ++sl)
+                if (pool.live[sl] == 0) free_slots.push_back(sl);
+            const uint32_t first = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_SEED], static_cast<unsigned long long>(free_slots.size())));
+            exhausted = first + free_slots.size() >= n_slots;
+            for (uint32_t r = 0; r < free_slots.size(); ++r) {
+                const uint32_t i = first + r;
+                if (i < n_slots && P.seeds[i].x != kInvalidQid) pool_load_seed(P, pool, free_slots[r], P.seeds[i], lanes[free_slots[r] % LANES]);
+            }
+        }
+        if (top == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        maxtop = std::max(maxtop, top);
+        const uint32_t n = pool_pop_width(top, maxpush, LANES, STACK);
+        uint2 f[LANES];
+        uint32_t sl[LANES];
+        for (uint32_t lane = 0; lane < n; ++lane) f[lane] = pool_get(pool, top - 1 - lane, sl[lane]);
+        top -= n;
+        for (uint32_t lane = 0; lane < n; ++lane)
+            pool_retire(pool, sl[lane], text_expand<EDIT>(P, steps, runs, pool, f[lane], sl[lane], lanes[lane], kRunRounds));
+    }
+    for (uint32_t sl = 0; sl < kPoolSlots; ++sl)
+        if (pool.live[sl] != 0) atomicExch(&P.counters[CT_OVERFLOW], 1ull);  // a seed was lost: report as failure
+    for (auto& ls : lanes) pool_finish(P, ls, maxtop);
+}
 }  // namespace
 
 extern "C" {
@@ -116,7 +165,10 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
             seed_cap = counters[CT_SEED_SLOTS];
             continue;
         }
-        if (P.sa32) {  // second kernel: in-text verification of the seeds
+        if (P.sa32 && (debug_flags & 8u)) {  // second kernel, pooled version: one warp of 32 lanes in lockstep
+            if (edit) run_text_pool<true>(P, steps.data(), runs.data(), kmax);
+            else run_text_pool<false>(P, steps.data(), runs.data(), kmax);
+        } else if (P.sa32) {  // second kernel: in-text verification of the seeds
             if (edit) text_thread<true, 96>(P, steps.data(), runs.data(), stage.data(), 1);
             else text_thread<false, 96>(P, steps.data(), runs.data(), stage.data(), 1);
         }

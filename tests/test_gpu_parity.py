@@ -339,3 +339,22 @@ def test_search_reads_compact_matches_full_call(sb, ctx, cases, monkeypatch):
         want_fwd = O.sort_rows(ix.locate(ix.search(reads, sch, True)))
         assert np.array_equal(fwd_only.astype(np.uint64), want_fwd)
     ctx.enable_text(False)
+
+
+def test_host_buffer_call_edge_and_middle_chunks(sb, ctx, cases, monkeypatch):
+    """Large batches are cut into a short first chunk, middle pieces and a short last chunk
+    (search_host_pipelined in csrc/capi.cu); the concatenated hit lists must equal the oracle's."""
+    rng, seqs, ix, path = cases[("repeats", 6)]
+    ctx.load_index(path)
+    ctx.enable_text(True)
+    m, k = 24, 1
+    q = W.sample_reads(rng, seqs, 70001, m, k, True)
+    reads = np.ascontiguousarray(q[0::2])
+    sch = sb.SearchScheme.generate("h2-k2", 0, k, m, limit_to_hamming=True)
+    ctx.set_scheme(sch, False)
+    want = O.sort_rows(ix.locate(ix.search(q, sch, False, 4), 4))
+    for chunk in ("40000", "2000000"):
+        monkeypatch.setenv("SB200_CHUNK", chunk)
+        assert np.array_equal(ctx.search_reads(reads).astype(np.uint64), want)
+        assert np.array_equal(ctx.search(q), want)
+    ctx.enable_text(False)

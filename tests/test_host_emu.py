@@ -41,8 +41,9 @@ def test_kernel_source_matches_oracle(indexes, key, edit, k):
         before = int(ix.counters[0])
         want = O.sort_rows(ix.search(q, sch, edit))
         nodes_oracle = int(ix.counters[0]) - before
-        for text in (None, tt):  # fm_kernel alone, fm_kernel + text_kernel
-            got, nodes = emu.search(ix, q, sch, edit, 0, text)
+        # fm_kernel alone, fm_kernel + text_kernel, fm_kernel + text_pool_kernel (full and tiny pool)
+        for text, flags, small in ((None, 0, False), (tt, 0, False), (tt, emu.POOL, False), (tt, emu.POOL, True)):
+            got, nodes = emu.search(ix, q, sch, edit, flags, text, small)
             assert got.shape == want.shape and np.array_equal(got, want)
             assert nodes == nodes_oracle  # every state the kernels expand is one extension of the reference recursion
 
