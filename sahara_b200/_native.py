@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _load(name):
-    path = os.path.join(_HERE, name)
+    # SB200_LIB_DIR: load a differently configured build of the same library (kernel tuning experiments)
+    path = os.path.join(os.environ.get("SB200_LIB_DIR", _HERE), name)
     if not os.path.exists(path):
         raise ImportError(
             f"{path} is missing: the CUDA extension must be built (make, or __graft_entry__.build()); "

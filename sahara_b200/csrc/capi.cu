@@ -608,10 +608,26 @@ void launch_search(sb200_ctx* c, const SearchParams& P) {
     if (P.sa32 && use_pool) {  // in-text verification, one frame pool per warp
         with_stack(c->kmax, [&](auto STACK) {
             const size_t tables = ((size_t(P.n_searches) * P.len + (size_t(P.n_searches) * P.len * kRunE + 3) / 4) * 4 + 7) & ~size_t{7};
-            const unsigned threads = std::min(kPoolThreads, blocks_per_sm("SB200_POOL_THREADS", kPoolThreads)) & ~31u;
-            const size_t psmem = tables + (threads / 32) * size_t(pool_bytes(P.len));
-            if (psmem > 200 * 1024) throw Error("search scheme table and frame pools do not fit shared memory (query too long)");
-            const unsigned per_sm = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(2048 / threads, (227 * 1024) / (psmem + 1024))));
+            // warps per block: as many resident warps per SM as shared memory (227 KB, 1 KB reserved per block) and
+            // registers (48 per thread: 42 warps) allow; measured on the headline workload: 36 warps 8.4 ms, 30 warps
+            // 9.2 ms, 24 warps 10.2 ms
+            unsigned threads = 0, per_sm = 1;
+            size_t psmem = 0;
+            for (unsigned w = kPoolThreads / 32; w >= 4; --w) {
+                const size_t bytes = tables + w * size_t(pool_bytes(P.len));
+                const unsigned blocks = static_cast<unsigned>(std::min<size_t>((227 * 1024) / (bytes + 1024), 42 / w));
+                if (blocks * w > per_sm * (threads / 32)) {
+                    threads = w * 32;
+                    per_sm = blocks;
+                    psmem = bytes;
+                }
+            }
+            if (const char* e = std::getenv("SB200_POOL_THREADS")) {
+                threads = std::min<unsigned>(kPoolThreads, std::max(32, std::atoi(e))) & ~31u;
+                psmem = tables + (threads / 32) * size_t(pool_bytes(P.len));
+                per_sm = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(42 / (threads / 32), (227 * 1024) / (psmem + 1024))));
+            }
+            if (threads == 0 || psmem > 226 * 1024) throw Error("search scheme table and frame pools do not fit shared memory (query too long)");
             unsigned tgrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_POOL_BLOCKS_PER_SM", per_sm);
             auto go = [&](auto kern) {
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem)));

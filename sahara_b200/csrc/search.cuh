@@ -623,11 +623,16 @@ __device__ __forceinline__ void text_thread(const SearchParams& P, const uint32_
 constexpr uint32_t kPoolCap = SB200_POOL_CAP;      // (tests: tiny pools exercise the spill area and the narrow pops)
 constexpr uint32_t kSpillCap = SB200_SPILL_CAP;
 #else
-constexpr uint32_t kPoolCap = 144;    // frames per warp held in shared memory
+constexpr uint32_t kPoolCap = 100;    // frames per warp held in shared memory
 constexpr uint32_t kSpillCap = 1024;  // frames per warp that spill to global memory behind them (rare)
 #endif
-constexpr uint32_t kPoolSlots = 64;   // seeds a warp works on at a time
-constexpr uint32_t kPoolThreads = 320;  // 10 warps per block: three blocks (30 warps) fit the shared memory of an SM at 150 bp
+#if defined(SB200_POOL_SLOTS)
+constexpr uint32_t kPoolSlots = SB200_POOL_SLOTS;
+constexpr uint32_t kPoolThreads = SB200_POOL_THREADS;
+#else
+constexpr uint32_t kPoolSlots = 56;   // seeds a warp works on at a time
+constexpr uint32_t kPoolThreads = 384;  // at most 12 warps per block: three blocks (36 warps) fit the shared memory of an SM at 150 bp
+#endif
 constexpr uint32_t kRunRounds = 4;    // rounds of 8 symbols per pop
 
 struct TextPool {
@@ -936,11 +941,12 @@ __global__ void __launch_bounds__(kPoolThreads) text_pool_kernel(const SearchPar
     while (true) {
         uint32_t top = *pool.top;
         if (top < 32u && !exhausted) {  // the warp starves: new seeds into every free slot
-            uint32_t my_free[kPoolSlots / 32];
-            uint32_t n_free = 0, my_rank[kPoolSlots / 32];
+            constexpr uint32_t kRounds = (kPoolSlots + 31u) / 32u;
+            uint32_t my_free[kRounds];
+            uint32_t n_free = 0, my_rank[kRounds];
 #pragma unroll
-            for (uint32_t j = 0; j < kPoolSlots / 32; ++j) {
-                const bool fr = pool.live[j * 32u + lane] == 0;
+            for (uint32_t j = 0; j < kRounds; ++j) {
+                const bool fr = j * 32u + lane < kPoolSlots && pool.live[j * 32u + lane] == 0;
                 const uint32_t m = __ballot_sync(0xffffffffu, fr);
                 my_free[j] = fr;
                 my_rank[j] = n_free + __popc(m & ((1u << lane) - 1u));
@@ -951,7 +957,7 @@ __global__ void __launch_bounds__(kPoolThreads) text_pool_kernel(const SearchPar
             first = __shfl_sync(0xffffffffu, first, 0);
             exhausted = first + n_free >= n_slots;
 #pragma unroll
-            for (uint32_t j = 0; j < kPoolSlots / 32; ++j) {
+            for (uint32_t j = 0; j < kRounds; ++j) {
                 const uint32_t i = first + my_rank[j];
                 if (my_free[j] && i < n_slots) {
                     const uint4 seed = P.seeds[i];
