@@ -631,7 +631,7 @@ void launch_search(sb200_ctx* c, const SearchParams& P) {
             unsigned tgrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_POOL_BLOCKS_PER_SM", per_sm);
             auto go = [&](auto kern) {
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem)));
-                c->d_spill.reserve(size_t(tgrid) * (threads / 32) * kSpillCap * sizeof(uint4));
+                c->d_spill.reserve(size_t(tgrid) * (threads / 32) * 2 * kSpillCap * sizeof(uint4));
                 kern<<<tgrid, threads, psmem, c->stream>>>(P, 2 * (c->kmax + 1), blocks_per_sm("SB200_RUN_ROUNDS", kRunRounds),
                                                            c->d_spill.get<uint4>());
             };

@@ -607,24 +607,30 @@ __device__ __forceinline__ void text_thread(const SearchParams& P, const uint32_
 }
 
 // ================================================================================================
-// text_pool_kernel: the same in-text verification, but the frames of a warp live in ONE pool in shared memory
-// instead of 32 private stacks.  Every trip the warp pops up to 32 frames from the top of the pool, each lane
-// expands one of them (any lane, any seed: the frame names the seed slot whose staged query it needs) and pushes
-// the children back.  Lanes therefore stay busy as long as the warp has frames at all — the private-stack version
-// (text_thread) keeps 6.6 of 32 lanes active because the lanes drift into different phases — and a heavy seed is
-// expanded by many lanes at once, which also shortens the drain at the end of the kernel.
-//   * 32 seeds are fetched at once when the pool runs empty (slot = lane).
-//   * a frame compares at most kRunRounds x 8 symbols of a match-only run per pop, then is pushed back, so one
-//     long run does not hold up the other 31 lanes.
-//   * pops narrow down when the pool is nearly full; with one frame per trip the order is depth first and the
-//     pool cannot grow by more than the private-stack bound (STACK), which is kept as head room.
+// text_pool_kernel: the same in-text verification, but the frames of a warp live in a pool in shared memory
+// instead of 32 private stacks.  Every trip the warp pops up to 32 frames, each lane expands one of them (any
+// lane, any seed: the frame names the seed slot whose staged query it needs) and pushes the children back.  Lanes
+// therefore stay busy as long as the warp has frames at all — the private-stack version (text_thread) keeps 6.6 of
+// 32 lanes active because the lanes drift into different phases — and a heavy seed is expanded by many lanes at
+// once, which also shortens the drain at the end of the kernel.
+//   * The pool is two stacks: RUN frames (next step is a match-only run: compare packed words) and STATE frames
+//     (expand search states).  A trip pops from one of them, so all lanes of a trip execute the same code.
+//   * kPoolSlots seeds are in flight per warp; a slot is refilled when the last frame of its seed is gone
+//     (live[] counts them).
+//   * A run frame compares at most kRunRounds x 8 symbols per pop, then is pushed back.
+//   * The first kPoolCapS / kPoolCapR frames of a stack live in shared memory, the rest spills to global memory
+//     (rare).  Pops of the state stack only narrow down when even the spill area is nearly full; with one frame per
+//     trip the order is depth first and the stack cannot grow by more than the private-stack bound (STACK), which
+//     is kept as head room.  Run frames never multiply (a pop pushes at most one frame).
 // ================================================================================================
 #if defined(SB200_POOL_CAP)
-constexpr uint32_t kPoolCap = SB200_POOL_CAP;      // (tests: tiny pools exercise the spill area and the narrow pops)
+constexpr uint32_t kPoolCapS = SB200_POOL_CAP;     // (tests: tiny pools exercise the spill area and the narrow pops)
+constexpr uint32_t kPoolCapR = SB200_POOL_CAP;
 constexpr uint32_t kSpillCap = SB200_SPILL_CAP;
 #else
-constexpr uint32_t kPoolCap = 100;    // frames per warp held in shared memory
-constexpr uint32_t kSpillCap = 1024;  // frames per warp that spill to global memory behind them (rare)
+constexpr uint32_t kPoolCapS = 64;    // state frames per warp held in shared memory
+constexpr uint32_t kPoolCapR = 48;    // run frames per warp held in shared memory
+constexpr uint32_t kSpillCap = 512;   // frames per warp and stack that spill to global memory behind them (rare)
 #endif
 #if defined(SB200_POOL_SLOTS)
 constexpr uint32_t kPoolSlots = SB200_POOL_SLOTS;
@@ -635,11 +641,15 @@ constexpr uint32_t kPoolThreads = 384;  // at most 12 warps per block: three blo
 #endif
 constexpr uint32_t kRunRounds = 4;    // rounds of 8 symbols per pop
 
+struct FrameStack {
+    uint2* frames;   // [cap] (a, meta): frames 0 .. cap-1 of the stack, shared memory
+    uint8_t* slots;  // [cap] seed slot of the frame
+    uint4* spill;    // [kSpillCap] (a, meta, slot, -): frames cap .. of the stack, global memory
+    uint32_t* top;   // number of frames
+    uint32_t cap;
+};
 struct TextPool {
-    uint2* frames;         // [kPoolCap] (a, meta): frames 0 .. kPoolCap-1 of the stack
-    uint8_t* slots;        // [kPoolCap] seed slot of the frame
-    uint4* spill;          // [kSpillCap] (a, meta, slot, -): frames kPoolCap .. of the stack, global memory
-    uint32_t* top;         // number of frames in the pool
+    FrameStack S, R;       // state frames, run frames
     uint32_t* live;        // [kPoolSlots] frames of the slot's seed that are still in the pool or being expanded
     uint32_t* ctx_qid;     // [kPoolSlots] query id of the seed in the slot
     uint32_t* ctx_search;  // [kPoolSlots] its search
@@ -654,135 +664,188 @@ struct PoolLane {
 __host__ __device__ inline uint32_t pool_query_stride(uint32_t len) { return packed_words(len) | 1u; }
 // bytes of shared memory one warp's pool takes
 __host__ __device__ inline uint32_t pool_bytes(uint32_t len) {
-    return kPoolCap * 8u + ((kPoolCap + 7u) & ~7u) + 8u + 3u * kPoolSlots * 4u + kPoolSlots * pool_query_stride(len) * 4u;
+    const uint32_t frames = kPoolCapS + kPoolCapR;
+    return frames * 8u + ((frames + 7u) & ~7u) + 8u + 3u * kPoolSlots * 4u + kPoolSlots * pool_query_stride(len) * 4u;
 }
-// How many frames the warp may pop when `top` are present and one frame pushes at most `maxpush` children.
-// Pops only narrow down when even the spill area is nearly full; with one frame per trip the order is depth first
-// and the stack cannot grow by more than the private-stack bound `stack`, which is kept as head room.
-__host__ __device__ inline uint32_t pool_pop_width(uint32_t top, uint32_t maxpush, uint32_t lanes, uint32_t stack) {
-    const uint32_t cap = kPoolCap + kSpillCap - stack;
+// carves one warp's pool out of `base` (8-byte aligned, pool_bytes(len) bytes); spill: 2 * kSpillCap entries
+__host__ __device__ inline TextPool pool_carve(uint8_t* base, uint4* spill, uint32_t len) {
+    TextPool pool;
+    const uint32_t frames = kPoolCapS + kPoolCapR;
+    uint2* fr = reinterpret_cast<uint2*>(base);
+    uint8_t* sl = base + frames * 8u;
+    uint32_t* words = reinterpret_cast<uint32_t*>(base + frames * 8u + ((frames + 7u) & ~7u));
+    pool.S = FrameStack{fr, sl, spill, words, kPoolCapS};
+    pool.R = FrameStack{fr + kPoolCapS, sl + kPoolCapS, spill + kSpillCap, words + 1, kPoolCapR};
+    pool.live = words + 2;
+    pool.ctx_qid = words + 2 + kPoolSlots;
+    pool.ctx_search = words + 2 + 2 * kPoolSlots;
+    pool.query = words + 2 + 3 * kPoolSlots;
+    pool.Wp = pool_query_stride(len);
+    return pool;
+}
+// How many state frames the warp may pop when `top` are present and one frame pushes at most `maxpush` children
+// (into either stack; `topR` run frames are present).
+__host__ __device__ inline uint32_t pool_pop_width(uint32_t top, uint32_t topR, uint32_t maxpush, uint32_t lanes, uint32_t stack) {
+    const uint32_t cap = kPoolCapS + kSpillCap - stack;
     uint32_t n = top < lanes ? top : lanes;
     const uint32_t room = top < cap ? (cap - top) / (maxpush - 1u) : 0u;
     if (n > room) n = room ? room : 1u;
+    const uint32_t capR = kPoolCapR + kSpillCap;
+    const uint32_t roomR = topR < capR ? (capR - topR) / maxpush : 0u;  // callers pop run frames first when this is 0
+    if (n > roomR) n = roomR;
     return n;
 }
-__device__ __forceinline__ void pool_push(const TextPool& pool, uint32_t a, uint32_t meta, uint32_t slot, PoolLane& ls) {
+__device__ __forceinline__ void stack_push(const FrameStack& st, uint32_t a, uint32_t meta, uint32_t slot, PoolLane& ls) {
 #if defined(SB200_HOST_EMU)
-    const uint32_t idx = (*pool.top)++;
+    const uint32_t idx = (*st.top)++;
 #else
-    const uint32_t idx = atomicAdd(pool.top, 1u);
+    const uint32_t idx = atomicAdd(st.top, 1u);
 #endif
-    if (idx < kPoolCap) {
-        pool.frames[idx] = make_uint2(a, meta);
-        pool.slots[idx] = static_cast<uint8_t>(slot);
-    } else if (idx - kPoolCap < kSpillCap) {
-        pool.spill[idx - kPoolCap] = make_uint4(a, meta, slot, 0);
+    if (idx < st.cap) {
+        st.frames[idx] = make_uint2(a, meta);
+        st.slots[idx] = static_cast<uint8_t>(slot);
+    } else if (idx - st.cap < kSpillCap) {
+        st.spill[idx - st.cap] = make_uint4(a, meta, slot, 0);
     } else {
         ls.overflow = true;
     }
 }
 // frame idx of the stack -> (a, meta), slot
-__device__ __forceinline__ uint2 pool_get(const TextPool& pool, uint32_t idx, uint32_t& slot) {
-    if (idx < kPoolCap) {
-        slot = pool.slots[idx];
-        return pool.frames[idx];
+__device__ __forceinline__ uint2 stack_get(const FrameStack& st, uint32_t idx, uint32_t& slot) {
+    if (idx < st.cap) {
+        slot = st.slots[idx];
+        return st.frames[idx];
     }
-    const uint4 v = pool.spill[idx - kPoolCap];
+    const uint4 v = st.spill[idx - st.cap];
     slot = v.z;
     return make_uint2(v.x, v.y);
 }
+// a frame goes to the run stack when its next step starts a match-only run
+__device__ __forceinline__ void pool_push(const TextPool& pool, const uint8_t* runs, uint32_t a, uint32_t meta, uint32_t slot, PoolLane& ls) {
+    const uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
+    const bool run = (meta & META_PAIR) == 0 && runs[step * kRunE + e] != 0;
+    stack_push(run ? pool.R : pool.S, a, meta, slot, ls);
+}
 
-// expands one frame exactly like one pop of text_thread; returns the number of frames it pushed
-template <bool EDIT>
-__device__ __forceinline__ uint32_t text_expand(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, const TextPool& pool,
-                                            const uint2 f, const uint32_t slot, PoolLane& ls, const uint32_t run_rounds) {
-    const uint32_t qlen = P.len;
-    const uint32_t W = packed_words(qlen);
-    const uint32_t* q = pool.query + slot * pool.Wp;
-    const uint32_t qid = pool.ctx_qid[slot];
-    const uint32_t sid = pool.ctx_search[slot];
-    const uint32_t* tbl = s_steps + sid * qlen;
-    const uint8_t* runs = s_runs + sid * qlen * kRunE;
-    auto qsym = [&](uint32_t pos) -> uint32_t { return (q[pos >> 3] >> ((pos & 7u) * 4u)) & 0xfu; };
-    auto query8 = [&](uint32_t pos) -> uint32_t {
+// per-frame view of the seed context
+struct SeedCtx {
+    const uint32_t* q;
+    const uint32_t* tbl;
+    const uint8_t* runs;
+    uint32_t qid, W;
+    __device__ __forceinline__ uint32_t qsym(uint32_t pos) const { return (q[pos >> 3] >> ((pos & 7u) * 4u)) & 0xfu; }
+    // the 8 query symbols that start at position pos; positions behind the query read as 0xF
+    __device__ __forceinline__ uint32_t query8(uint32_t pos) const {
         const uint32_t w = pos >> 3;
         const uint32_t lo = q[w];
         const uint32_t hi = w + 1 < W ? q[w + 1] : 0xffffffffu;
         return funnel_r(lo, hi, (pos & 7u) * 4u);
-    };
-    auto emit = [&](uint32_t a, uint32_t e) {
-        ls.outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], make_uint4(qid, P.isa32[a], 1, e));
-        ++ls.emitted;
-    };
+    }
+};
+__device__ __forceinline__ SeedCtx seed_ctx(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, const TextPool& pool,
+                                            uint32_t slot) {
+    const uint32_t sid = pool.ctx_search[slot];
+    return SeedCtx{pool.query + slot * pool.Wp, s_steps + sid * P.len, s_runs + sid * P.len * kRunE, pool.ctx_qid[slot], packed_words(P.len)};
+}
+__device__ __forceinline__ void pool_emit(const SearchParams& P, PoolLane& ls, uint32_t qid, uint32_t a, uint32_t e) {
+    ls.outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], make_uint4(qid, P.isa32[a], 1, e));
+    ++ls.emitted;
+}
+
+// RUN frame: the match-only run(s) that start at its step, exactly like the run loop of text_thread; returns the
+// number of frames pushed (0 or 1)
+template <bool EDIT>
+__device__ __forceinline__ uint32_t text_run(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, const TextPool& pool,
+                                             const uint2 f, const uint32_t slot, PoolLane& ls, const uint32_t run_rounds) {
+    const SeedCtx cx = seed_ctx(P, s_steps, s_runs, pool, slot);
+    const uint32_t qlen = P.len;
+    uint32_t a = f.x;
+    const uint32_t meta = f.y;
+    uint32_t step = meta & 0x3ffu;
+    const uint32_t e = (meta >> 10) & 0xfu;
+    uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
+    uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
+    uint32_t nodes = 0;
+    uint32_t R = cx.runs[step * kRunE + e];
+    uint32_t budget = run_rounds;
+    while (R != 0) {
+        const uint32_t st = cx.tbl[step];
+        const bool right = (st >> 24) & 1u;
+        const uint32_t p0 = st & 0xffffu;
+        uint32_t r = 0;
+        bool differs = false;
+        // one code path for both directions: a window of n symbols that starts at tpos / qpos
+        while (r < R && budget != 0) {
+            uint32_t n = R - r < 8u ? R - r : 8u;
+            if (!right) {
+                if (a < r + 1) { differs = true; break; }  // the delimiter before position 0
+                if (n > a - r) n = a - r;
+            }
+            --budget;
+            const uint32_t tpos = right ? a + tlen + r : a - r - n;
+            const uint32_t qpos = right ? p0 + r : p0 + 1 - r - n;
+            const uint32_t x = (text8(P.text4, tpos) ^ cx.query8(qpos)) & nib_mask(n);
+            if (x != 0) {
+                r += right ? (ctz32(x) >> 2) : n - 1 - ((31u - clz32(x)) >> 2);
+                differs = true;
+                break;
+            }
+            r += n;
+        }
+        if (differs) {  // the state at step + r has no child
+            ls.nodes += nodes + r + 1;
+            return 0;
+        }
+        nodes += r;
+        step += r;
+        tlen += r;
+        if (r != 0) {
+            if (right) Rinfo = INFO_M;
+            else { Linfo = INFO_M; a -= r; }
+        }
+        if (r < R) {  // out of rounds: the rest of the run waits for the next pop
+            ls.nodes += nodes;
+            stack_push(pool.R, a, pack_meta(step, e, Linfo, Rinfo) | (tlen << META_TLEN_SHIFT), slot, ls);
+            return 1;
+        }
+        if (step == qlen) {  // the last step matched
+            const uint32_t O = right ? Linfo : Rinfo;
+            if (!EDIT || (O & 1u) == 0) pool_emit(P, ls, cx.qid, a, e);
+            ls.nodes += nodes;
+            return 0;
+        }
+        if (((cx.tbl[step] >> 16) & 0xfu) > e + 1) { ls.nodes += nodes; return 0; }  // dead at the next step
+        R = cx.runs[step * kRunE + e];
+    }
+    ls.nodes += nodes;
+    stack_push(pool.S, a, pack_meta(step, e, Linfo, Rinfo) | (tlen << META_TLEN_SHIFT), slot, ls);  // states follow
+    return 1;
+}
+
+// STATE frame: the states on its cursor (pair halves, insertion chain), exactly like text_thread; returns the
+// number of frames pushed
+template <bool EDIT>
+__device__ __forceinline__ uint32_t text_states(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, const TextPool& pool,
+                                                const uint2 f, const uint32_t slot, PoolLane& ls) {
+    const SeedCtx cx = seed_ctx(P, s_steps, s_runs, pool, slot);
+    const uint32_t qlen = P.len;
+    const uint32_t* tbl = cx.tbl;
     uint32_t pushed = 0;
     auto push = [&](uint32_t a, uint32_t m) {
-        pool_push(pool, a, m, slot, ls);
+        pool_push(pool, cx.runs, a, m, slot, ls);
         ++pushed;
     };
-
-    uint32_t a = f.x;
+    const uint32_t a = f.x;
     const uint32_t meta = f.y;
     uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
     uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
     const bool pair = (meta & META_PAIR) != 0;
-    uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
+    const uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
     uint32_t nodes = 0;
 
-    if (!pair) {
-        uint32_t R = runs[step * kRunE + e];
-        uint32_t budget = run_rounds;
-        while (R != 0) {
-            const uint32_t st = tbl[step];
-            const bool right = (st >> 24) & 1u;
-            const uint32_t p0 = st & 0xffffu;
-            uint32_t r = 0;
-            bool differs = false;
-            // one code path for both directions: a window of n symbols that starts at tpos / qpos
-            while (r < R && budget != 0) {
-                uint32_t n = R - r < 8u ? R - r : 8u;
-                if (!right) {
-                    if (a < r + 1) { differs = true; break; }  // the delimiter before position 0
-                    if (n > a - r) n = a - r;
-                }
-                --budget;
-                const uint32_t tpos = right ? a + tlen + r : a - r - n;
-                const uint32_t qpos = right ? p0 + r : p0 + 1 - r - n;
-                const uint32_t x = (text8(P.text4, tpos) ^ query8(qpos)) & nib_mask(n);
-                if (x != 0) {
-                    r += right ? (ctz32(x) >> 2) : n - 1 - ((31u - clz32(x)) >> 2);
-                    differs = true;
-                    break;
-                }
-                r += n;
-            }
-            if (differs) {  // the state at step + r has no child
-                ls.nodes += nodes + r + 1;
-                return pushed;
-            }
-            nodes += r;
-            step += r;
-            tlen += r;
-            if (r != 0) {
-                if (right) Rinfo = INFO_M;
-                else { Linfo = INFO_M; a -= r; }
-            }
-            if (r < R) {  // out of rounds: the rest of the run waits for the next pop
-                ls.nodes += nodes;
-                push(a, pack_meta(step, e, Linfo, Rinfo) | (tlen << META_TLEN_SHIFT));
-                return pushed;
-            }
-            if (step == qlen) {  // the last step matched
-                const uint32_t O = right ? Linfo : Rinfo;
-                if (!EDIT || (O & 1u) == 0) emit(a, e);
-                ls.nodes += nodes;
-                return pushed;
-            }
-            if (((tbl[step] >> 16) & 0xfu) > e + 1) { ls.nodes += nodes; return pushed; }  // dead at the next step
-            R = runs[step * kRunE + e];
-        }
-    }
     const uint32_t b = a + tlen;
-    const bool rightFrame = (tbl[step] >> 24) & 1u;
+    const bool rightFrame = (tbl[step] >> 24) & 1u;  // the end the frame's own error (D / S) sits on
+    // the text symbols left and right of the occurrence (the delimiter before position 0)
     uint32_t tL = 0;
     if (a != 0) tL = (P.text4[(a - 1) >> 3] >> (((a - 1) & 7u) * 4u)) & 0xfu;
     const uint32_t tR = (P.text4[b >> 3] >> ((b & 7u) * 4u)) & 0xfu;
@@ -793,7 +856,7 @@ __device__ __forceinline__ uint32_t text_expand(const SearchParams& P, const uin
         const uint32_t st = tbl[step];
         const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
         const bool right = (st >> 24) & 1u;
-        const uint32_t c = qsym(st & 0xffffu);
+        const uint32_t c = cx.qsym(st & 0xffffu);
         const bool last = step + 1 == qlen;
         const uint32_t stn = last ? 0u : tbl[step + 1];
         const uint32_t lnext = (stn >> 16) & 0xfu;
@@ -803,8 +866,8 @@ __device__ __forceinline__ uint32_t text_expand(const SearchParams& P, const uin
         const uint32_t T = right ? Rinfo : Linfo;
         const uint32_t O = right ? Linfo : Rinfo;
         const bool otherEndOK = !EDIT || (O & 1u) == 0;
-        const uint32_t t = right ? tR : tL;
-        const uint32_t na = right ? a : a - 1;
+        const uint32_t t = right ? tR : tL;    // the only symbol whose child cursor is not empty
+        const uint32_t na = right ? a : a - 1;  // child occurrence T[na, na + tlen + 1)
         const uint32_t keepL = right ? Linfo : 0u, keepR = right ? 0u : Rinfo;
         const uint32_t sideShift = right ? 16u : 14u;
         const uint32_t metaBase = (keepL << 14) | (keepR << 16) | ((tlen + 1) << META_TLEN_SHIFT);
@@ -812,7 +875,7 @@ __device__ __forceinline__ uint32_t text_expand(const SearchParams& P, const uin
             if (t == c) {
                 if (matchOK) {
                     if (last) {
-                        if (otherEndOK) emit(na, e);
+                        if (otherEndOK) pool_emit(P, ls, cx.qid, na, e);
                     } else if (lnext <= e + 1) {
                         push(na, metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift));
                     }
@@ -822,25 +885,27 @@ __device__ __forceinline__ uint32_t text_expand(const SearchParams& P, const uin
                 const bool subAlive = !last && lnext <= e + 2;
                 const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift);
                 const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift);
+                // a pair only when both halves extend the same end (as in fm_kernel)
                 if (delOK && subAlive && sameDirNext) push(na, mD | META_PAIR);
                 else {
                     if (delOK) push(na, mD);
                     if (subAlive) push(na, mS);
                 }
-                if (!EDIT && last) emit(na, e + 1);
+                if (!EDIT && last) pool_emit(P, ls, cx.qid, na, e + 1);
             }
         }
+        // next state on the same cursor
         if (pair) {
             if (second) break;
             second = true;
-            step += 1;
+            step += 1;  // the substitution half: (step + 1, e), S at the end both halves extend
             if (rightFrame) Rinfo = INFO_S; else Linfo = INFO_S;
             continue;
         }
         const bool insOK = EDIT && mmOK && (T == INFO_M || T == INFO_I);
         if (!insOK) break;
         if (last) {
-            if (otherEndOK) emit(a, e + 1);
+            if (otherEndOK) pool_emit(P, ls, cx.qid, a, e + 1);
             break;
         }
         if (lnext > e + 2) break;
@@ -853,7 +918,8 @@ __device__ __forceinline__ uint32_t text_expand(const SearchParams& P, const uin
 }
 
 // one seed into slot `slot`: stage its query, remember its context, push its root frame
-__device__ __forceinline__ void pool_load_seed(const SearchParams& P, const TextPool& pool, uint32_t slot, const uint4 seed, PoolLane& ls) {
+__device__ __forceinline__ void pool_load_seed(const SearchParams& P, const uint8_t* s_runs, const TextPool& pool, uint32_t slot,
+                                               const uint4 seed, PoolLane& ls) {
     const uint32_t W = packed_words(P.len);
     const uint32_t* src = P.packed + static_cast<uint64_t>(seed.x) * W;
     uint32_t* dst = pool.query + slot * pool.Wp;
@@ -861,7 +927,7 @@ __device__ __forceinline__ void pool_load_seed(const SearchParams& P, const Text
     pool.ctx_qid[slot] = seed.x;
     pool.ctx_search[slot] = seed.z;
     pool.live[slot] = 1;
-    pool_push(pool, P.sa32[seed.y], seed.w, slot, ls);
+    pool_push(pool, s_runs + seed.z * P.len * kRunE, P.sa32[seed.y], seed.w, slot, ls);
 }
 
 // the expanded frame is gone, `pushed` frames of the same seed were added
@@ -872,6 +938,15 @@ __device__ __forceinline__ void pool_retire(const TextPool& pool, uint32_t slot,
 #else
     atomicAdd(&pool.live[slot], pushed - 1u);
 #endif
+}
+
+// which stack the next trip pops: run frames first when there is a full trip of them or the state stack could not
+// push into the run stack; else the fuller stack
+__host__ __device__ inline bool pool_pick_run(uint32_t topS, uint32_t topR, uint32_t maxpush) {
+    if (topR == 0) return false;
+    if (topS == 0 || topR >= 32u) return true;
+    if (topR + 32u * maxpush > kPoolCapR + kSpillCap) return true;
+    return topR > topS;
 }
 
 __device__ __forceinline__ void pool_finish(const SearchParams& P, PoolLane& ls, uint32_t maxtop) {
@@ -907,7 +982,7 @@ __global__ void __launch_bounds__(256) text_kernel(const SearchParams P) {
 }
 
 template <bool EDIT, int STACK>
-__global__ void __launch_bounds__(kPoolThreads) text_pool_kernel(const SearchParams P, const uint32_t maxpush, const uint32_t run_rounds, uint4* spill) {
+__global__ void __launch_bounds__(kPoolThreads, 3) text_pool_kernel(const SearchParams P, const uint32_t maxpush, const uint32_t run_rounds, uint4* spill) {
     extern __shared__ uint32_t s_steps[];
     const uint32_t n_steps = P.n_searches * P.len;
     const uint32_t n_run_words = (n_steps * kRunE + 3) / 4;
@@ -917,18 +992,8 @@ __global__ void __launch_bounds__(kPoolThreads) text_pool_kernel(const SearchPar
     // this warp's pool (8-byte aligned region behind the tables)
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint8_t* base = reinterpret_cast<uint8_t*>(s_steps) + (((n_steps + n_run_words) * 4u + 7u) & ~7u) + warp * pool_bytes(P.len);
-    TextPool pool;
-    pool.frames = reinterpret_cast<uint2*>(base);
-    pool.slots = base + kPoolCap * 8u;
-    pool.spill = spill + (static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * kSpillCap;
-    uint32_t* words = reinterpret_cast<uint32_t*>(base + kPoolCap * 8u + ((kPoolCap + 7u) & ~7u));
-    pool.top = words;
-    pool.live = words + 2;
-    pool.ctx_qid = words + 2 + kPoolSlots;
-    pool.ctx_search = words + 2 + 2 * kPoolSlots;
-    pool.query = words + 2 + 3 * kPoolSlots;
-    pool.Wp = pool_query_stride(P.len);
-    if (lane == 0) *pool.top = 0;
+    const TextPool pool = pool_carve(base, spill + (static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * 2u * kSpillCap, P.len);
+    if (lane == 0) { *pool.S.top = 0; *pool.R.top = 0; }
     for (uint32_t i = lane; i < kPoolSlots; i += 32u) pool.live[i] = 0;
     __syncthreads();
 
@@ -939,8 +1004,8 @@ __global__ void __launch_bounds__(kPoolThreads) text_pool_kernel(const SearchPar
     uint32_t maxtop = 0;
     bool exhausted = false;  // (warp uniform) the seed list has been handed out
     while (true) {
-        uint32_t top = *pool.top;
-        if (top < 32u && !exhausted) {  // the warp starves: new seeds into every free slot
+        uint32_t topS = *pool.S.top, topR = *pool.R.top;
+        if (topS < 32u && topR < 32u && !exhausted) {  // the warp starves: new seeds into every free slot
             constexpr uint32_t kRounds = (kPoolSlots + 31u) / 32u;
             uint32_t my_free[kRounds];
             uint32_t n_free = 0, my_rank[kRounds];
@@ -961,25 +1026,35 @@ __global__ void __launch_bounds__(kPoolThreads) text_pool_kernel(const SearchPar
                 const uint32_t i = first + my_rank[j];
                 if (my_free[j] && i < n_slots) {
                     const uint4 seed = P.seeds[i];
-                    if (seed.x != kInvalidQid) pool_load_seed(P, pool, j * 32u + lane, seed, ls);
+                    if (seed.x != kInvalidQid) pool_load_seed(P, runs8, pool, j * 32u + lane, seed, ls);
                 }
             }
             __syncwarp();
-            top = *pool.top;
+            topS = *pool.S.top;
+            topR = *pool.R.top;
         }
-        if (top == 0) {
+        if (topS + topR == 0) {
             if (exhausted) break;
             continue;  // only padding entries were fetched
         }
-        maxtop = top > maxtop ? top : maxtop;
-        const uint32_t n = pool_pop_width(top, maxpush, 32u, STACK);
+        maxtop = topS + topR > maxtop ? topS + topR : maxtop;
         uint2 f = make_uint2(0, 0);
         uint32_t slot = 0;
-        if (lane < n) f = pool_get(pool, top - 1 - lane, slot);
-        __syncwarp();
-        if (lane == 0) *pool.top = top - n;
-        __syncwarp();
-        if (lane < n) pool_retire(pool, slot, text_expand<EDIT>(P, s_steps, runs8, pool, f, slot, ls, run_rounds));
+        if (pool_pick_run(topS, topR, maxpush)) {
+            const uint32_t n = topR < 32u ? topR : 32u;
+            if (lane < n) f = stack_get(pool.R, topR - 1 - lane, slot);
+            __syncwarp();
+            if (lane == 0) *pool.R.top = topR - n;
+            __syncwarp();
+            if (lane < n) pool_retire(pool, slot, text_run<EDIT>(P, s_steps, runs8, pool, f, slot, ls, run_rounds));
+        } else {
+            const uint32_t n = pool_pop_width(topS, topR, maxpush, 32u, STACK);
+            if (lane < n) f = stack_get(pool.S, topS - 1 - lane, slot);
+            __syncwarp();
+            if (lane == 0) *pool.S.top = topS - n;
+            __syncwarp();
+            if (lane < n) pool_retire(pool, slot, text_states<EDIT>(P, s_steps, runs8, pool, f, slot, ls));
+        }
         __syncwarp();
     }
     pool_finish(P, ls, maxtop);

@@ -44,21 +44,18 @@ struct HostOcc {
 template <bool EDIT>
 void run_text_pool(const SearchParams& P, const uint32_t* steps, const uint8_t* runs, uint32_t kmax) {
     constexpr uint32_t STACK = 96, LANES = 32;
-    std::vector<uint2> frames(kPoolCap);
-    std::vector<uint8_t> slots(kPoolCap);
-    std::vector<uint4> spill(kSpillCap);
-    std::vector<uint32_t> ctx(3 * kPoolSlots, 0), query(kPoolSlots * pool_query_stride(P.len));
-    uint32_t top = 0;
-    TextPool pool{frames.data(), slots.data(), spill.data(), &top, ctx.data(), ctx.data() + kPoolSlots, ctx.data() + 2 * kPoolSlots,
-                  query.data(), pool_query_stride(P.len)};
+    std::vector<uint64_t> smem(pool_bytes(P.len) / 8 + 1, 0);
+    std::vector<uint4> spill(2 * kSpillCap);
+    const TextPool pool = pool_carve(reinterpret_cast<uint8_t*>(smem.data()), spill.data(), P.len);
     PoolLane lanes[LANES];
     const uint32_t maxpush = 2 * (kmax + 1);
     const unsigned long long slots_total = P.counters[CT_SEED_SLOTS];
     const uint32_t n_slots = static_cast<uint32_t>(slots_total < P.seed_cap ? slots_total : P.seed_cap);
     uint32_t maxtop = 0;
     bool exhausted = false;
+    uint32_t &topS = *pool.S.top, &topR = *pool.R.top;
     while (true) {
-        if (top < LANES && !exhausted) {
+        if (topS < LANES && topR < LANES && !exhausted) {
             std::vector<uint32_t> free_slots;
             for (uint32_t sl = 0; sl < kPoolSlots; ++sl)
                 if (pool.live[sl] == 0) free_slots.push_back(sl);
@@ -66,24 +63,36 @@ void run_text_pool(const SearchParams& P, const uint32_t* steps, const uint8_t* 
             exhausted = first + free_slots.size() >= n_slots;
             for (uint32_t r = 0; r < free_slots.size(); ++r) {
                 const uint32_t i = first + r;
-                if (i < n_slots && P.seeds[i].x != kInvalidQid) pool_load_seed(P, pool, free_slots[r], P.seeds[i], lanes[free_slots[r] % LANES]);
+                if (i < n_slots && P.seeds[i].x != kInvalidQid)
+                    pool_load_seed(P, runs, pool, free_slots[r], P.seeds[i], lanes[free_slots[r] % LANES]);
             }
         }
-        if (top == 0) {
+        if (topS + topR == 0) {
             if (exhausted) break;
             continue;
         }
-        maxtop = std::max(maxtop, top);
-        const uint32_t n = pool_pop_width(top, maxpush, LANES, STACK);
+        maxtop = std::max(maxtop, topS + topR);
         uint2 f[LANES];
         uint32_t sl[LANES];
-        for (uint32_t lane = 0; lane < n; ++lane) f[lane] = pool_get(pool, top - 1 - lane, sl[lane]);
-        top -= n;
-        for (uint32_t lane = 0; lane < n; ++lane)
-            pool_retire(pool, sl[lane], text_expand<EDIT>(P, steps, runs, pool, f[lane], sl[lane], lanes[lane], kRunRounds));
+        if (pool_pick_run(topS, topR, maxpush)) {
+            const uint32_t n = std::min(topR, LANES);
+            for (uint32_t lane = 0; lane < n; ++lane) f[lane] = stack_get(pool.R, topR - 1 - lane, sl[lane]);
+            topR -= n;
+            for (uint32_t lane = 0; lane < n; ++lane)
+                pool_retire(pool, sl[lane], text_run<EDIT>(P, steps, runs, pool, f[lane], sl[lane], lanes[lane], kRunRounds));
+        } else {
+            const uint32_t n = pool_pop_width(topS, topR, maxpush, LANES, STACK);
+            if (n == 0) {  // cannot happen: pool_pick_run pops run frames first when the run stack is that full
+                atomicExch(&P.counters[CT_OVERFLOW], 1ull);
+                break;
+            }
+            for (uint32_t lane = 0; lane < n; ++lane) f[lane] = stack_get(pool.S, topS - 1 - lane, sl[lane]);
+            topS -= n;
+            for (uint32_t lane = 0; lane < n; ++lane) pool_retire(pool, sl[lane], text_states<EDIT>(P, steps, runs, pool, f[lane], sl[lane], lanes[lane]));
+        }
     }
-    for (uint32_t sl = 0; sl < kPoolSlots; ++sl)
-        if (pool.live[sl] != 0) atomicExch(&P.counters[CT_OVERFLOW], 1ull);  // a seed was lost: report as failure
+    for (uint32_t sl2 = 0; sl2 < kPoolSlots; ++sl2)
+        if (pool.live[sl2] != 0) atomicExch(&P.counters[CT_OVERFLOW], 1ull);  // a seed was lost: report as failure
     for (auto& ls : lanes) pool_finish(P, ls, maxtop);
 }
 }  // namespace
