@@ -167,6 +167,8 @@ struct sb200_ctx {
     uint32_t n_searches{}, qlen{}, kmax{};
     bool edit{}, have_scheme{};
     // work buffers
+    uint32_t fused_shift{0};  // hit keys of the last locate carry the query id above this bit (0: separate array)
+    int sorted_keys{0};       // d_keys[] buffer that holds the sorted hits
     DevBuf d_seeds, d_spill, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
     uint64_t cursor_cap{}, seed_cap{};
     uint64_t last_cursors{}, last_real_cursors{}, last_hits{};
@@ -743,7 +745,7 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
 }
 
 // kernel 3 over the n_cursors cursors in c->d_cursors (room for one extra slot), then sort by
-// (qid, seq/pos, e).  Sorted hits end in d_keys[0] / d_qids[0].
+// (qid, seq/pos, e).  Sorted hits end in d_keys[sorted_keys] (fused keys) or d_keys[0] / d_qids[0].
 void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
     auto& ix = c->idx;
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -764,9 +766,19 @@ void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
         CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
     if (total_rows >= (1ull << 32)) throw Error("more than 2^32 hits in one call; split the batch");
+    // one 64-bit key (query id above value and errors) when it fits: a single keys-only radix sort
+    const int key_bits = static_cast<int>(ix.key_bits) + 4;
+    const int qid_bits = std::max(1, static_cast<int>(bits_of(n_queries_hint ? n_queries_hint - 1 : 0xffffffffull)));
+    // (measured at equal pass counts, 16 M hits: two pair sorts 1.19 ms, one 64-bit keys-only sort 1.38 ms — so only
+    // when it saves a radix pass)
+    const bool fewer_passes = (key_bits + qid_bits + 7) / 8 < (key_bits + 7) / 8 + (qid_bits + 7) / 8;
+    const char* force = std::getenv("SB200_FUSED_SORT");
+    const bool fused = key_bits + qid_bits <= 64 && (force ? std::atoi(force) != 0 : fewer_passes);
+    c->fused_shift = fused ? static_cast<uint32_t>(key_bits) : 0u;
+    c->sorted_keys = 0;
     for (int i = 0; i < 2; ++i) {
         c->d_keys[i].reserve(std::max<uint64_t>(1, total_rows) * 8);
-        c->d_qids[i].reserve(std::max<uint64_t>(1, total_rows) * 4);
+        if (!fused) c->d_qids[i].reserve(std::max<uint64_t>(1, total_rows) * 4);
     }
     if (total_rows > 0) {
         LocateParams L{};
@@ -779,7 +791,8 @@ void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
         L.n_cursors = static_cast<uint32_t>(n_cursors);
         L.n_rows_total = total_rows;
         L.out_key = c->d_keys[0].get<uint64_t>();
-        L.out_qid = c->d_qids[0].get<uint32_t>();
+        L.out_qid = fused ? nullptr : c->d_qids[0].get<uint32_t>();
+        L.fused_shift = c->fused_shift;
         L.counters = c->d_counters.get<unsigned long long>();
         with_sigma(ix.sigma, [&](auto S) {
             locate_kernel<S()><<<grid_for(total_rows), 256, 0, c->stream>>>(L);
@@ -788,9 +801,16 @@ void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
         launch_check(c);
     }
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-    if (total_rows > 1) {
-        int key_bits = static_cast<int>(ix.key_bits) + 4;
-        int qid_bits = std::max(1, static_cast<int>(bits_of(n_queries_hint ? n_queries_hint - 1 : 0xffffffffull)));
+    if (total_rows > 1 && fused) {
+        size_t t1 = 0;
+        CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, t1, c->d_keys[0].get<uint64_t>(), c->d_keys[1].get<uint64_t>(), total_rows, 0,
+                                                key_bits + qid_bits, c->stream));
+        c->d_tmp.reserve(t1);
+        CUDA_TRY(cub::DeviceRadixSort::SortKeys(c->d_tmp.p, t1, c->d_keys[0].get<uint64_t>(), c->d_keys[1].get<uint64_t>(), total_rows, 0,
+                                                key_bits + qid_bits, c->stream));
+        c->sorted_keys = 1;
+        c->ct.kernel_launches += (key_bits + qid_bits + 7) / 8 + 2;
+    } else if (total_rows > 1) {
         size_t t1 = 0, t2 = 0;
         CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t1, c->d_keys[0].get<uint64_t>(), c->d_keys[1].get<uint64_t>(),
                                                  c->d_qids[0].get<uint32_t>(), c->d_qids[1].get<uint32_t>(), total_rows, 0, key_bits,
@@ -829,8 +849,8 @@ void fetch_hits(sb200_ctx* c, sb200_hit** hits, uint64_t* n_hits) {
     if (n) {
         // expand to the reference tuple on the device, then one pinned copy
         c->d_scratch.reserve(n * sizeof(sb200_hit));
-        expand_hits_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->d_keys[0].get<uint64_t>(), c->d_qids[0].get<uint32_t>(), n,
-                                                               static_cast<uint32_t>(ix.bits_for_position), 0,
+        expand_hits_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->d_keys[c->sorted_keys].get<uint64_t>(), c->d_qids[0].get<uint32_t>(), n,
+                                                               static_cast<uint32_t>(ix.bits_for_position), 0, c->fused_shift,
                                                                c->d_scratch.get<uint64_t>());
         launch_check(c);
         CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
@@ -949,12 +969,15 @@ void search_host_pipelined(sb200_ctx* c, const uint8_t* src, uint64_t n_items, u
                 if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_out[b], 0));  // hits of chunk k-2 have left this buffer
                 c->d_hitchunk[b].reserve(nh * hit_bytes);
                 if (compact)
-                    compact_hits_kernel<<<grid_for(nh), 256, 0, c->stream>>>(c->d_keys[0].get<uint64_t>(), c->d_qids[0].get<uint32_t>(), nh,
+                    compact_hits_kernel<<<grid_for(nh), 256, 0, c->stream>>>(c->d_keys[c->sorted_keys].get<uint64_t>(),
+                                                                             c->d_qids[0].get<uint32_t>(), nh,
                                                                              static_cast<uint32_t>(ix.bits_for_position),
-                                                                             static_cast<uint32_t>(q0), c->d_hitchunk[b].get<uint4>());
+                                                                             static_cast<uint32_t>(q0), c->fused_shift,
+                                                                             c->d_hitchunk[b].get<uint4>());
                 else
-                    expand_hits_kernel<<<grid_for(nh), 256, 0, c->stream>>>(c->d_keys[0].get<uint64_t>(), c->d_qids[0].get<uint32_t>(), nh,
-                                                                            static_cast<uint32_t>(ix.bits_for_position), q0,
+                    expand_hits_kernel<<<grid_for(nh), 256, 0, c->stream>>>(c->d_keys[c->sorted_keys].get<uint64_t>(),
+                                                                            c->d_qids[0].get<uint32_t>(), nh,
+                                                                            static_cast<uint32_t>(ix.bits_for_position), q0, c->fused_shift,
                                                                             c->d_hitchunk[b].get<uint64_t>());
                 launch_check(c);
                 CUDA_TRY(cudaEventRecord(c->ev_expanded[b], c->stream));

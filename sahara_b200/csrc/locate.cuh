@@ -77,8 +77,9 @@ struct LocateParams {
     const uint64_t* offsets;  // exclusive prefix sum of len, n_cursors + 1 entries
     uint32_t n_cursors;
     uint64_t n_rows_total;
-    uint64_t* out_key;        // ((seqId << bits | pos) << 4) | e
-    uint32_t* out_qid;
+    uint64_t* out_key;        // ((seqId << bits | pos) << 4) | e; with fused_shift != 0 the query id sits above it
+    uint32_t* out_qid;        // unused when fused
+    uint32_t fused_shift;     // 0, or the width of the (value, e) part: key = qid << fused_shift | (value << 4 | e)
     unsigned long long* counters;  // [4] LF steps
 };
 
@@ -97,8 +98,12 @@ __global__ void __launch_bounds__(256) locate_kernel(const LocateParams P) {
         uint4 cur = P.cursors[lo];
         uint32_t row = cur.y + static_cast<uint32_t>(j - P.offsets[lo]);
         uint64_t v = locate_row<SIGMA>(P.index, row, steps);
-        P.out_key[j] = (v << 4) | cur.w;
-        P.out_qid[j] = cur.x;
+        if (P.fused_shift) {
+            P.out_key[j] = (static_cast<uint64_t>(cur.x) << P.fused_shift) | (v << 4) | cur.w;
+        } else {
+            P.out_key[j] = (v << 4) | cur.w;
+            P.out_qid[j] = cur.x;
+        }
     }
     // warp-aggregated step counter
     for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
@@ -113,28 +118,44 @@ struct BitFlag {
     __host__ __device__ bool operator()(uint64_t i) const { return (words[i >> 6] >> (i & 63)) & 1u; }
 };
 
-// sorted (key, qid) pairs -> the reference's result tuple (queryId, seqId, pos, errors), 4 x u64
+// sorted hit i -> (query id, (value << 4) | e); fused keys carry the query id above bit fused_shift
+__device__ __forceinline__ void hit_key(const uint64_t* keys, const uint32_t* qids, uint64_t i, uint32_t fused_shift, uint32_t& qid, uint64_t& k) {
+    k = keys[i];
+    if (fused_shift) {
+        qid = static_cast<uint32_t>(k >> fused_shift);
+        k &= (uint64_t{1} << fused_shift) - 1;
+    } else {
+        qid = qids[i];
+    }
+}
+
+// sorted hits -> the reference's result tuple (queryId, seqId, pos, errors), 4 x u64
 __global__ void expand_hits_kernel(const uint64_t* keys, const uint32_t* qids, uint64_t n, uint32_t bits, uint64_t first_query,
-                                   uint64_t* out) {
+                                   uint32_t fused_shift, uint64_t* out) {
     uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (i >= n) return;
-    uint64_t k = keys[i];
+    uint32_t qid;
+    uint64_t k;
+    hit_key(keys, qids, i, fused_shift, qid, k);
     uint64_t v = k >> 4;
     ulonglong4 h;
-    h.x = first_query + qids[i];
+    h.x = first_query + qid;
     h.y = v >> bits;
     h.z = v & ((uint64_t{1} << bits) - 1);
     h.w = k & 15u;
     reinterpret_cast<ulonglong4*>(out)[i] = h;
 }
 
-// sorted (key, qid) pairs -> compact hits (query_id, seq_id, pos, errors) as 4 x u32
-__global__ void compact_hits_kernel(const uint64_t* keys, const uint32_t* qids, uint64_t n, uint32_t bits, uint32_t first_query, uint4* out) {
+// sorted hits -> compact hits (query_id, seq_id, pos, errors) as 4 x u32
+__global__ void compact_hits_kernel(const uint64_t* keys, const uint32_t* qids, uint64_t n, uint32_t bits, uint32_t first_query,
+                                    uint32_t fused_shift, uint4* out) {
     uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (i >= n) return;
-    uint64_t k = keys[i];
+    uint32_t qid;
+    uint64_t k;
+    hit_key(keys, qids, i, fused_shift, qid, k);
     uint64_t v = k >> 4;
-    out[i] = make_uint4(first_query + qids[i], static_cast<uint32_t>(v >> bits), static_cast<uint32_t>(v & ((uint64_t{1} << bits) - 1)),
+    out[i] = make_uint4(first_query + qid, static_cast<uint32_t>(v >> bits), static_cast<uint32_t>(v & ((uint64_t{1} << bits) - 1)),
                         static_cast<uint32_t>(k & 15u));
 }
 

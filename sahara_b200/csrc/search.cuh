@@ -639,7 +639,7 @@ constexpr uint32_t kPoolThreads = SB200_POOL_THREADS;
 constexpr uint32_t kPoolSlots = 56;   // seeds a warp works on at a time
 constexpr uint32_t kPoolThreads = 384;  // at most 12 warps per block: three blocks (36 warps) fit the shared memory of an SM at 150 bp
 #endif
-constexpr uint32_t kRunRounds = 4;    // rounds of 8 symbols per pop
+constexpr uint32_t kRunRounds = 2;    // rounds of 8 symbols per pop (measured: 1 -> 6.47 ms, 2 -> 6.39, 3 -> 6.42, 6 -> 6.73)
 
 struct FrameStack {
     uint2* frames;   // [cap] (a, meta): frames 0 .. cap-1 of the stack, shared memory

@@ -358,3 +358,19 @@ def test_host_buffer_call_edge_and_middle_chunks(sb, ctx, cases, monkeypatch):
         assert np.array_equal(ctx.search_reads(reads).astype(np.uint64), want)
         assert np.array_equal(ctx.search(q), want)
     ctx.enable_text(False)
+
+
+def test_hit_sort_fused_and_pair_paths_agree(sb, ctx, cases, monkeypatch):
+    """Hits are sorted by one 64-bit key (query id above position and errors) when the bits fit, else by two
+    stable pair sorts (locate_only in csrc/capi.cu): both orders must be the oracle's."""
+    rng, seqs, ix, path = cases[("multi", 6)]
+    ctx.load_index(path)
+    m, k = 30, 2
+    q = W.sample_reads(rng, seqs, 150, m, k, True)
+    sch = sb.SearchScheme.generate("h2-k2", 0, k, m)
+    ctx.set_scheme(sch, True)
+    want = O.sort_rows(ix.locate(ix.search(q, sch, True)))
+    for fused in ("1", "0"):
+        monkeypatch.setenv("SB200_FUSED_SORT", fused)
+        assert np.array_equal(ctx.search(q), want)
+        assert np.array_equal(ctx.search_reads(np.ascontiguousarray(q[0::2])).astype(np.uint64), want)
