@@ -175,7 +175,8 @@ struct sb200_ctx {
     uint64_t nodes_text{};
     float ms_fm{}, ms_text{};
     bool hits_in_second{};  // which of the double buffers holds the sorted hits
-    unsigned long long* h_counters{};  // pinned, CT_COUNT entries
+    unsigned long long* h_counters{};  // pinned + mapped, CT_COUNT entries + 1 scratch word
+    unsigned long long* h_counters_dev{};  // its device alias
     sb200_counters ct{};
     cudaEvent_t ev[12]{};
     int sms{};
@@ -585,6 +586,16 @@ unsigned blocks_per_sm(const char* env, unsigned def) {
     return def;
 }
 
+__global__ void mirror_words_kernel(const unsigned long long* src, unsigned long long* dst, int n) {
+    if (threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+// n (<= CT_COUNT + 1) device words -> c->h_counters[at ...], then waits for the stream
+void read_back_words(sb200_ctx* c, const void* d_src, int n, int at = 0) {
+    mirror_words_kernel<<<1, 32, 0, c->stream>>>(static_cast<const unsigned long long*>(d_src), c->h_counters_dev + at, n);
+    launch_check(c);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+}
+
 void launch_search(sb200_ctx* c, const SearchParams& P) {
     // shared memory: scheme table + one staged packed query per thread
     size_t smem = (size_t(P.n_searches) * P.len + (size_t(P.n_searches) * P.len * kRunE + 3) / 4 + size_t(packed_words(P.len)) * 256) * 4;
@@ -705,8 +716,7 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         P.text4 = ix.text_mode ? ix.text4.get<uint32_t>() : nullptr;
         if (const char* dbg = std::getenv("SB200_DEBUG")) P.debug_flags = static_cast<uint32_t>(std::atoi(dbg));
         launch_search(c, P);
-        CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->d_counters.p, CT_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        read_back_words(c, c->d_counters.p, CT_COUNT);
         if (std::getenv("SB200_DEBUG"))
             fprintf(stderr, "[sb200 debug] max stack depth %llu overflow %llu seeds %llu\n", c->h_counters[CT_MAX_SP], c->h_counters[CT_OVERFLOW],
                     c->h_counters[CT_SEEDS]);
@@ -762,8 +772,8 @@ void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
         CUDA_TRY(cudaMemsetAsync(c->d_cursors.get<uint4>() + n_cursors, 0, sizeof(uint4), c->stream));
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_tmp.p, tmp_bytes, lens, c->d_offsets.get<uint64_t>(), n_cursors + 1, c->stream));
         c->ct.kernel_launches += 1;
-        CUDA_TRY(cudaMemcpyAsync(&total_rows, c->d_offsets.get<uint64_t>() + n_cursors, 8, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        read_back_words(c, c->d_offsets.get<uint64_t>() + n_cursors, 1, CT_COUNT);
+        total_rows = c->h_counters[CT_COUNT];
     }
     if (total_rows >= (1ull << 32)) throw Error("more than 2^32 hits in one call; split the batch");
     // one 64-bit key (query id above value and errors) when it fits: a single keys-only radix sort
@@ -828,8 +838,7 @@ void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
         c->ct.kernel_launches += 2 * ((key_bits + 7) / 8 + 1) + 2 * ((qid_bits + 7) / 8 + 1);
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->d_counters.p, CT_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    read_back_words(c, c->d_counters.p, CT_COUNT);
     c->ct.lf_steps += c->h_counters[CT_LF_STEPS];
     c->ct.hits += total_rows;
     c->last_hits = total_rows;
@@ -890,7 +899,7 @@ void search_host_pipelined(sb200_ctx* c, const uint8_t* src, uint64_t n_items, u
     // Chunk boundaries (in queries).  Every chunk costs ~0.9 ms of kernel drain (the longest single seed), so few
     // chunks: a short first one (its copy-in cannot be hidden), a short last one (its copy-out cannot be hidden),
     // and the rest in pieces of at most `chunk` queries whose copies hide behind the neighbours' kernels.
-    uint64_t chunk = 2000000, edge_div = 8;
+    uint64_t chunk = 2000000, edge_div = 6;
     if (const char* e = std::getenv("SB200_CHUNK")) chunk = std::max<uint64_t>(2, std::strtoull(e, nullptr, 10));
     if (const char* e = std::getenv("SB200_EDGE_DIV")) edge_div = std::max<uint64_t>(2, std::strtoull(e, nullptr, 10));
     chunk += chunk & 1;  // both strands of a read stay together
@@ -1051,7 +1060,10 @@ int sb200_create(int device, sb200_ctx** out) {
             CUDA_TRY(cudaEventCreateWithFlags(&c->ev_expanded[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
         }
-        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counters), CT_COUNT * sizeof(unsigned long long), cudaHostAllocDefault));
+        // mapped: small read-backs are written by a kernel straight into host memory, so they never queue behind
+        // a large hit transfer on the copy engine
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counters), (CT_COUNT + 1) * sizeof(unsigned long long), cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->h_counters_dev), c->h_counters, 0));
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, device));
         c->sms = prop.multiProcessorCount;

@@ -688,6 +688,7 @@ __host__ __device__ inline TextPool pool_carve(uint8_t* base, uint4* spill, uint
 __host__ __device__ inline uint32_t pool_pop_width(uint32_t top, uint32_t topR, uint32_t maxpush, uint32_t lanes, uint32_t stack) {
     const uint32_t cap = kPoolCapS + kSpillCap - stack;
     uint32_t n = top < lanes ? top : lanes;
+    if (top + lanes * (maxpush - 1u) <= cap && topR + lanes * maxpush <= kPoolCapR + kSpillCap) return n;  // (no division on the common path)
     const uint32_t room = top < cap ? (cap - top) / (maxpush - 1u) : 0u;
     if (n > room) n = room ? room : 1u;
     const uint32_t capR = kPoolCapR + kSpillCap;
