@@ -334,7 +334,7 @@ def main():
     # ---- roofline (SURVEY.md §8d accounting: one search node = 2 rank-ops = 128 B, however it is served) ----
     peak, peak_src = measured_peak()
     nodes = ct["nodes"]            # extensions over the K timed steps == the oracle's extension count (tests assert it)
-    nodes_text = ct["nodes_text"]  # of those, verified in the text by text_kernel
+    nodes_text = ct["nodes_text"]  # of those, verified in the text by text_pool_kernel
     nodes_fm = nodes - nodes_text
     traffic = ncu_traffic() or {}
 
@@ -347,8 +347,9 @@ def main():
 
     k_fm = kern("fm_kernel", nodes_fm, ms_fm, "cursor extensions by rank probes (cursors covering several rows)",
                 "HBM random access: 38.4 G L2-miss requests/s measured (tools/gather_bench.cu), 1 request per probe")
-    k_text = kern("text_kernel", nodes_text, ms_text, "cursor extensions of unique cursors verified in the text",
-                  "instruction issue (DRAM < 2 % busy): the probes are replaced by cached text symbols")
+    k_text = kern("text_pool_kernel" if a.text else "text_kernel", nodes_text, ms_text,
+                  "cursor extensions of unique cursors verified in the text (warp-level frame pools)",
+                  "instruction issue (76 % issue-active, DRAM 4 % busy): the probes are replaced by cached text symbols")
     dom = k_text if ms_text >= ms_fm else k_fm
     roofline = {"bound": "hbm", "kernel": "sb200::" + dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src,
