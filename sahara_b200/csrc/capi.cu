@@ -169,7 +169,7 @@ struct sb200_ctx {
     // work buffers
     uint32_t fused_shift{0};  // hit keys of the last locate carry the query id above this bit (0: separate array)
     int sorted_keys{0};       // d_keys[] buffer that holds the sorted hits
-    DevBuf d_seeds, d_spill, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
+    DevBuf d_items, d_item_tags, d_seeds, d_spill, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
     uint64_t cursor_cap{}, seed_cap{};
     uint64_t last_cursors{}, last_real_cursors{}, last_hits{};
     uint64_t nodes_text{};
@@ -604,20 +604,37 @@ void launch_search(sb200_ctx* c, const SearchParams& P) {
     unsigned need = grid_for((uint64_t(P.n_queries) + kQueryBatch - 1) / kQueryBatch);
     if (need < grid) grid = std::max(1u, need);
     CUDA_TRY(cudaEventRecord(c->ev[8], c->stream));
-    with_sigma(c->idx.sigma, [&](auto S) {
-        with_stack(c->kmax, [&](auto STACK) {
-            auto go = [&](auto kern) {
-                if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                kern<<<grid, 256, smem, c->stream>>>(P);
-            };
-            if (c->edit) go(fm_kernel<S(), true, STACK()>);
-            else go(fm_kernel<S(), false, STACK()>);
+    if (P.items) {  // root frames of all (query, search) in one pass, then the warp-synchronous walk over the live ones
+        fm_roots_kernel<<<grid_for(P.n_queries), 256, 0, c->stream>>>(P);
+        launch_check(c);
+        const size_t ismem = size_t(P.n_searches) * P.len * 4;
+        if (ismem > 48 * 1024) throw Error("search scheme table does not fit shared memory (query too long)");
+        unsigned igrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_BLOCKS_PER_SM", 4);
+        igrid = std::max(1u, std::min(igrid, grid_for(P.n_queries)));
+        with_sigma(c->idx.sigma, [&](auto S) {
+            with_stack(c->kmax, [&](auto STACK) {
+                if (c->edit) fm_items_kernel<S(), true, STACK()><<<igrid, 256, ismem, c->stream>>>(P);
+                else fm_items_kernel<S(), false, STACK()><<<igrid, 256, ismem, c->stream>>>(P);
+            });
+            return 0;
         });
-        return 0;
-    });
-    launch_check(c);
+        launch_check(c);
+    } else {
+        with_sigma(c->idx.sigma, [&](auto S) {
+            with_stack(c->kmax, [&](auto STACK) {
+                auto go = [&](auto kern) {
+                    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                    kern<<<grid, 256, smem, c->stream>>>(P);
+                };
+                if (c->edit) go(fm_kernel<S(), true, STACK()>);
+                else go(fm_kernel<S(), false, STACK()>);
+            });
+            return 0;
+        });
+        launch_check(c);
+    }
     CUDA_TRY(cudaEventRecord(c->ev[9], c->stream));
-    static const bool use_pool = !(std::getenv("SB200_TEXT_POOL") && std::atoi(std::getenv("SB200_TEXT_POOL")) == 0);
+    const bool use_pool = !(std::getenv("SB200_TEXT_POOL") && std::atoi(std::getenv("SB200_TEXT_POOL")) == 0);
     if (P.sa32 && use_pool) {  // in-text verification, one frame pool per warp
         with_stack(c->kmax, [&](auto STACK) {
             const size_t tables = ((size_t(P.n_searches) * P.len + (size_t(P.n_searches) * P.len * kRunE + 3) / 4) * 4 + 7) & ~size_t{7};
@@ -692,7 +709,8 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         c->d_cursors.reserve((c->cursor_cap + 1) * sizeof(uint4));
         if (ix.text_mode) c->d_seeds.reserve((c->seed_cap + 1) * sizeof(uint4));
         CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, CT_BAD_QUERY * sizeof(unsigned long long), c->stream));  // keeps CT_BAD_QUERY
-        CUDA_TRY(cudaMemsetAsync(c->d_counters.get<unsigned long long>() + CT_NODES_TEXT, 0, sizeof(unsigned long long), c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->d_counters.get<unsigned long long>() + CT_NODES_TEXT, 0, (CT_NEXT_ITEM + 1 - CT_NODES_TEXT) * sizeof(unsigned long long),
+                                 c->stream));
         SearchParams P{};
         P.bwt = ix.bwt();
         P.bwtRev = ix.rev();
@@ -711,6 +729,16 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         P.counters = c->d_counters.get<unsigned long long>();
         P.qgram = ix.qgram_q ? ix.qgram.get<uint4>() : nullptr;
         P.qgram_q = ix.qgram_q;
+        // item-based walk (fm_roots_kernel + fm_items_kernel); SB200_FM_ITEMS=0 keeps the query-owning fm_kernel
+        const bool use_items = !(std::getenv("SB200_FM_ITEMS") && std::atoi(std::getenv("SB200_FM_ITEMS")) == 0);
+        if (use_items && c->n_searches <= 255) {  // (search index and slot count share a tag word)
+            if (P.qgram_q >= len) P.qgram = nullptr, P.qgram_q = 0;  // (a table that covers the whole query: plain walk)
+            const uint64_t total = n_queries * uint64_t(c->n_searches);
+            c->d_items.reserve(total * sizeof(uint4));
+            c->d_item_tags.reserve(total * sizeof(uint2));
+            P.items = c->d_items.get<uint4>();
+            P.item_tags = c->d_item_tags.get<uint2>();
+        }
         P.sa32 = ix.text_mode ? ix.sa32.get<uint32_t>() : nullptr;
         P.isa32 = ix.text_mode ? ix.isa32.get<uint32_t>() : nullptr;
         P.text4 = ix.text_mode ? ix.text4.get<uint32_t>() : nullptr;
@@ -1077,7 +1105,7 @@ int sb200_destroy(sb200_ctx* c) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         c->idx.release();
-        for (DevBuf* b : {&c->d_steps, &c->d_runs, &c->d_seeds, &c->d_spill, &c->d_packed, &c->d_queries, &c->d_cursors, &c->d_counters, &c->d_offsets, &c->d_keys[0], &c->d_keys[1],
+        for (DevBuf* b : {&c->d_steps, &c->d_runs, &c->d_items, &c->d_item_tags, &c->d_seeds, &c->d_spill, &c->d_packed, &c->d_queries, &c->d_cursors, &c->d_counters, &c->d_offsets, &c->d_keys[0], &c->d_keys[1],
                           &c->d_qids[0], &c->d_qids[1], &c->d_tmp, &c->d_scratch})
             b->release();
         for (auto& ev : c->ev) cudaEventDestroy(ev);
@@ -1423,7 +1451,7 @@ int sb200_index_build_qgram(sb200_ctx* c, uint32_t q) {
         use(c);
         auto& ix = c->idx;
         if (!ix.loaded) throw Error("no index loaded");
-        if (q > 13) throw Error("q-gram length above 13 is not supported");
+        if (q > 15) throw Error("q-gram length above 15 is not supported");
         ix.qgram.release();
         ix.qgram_q = 0;
         if (q == 0) return;

@@ -87,6 +87,7 @@ enum : int {
     CT_SEEDS = 9,        // seeds produced
     CT_BAD_QUERY = 10,   // 1 + offset of a query symbol outside the alphabet (0 = none)
     CT_NODES_TEXT = 11,  // states expanded by text_kernel (subset of CT_NODES)
+    CT_NEXT_ITEM = 12,   // work distribution of fm_items_kernel
     CT_COUNT = 16
 };
 
@@ -110,6 +111,10 @@ struct SearchParams {
     const uint32_t* text4;
     uint4* seeds;            // (qid, lb, search, meta) handed from fm_kernel to text_kernel
     uint32_t seed_cap;
+    // work items of fm_items_kernel, n_searches slots per query: root frame (lb, lbRev, len, meta) and
+    // (qid, search | toText << 8 | live slots of the query << 16)
+    uint4* items;
+    uint2* item_tags;
 };
 
 __host__ __device__ inline uint32_t packed_words(uint32_t len) { return (len + 7) / 8; }
@@ -164,8 +169,202 @@ __device__ __forceinline__ bool stage_query(const SearchParams& P, uint32_t qid,
 }
 
 // ================================================================================================
-// fm_kernel body.  s_steps: scheme table (shared memory); s_query: this thread's staged query, word w at
-// s_query[w * qstride].
+// Shared pieces of the FM-index walk.
+// ================================================================================================
+#if defined(SB200_HOST_EMU)
+// the emulated "warp" has one lane
+static inline uint32_t warp_ballot(bool p) { return p ? 1u : 0u; }
+static inline uint32_t warp_bcast0(uint32_t v) { return v; }
+static inline uint32_t warp_lane() { return 0u; }
+static inline uint32_t popc32(uint32_t v) { return static_cast<uint32_t>(__builtin_popcount(v)); }
+static inline uint32_t ldg32(const uint32_t* p) { return *p; }
+static inline uint4 ldg128(const uint4* p) { return *p; }
+static inline uint2 ldg64(const uint2* p) { return *p; }
+#else
+__device__ __forceinline__ uint32_t warp_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+__device__ __forceinline__ uint32_t warp_bcast0(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint32_t warp_lane() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t popc32(uint32_t v) { return static_cast<uint32_t>(__popc(v)); }
+__device__ __forceinline__ uint32_t ldg32(const uint32_t* p) { return __ldg(p); }
+__device__ __forceinline__ uint4 ldg128(const uint4* p) { return __ldg(p); }
+__device__ __forceinline__ uint2 ldg64(const uint2* p) { return __ldg(p); }
+#endif
+
+// Root frame of one search of one query.  tbl: the steps of the search, qsym(pos): query symbol.
+// Returns 0 = the search cannot start (dead), 1 = `root` is the frame to expand, 2 = the q-gram covers the
+// whole query: `root` is the final cursor (lb, -, len, -) with 0 errors.
+template <typename QSym>
+__device__ __forceinline__ int fm_root(const SearchParams& P, const uint32_t* tbl, QSym&& qsym, uint4& root) {
+    const uint32_t qlen = P.len;
+    const uint32_t st0 = tbl[0];
+    if (((st0 >> 16) & 0xfu) > 1) return 0;  // neither a match nor a mismatch allowed at step 0
+    root = make_uint4(0, 0, P.n_rows, 0);
+    if (P.qgram_q) {  // q-gram jump: skip the leading steps that allow no error
+        const uint32_t qq = P.qgram_q;
+        bool ok = qq <= qlen;
+        uint32_t code = 0;
+        const bool right0 = (st0 >> 24) & 1u;
+        for (uint32_t i = 0; ok && i < qq; ++i) {
+            const uint32_t st = tbl[i];
+            const uint32_t c = qsym(st & 0xffffu);
+            ok = ((st >> 20) & 0xfu) == 0 && c >= 1 && c <= 4 && (((st >> 24) & 1u) == right0);
+            // the table is keyed by the string in text order, first symbol most significant
+            if (right0) code = (code << 2) | (c - 1);
+            else code |= (c - 1) << (2 * i);
+        }
+        if (ok) {
+            const uint4 g = P.qgram[code];
+            if (g.z == 0) return 0;
+            if (qq == qlen) {
+                root = g;
+                return 2;
+            }
+            if (((tbl[qq] >> 16) & 0xfu) > 1) return 0;
+            root = make_uint4(g.x, g.y, g.z, pack_meta(qq, 0, INFO_M, INFO_M) | (qq << META_TLEN_SHIFT));
+        }
+    }
+    return 1;
+}
+
+// One node of the walk: ONE probe of the occurrence table for the cursor of frame f, then every state that lives
+// on this cursor is expanded.  push(lb, lbRev, len, meta) takes a child frame, emit(lb, len, e) a reported cursor.
+template <int SIGMA, bool EDIT, typename QSym, typename Push, typename Emit>
+__device__ __forceinline__ void fm_node(const SearchParams& P, const uint32_t* tbl, const uint4 f, uint32_t& nodes, QSym&& qsym, Push&& push,
+                                        Emit&& emit) {
+    const uint32_t qlen = P.len;
+    const uint32_t lb = f.x, lbRev = f.y, len = f.z, meta = f.w;
+    uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
+    uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
+    const bool pair = (meta & META_PAIR) != 0;
+    const uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
+    const bool right = (tbl[step] >> 24) & 1u;
+    uint32_t c_next = qsym(tbl[step] & 0xffffu);  // query symbol of the first state: requested before the probe
+    // child cursors per symbol: (klb[s], klbRev[s], cnt[s]).  The probed side continues at C[s] + rank(lo, s),
+    // the other side moves by the number of smaller symbols inside the interval.  (The selection by `right`
+    // is done once here, outside the state loop.)
+    uint32_t klb[SIGMA], klbRev[SIGMA], cnt[SIGMA];
+    {
+        const OccTable& tab = right ? P.bwtRev : P.bwt;
+        const uint32_t lo = right ? lbRev : lb;
+        const uint32_t hi = lo + len;
+        OccBlk b1 = load_blk(tab.blk + (lo >> kBlkShift));
+        OccSup s1 = load_sup(tab.sup + (lo >> kSupShift));
+        OccBlk b2 = b1;
+        OccSup s2 = s1;
+        if ((lo >> kBlkShift) != (hi >> kBlkShift)) {
+            b2 = load_blk(tab.blk + (hi >> kBlkShift));
+            if ((lo >> kSupShift) != (hi >> kSupShift)) s2 = load_sup(tab.sup + (hi >> kSupShift));
+        }
+        uint32_t own[SIGMA];
+        uint32_t sum1 = 0, sumc = 0;
+#pragma unroll
+        for (int s = 1; s < SIGMA; ++s) {
+            uint32_t a = s1.c[s] + blk_ctr(b1, s) + blk_count(b1, lo & 63u, s);
+            uint32_t b = s2.c[s] + blk_ctr(b2, s) + blk_count(b2, hi & 63u, s);
+            own[s] = P.C[s] + a;
+            cnt[s] = b - a;
+            sum1 += a;
+            sumc += b - a;
+        }
+        own[0] = lo - sum1;  // C[0] == 0
+        cnt[0] = len - sumc;
+        uint32_t other = right ? lb : lbRev;  // interval start on the side that is not probed
+#pragma unroll
+        for (int s = 0; s < SIGMA; ++s) {
+            klb[s] = right ? other : own[s];
+            klbRev[s] = right ? own[s] : other;
+            other += cnt[s];
+        }
+    }
+    const uint32_t tlenSame = tlen << META_TLEN_SHIFT, tlenNext = (tlen + 1) << META_TLEN_SHIFT;
+
+    // ---- expand every state that lives on this cursor ------------------------------------------
+    bool second = false;  // second half of a pair already taken
+    bool first = true;
+    while (true) {
+        ++nodes;
+#if defined(SB200_TRACE)
+        if (P.debug_flags & 4u)
+            printf("STATE lb=%u lbRev=%u len=%u step=%u e=%u L=%u R=%u pair=%d second=%d right=%d\n", lb, lbRev, len, step, e, Linfo, Rinfo,
+                   (int)pair, (int)second, (int)right);
+#endif
+        const uint32_t st = tbl[step];
+        const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
+        const uint32_t c = first ? c_next : qsym(st & 0xffffu);
+        first = false;
+        const bool last = step + 1 == qlen;
+        const uint32_t stn = last ? 0u : tbl[step + 1];
+        const uint32_t lnext = (stn >> 16) & 0xfu;
+        const bool rightNext = (stn >> 24) & 1u;
+        const bool sameDirNext = !last && (rightNext == right);
+        const bool matchOK = l <= e && e <= u;
+        const bool mmOK = l <= e + 1 && e + 1 <= u;
+        const uint32_t T = right ? Rinfo : Linfo;
+        const uint32_t O = right ? Linfo : Rinfo;          // info of the other end
+        const bool otherEndOK = !EDIT || (O & 1u) == 0;    // M or I
+        // metas of the possible children: the moving side gets the new info
+        const uint32_t keepL = right ? Linfo : 0u, keepR = right ? 0u : Rinfo;
+        const uint32_t sideShift = right ? 16u : 14u;
+        const uint32_t metaBase = (keepL << 14) | (keepR << 16);
+        const uint32_t mM = metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift) | tlenNext;
+        const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift) | tlenNext;
+        const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift) | tlenNext;
+        const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift) | tlenSame;
+        // match
+        {
+            uint32_t mc = 0, nlb = 0, nlbRev = 0;
+#pragma unroll
+            for (int s = 0; s < SIGMA; ++s)
+                if (static_cast<uint32_t>(s) == c) { mc = cnt[s]; nlb = klb[s]; nlbRev = klbRev[s]; }
+            const bool alive = matchOK && mc != 0;
+            if (alive && last) {
+                if (otherEndOK) emit(nlb, mc, e);
+            } else if (alive && lnext <= e + 1) {
+                push(nlb, nlbRev, mc, mM);
+            }
+        }
+        if (mmOK) {
+            const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
+            const bool subAlive = !last && lnext <= e + 2;
+            const bool asPair = delOK && subAlive && sameDirNext && !(P.debug_flags & 1u);
+#pragma unroll
+            for (int s = 1; s < SIGMA; ++s) {
+                const bool live = static_cast<uint32_t>(s) != c && cnt[s] != 0;
+                const uint32_t nlb = klb[s], nlbRev = klbRev[s];
+                if (live && (asPair || delOK)) push(nlb, nlbRev, cnt[s], asPair ? (mD | META_PAIR) : mD);
+                if (live && !asPair && subAlive) push(nlb, nlbRev, cnt[s], mS);
+                if (!EDIT && live && last) emit(nlb, cnt[s], e + 1);
+            }
+        }
+        // next state on the same cursor
+        if (pair) {
+            if (second) break;
+            second = true;
+            // second half of the pair: the substitution (step + 1, e, side = S)
+            step += 1;
+            if (right) Rinfo = INFO_S; else Linfo = INFO_S;
+            continue;
+        }
+        const bool insOK = EDIT && mmOK && (T == INFO_M || T == INFO_I);
+        if (!insOK) break;
+        if (last) {
+            if (otherEndOK) emit(lb, len, e + 1);
+            break;
+        }
+        if (lnext > e + 2) break;  // dead at the next step
+        if (!sameDirNext || (P.debug_flags & 2u)) {  // direction changes: needs a probe of the other table
+            push(lb, lbRev, len, mI);
+            break;
+        }
+        step += 1;
+        e += 1;
+        if (right) Rinfo = INFO_I; else Linfo = INFO_I;
+    }
+}
+
+// ================================================================================================
+// fm_kernel body (one thread owns one query at a time).  s_steps: scheme table (shared memory); s_query: this
+// thread's staged query, word w at s_query[w * qstride].
 // ================================================================================================
 template <int SIGMA, bool EDIT, int STACK>
 __device__ __forceinline__ void fm_thread(const SearchParams& P, const uint32_t* s_steps, uint32_t* s_query, uint32_t qstride) {
@@ -216,167 +415,171 @@ __device__ __forceinline__ void fm_thread(const SearchParams& P, const uint32_t*
             }
             tbl = s_steps + next_search * qlen;
             ++next_search;
-            uint32_t st0 = tbl[0];
-            if (((st0 >> 16) & 0xfu) > 1) continue;  // neither a match nor a mismatch allowed at step 0
-            uint4 root = make_uint4(0, 0, P.n_rows, 0);
-            if (P.qgram_q) {  // q-gram jump: skip the leading steps that allow no error
-                uint32_t qq = P.qgram_q;
-                bool ok = qq <= qlen;
-                uint32_t code = 0;
-                bool right0 = (st0 >> 24) & 1u;
-                for (uint32_t i = 0; ok && i < qq; ++i) {
-                    uint32_t st = tbl[i];
-                    uint32_t c = qsym(st & 0xffffu);
-                    ok = ((st >> 20) & 0xfu) == 0 && c >= 1 && c <= 4 && (((st >> 24) & 1u) == right0);
-                    // the table is keyed by the string in text order, first symbol most significant
-                    if (right0) code = (code << 2) | (c - 1);
-                    else code |= (c - 1) << (2 * i);
-                }
-                if (ok) {
-                    uint4 g = P.qgram[code];
-                    if (g.z == 0) continue;
-                    if (qq == qlen) {
-                        emit(g.x, g.z, 0);
-                        continue;
-                    }
-                    if (((tbl[qq] >> 16) & 0xfu) > 1) continue;
-                    root = make_uint4(g.x, g.y, g.z, pack_meta(qq, 0, INFO_M, INFO_M) | (qq << META_TLEN_SHIFT));
-                }
-            }
-            push(root.x, root.y, root.z, root.w);
+            uint4 root;
+            const int rc = fm_root(P, tbl, qsym, root);
+            if (rc == 2) emit(root.x, root.z, 0);
+            if (rc == 1) push(root.x, root.y, root.z, root.w);
         }
         if (done) break;
         maxsp = sp > maxsp ? sp : maxsp;
-        uint32_t lb, lbRev, len, meta;
-        {
-            uint4 f = stack[--sp];
-            lb = f.x; lbRev = f.y; len = f.z; meta = f.w;
-        }
+        const uint4 f = stack[--sp];
+        fm_node<SIGMA, EDIT>(P, tbl, f, nodes, qsym, push, emit);
+    }
+    outW.finish(P.out, P.out_cap);
+    seedW.finish(P.seeds, P.seed_cap);
+    if (nodes) atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(nodes));
+    if (overflow) atomicExch(&P.counters[CT_OVERFLOW], 1ull);
+    atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxsp));
+    if (emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(emitted));
+    if (seeded) atomicAdd(&P.counters[CT_SEEDS], static_cast<unsigned long long>(seeded));
+}
 
-        // ---- one probe of the occurrence table for this cursor ------------------------------------
-        uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
-        uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
-        const bool pair = (meta & META_PAIR) != 0;
-        const uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
-        const bool right = (tbl[step] >> 24) & 1u;
-        // child cursors per symbol: (klb[s], klbRev[s], cnt[s]).  The probed side continues at C[s] + rank(lo, s),
-        // the other side moves by the number of smaller symbols inside the interval.  (The selection by `right`
-        // is done once here, outside the state loop.)
-        uint32_t klb[SIGMA], klbRev[SIGMA], cnt[SIGMA];
-        {
-            const OccTable& tab = right ? P.bwtRev : P.bwt;
-            const uint32_t lo = right ? lbRev : lb;
-            const uint32_t hi = lo + len;
-            OccBlk b1 = load_blk(tab.blk + (lo >> kBlkShift));
-            OccSup s1 = load_sup(tab.sup + (lo >> kSupShift));
-            OccBlk b2 = b1;
-            OccSup s2 = s1;
-            if ((lo >> kBlkShift) != (hi >> kBlkShift)) {
-                b2 = load_blk(tab.blk + (hi >> kBlkShift));
-                if ((lo >> kSupShift) != (hi >> kSupShift)) s2 = load_sup(tab.sup + (hi >> kSupShift));
+// ================================================================================================
+// Item-based walk (fm_roots_kernel + fm_items_kernel).
+// In fm_thread a lane that runs out of frames fetches its next query (work atomic, staging, q-gram entries of up
+// to n_searches dead searches in a row) while the other 31 lanes of the warp wait at the reconvergence point in
+// front of the probe: 12.8 us per warp iteration instead of one memory latency (profiles/r01i_*).  Here
+//   * fm_roots_kernel makes the root frames of every query in one fully parallel pass: the live ones of query q
+//     sit in items[q * n_searches + 0 .. count) with tags (qid, search | toText << 8 | count << 16);
+//   * fm_items_kernel walks them: the loop is warp synchronous; a lane still owns one query at a time (so its
+//     seeds stay grouped by query, which the in-text verification needs for its cache hits), but the root it
+//     continues with has ALREADY been loaded: the next slot of its query, or slot 0 of the next query of the range
+//     the warp claims 32 queries at a time (the next claim is issued before the range runs out).  Query symbols
+//     are read through L1 from the packed queries (requested before the probe).  No long-latency operation of the
+//     refill is on the critical path of an iteration any more.
+// ================================================================================================
+constexpr uint32_t kItemClaim = 32;  // queries a warp claims per atomic
+constexpr uint32_t kItemToText = 0x100u;
+
+// root frames of all searches of query qid -> its slots of P.items / P.item_tags
+__device__ __forceinline__ void fm_make_items(const SearchParams& P, const uint32_t* steps, uint32_t qid) {
+    const uint32_t W = packed_words(P.len);
+    const uint32_t* q = P.packed + static_cast<uint64_t>(qid) * W;
+    auto qsym = [&](uint32_t pos) -> uint32_t { return (ldg32(q + (pos >> 3)) >> ((pos & 7u) * 4u)) & 0xfu; };
+    bool delim = false;
+    for (uint32_t w = 0; w < W; ++w) {
+        const uint32_t v = ldg32(q + w);
+        delim = delim || (((v - 0x11111111u) & ~v & 0x88888888u) != 0);  // some nibble is 0
+    }
+    const uint32_t flags = (P.sa32 != nullptr && !delim) ? kItemToText : 0u;  // a query with the delimiter stays on the FM path
+    const uint64_t base = static_cast<uint64_t>(qid) * P.n_searches;
+    uint32_t count = 0;
+    for (uint32_t j = 0; j < P.n_searches; ++j) {
+        uint4 root;
+        if (fm_root(P, steps + j * P.len, qsym, root) != 1) continue;  // (the host never enables a table with q >= len here)
+        P.items[base + count] = root;
+        P.item_tags[base + count] = make_uint2(qid, j | flags);
+        ++count;
+    }
+    // the number of live slots goes into every tag of the query (slot 0 is written even when it is 0)
+    for (uint32_t j = 0; j < (count ? count : 1u); ++j) {
+        const uint32_t y = j < count ? P.item_tags[base + j].y : 0u;
+        P.item_tags[base + j] = make_uint2(qid, y | (count << 16));
+    }
+}
+
+template <int SIGMA, bool EDIT, int STACK>
+__device__ __forceinline__ void fm_items_thread(const SearchParams& P, const uint32_t* s_steps) {
+    uint4 stack[STACK];
+    int sp = 0;
+    uint32_t nodes = 0, emitted = 0, seeded = 0;
+    ChunkWriter outW, seedW;
+    bool overflow = false;
+    int maxsp = 0;
+    const uint32_t qlen = P.len;
+    const uint32_t W = packed_words(qlen);
+    const uint32_t n_queries = P.n_queries;
+    const uint32_t lane = warp_lane();
+
+    // the item being walked
+    uint32_t qid = 0, search = 0;
+    bool toText = false;
+    const uint32_t* tbl = s_steps;
+    const uint32_t* qwords = P.packed;
+    // the root loaded ahead: slot pj of query pq
+    uint4 nroot = make_uint4(0, 0, 0, 0);
+    uint2 ntag = make_uint2(0, 0);
+    uint32_t pq = 0, pj = 0;
+    bool have_next = false;
+    // warp-uniform: the claimed range of queries, the claim made ahead (valid in lane 0), end of the batch seen
+    uint32_t wnext = 0, wend = 0, cnext = 0;
+    bool chave = false, exhausted = n_queries == 0;
+
+    auto qsym = [&](uint32_t pos) -> uint32_t { return (ldg32(qwords + (pos >> 3)) >> ((pos & 7u) * 4u)) & 0xfu; };
+    auto emit = [&](uint32_t lb, uint32_t len, uint32_t e) {
+        outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], make_uint4(qid, lb, len, e));
+        ++emitted;
+    };
+    auto push = [&](uint32_t nlb, uint32_t nlbRev, uint32_t nlen, uint32_t m) {
+        if (toText && nlen == 1) {
+            seedW.put(P.seeds, P.seed_cap, &P.counters[CT_SEED_SLOTS], make_uint4(qid, nlb, search, m));
+            ++seeded;
+        } else {
+            if (sp < STACK) stack[sp] = make_uint4(nlb, nlbRev, nlen, m);
+            else overflow = true;
+            ++sp;
+        }
+    };
+
+    while (true) {
+        // ---- a lane without frames continues with the root it loaded ahead ---------------------------
+        if (sp == 0 && have_next) {
+            const uint32_t count = ntag.y >> 16;
+            if (pj < count) {
+                qid = pq;
+                search = ntag.y & 0xffu;
+                toText = (ntag.y & kItemToText) != 0;
+                tbl = s_steps + search * qlen;
+                qwords = P.packed + static_cast<uint64_t>(qid) * W;
+                push(nroot.x, nroot.y, nroot.z, nroot.w);
             }
-            uint32_t own[SIGMA];
-            uint32_t sum1 = 0, sumc = 0;
-#pragma unroll
-            for (int s = 1; s < SIGMA; ++s) {
-                uint32_t a = s1.c[s] + blk_ctr(b1, s) + blk_count(b1, lo & 63u, s);
-                uint32_t b = s2.c[s] + blk_ctr(b2, s) + blk_count(b2, hi & 63u, s);
-                own[s] = P.C[s] + a;
-                cnt[s] = b - a;
-                sum1 += a;
-                sumc += b - a;
-            }
-            own[0] = lo - sum1;  // C[0] == 0
-            cnt[0] = len - sumc;
-            uint32_t other = right ? lb : lbRev;  // interval start on the side that is not probed
-#pragma unroll
-            for (int s = 0; s < SIGMA; ++s) {
-                klb[s] = right ? other : own[s];
-                klbRev[s] = right ? own[s] : other;
-                other += cnt[s];
+            have_next = false;
+            if (pj + 1 < count) {  // the next slot of the same query
+                ++pj;
+                const uint64_t at = static_cast<uint64_t>(pq) * P.n_searches + pj;
+                nroot = ldg128(P.items + at);
+                ntag = ldg64(P.item_tags + at);
+                have_next = true;
             }
         }
-        const uint32_t tlenSame = tlen << META_TLEN_SHIFT, tlenNext = (tlen + 1) << META_TLEN_SHIFT;
-
-        // ---- expand every state that lives on this cursor ------------------------------------------
-        bool second = false;  // second half of a pair already taken
-        while (true) {
-            ++nodes;
-#if defined(SB200_TRACE)
-            if (P.debug_flags & 4u)
-                printf("STATE q=%u lb=%u lbRev=%u len=%u step=%u e=%u L=%u R=%u pair=%d second=%d right=%d\n", qid, lb, lbRev, len, step, e,
-                       Linfo, Rinfo, (int)pair, (int)second, (int)right);
-#endif
-            const uint32_t st = tbl[step];
-            const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
-            const uint32_t c = qsym(st & 0xffffu);
-            const bool last = step + 1 == qlen;
-            const uint32_t stn = last ? 0u : tbl[step + 1];
-            const uint32_t lnext = (stn >> 16) & 0xfu;
-            const bool rightNext = (stn >> 24) & 1u;
-            const bool sameDirNext = !last && (rightNext == right);
-            const bool matchOK = l <= e && e <= u;
-            const bool mmOK = l <= e + 1 && e + 1 <= u;
-            const uint32_t T = right ? Rinfo : Linfo;
-            const uint32_t O = right ? Linfo : Rinfo;          // info of the other end
-            const bool otherEndOK = !EDIT || (O & 1u) == 0;    // M or I
-            // metas of the possible children: the moving side gets the new info
-            const uint32_t keepL = right ? Linfo : 0u, keepR = right ? 0u : Rinfo;
-            const uint32_t sideShift = right ? 16u : 14u;
-            const uint32_t metaBase = (keepL << 14) | (keepR << 16);
-            const uint32_t mM = metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift) | tlenNext;
-            const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift) | tlenNext;
-            const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift) | tlenNext;
-            const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift) | tlenSame;
-            // match
-            {
-                uint32_t mc = 0, nlb = 0, nlbRev = 0;
-#pragma unroll
-                for (int s = 0; s < SIGMA; ++s)
-                    if (static_cast<uint32_t>(s) == c) { mc = cnt[s]; nlb = klb[s]; nlbRev = klbRev[s]; }
-                const bool alive = matchOK && mc != 0;
-                if (alive && last) {
-                    if (otherEndOK) emit(nlb, mc, e);
-                } else if (alive && lnext <= e + 1) {
-                    push(nlb, nlbRev, mc, mM);
+        // ---- lanes without a root loaded ahead take the next queries of the warp's range -------------
+        const uint32_t want = exhausted ? 0u : warp_ballot(!have_next);
+        if (want != 0) {
+            if (wnext == wend) {  // the range is used up: continue with the claim made ahead
+                if (!chave && lane == 0) cnext = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_ITEM], static_cast<unsigned long long>(kItemClaim)));
+                wnext = warp_bcast0(cnext);
+                chave = false;
+                if (wnext >= n_queries) {
+                    exhausted = true;
+                    wnext = wend = 0;
+                } else {
+                    wend = wnext + kItemClaim < n_queries ? wnext + kItemClaim : n_queries;
                 }
             }
-            if (mmOK) {
-                const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
-                const bool subAlive = !last && lnext <= e + 2;
-                const bool asPair = delOK && subAlive && sameDirNext && !(P.debug_flags & 1u);
-#pragma unroll
-                for (int s = 1; s < SIGMA; ++s) {
-                    const bool live = static_cast<uint32_t>(s) != c && cnt[s] != 0;
-                    const uint32_t nlb = klb[s], nlbRev = klbRev[s];
-                    if (live && (asPair || delOK)) push(nlb, nlbRev, cnt[s], asPair ? (mD | META_PAIR) : mD);
-                    if (live && !asPair && subAlive) push(nlb, nlbRev, cnt[s], mS);
-                    if (!EDIT && live && last) emit(nlb, cnt[s], e + 1);
-                }
+            const uint32_t left = wend - wnext;
+            const uint32_t n = popc32(want);
+            const uint32_t take = n < left ? n : left;
+            const uint32_t rank = popc32(want & ((1u << lane) - 1u));
+            if (!have_next && rank < take) {
+                pq = wnext + rank;
+                pj = 0;
+                const uint64_t at = static_cast<uint64_t>(pq) * P.n_searches;
+                nroot = ldg128(P.items + at);
+                ntag = ldg64(P.item_tags + at);
+                have_next = true;
             }
-            // next state on the same cursor
-            if (pair) {
-                if (second) break;
-                second = true;
-                // second half of the pair: the substitution (step + 1, e, side = S)
-                step += 1;
-                if (right) Rinfo = INFO_S; else Linfo = INFO_S;
-                continue;
+            wnext += take;
+            if (!chave && !exhausted && wend - wnext < kItemClaim / 2) {  // claim ahead: the result is needed much later
+                if (lane == 0) cnext = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_ITEM], static_cast<unsigned long long>(kItemClaim)));
+                chave = true;
             }
-            const bool insOK = EDIT && mmOK && (T == INFO_M || T == INFO_I);
-            if (!insOK) break;
-            if (last) {
-                if (otherEndOK) emit(lb, len, e + 1);
-                break;
-            }
-            if (lnext > e + 2) break;  // dead at the next step
-            if (!sameDirNext || (P.debug_flags & 2u)) {  // direction changes: needs a probe of the other table
-                push(lb, lbRev, len, mI);
-                break;
-            }
-            step += 1;
-            e += 1;
-            if (right) Rinfo = INFO_I; else Linfo = INFO_I;
+        }
+        if (warp_ballot(sp != 0 || have_next) == 0) break;
+        // ---- one node ---------------------------------------------------------------------------
+        if (sp != 0) {
+            maxsp = sp > maxsp ? sp : maxsp;
+            const uint4 f = stack[--sp];
+            fm_node<SIGMA, EDIT>(P, tbl, f, nodes, qsym, push, emit);
         }
     }
     outW.finish(P.out, P.out_cap);
@@ -968,6 +1171,21 @@ __global__ void __launch_bounds__(256, 4) fm_kernel(const SearchParams P) {
     __syncthreads();
     // word w of this thread's query lives at s_query[w * blockDim.x]: every lane stays in its own bank
     fm_thread<SIGMA, EDIT, STACK>(P, s_steps, s_steps + n_steps + threadIdx.x, blockDim.x);
+}
+
+// one thread per query: its live root frames become the work items of fm_items_kernel
+__global__ void __launch_bounds__(256) fm_roots_kernel(const SearchParams P) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i < P.n_queries) fm_make_items(P, P.steps, static_cast<uint32_t>(i));
+}
+
+template <int SIGMA, bool EDIT, int STACK>
+__global__ void __launch_bounds__(256, 4) fm_items_kernel(const SearchParams P) {
+    extern __shared__ uint32_t s_steps[];
+    const uint32_t n_steps = P.n_searches * P.len;
+    for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) s_steps[i] = P.steps[i];
+    __syncthreads();
+    fm_items_thread<SIGMA, EDIT, STACK>(P, s_steps);
 }
 
 template <bool EDIT, int STACK>

@@ -29,6 +29,12 @@ _lib = _load("libsearch_emu.so", [])
 _lib_small_pool = _load("libsearch_emu_smallpool.so", ["-DSB200_POOL_CAP=24", "-DSB200_SPILL_CAP=120"])
 
 POOL = 8  # debug flag: run the in-text verification with the pooled kernel body (text_pool_kernel)
+ITEMS = 16  # debug flag: item-based walk (fm_roots_kernel + fm_items_kernel) instead of fm_kernel
+
+
+def QGRAM(q):
+    """debug flag bits: start the searches from a q-gram jump table (q <= 6 here)"""
+    return (q & 0xF) << 8
 
 
 def _p(a):

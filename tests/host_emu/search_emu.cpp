@@ -134,6 +134,35 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
             uint32_t& w = packed[qi * W + i / 8];
             w = (w & ~(0xfu << (4 * (i % 8)))) | (uint32_t(queries[qi * len + i] & 0xf) << (4 * (i % 8)));
         }
+    // optional q-gram jump table (debug_flags bits 8..11 = q): cursor of every A/C/G/T string of length q, first
+    // symbol most significant, made by right extensions over bwtRev (what qgram_level_kernel does on the device)
+    const uint32_t qgram_q = (debug_flags >> 8) & 0xfu;
+    std::vector<uint4> qgram;
+    if (qgram_q) {
+        qgram.assign(size_t(1) << (2 * qgram_q), uint4{0, 0, 0, 0});
+        const OccTable rev{b.blk.data(), b.sup.data()};
+        for (uint32_t code = 0; code < qgram.size(); ++code) {
+            uint32_t lb = 0, lbRev = 0, ln = static_cast<uint32_t>(n_rows);
+            for (uint32_t i = 0; i < qgram_q && ln; ++i) {
+                const uint32_t c = ((code >> (2 * (qgram_q - 1 - i))) & 3u) + 1;
+                uint32_t r1[8] = {0}, r2[8] = {0};
+                all_ranks<6>(rev, lbRev, r1);
+                all_ranks<6>(rev, lbRev + ln, r2);
+                uint32_t smaller = 0;
+                for (uint32_t t = 0; t < c; ++t) smaller += r2[t] - r1[t];
+                lb += smaller;
+                lbRev = static_cast<uint32_t>(C[c]) + r1[c];
+                ln = r2[c] - r1[c];
+            }
+            qgram[code] = uint4{lb, lbRev, ln, 0};
+        }
+    }
+    std::vector<uint4> items;
+    std::vector<uint2> item_tags;
+    if (debug_flags & 16u) {
+        items.resize(size_t(n_queries) * n_searches + 1);
+        item_tags.resize(size_t(n_queries) * n_searches + 1);
+    }
     uint64_t cap = 1 << 16, seed_cap = 1 << 16;
     std::vector<uint4> buf, seeds;
     unsigned long long counters[CT_COUNT];
@@ -157,13 +186,25 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
         P.out = buf.data();
         P.out_cap = static_cast<uint32_t>(cap);
         P.counters = counters;
-        P.qgram = nullptr;
-        P.qgram_q = 0;
-        P.debug_flags = debug_flags;
+        P.qgram = qgram_q ? qgram.data() : nullptr;
+        P.qgram_q = qgram_q;
+        P.debug_flags = debug_flags & 0xffu;
         P.sa32 = isa.empty() ? nullptr : sa32;
         P.isa32 = isa.empty() ? nullptr : isa.data();
         P.text4 = isa.empty() ? nullptr : text4.data();
-        if (sigma == 6) {
+        if (debug_flags & 16u) {  // item-based walk: fm_roots_kernel as a host loop, then fm_items_kernel as a one-lane warp
+            if (P.qgram_q >= len) P.qgram = nullptr, P.qgram_q = 0;
+            P.items = items.data();
+            P.item_tags = item_tags.data();
+            for (uint64_t i = 0; i < n_queries; ++i) fm_make_items(P, steps.data(), static_cast<uint32_t>(i));
+            if (sigma == 6) {
+                if (edit) fm_items_thread<6, true, 96>(P, steps.data());
+                else fm_items_thread<6, false, 96>(P, steps.data());
+            } else if (sigma == 5) {
+                if (edit) fm_items_thread<5, true, 96>(P, steps.data());
+                else fm_items_thread<5, false, 96>(P, steps.data());
+            } else return 3;
+        } else if (sigma == 6) {
             if (edit) fm_thread<6, true, 96>(P, steps.data(), stage.data(), 1);
             else fm_thread<6, false, 96>(P, steps.data(), stage.data(), 1);
         } else if (sigma == 5) {

@@ -374,3 +374,32 @@ def test_hit_sort_fused_and_pair_paths_agree(sb, ctx, cases, monkeypatch):
         monkeypatch.setenv("SB200_FUSED_SORT", fused)
         assert np.array_equal(ctx.search(q), want)
         assert np.array_equal(ctx.search_reads(np.ascontiguousarray(q[0::2])).astype(np.uint64), want)
+
+
+@pytest.mark.parametrize("key", [("multi", 6), ("repeats", 6)])
+def test_kernel_variants_agree(sb, ctx, cases, key, monkeypatch):
+    """The walk has two formulations (fm_roots_kernel + fm_items_kernel, or the query-owning fm_kernel:
+    SB200_FM_ITEMS=0) and so has the in-text verification (text_pool_kernel, or text_kernel: SB200_TEXT_POOL=0);
+    every combination, with and without the q-gram table, reports the oracle's cursors and hits."""
+    rng, seqs, ix, path = cases[key]
+    ctx.load_index(path)
+    ctx.enable_text(True)
+    m, k = 40, 2
+    q = W.sample_reads(rng, seqs, 400, m, k, True)
+    q[7, 11] = 0
+    sch = sb.SearchScheme.generate("h2-k2", 0, k, m)
+    ctx.set_scheme(sch, True)
+    want_cur = O.sort_rows(ix.search(q, sch, True))
+    want = O.sort_rows(ix.locate(want_cur))
+    try:
+        for qlen in (0, 4, 9):
+            ctx.build_qgram(qlen)
+            for items in ("1", "0"):
+                for pool in ("1", "0"):
+                    monkeypatch.setenv("SB200_FM_ITEMS", items)
+                    monkeypatch.setenv("SB200_TEXT_POOL", pool)
+                    assert np.array_equal(ctx.search_cursors(q), want_cur), (qlen, items, pool)
+                    assert np.array_equal(ctx.search(q), want), (qlen, items, pool)
+    finally:
+        ctx.build_qgram(0)
+        ctx.enable_text(False)
