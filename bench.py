@@ -214,9 +214,9 @@ def main():
 
     # ---------------- GPU arm ----------------
     qauto = a.qgram
-    if qauto < 0:  # auto: leave ~3 levels below the expected depth at which cursors become unique
+    if qauto < 0:  # auto (as the CLI): one level below the expected depth at which cursors become unique, 4.3 GB at most
         import math
-        qauto = max(0, min(12, int(math.log(max(4, info["n_rows"]), 4)) - 3))
+        qauto = max(0, min(14, int(math.log(max(4, info["n_rows"]), 4)) - 1))
     if a.device_sa_rate:
         ctx.densify(a.device_sa_rate)
     if a.text:

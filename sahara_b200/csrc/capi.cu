@@ -140,15 +140,17 @@ struct DeviceIndex {
     DevBuf qgram;
     uint32_t qgram_q{};
     DevBuf sa32, isa32, text4;  // in-text verification tables
+    DevBuf seq_start;           // u64[n_seqs + 1]: start of every sequence in the delimited text (with the tables above)
+    uint64_t n_seqs{};
     bool text_mode{};
     OccTable bwt() const { return OccTable{bwt_blk.get<OccBlk>(), bwt_sup.get<OccSup>()}; }
     OccTable rev() const { return OccTable{rev_blk.get<OccBlk>(), rev_sup.get<OccSup>()}; }
     uint64_t bytes() const {
         return bwt_blk.cap + bwt_sup.cap + rev_blk.cap + rev_sup.cap + marks.cap + ssa.cap + ref_mark_words.cap + ref_ssa.cap +
-               qgram.cap + sa32.cap + isa32.cap + text4.cap;
+               qgram.cap + sa32.cap + isa32.cap + text4.cap + seq_start.cap;
     }
     void release() {
-        for (DevBuf* b : {&bwt_blk, &bwt_sup, &rev_blk, &rev_sup, &d_C, &marks, &ssa, &ref_mark_words, &ref_ssa, &qgram, &sa32, &isa32, &text4})
+        for (DevBuf* b : {&bwt_blk, &bwt_sup, &rev_blk, &rev_sup, &d_C, &marks, &ssa, &ref_mark_words, &ref_ssa, &qgram, &sa32, &isa32, &text4, &seq_start})
             b->release();
         loaded = false;
         qgram_q = 0;
@@ -169,13 +171,13 @@ struct sb200_ctx {
     // work buffers
     uint32_t fused_shift{0};  // hit keys of the last locate carry the query id above this bit (0: separate array)
     int sorted_keys{0};       // d_keys[] buffer that holds the sorted hits
-    DevBuf d_items, d_item_tags, d_seeds, d_spill, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
+    DevBuf d_qpos, d_tasks, d_bigsegs, d_lc, d_items, d_item_tags, d_seeds, d_spill, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
     uint64_t cursor_cap{}, seed_cap{};
     uint64_t last_cursors{}, last_real_cursors{}, last_hits{};
     uint64_t nodes_text{};
     float ms_fm{}, ms_text{};
     bool hits_in_second{};  // which of the double buffers holds the sorted hits
-    unsigned long long* h_counters{};  // pinned + mapped, CT_COUNT entries + 1 scratch word
+    unsigned long long* h_counters{};  // pinned + mapped, CT_COUNT entries + 8 scratch words
     unsigned long long* h_counters_dev{};  // its device alias
     sb200_counters ct{};
     cudaEvent_t ev[12]{};
@@ -685,7 +687,7 @@ void launch_search(sb200_ctx* c, const SearchParams& P) {
 }
 
 // kernel 2 on device-resident queries; cursors stay in c->d_cursors
-void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uint32_t len) {
+void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uint32_t len, bool for_locate = false) {
     auto& ix = c->idx;
     if (!ix.loaded) throw Error("no index loaded");
     if (!c->have_scheme) throw Error("no search scheme set");
@@ -742,6 +744,8 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         P.sa32 = ix.text_mode ? ix.sa32.get<uint32_t>() : nullptr;
         P.isa32 = ix.text_mode ? ix.isa32.get<uint32_t>() : nullptr;
         P.text4 = ix.text_mode ? ix.text4.get<uint32_t>() : nullptr;
+        // cursors that go straight to the locate step carry the text position of a verified occurrence instead of its row
+        P.textpos_out = (for_locate && ix.text_mode && !(std::getenv("SB200_TEXTPOS") && std::atoi(std::getenv("SB200_TEXTPOS")) == 0)) ? 1u : 0u;
         if (const char* dbg = std::getenv("SB200_DEBUG")) P.debug_flags = static_cast<uint32_t>(std::atoi(dbg));
         launch_search(c, P);
         read_back_words(c, c->d_counters.p, CT_COUNT);
@@ -782,10 +786,114 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
     c->last_hits = 0;
 }
 
+static_assert(kCursorTextPosFlag == kCursorTextPos, "search.cuh and locate.cuh agree on the flag");
+
+__global__ void mirror_u32_kernel(const uint32_t* src, unsigned long long* dst, int n) {
+    if (threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+
+LocateIndex locate_index(sb200_ctx* c) {
+    auto& ix = c->idx;
+    LocateIndex L{};
+    L.bwt = ix.bwt();
+    for (int i = 0; i < 8; ++i) L.C[i] = ix.C[i];
+    L.marks = ix.full_sa ? nullptr : ix.marks.get<MarkRec>();
+    L.ssa = ix.ssa.get<uint64_t>();
+    L.seq_start = ix.text_mode ? ix.seq_start.get<uint64_t>() : nullptr;
+    L.n_seqs = static_cast<uint32_t>(ix.n_seqs);
+    L.bits = static_cast<uint32_t>(ix.bits_for_position);
+    return L;
+}
+
+// Locate + sort through per-query buckets (locate.cuh) for the cursors of a search over queries 0 .. n_queries-1.
+// Returns false when some query has more hits than a block sorts (the caller then takes the global radix sort).
+bool locate_bucketed(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries) {
+    auto& ix = c->idx;
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    c->d_counters.reserve(CT_COUNT * sizeof(unsigned long long));
+    CUDA_TRY(cudaMemsetAsync(c->d_counters.get<unsigned long long>() + CT_LF_STEPS, 0, sizeof(unsigned long long), c->stream));
+    c->d_qpos.reserve((n_queries + 1) * 4);
+    c->d_lc.reserve(LC_COUNT * 4);
+    CUDA_TRY(cudaMemsetAsync(c->d_qpos.p, 0, (n_queries + 1) * 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_lc.p, 0, LC_COUNT * 4, c->stream));
+    uint64_t total_rows = 0;
+    if (n_cursors > 0) {
+        hit_count_kernel<<<grid_for(n_cursors), 256, 0, c->stream>>>(c->d_cursors.get<uint4>(), static_cast<uint32_t>(n_cursors),
+                                                                    c->d_qpos.get<uint32_t>());
+        launch_check(c);
+        size_t tmp_bytes = 0;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->d_qpos.get<uint32_t>(), c->d_qpos.get<uint32_t>(), n_queries + 1, c->stream));
+        c->d_tmp.reserve(tmp_bytes);
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_tmp.p, tmp_bytes, c->d_qpos.get<uint32_t>(), c->d_qpos.get<uint32_t>(), n_queries + 1, c->stream));
+        c->ct.kernel_launches += 2;
+        mirror_u32_kernel<<<1, 32, 0, c->stream>>>(c->d_qpos.get<uint32_t>() + n_queries, c->h_counters_dev + CT_COUNT, 1);
+        launch_check(c);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        total_rows = c->h_counters[CT_COUNT];
+    }
+    c->fused_shift = 0;
+    c->sorted_keys = 0;
+    c->d_keys[0].reserve(std::max<uint64_t>(1, total_rows) * 8);
+    c->d_qids[0].reserve(std::max<uint64_t>(1, total_rows) * 4);
+    bool ok = true;
+    if (total_rows > 0) {
+        BucketParams B{};
+        B.index = locate_index(c);
+        B.cursors = c->d_cursors.get<uint4>();
+        B.n_cursors = static_cast<uint32_t>(n_cursors);
+        B.n_queries = static_cast<uint32_t>(n_queries);
+        B.qpos = c->d_qpos.get<uint32_t>();
+        B.keys = c->d_keys[0].get<uint64_t>();
+        B.qids = c->d_qids[0].get<uint32_t>();
+        B.task_cap = static_cast<uint32_t>(std::min<uint64_t>(total_rows / kInlineRows + 1024, 0xfffffff0ull));
+        B.big_cap = static_cast<uint32_t>(total_rows / kWarpSeg + 16);
+        c->d_tasks.reserve(uint64_t(B.task_cap) * sizeof(uint4));
+        c->d_bigsegs.reserve(uint64_t(B.big_cap) * 4);
+        B.tasks = c->d_tasks.get<uint4>();
+        B.big_segs = c->d_bigsegs.get<uint32_t>();
+        B.lc = c->d_lc.get<unsigned int>();
+        B.counters = c->d_counters.get<unsigned long long>();
+        const unsigned wide = static_cast<unsigned>(c->sms) * 4;
+        with_sigma(ix.sigma, [&](auto S) {
+            locate_scatter_kernel<S()><<<grid_for(n_cursors), 256, 0, c->stream>>>(B);
+            launch_check(c);
+            locate_tasks_kernel<S()><<<wide, 256, 0, c->stream>>>(B);
+            return 0;
+        });
+        launch_check(c);
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        segment_sort_kernel<<<grid_for((n_queries + 31) / 32 * 32), 256, 0, c->stream>>>(B);  // one lane per query
+        launch_check(c);
+        segment_sort_big_kernel<<<wide, 256, 0, c->stream>>>(B);
+        launch_check(c);
+        CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+        mirror_u32_kernel<<<1, 32, 0, c->stream>>>(c->d_lc.get<uint32_t>(), c->h_counters_dev + CT_COUNT, LC_COUNT);
+        launch_check(c);
+        read_back_words(c, c->d_counters.p, CT_COUNT);
+        ok = c->h_counters[CT_COUNT + LC_HUGE] == 0 && c->h_counters[CT_COUNT + LC_TASKS] <= B.task_cap;
+    } else {
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+        read_back_words(c, c->d_counters.p, CT_COUNT);
+    }
+    if (!ok) return false;
+    c->ct.lf_steps += c->h_counters[CT_LF_STEPS];
+    c->ct.hits += total_rows;
+    c->last_hits = total_rows;
+    CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_locate, c->ev[1], c->ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_sort, c->ev[2], c->ev[3]));
+    return true;
+}
+
 // kernel 3 over the n_cursors cursors in c->d_cursors (room for one extra slot), then sort by
 // (qid, seq/pos, e).  Sorted hits end in d_keys[sorted_keys] (fused keys) or d_keys[0] / d_qids[0].
 void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
     auto& ix = c->idx;
+    // cursors of our own search (query ids 0 .. n_queries_hint-1): per-query buckets; SB200_BUCKET_SORT=0 or a query with
+    // thousands of hits: global radix sort
+    const bool bucketed = n_queries_hint > 0 && n_queries_hint < 0xffffffffull && n_cursors < 0xffffffffull &&
+                          !(std::getenv("SB200_BUCKET_SORT") && std::atoi(std::getenv("SB200_BUCKET_SORT")) == 0);
+    if (bucketed && locate_bucketed(c, n_cursors, n_queries_hint)) return;
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     c->d_counters.reserve(CT_COUNT * sizeof(unsigned long long));
     CUDA_TRY(cudaMemsetAsync(c->d_counters.get<unsigned long long>() + CT_LF_STEPS, 0, sizeof(unsigned long long), c->stream));
@@ -820,10 +928,7 @@ void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
     }
     if (total_rows > 0) {
         LocateParams L{};
-        L.index.bwt = ix.bwt();
-        for (int i = 0; i < 8; ++i) L.index.C[i] = ix.C[i];
-        L.index.marks = ix.full_sa ? nullptr : ix.marks.get<MarkRec>();
-        L.index.ssa = ix.ssa.get<uint64_t>();
+        L.index = locate_index(c);
         L.cursors = c->d_cursors.get<uint4>();
         L.offsets = c->d_offsets.get<uint64_t>();
         L.n_cursors = static_cast<uint32_t>(n_cursors);
@@ -875,7 +980,7 @@ void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
 }
 
 void run_pipeline(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uint32_t len, bool do_locate) {
-    search_only(c, d_queries, n_queries, len);
+    search_only(c, d_queries, n_queries, len, do_locate);
     if (do_locate) locate_only(c, c->last_cursors, n_queries);
 }
 
@@ -1090,7 +1195,7 @@ int sb200_create(int device, sb200_ctx** out) {
         }
         // mapped: small read-backs are written by a kernel straight into host memory, so they never queue behind
         // a large hit transfer on the copy engine
-        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counters), (CT_COUNT + 1) * sizeof(unsigned long long), cudaHostAllocMapped));
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counters), (CT_COUNT + 8) * sizeof(unsigned long long), cudaHostAllocMapped));
         CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->h_counters_dev), c->h_counters, 0));
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -1105,7 +1210,7 @@ int sb200_destroy(sb200_ctx* c) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         c->idx.release();
-        for (DevBuf* b : {&c->d_steps, &c->d_runs, &c->d_items, &c->d_item_tags, &c->d_seeds, &c->d_spill, &c->d_packed, &c->d_queries, &c->d_cursors, &c->d_counters, &c->d_offsets, &c->d_keys[0], &c->d_keys[1],
+        for (DevBuf* b : {&c->d_steps, &c->d_runs, &c->d_qpos, &c->d_tasks, &c->d_bigsegs, &c->d_lc, &c->d_items, &c->d_item_tags, &c->d_seeds, &c->d_spill, &c->d_packed, &c->d_queries, &c->d_cursors, &c->d_counters, &c->d_offsets, &c->d_keys[0], &c->d_keys[1],
                           &c->d_qids[0], &c->d_qids[1], &c->d_tmp, &c->d_scratch})
             b->release();
         for (auto& ev : c->ev) cudaEventDestroy(ev);
@@ -1331,7 +1436,7 @@ int sb200_index_enable_text(sb200_ctx* c, int enable) {
         auto& ix = c->idx;
         if (!ix.loaded) throw Error("no index loaded");
         if (!enable) {
-            for (DevBuf* b : {&ix.sa32, &ix.isa32, &ix.text4}) b->release();
+            for (DevBuf* b : {&ix.sa32, &ix.isa32, &ix.text4, &ix.seq_start}) b->release();
             ix.text_mode = false;
             return;
         }
@@ -1353,9 +1458,10 @@ int sb200_index_enable_text(sb200_ctx* c, int enable) {
         }
         for (uint64_t i = 0; i < n_seqs; ++i) start[i + 1] = start[i] + lens[i] + 1;
         if (start[n_seqs] != n) throw Error("index layout not understood: sequence lengths do not add up to the text length");
-        DevBuf d_start;
+        DevBuf& d_start = ix.seq_start;
         d_start.reserve((n_seqs + 1) * 8);
         CUDA_TRY(cudaMemcpyAsync(d_start.p, start.data(), (n_seqs + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        ix.n_seqs = n_seqs;
         ix.sa32.reserve(n * 4);
         ix.isa32.reserve(n * 4);
         uint64_t n_words = n / 8 + 2;
@@ -1371,7 +1477,6 @@ int sb200_index_enable_text(sb200_ctx* c, int enable) {
         });
         launch_check(c);
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        d_start.release();
         ix.text_mode = true;
     });
 }

@@ -36,7 +36,27 @@ struct LocateIndex {
     uint32_t C[8];
     const MarkRec* marks;  // nullptr when the device suffix array is complete (rate 1)
     const uint64_t* ssa;   // (seqId << bits) | seqPos of the marked rows, in row order
+    // for cursors that carry a text position instead of a row (in-text verification): start of every sequence in the
+    // delimited text, n_seqs + 1 entries
+    const uint64_t* seq_start;
+    uint32_t n_seqs;
+    uint32_t bits;         // bits_for_position
 };
+
+// cursor.w flag: cursor.y is the text position of the (single) occurrence, not a suffix-array row.  The in-text
+// verification knows the position; going through ISA and SA again would cost two random reads per hit.
+constexpr uint32_t kCursorTextPos = 0x10u;
+
+// text position -> (seqId << bits) | seqPos
+__device__ __forceinline__ uint64_t textpos_value(const LocateIndex& X, uint32_t a) {
+    uint32_t lo = 0, hi = X.n_seqs;  // largest i with seq_start[i] <= a
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (X.seq_start[mid] <= a) lo = mid;
+        else hi = mid;
+    }
+    return (static_cast<uint64_t>(lo) << X.bits) | (a - X.seq_start[lo]);
+}
 
 // LF-walk from `row` to the next sampled row; returns the sample value + number of steps walked
 template <int SIGMA>
@@ -97,17 +117,205 @@ __global__ void __launch_bounds__(256) locate_kernel(const LocateParams P) {
         }
         uint4 cur = P.cursors[lo];
         uint32_t row = cur.y + static_cast<uint32_t>(j - P.offsets[lo]);
-        uint64_t v = locate_row<SIGMA>(P.index, row, steps);
+        uint64_t v = (cur.w & kCursorTextPos) ? textpos_value(P.index, cur.y) : locate_row<SIGMA>(P.index, row, steps);
+        const uint32_t e = cur.w & 0xfu;
         if (P.fused_shift) {
-            P.out_key[j] = (static_cast<uint64_t>(cur.x) << P.fused_shift) | (v << 4) | cur.w;
+            P.out_key[j] = (static_cast<uint64_t>(cur.x) << P.fused_shift) | (v << 4) | e;
         } else {
-            P.out_key[j] = (v << 4) | cur.w;
+            P.out_key[j] = (v << 4) | e;
             P.out_qid[j] = cur.x;
         }
     }
     // warp-aggregated step counter
     for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
     if ((threadIdx.x & 31) == 0 && steps) atomicAdd(&P.counters[4], static_cast<unsigned long long>(steps));
+}
+
+// ---- locate + sort by query buckets ------------------------------------------------------------------
+// The hits of a search are wanted in the order (query, sequence, position, errors).  A query has few hits (8 on
+// average in the headline workload), so instead of radix-sorting all hits by 57 bits (8 passes over 16 M pairs):
+//   hit_count_kernel      hits per query (one pass over the cursors, red.add)
+//   (exclusive scan)      first slot of every query
+//   locate_scatter_kernel one thread per cursor: locates its rows and writes them into the slots of its query
+//                         (cursors with many rows are cut into tasks for locate_tasks_kernel)
+//   segment_sort_kernel   one warp per 32 queries: bitonic sort of each segment (<= 32 keys in registers over shuffles,
+//                         <= 256 in shared memory); longer segments go to
+//   segment_sort_big_kernel (one block per segment, bitonic sort of <= 2048 keys in shared memory); a query with
+//                         more hits than that sets a flag and the host falls back to the global radix sort.
+constexpr uint32_t kInlineRows = 8;      // rows a thread of locate_scatter_kernel locates itself
+constexpr uint32_t kTaskRows = 1024;     // rows per task of locate_tasks_kernel
+constexpr uint32_t kWarpSeg = 256;       // keys a warp of segment_sort_kernel sorts
+constexpr uint32_t kBigSeg = 2048;       // keys a block of segment_sort_big_kernel sorts
+enum : int { LC_TASKS = 0, LC_BIG_SEGS = 1, LC_HUGE = 2, LC_COUNT = 4 };
+
+struct BucketParams {
+    LocateIndex index;
+    const uint4* cursors;  // (qid, lb or text position, len, e | flags)
+    uint32_t n_cursors;
+    uint32_t n_queries;
+    uint32_t* qpos;        // [n_queries + 1] hits per query -> first slot -> (after the scatter) end of the segment
+    uint64_t* keys;        // (value << 4) | e
+    uint32_t* qids;
+    uint4* tasks;          // (cursor, first row of the task, first slot, -)
+    uint32_t task_cap;
+    uint32_t* big_segs;    // queries with more than kWarpSeg hits
+    uint32_t big_cap;
+    unsigned int* lc;      // LC_* counters
+    unsigned long long* counters;  // [4] LF steps
+};
+
+__global__ void __launch_bounds__(256) hit_count_kernel(const uint4* cursors, uint32_t n_cursors, uint32_t* qcount) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cursors) return;
+    const uint4 c = cursors[i];
+    if (c.z != 0) atomicAdd(&qcount[c.x], c.z);
+}
+
+template <int SIGMA>
+__global__ void __launch_bounds__(256) locate_scatter_kernel(const BucketParams P) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t steps = 0;
+    if (i < P.n_cursors) {
+        const uint4 c = P.cursors[i];
+        if (c.z != 0) {
+            const uint32_t base = atomicAdd(&P.qpos[c.x], c.z);
+            const uint32_t e = c.w & 0xfu;
+            if (c.w & kCursorTextPos) {  // (always a single row)
+                P.keys[base] = (textpos_value(P.index, c.y) << 4) | e;
+                P.qids[base] = c.x;
+            } else if (c.z <= kInlineRows) {
+                for (uint32_t r = 0; r < c.z; ++r) {
+                    uint32_t st = 0;
+                    P.keys[base + r] = (locate_row<SIGMA>(P.index, c.y + r, st) << 4) | e;
+                    P.qids[base + r] = c.x;
+                    steps += st;
+                }
+            } else {
+                for (uint32_t off = 0; off < c.z; off += kTaskRows) {
+                    const uint32_t t = atomicAdd(&P.lc[LC_TASKS], 1u);
+                    if (t < P.task_cap) P.tasks[t] = make_uint4(i, off, base + off, 0);
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
+    if ((threadIdx.x & 31) == 0 && steps) atomicAdd(&P.counters[4], static_cast<unsigned long long>(steps));
+}
+
+// one warp per task: up to kTaskRows rows of one cursor
+template <int SIGMA>
+__global__ void __launch_bounds__(256) locate_tasks_kernel(const BucketParams P) {
+    const uint32_t n_tasks = P.lc[LC_TASKS] < P.task_cap ? P.lc[LC_TASKS] : P.task_cap;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    uint32_t steps = 0;
+    for (uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tasks; t += warps) {
+        const uint4 task = P.tasks[t];
+        const uint4 c = P.cursors[task.x];
+        const uint32_t end = task.y + kTaskRows < c.z ? task.y + kTaskRows : c.z;
+        for (uint32_t r = task.y + lane; r < end; r += 32u) {
+            uint32_t st = 0;
+            P.keys[task.z + (r - task.y)] = (locate_row<SIGMA>(P.index, c.y + r, st) << 4) | (c.w & 0xfu);
+            P.qids[task.z + (r - task.y)] = c.x;
+            steps += st;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
+    if (lane == 0 && steps) atomicAdd(&P.counters[4], static_cast<unsigned long long>(steps));
+}
+
+// one warp per 32 consecutive queries: the lanes read the segment bounds, then the warp sorts the segments with two
+// or more keys one after the other — up to 32 keys in registers (bitonic network over shuffles), up to kWarpSeg keys
+// in the warp's shared buffer; longer segments go to segment_sort_big_kernel
+__global__ void __launch_bounds__(256) segment_sort_kernel(const BucketParams P) {
+    __shared__ uint64_t sbuf[8][kWarpSeg];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t q = (blockIdx.x * (blockDim.x >> 5) + warp) * 32u + lane;
+    uint32_t s_l = 0, n_l = 0;
+    if (q < P.n_queries) {
+        s_l = q ? P.qpos[q - 1] : 0u;
+        n_l = P.qpos[q] - s_l;
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, n_l >= 2);
+    uint64_t* buf = sbuf[warp];
+    while (todo != 0) {
+        const int src = __ffs(static_cast<int>(todo)) - 1;
+        todo &= todo - 1;
+        const uint32_t s = __shfl_sync(0xffffffffu, s_l, src), n = __shfl_sync(0xffffffffu, n_l, src);
+        uint64_t* k = P.keys + s;
+        if (n <= 32u) {
+            uint64_t v = lane < n ? k[lane] : ~uint64_t{0};
+#pragma unroll
+            for (uint32_t size = 2; size <= 32u; size <<= 1)
+#pragma unroll
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    const uint64_t o = __shfl_xor_sync(0xffffffffu, v, stride);
+                    const bool up = (lane & size) == 0 || size == 32u;
+                    const bool lower = (lane & stride) == 0;  // this lane keeps the smaller key of the pair when ascending
+                    v = ((v < o) == (lower == up)) ? v : o;
+                }
+            if (lane < n) k[lane] = v;
+        } else if (n <= kWarpSeg) {
+            uint32_t m = 64;  // power of two >= n
+            while (m < n) m <<= 1;
+            for (uint32_t i = lane; i < m; i += 32u) buf[i] = i < n ? k[i] : ~uint64_t{0};
+            __syncwarp();
+            for (uint32_t size = 2; size <= m; size <<= 1)
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (uint32_t i = lane; i < m / 2; i += 32u) {
+                        const uint32_t lo = 2 * i - (i & (stride - 1));
+                        const uint32_t hi = lo + stride;
+                        const bool up = (lo & size) == 0;
+                        const uint64_t x = buf[lo], y = buf[hi];
+                        if ((x > y) == up) {
+                            buf[lo] = y;
+                            buf[hi] = x;
+                        }
+                    }
+                    __syncwarp();
+                }
+            for (uint32_t i = lane; i < n; i += 32u) k[i] = buf[i];
+            __syncwarp();
+        } else if (lane == 0) {
+            const uint32_t qq = (blockIdx.x * (blockDim.x >> 5) + warp) * 32u + static_cast<uint32_t>(src);
+            if (n > kBigSeg) {
+                P.lc[LC_HUGE] = 1u;
+            } else {
+                const uint32_t t = atomicAdd(&P.lc[LC_BIG_SEGS], 1u);
+                if (t < P.big_cap) P.big_segs[t] = qq;
+                else P.lc[LC_HUGE] = 1u;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) segment_sort_big_kernel(const BucketParams P) {
+    __shared__ uint64_t sk[kBigSeg];
+    const uint32_t n_big = P.lc[LC_BIG_SEGS] < P.big_cap ? P.lc[LC_BIG_SEGS] : P.big_cap;
+    for (uint32_t b = blockIdx.x; b < n_big; b += gridDim.x) {
+        const uint32_t q = P.big_segs[b];
+        const uint32_t s = q ? P.qpos[q - 1] : 0u, n = P.qpos[q] - s;
+        uint32_t m = 64;  // power of two >= n
+        while (m < n) m <<= 1;
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) sk[i] = i < n ? P.keys[s + i] : ~uint64_t{0};
+        __syncthreads();
+        for (uint32_t size = 2; size <= m; size <<= 1)
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t i = threadIdx.x; i < m / 2; i += blockDim.x) {
+                    const uint32_t lo = 2 * i - (i & (stride - 1));  // element with the stride bit clear
+                    const uint32_t hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const uint64_t x = sk[lo], y = sk[hi];
+                    if ((x > y) == up) {
+                        sk[lo] = y;
+                        sk[hi] = x;
+                    }
+                }
+                __syncthreads();
+            }
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) P.keys[s + i] = sk[i];
+        __syncthreads();
+    }
 }
 
 struct CursorLen {

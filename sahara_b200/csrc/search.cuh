@@ -48,6 +48,7 @@ constexpr uint32_t kEmitChunk = 16;   // output slots a thread reserves per atom
 constexpr uint32_t kQueryBatch = 2;   // queries a thread takes per atomic
 constexpr uint32_t kInvalidQid = 0xffffffffu;
 constexpr uint32_t kRunE = 5;         // error levels 0..4 in the run table
+constexpr uint32_t kCursorTextPosFlag = 0x10u;  // == kCursorTextPos of locate.cuh
 
 // Match-only runs.  At (step, e) with u[step] == e and l[step] <= e only a match is possible (no error may be
 // added) — in the text kernel such steps are compared symbol by symbol without touching the stack.  run(step, e)
@@ -115,6 +116,7 @@ struct SearchParams {
     // (qid, search | toText << 8 | live slots of the query << 16)
     uint4* items;
     uint2* item_tags;
+    uint32_t textpos_out;    // 1: verified occurrences are reported as (qid, text position, 1, e | kCursorTextPos) for the locate step
 };
 
 __host__ __device__ inline uint32_t packed_words(uint32_t len) { return (len + 7) / 8; }
@@ -448,8 +450,19 @@ __device__ __forceinline__ void fm_thread(const SearchParams& P, const uint32_t*
 //     are read through L1 from the packed queries (requested before the probe).  No long-latency operation of the
 //     refill is on the critical path of an iteration any more.
 // ================================================================================================
-constexpr uint32_t kItemClaim = 32;  // queries a warp claims per atomic
+constexpr uint32_t kItemClaim = 32;  // queries a warp claims per atomic (fewer when the batch is small: see item_claim)
 constexpr uint32_t kItemToText = 0x100u;
+
+// queries per claim: every warp should come back for work at least ~6 times, or the last claims decide the run time
+__device__ __forceinline__ uint32_t item_claim(uint32_t n_queries) {
+#if defined(SB200_HOST_EMU)
+    const uint32_t warps = 1;
+#else
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+#endif
+    const uint32_t c = n_queries / (warps * 6u);
+    return c < 4u ? 4u : (c > kItemClaim ? kItemClaim : c);
+}
 
 // root frames of all searches of query qid -> its slots of P.items / P.item_tags
 __device__ __forceinline__ void fm_make_items(const SearchParams& P, const uint32_t* steps, uint32_t qid) {
@@ -490,6 +503,7 @@ __device__ __forceinline__ void fm_items_thread(const SearchParams& P, const uin
     const uint32_t W = packed_words(qlen);
     const uint32_t n_queries = P.n_queries;
     const uint32_t lane = warp_lane();
+    const uint32_t claim = item_claim(n_queries);
 
     // the item being walked
     uint32_t qid = 0, search = 0;
@@ -546,14 +560,14 @@ __device__ __forceinline__ void fm_items_thread(const SearchParams& P, const uin
         const uint32_t want = exhausted ? 0u : warp_ballot(!have_next);
         if (want != 0) {
             if (wnext == wend) {  // the range is used up: continue with the claim made ahead
-                if (!chave && lane == 0) cnext = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_ITEM], static_cast<unsigned long long>(kItemClaim)));
+                if (!chave && lane == 0) cnext = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_ITEM], static_cast<unsigned long long>(claim)));
                 wnext = warp_bcast0(cnext);
                 chave = false;
                 if (wnext >= n_queries) {
                     exhausted = true;
                     wnext = wend = 0;
                 } else {
-                    wend = wnext + kItemClaim < n_queries ? wnext + kItemClaim : n_queries;
+                    wend = wnext + claim < n_queries ? wnext + claim : n_queries;
                 }
             }
             const uint32_t left = wend - wnext;
@@ -569,8 +583,8 @@ __device__ __forceinline__ void fm_items_thread(const SearchParams& P, const uin
                 have_next = true;
             }
             wnext += take;
-            if (!chave && !exhausted && wend - wnext < kItemClaim / 2) {  // claim ahead: the result is needed much later
-                if (lane == 0) cnext = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_ITEM], static_cast<unsigned long long>(kItemClaim)));
+            if (!chave && !exhausted && wend - wnext < claim / 2) {  // claim ahead: the result is needed much later
+                if (lane == 0) cnext = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_ITEM], static_cast<unsigned long long>(claim)));
                 chave = true;
             }
         }
@@ -639,7 +653,7 @@ __device__ __forceinline__ void text_thread(const SearchParams& P, const uint32_
         return funnel_r(lo, hi, (pos & 7u) * 4u);
     };
     auto emit = [&](uint32_t a, uint32_t e) {
-        outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], make_uint4(qid, P.isa32[a], 1, e));
+        outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], P.textpos_out ? make_uint4(qid, a, 1, e | kCursorTextPosFlag) : make_uint4(qid, P.isa32[a], 1, e));
         ++emitted;
     };
     auto push = [&](uint32_t a, uint32_t m) {
@@ -952,7 +966,7 @@ __device__ __forceinline__ SeedCtx seed_ctx(const SearchParams& P, const uint32_
     return SeedCtx{pool.query + slot * pool.Wp, s_steps + sid * P.len, s_runs + sid * P.len * kRunE, pool.ctx_qid[slot], packed_words(P.len)};
 }
 __device__ __forceinline__ void pool_emit(const SearchParams& P, PoolLane& ls, uint32_t qid, uint32_t a, uint32_t e) {
-    ls.outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], make_uint4(qid, P.isa32[a], 1, e));
+    ls.outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], P.textpos_out ? make_uint4(qid, a, 1, e | kCursorTextPosFlag) : make_uint4(qid, P.isa32[a], 1, e));
     ++ls.emitted;
 }
 

@@ -256,7 +256,7 @@ void runSearch(Args const& a) {
         if (!a.has("--no-text")) check(sb200_index_enable_text(ctxs[g], 1));
         unsigned q = 0;
         for (uint64_t n = image.n_rows; n >= 4 && q < 15; n /= 4) ++q;  // floor(log4(rows))
-        q = q > 3 ? std::min(12u, q - 3) : 0;
+        q = q > 1 ? std::min(14u, q - 1) : 0;  // one level below the depth at which cursors become unique; 4^14 x 16 B = 4.3 GB at most
         if (a.has("--qgram")) q = static_cast<unsigned>(std::stoul(a.get("--qgram")));
         check(sb200_index_build_qgram(ctxs[g], q));
     }

@@ -403,3 +403,37 @@ def test_kernel_variants_agree(sb, ctx, cases, key, monkeypatch):
     finally:
         ctx.build_qgram(0)
         ctx.enable_text(False)
+
+
+def test_bucketed_locate_sort_all_segment_sizes(sb, ctx, monkeypatch):
+    """Hits are located into per-query buckets and sorted per query (locate.cuh): a thread sorts <= 32 hits, a block
+    <= 2048, a query with more falls back to the global radix sort; cursors with more than 8 rows are located by
+    warp tasks.  Repeats of 40 / 300 / 3000 copies reach every one of these paths, with the sampled and the complete
+    suffix array, with text positions or rows in the cursors."""
+    rng = np.random.default_rng(5)
+    units = [W.random_genome(rng, 50) for _ in range(3)]
+    seqs = [np.concatenate([np.tile(units[0], 40), W.random_genome(rng, 3000), np.tile(units[1], 300)]),
+            np.concatenate([W.random_genome(rng, 500), np.tile(units[2], 3000)])]
+    ix = O.OracleIndex.build(seqs, 6, 16)
+    m, k = 30, 1
+    sch = sb.SearchScheme.generate("h2-k2", 0, k, m)
+    reads = [W.sample_reads(rng, [np.tile(u, 3)], 6, m, k, True) for u in units[:2]] + [W.sample_reads(rng, seqs, 60, m, k, True)]
+    q_small = np.concatenate(reads)
+    q_huge = np.concatenate([q_small, W.sample_reads(rng, [np.tile(units[2], 3)], 4, m, k, True)])
+    ctx.build_index(seqs, sigma=6, sampling_rate=16)
+    ctx.set_scheme(sch, True)
+    try:
+        for q in (q_small, q_huge):
+            want = O.sort_rows(ix.locate(ix.search(q, sch, True)))
+            for text in (False, True):
+                ctx.enable_text(text)
+                for bucket in ("1", "0"):
+                    for textpos in ("1", "0"):
+                        monkeypatch.setenv("SB200_BUCKET_SORT", bucket)
+                        monkeypatch.setenv("SB200_TEXTPOS", textpos)
+                        got = ctx.search(q)
+                        assert got.shape == want.shape and np.array_equal(got, want), (text, bucket, textpos)
+                        got32 = ctx.search_reads(np.ascontiguousarray(q[0::2])).astype(np.uint64)
+                        assert np.array_equal(got32, want), (text, bucket, textpos)
+    finally:
+        ctx.enable_text(False)
