@@ -687,7 +687,8 @@ void launch_search(sb200_ctx* c, const SearchParams& P) {
 }
 
 // kernel 2 on device-resident queries; cursors stay in c->d_cursors
-void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uint32_t len, bool for_locate = false) {
+// d_queries: the queries (both strands), or with from_reads the n_queries / 2 reads (the reverse complements are made while packing)
+void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uint32_t len, bool for_locate = false, bool from_reads = false) {
     auto& ix = c->idx;
     if (!ix.loaded) throw Error("no index loaded");
     if (!c->have_scheme) throw Error("no search scheme set");
@@ -703,8 +704,12 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
     const uint32_t W = packed_words(len);
     c->d_packed.reserve(n_queries * W * 4);
     CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, CT_COUNT * sizeof(unsigned long long), c->stream));
-    pack_queries_kernel<<<grid_for(n_queries * W), 256, 0, c->stream>>>(d_queries, n_queries, len, ix.sigma, c->d_packed.get<uint32_t>(),
-                                                                        c->d_counters.get<unsigned long long>());
+    if (from_reads)
+        pack_reads_kernel<<<grid_for(n_queries * W), 256, 0, c->stream>>>(d_queries, n_queries, len, ix.sigma, c->d_packed.get<uint32_t>(),
+                                                                          c->d_counters.get<unsigned long long>());
+    else
+        pack_queries_kernel<<<grid_for(n_queries * W), 256, 0, c->stream>>>(d_queries, n_queries, len, ix.sigma, c->d_packed.get<uint32_t>(),
+                                                                            c->d_counters.get<unsigned long long>());
     launch_check(c);
     uint64_t n_cursors = 0;
     while (true) {
@@ -979,8 +984,8 @@ void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
     CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_sort, c->ev[2], c->ev[3]));
 }
 
-void run_pipeline(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uint32_t len, bool do_locate) {
-    search_only(c, d_queries, n_queries, len, do_locate);
+void run_pipeline(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uint32_t len, bool do_locate, bool from_reads = false) {
+    search_only(c, d_queries, n_queries, len, do_locate, from_reads);
     if (do_locate) locate_only(c, c->last_cursors, n_queries);
 }
 
@@ -1032,7 +1037,7 @@ void search_host_pipelined(sb200_ctx* c, const uint8_t* src, uint64_t n_items, u
     // Chunk boundaries (in queries).  Every chunk costs ~0.9 ms of kernel drain (the longest single seed), so few
     // chunks: a short first one (its copy-in cannot be hidden), a short last one (its copy-out cannot be hidden),
     // and the rest in pieces of at most `chunk` queries whose copies hide behind the neighbours' kernels.
-    uint64_t chunk = 2000000, edge_div = 6;
+    uint64_t chunk = 2000000, edge_div = 5;
     if (const char* e = std::getenv("SB200_CHUNK")) chunk = std::max<uint64_t>(2, std::strtoull(e, nullptr, 10));
     if (const char* e = std::getenv("SB200_EDGE_DIV")) edge_div = std::max<uint64_t>(2, std::strtoull(e, nullptr, 10));
     chunk += chunk & 1;  // both strands of a read stay together
@@ -1054,7 +1059,6 @@ void search_host_pipelined(sb200_ctx* c, const uint8_t* src, uint64_t n_items, u
     uint64_t max_chunk = 0;
     for (uint64_t k = 0; k < n_chunks; ++k) max_chunk = std::max(max_chunk, bounds[k + 1] - bounds[k]);
     for (int i = 0; i < 2; ++i) c->d_qchunk[i].reserve(max_chunk * len);
-    if (make_rc) c->d_queries.reserve(max_chunk * len);
     // wait until earlier work on the caller's stream is done before the copy streams touch the buffers
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     auto copy_in = [&](uint64_t k) {
@@ -1076,13 +1080,8 @@ void search_host_pipelined(sb200_ctx* c, const uint8_t* src, uint64_t n_items, u
             if (k + 1 < n_chunks) copy_in(k + 1);
             CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
             const uint8_t* dq = c->d_qchunk[b].get<uint8_t>();
-            if (make_rc) {
-                revcomp_kernel<<<grid_for(n / 2 * len), 256, 0, c->stream>>>(dq, n / 2, len, c->d_queries.get<uint8_t>());
-                launch_check(c);
-                dq = c->d_queries.get<uint8_t>();
-            }
             auto tc0 = std::chrono::steady_clock::now();
-            run_pipeline(c, dq, n, len, true);  // search + locate + sort of this chunk
+            run_pipeline(c, dq, n, len, true, make_rc);  // search + locate + sort of this chunk (make_rc: dq holds the reads only)
             if (std::getenv("SB200_DEBUG"))
                 fprintf(stderr,
                         "[sb200 debug] chunk %llu: %llu queries, host wall %.3f ms, device search %.3f (fm %.3f text %.3f) locate %.3f sort %.3f ms\n",

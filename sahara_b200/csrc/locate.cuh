@@ -367,17 +367,6 @@ __global__ void compact_hits_kernel(const uint64_t* keys, const uint32_t* qids, 
                         static_cast<uint32_t>(k & 15u));
 }
 
-// queries[2i] = read i, queries[2i+1] = its reverse complement (A<->T, C<->G on ranks 1..4, others unchanged)
-__global__ void revcomp_kernel(const uint8_t* reads, uint64_t n_reads, uint32_t len, uint8_t* queries) {
-    uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (i >= n_reads * len) return;
-    uint64_t r = i / len;
-    uint32_t p = static_cast<uint32_t>(i % len);
-    uint8_t c = reads[i];
-    queries[(2 * r) * len + p] = c;
-    queries[(2 * r + 1) * len + (len - 1 - p)] = (c >= 1 && c <= 4) ? static_cast<uint8_t>(5 - c) : c;
-}
-
 // ---- densify: re-sample the suffix array at a denser rate ------------------------------------------
 // Every row locates itself through the existing samples; rows whose in-sequence position is a multiple
 // of new_rate are marked and their value kept in row_value[row] (compacted afterwards in row order).

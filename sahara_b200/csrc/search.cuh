@@ -138,6 +138,28 @@ __global__ void pack_queries_kernel(const uint8_t* q, uint64_t n_queries, uint32
     }
     out[i] = v;
 }
+
+// the same from the reads alone: query 2r = read r, query 2r + 1 = its reverse complement (A<->T, C<->G on ranks 1..4,
+// others unchanged; /root/reference/src/sahara/search.cpp:121-123) — packed directly, no byte copy of the second strand
+__global__ void pack_reads_kernel(const uint8_t* reads, uint64_t n_queries, uint32_t len, uint32_t sigma, uint32_t* out,
+                                  unsigned long long* counters) {
+    uint32_t W = packed_words(len);
+    uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n_queries * W) return;
+    uint64_t qi = i / W;
+    uint32_t w = static_cast<uint32_t>(i % W);
+    const uint8_t* src = reads + (qi >> 1) * len;
+    const bool rc = qi & 1u;
+    uint32_t v = 0xffffffffu;
+    for (uint32_t k = 0; k < 8 && w * 8 + k < len; ++k) {
+        const uint32_t p = w * 8 + k;
+        uint8_t c = rc ? src[len - 1 - p] : src[p];
+        if (rc && c >= 1 && c <= 4) c = static_cast<uint8_t>(5 - c);
+        if (c >= sigma) atomicMax(&counters[CT_BAD_QUERY], static_cast<unsigned long long>(qi * len + p + 1));
+        v = (v & ~(0xfu << (4 * k))) | (static_cast<uint32_t>(c & 0xfu) << (4 * k));
+    }
+    out[i] = v;
+}
 #endif
 
 // chunked append to a global array: one atomic per kEmitChunk entries
