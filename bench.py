@@ -214,9 +214,9 @@ def main():
 
     # ---------------- GPU arm ----------------
     qauto = a.qgram
-    if qauto < 0:  # auto (as the CLI): one level below the expected depth at which cursors become unique, 4.3 GB at most
+    if qauto < 0:  # auto (as the CLI): the expected depth at which cursors become unique, floor(log4(rows)); 17 GB at most
         import math
-        qauto = max(0, min(14, int(math.log(max(4, info["n_rows"]), 4)) - 1))
+        qauto = max(0, min(15, int(math.log(max(4, info["n_rows"]), 4))))
     if a.device_sa_rate:
         ctx.densify(a.device_sa_rate)
     if a.text:
@@ -345,7 +345,8 @@ def main():
                 "algorithmic_bytes_per_launch": int(per_launch), "achieved": round(ach, 1), "frac": round(ach / peak, 4),
                 "traffic": traffic.get(name), "limited_by": bound, "does": what}
 
-    k_fm = kern("fm_kernel", nodes_fm, ms_fm, "cursor extensions by rank probes (cursors covering several rows)",
+    k_fm = kern("fm_items_kernel", nodes_fm, ms_fm, "cursor extensions by rank probes (cursors covering several rows); the time includes "
+                "fm_roots_kernel (root frames of every query from the q-gram table)",
                 "HBM random access: 38.4 G L2-miss requests/s measured (tools/gather_bench.cu), 1 request per probe")
     k_text = kern("text_pool_kernel" if a.text else "text_kernel", nodes_text, ms_text,
                   "cursor extensions of unique cursors verified in the text (warp-level frame pools)",

@@ -103,7 +103,7 @@ int sb200_index_densify(sb200_ctx* ctx, uint32_t device_sampling_rate);
 int sb200_index_enable_text(sb200_ctx* ctx, int enable);
 
 /* builds the q-gram jump table: the cursor of every string of `q` symbols over A,C,G,T, used to skip
- * the first error-free steps of a search (q = 0 removes it). */
+ * the first error-free steps of a search (q = 0 removes it; q <= 15, 16 bytes x 4^q of device memory). */
 int sb200_index_build_qgram(sb200_ctx* ctx, uint32_t q);
 
 /* ---- search scheme ---------------------------------------------------------------------------------
@@ -184,7 +184,7 @@ typedef struct sb200_counters {
     uint64_t hits;         /* located positions */
     uint64_t kernel_launches; /* kernels launched by this context */
     float ms_search, ms_locate, ms_sort, ms_h2d, ms_d2h; /* last call, CUDA events */
-    float ms_fm, ms_text;     /* last call: the two search kernels (fm_kernel, text_kernel) */
+    float ms_fm, ms_text;     /* last call: the walk over the occurrence tables (fm_roots_kernel + fm_items_kernel), the in-text verification (text_pool_kernel) */
     uint64_t nodes_text;      /* extensions verified in the text instead of the occurrence tables (subset of nodes) */
 } sb200_counters;
 int sb200_get_counters(sb200_ctx* ctx, sb200_counters* out);

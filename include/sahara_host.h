@@ -25,6 +25,12 @@ const char* sbh_scheme_names(void);
  * [n_searches][n_entries] tables released with sbh_free. */
 int sbh_scheme_generate(const char* name, int minK, int maxK, uint32_t len, int limit_to_hamming, uint32_t* n_searches,
                         uint32_t* n_entries, uint16_t** pi, uint8_t** l, uint8_t** u);
+/* `--dynamic_generator` (src/sahara/search.cpp:193-195, 203-205): the parts are sized by optimizeByWNCTopDown<Edit>(scheme,
+ * len, sigma, ref_len, 1) instead of len / parts each; limitToHamming is applied when edit == 0 (search.cpp:226).
+ * partition (optional, partition_cap entries) receives the part sizes, n_parts their number. */
+int sbh_scheme_generate_dynamic(const char* name, int minK, int maxK, uint32_t len, int edit, uint64_t sigma, uint64_t ref_len,
+                                uint32_t* n_searches, uint32_t* n_entries, uint16_t** pi, uint8_t** l, uint8_t** u, uint32_t* partition,
+                                uint32_t partition_cap, uint32_t* n_parts);
 /* same from a Columba-format text ("{pi} {L} {U}" per line, 0-based) */
 int sbh_scheme_from_columba(const char* text, uint32_t len, int limit_to_hamming, uint32_t* n_searches, uint32_t* n_entries,
                             uint16_t** pi, uint8_t** l, uint8_t** u);

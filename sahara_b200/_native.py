@@ -100,6 +100,9 @@ SBH_SYMBOLS = {
     "sbh_scheme_names": (C.c_char_p, []),
     "sbh_scheme_generate": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_uint32, C.c_int, u32p, u32p, C.POINTER(C.c_void_p),
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "sbh_scheme_generate_dynamic": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, u32p, u32p,
+                                              C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_uint32,
+                                              u32p]),
     "sbh_scheme_from_columba": (C.c_int, [C.c_char_p, C.c_uint32, C.c_int, u32p, u32p, C.POINTER(C.c_void_p),
                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "sbh_scheme_check": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

@@ -60,6 +60,16 @@ class SearchScheme:
         return SearchScheme._take(ns, ne, ppi, pl, pu)
 
     @staticmethod
+    def generate_dynamic(name, min_k, max_k, length, edit, sigma, ref_len):
+        """`--dynamic_generator`: part sizes by weighted node count -> (scheme, partition)"""
+        ns, ne, npart = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        ppi, pl, pu = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        part = (C.c_uint32 * 64)()
+        check_host(host.sbh_scheme_generate_dynamic(name.encode(), min_k, max_k, length, int(edit), sigma, ref_len, C.byref(ns),
+                                                    C.byref(ne), C.byref(ppi), C.byref(pl), C.byref(pu), part, 64, C.byref(npart)))
+        return SearchScheme._take(ns, ne, ppi, pl, pu), [int(part[i]) for i in range(min(64, npart.value))]
+
+    @staticmethod
     def from_columba(text, length=0, limit_to_hamming=False):
         ns, ne = C.c_uint32(), C.c_uint32()
         ppi, pl, pu = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -87,6 +87,21 @@ int sbh_scheme_generate(const char* name, int minK, int maxK, uint32_t len, int 
     });
 }
 
+int sbh_scheme_generate_dynamic(const char* name, int minK, int maxK, uint32_t len, int edit, uint64_t sigma, uint64_t ref_len,
+                                uint32_t* n_searches, uint32_t* n_entries, uint16_t** pi, uint8_t** l, uint8_t** u, uint32_t* partition,
+                                uint32_t partition_cap, uint32_t* n_parts) {
+    return guard([&] {
+        auto ss = sahara::scheme::generator::generate(name, minK, maxK);
+        auto counts = edit ? sahara::scheme::optimizeByWNCTopDown<true>(ss, len, sigma, ref_len, 1)
+                           : sahara::scheme::optimizeByWNCTopDown<false>(ss, len, sigma, ref_len, 1);
+        if (n_parts) *n_parts = static_cast<uint32_t>(counts.size());
+        for (size_t i = 0; partition && i < counts.size() && i < partition_cap; ++i) partition[i] = static_cast<uint32_t>(counts[i]);
+        auto ex = sahara::scheme::expand(ss, counts);
+        if (!edit) ex = sahara::scheme::limitToHamming(ex);
+        exportTables(ex, n_searches, n_entries, pi, l, u);
+    });
+}
+
 int sbh_scheme_from_columba(const char* text, uint32_t len, int limit, uint32_t* n_searches, uint32_t* n_entries, uint16_t** pi,
                             uint8_t** l, uint8_t** u) {
     return guard([&] {

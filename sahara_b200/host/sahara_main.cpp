@@ -13,7 +13,8 @@
 // 0, 1, ..., k errors are searched in turn (schemes generator(j, j)) and the first stratum with a hit ends the
 // query; as in the reference this mode always uses edit distance.
 // Not implemented on the GPU path (fails with a clear message): --max_hits > 0 (its result depends on the
-// reference's recursion order) and --dynamic_generator (SURVEY.md §8f "next" rows).
+// reference's recursion order; SURVEY.md §8f "next" row).  --dynamic_generator follows a reconstruction of
+// optimizeByWNCTopDown (host/scheme.hpp).
 #include <algorithm>
 #include <chrono>
 #include <cinttypes>
@@ -194,7 +195,7 @@ void runSearch(Args const& a) {
     if (metric != "ham" && metric != "lev") fail("unknown distance metric \"" + metric + "\"");
     const bool bestHits = mode == "besthits";
     if (maxHits != 0) fail("--max_hits is not available on the GPU path yet");
-    if (a.has("--dynamic_generator")) fail("--dynamic_generator is not available on the GPU path yet");
+    const bool dynGenerator = a.has("--dynamic_generator");
     bool edit = metric == "lev" || bestHits;  // search_best has no Hamming variant (search.cpp:239)
 
     std::vector<std::pair<std::string, double>> timing;
@@ -234,7 +235,7 @@ void runSearch(Args const& a) {
     printf("config:\n  query:               %s\n  index:               %s\n  generator:           %s\n  dynamic expansion:   %s\n"
            "  allowed errors:      %zu\n  reverse complements: %s\n  search mode:         %s\n  max hits:            %ld\n"
            "  output path:         %s\n",
-           queryPath.c_str(), indexPath.c_str(), generator.c_str(), "false", k, noReverse ? "false" : "true", mode.c_str(), maxHits,
+           queryPath.c_str(), indexPath.c_str(), generator.c_str(), dynGenerator ? "true" : "false", k, noReverse ? "false" : "true", mode.c_str(), maxHits,
            outPath.c_str());
     {
         size_t fwd = nQueries / (noReverse ? 1 : 2);
@@ -256,7 +257,7 @@ void runSearch(Args const& a) {
         if (!a.has("--no-text")) check(sb200_index_enable_text(ctxs[g], 1));
         unsigned q = 0;
         for (uint64_t n = image.n_rows; n >= 4 && q < 15; n /= 4) ++q;  // floor(log4(rows))
-        q = q > 1 ? std::min(14u, q - 1) : 0;  // one level below the depth at which cursors become unique; 4^14 x 16 B = 4.3 GB at most
+        q = std::min(15u, q);  // the depth at which cursors become unique; 4^15 x 16 B = 17 GB at most (3.1 Gbp genomes)
         if (a.has("--qgram")) q = static_cast<unsigned>(std::stoul(a.get("--qgram")));
         check(sb200_index_build_qgram(ctxs[g], q));
     }
@@ -280,7 +281,16 @@ void runSearch(Args const& a) {
         } else {
             scheme = ss::generator::generate(generator, minK, maxK);
         }
-        scheme = ss::expand(scheme, qlen);
+        if (!dynGenerator) {
+            scheme = ss::expand(scheme, qlen);
+        } else {  // search.cpp:193-195 / 203-205: part sizes by weighted node count (Sigma, index.size(), steps = 1)
+            auto partition = edit ? ss::optimizeByWNCTopDown<true>(scheme, qlen, Sigma, image.n_rows, 1)
+                                  : ss::optimizeByWNCTopDown<false>(scheme, qlen, Sigma, image.n_rows, 1);
+            std::string txt;
+            for (size_t i = 0; i < partition.size(); ++i) txt += (i ? ", " : "") + std::to_string(partition[i]);
+            printf("partition: [%s]\n", txt.c_str());
+            scheme = ss::expand(scheme, partition);
+        }
         if (edit) {
             printf("node count: %.0Lf\n", ss::nodeCount<true>(scheme, Sigma));
             printf("weighted node count: %.2Lf\n", ss::weightedNodeCount<true>(scheme, Sigma, image.n_rows));

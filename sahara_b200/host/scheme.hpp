@@ -246,6 +246,47 @@ long double weightedNodeCount(Scheme const& ss, size_t sigma, size_t n) {
 }
 
 // ---- generators ------------------------------------------------------------------------------------
+// ---- dynamic expansion (`sahara search --dynamic_generator`, search.cpp:193-195,203-205) ------------
+// optimizeByWNCTopDown / expandByWNCTopDown of fmindex-collection: part sizes chosen to minimise the weighted node
+// count instead of len / P each.  Upstream source is not available here; this is a reconstruction
+// of the published idea: start from the uniform partition ("top") and move `steps` characters from one part to
+// another as long as the weighted node count over a text of N symbols goes down (first improvement, parts in
+// order; every part keeps at least one character).  The partition is printed by the CLI like upstream's
+// "partition: [..]" line; the hit SET of a complete scheme does not depend on it.
+template <bool Edit>
+inline std::vector<size_t> optimizeByWNCTopDown(Scheme const& ss, size_t len, size_t sigma, size_t N, size_t steps) {
+    if (ss.empty()) return {};
+    size_t const P = ss[0].pi.size();
+    if (P > len) throw std::runtime_error("search scheme has more parts than the query has characters");
+    if (steps == 0) steps = 1;
+    auto counts = expandCount(P, len);
+    auto best = weightedNodeCount<Edit>(expand(ss, counts), sigma, N);
+    bool improved = true;
+    while (improved) {
+        improved = false;
+        for (size_t i = 0; i < P; ++i)
+            for (size_t j = 0; j < P; ++j) {
+                if (i == j || counts[i] <= steps) continue;
+                counts[i] -= steps;
+                counts[j] += steps;
+                auto v = weightedNodeCount<Edit>(expand(ss, counts), sigma, N);
+                if (v < best) {
+                    best = v;
+                    improved = true;
+                } else {
+                    counts[i] += steps;
+                    counts[j] -= steps;
+                }
+            }
+    }
+    return counts;
+}
+
+template <bool Edit>
+inline Scheme expandByWNCTopDown(Scheme const& ss, size_t len, size_t sigma, size_t N, size_t steps) {
+    return expand(ss, optimizeByWNCTopDown<Edit>(ss, len, sigma, N, steps));
+}
+
 namespace generator {
 
 // order of parts for a search that starts at part `start`, walks right to the end, then left to 0

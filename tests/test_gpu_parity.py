@@ -231,13 +231,19 @@ def test_cli_index_and_search_roundtrip(sb, cases, tmp_path):
         for i in range(0, q.shape[0], 2):
             f.write(f">r{i // 2}\n" + "".join("$ACGTN"[c] for c in q[i]) + "\n")
     out = os.path.join(tmp_path, "out.txt")
-    for extra, edit in (([], True), (["-d", "ham"], False)):
+    n_rows = ix.info()["n_rows"]
+    for extra, edit, dyn in (([], True, False), (["-d", "ham"], False, False), (["--dynamic_generator"], True, True),
+                             (["--dynamic_generator", "-d", "ham"], False, True)):
         res = subprocess.run([exe, "search", "-q", qa, "-i", fa + ".idx", "-e", str(k), "-o", out, "--batch", "100"] + extra,
                              capture_output=True, text=True)
         assert res.returncode == 0, res.stderr
         assert "queries per second" in res.stdout and "number of hits" in res.stdout
         got = sorted(tuple(int(x) for x in line.split()) for line in open(out))
-        sch = sb.SearchScheme.generate("h2-k2", 0, k, m, limit_to_hamming=not edit)
+        if dyn:  # search.cpp:193-195: parts sized by weighted node count, the partition is printed
+            sch, part = sb.SearchScheme.generate_dynamic("h2-k2", 0, k, m, edit, 6, n_rows)
+            assert "partition: [" + ", ".join(str(x) for x in part) + "]" in res.stdout
+        else:
+            sch = sb.SearchScheme.generate("h2-k2", 0, k, m, limit_to_hamming=not edit)
         want = sorted((int(a), int(b), int(c)) for a, b, c, d in ix.locate(ix.search(q, sch, edit)))
         assert got == want
     # error behaviour of the reference CLI: message + exit code 1

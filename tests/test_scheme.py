@@ -81,3 +81,34 @@ def test_node_counts_are_monotone_in_k():
         nc, wnc = s.node_count(True, 6, 3_100_000_000)
         assert nc >= prev and wnc <= nc
         prev = nc
+
+
+@pytest.mark.parametrize("name,k,edit", [("h2-k2", 2, True), ("h2-k2", 3, True), ("pigeon_opt", 2, False), ("01*0_opt", 2, True), ("optimum", 2, True)])
+def test_dynamic_expansion(name, k, edit):
+    """`--dynamic_generator` (search.cpp:193-195): part sizes by weighted node count — a partition of the query
+    length with no empty part, never worse than the uniform expansion, still a valid expansion of the scheme."""
+    m, sigma, n = 100, 6, 50_000_001
+    dyn, part = sb.SearchScheme.generate_dynamic(name, 0, k, m, edit, sigma, n)
+    uni = sb.SearchScheme.generate(name, 0, k, m, limit_to_hamming=not edit)
+    base = sb.SearchScheme.generate(name, 0, k)
+    assert sum(part) == m and min(part) >= 1 and len(part) == base.n_entries
+    assert dyn.n_searches == uni.n_searches and dyn.n_entries == m
+    assert dyn.node_count(edit, sigma, n)[1] <= uni.node_count(edit, sigma, n)[1] + 1e-9
+    for j in range(dyn.n_searches):  # every search still visits every query position once, bounds monotone
+        assert sorted(int(x) for x in dyn.pi[j]) == list(range(m))
+        assert all(int(a) <= int(b) for a, b in zip(dyn.u[j][:-1], dyn.u[j][1:]))
+
+
+def test_dynamic_expansion_finds_the_same_hamming_hits():
+    import oracle as O
+    import workloads as W
+    import numpy as np
+    rng = np.random.default_rng(3)
+    seqs = [W.random_genome(rng, 4000)]
+    ix = O.OracleIndex.build(seqs, 6, 16)
+    q = W.sample_reads(rng, seqs, 40, 30, 2, False)
+    dyn, _ = sb.SearchScheme.generate_dynamic("h2-k2", 0, 2, 30, False, 6, ix.info()["n_rows"])
+    uni = sb.SearchScheme.generate("h2-k2", 0, 2, 30, limit_to_hamming=True)
+    a = O.sort_rows(ix.locate(ix.search(q, dyn, False)))
+    b = O.sort_rows(ix.locate(ix.search(q, uni, False)))
+    assert np.array_equal(np.unique(a, axis=0), np.unique(b, axis=0))  # the hit SET does not depend on the partition

@@ -7,7 +7,7 @@ import sahara_b200 as sb
 from sahara_b200._native import cuda, check
 n = int(os.environ.get("GENOME", 3100000000)); R = 1000000; m = 150; k = 2
 ctx = sb.Context(0)
-dg = ctx.synth_genome(n, 42); ctx.build_index_device(dg, [n], 6, 16); ctx.enable_text(True); ctx.build_qgram(int(os.environ.get('QGRAM', 14)))
+dg = ctx.synth_genome(n, 42); ctx.build_index_device(dg, [n], 6, 16); ctx.enable_text(True); ctx.build_qgram(int(os.environ.get('QGRAM', 15)))
 ctx.set_scheme(sb.SearchScheme.generate("h2-k2", 0, k, m), True)
 bufs = []
 for b in range(3):

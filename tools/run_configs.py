@@ -33,7 +33,7 @@ def main():
         ctx.build_index_device(dg, [n], 6, 16)
         t_build = time.time() - t
         ctx.enable_text(True)
-        ctx.build_qgram(max(0, min(12, int(math.log(n, 4)) - 3)))
+        ctx.build_qgram(max(0, min(15, int(math.log(n + 1, 4)))))  # the CLI's choice
         view = ctx.download_view()
         try:
             oix = O.OracleIndex.from_view(view)

@@ -7,7 +7,7 @@ n = int(os.environ.get("GENOME", 3100000000)); m = 150; k = 2
 sizes = [int(x) for x in sys.argv[1:]] or [100, 1000, 10000, 50000, 166666, 500000, 1000000]
 ctx = sb.Context(0)
 dg = ctx.synth_genome(n, 42); ctx.build_index_device(dg, [n], 6, 16); ctx.enable_text(True)
-ctx.build_qgram(int(os.environ.get("QGRAM", 14)))
+ctx.build_qgram(int(os.environ.get("QGRAM", 15)))
 ctx.set_scheme(sb.SearchScheme.generate("h2-k2", 0, k, m), True)
 for R in sizes:
     dq = ctx.synth_reads(dg, n, R, m, k, True, 43, 0)
