@@ -115,8 +115,21 @@ def ncu_traffic():
         return None
 
 
+_JSON_OUT = None
+
+
+def emit_json(line):
+    """the one JSON line goes to the real stdout; everything libraries print meanwhile (NCCL's version banner ...)
+    was sent to stderr by main()"""
+    os.write(_JSON_OUT if _JSON_OUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _JSON_OUT
     a = parse_args()
+    sys.stdout.flush()
+    _JSON_OUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -135,6 +148,9 @@ def main():
     torch.cuda.set_device(local)
     if use_dist:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL_DEBUG=VERSION / WARN make NCCL print its version on stdout, in front of the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     ctx = sb.Context(local)
@@ -171,7 +187,8 @@ def main():
             oix = O.OracleIndex.from_view(view)
         finally:
             ctx.free_view(view)
-        threads = O.max_threads()
+        # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what is asked for here)
+        threads = max(O.max_threads(), len(os.sched_getaffinity(0)))
         d_q = ctx.synth_reads(d_genome, a.genome, sample_reads * (steps + warm), m, k, edit, 43, batch_first_read(0))
         q = ctx.to_host(d_q, 2 * sample_reads * (steps + warm) * m).reshape(-1, m)
         ctx.device_free(d_q)
@@ -209,7 +226,7 @@ def main():
                                            f"{res['threads']} OpenMP threads; 1 thread: {res['one_thread_reads_s']:.0f} reads/s"},
                 "e2e": {"value": round(value, 1), "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit_json(line)
         return 0
 
     # ---------------- GPU arm ----------------
@@ -379,7 +396,7 @@ def main():
             "gpu_launches": launches, "roofline": roofline,
             "hits_per_step": int(hits_total / a.steps), "cursors_per_step": int(cursors_total / a.steps)}
 
-    if rank == 0 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:  # (the contract: on rank 0 at N = 1 only)
         sample = a.cpu_sample or 20_000
         res = cpu_baseline(sample, 1, 0)
         cpu_v = sample / res["times"][0]
@@ -405,7 +422,7 @@ def main():
                                           f"{res['threads']} OpenMP threads",
                                 "one_thread_value": round(res["one_thread_reads_s"], 1)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -639,7 +639,7 @@ void launch_search(sb200_ctx* c, const SearchParams& P) {
     const bool use_pool = !(std::getenv("SB200_TEXT_POOL") && std::atoi(std::getenv("SB200_TEXT_POOL")) == 0);
     if (P.sa32 && use_pool) {  // in-text verification, one frame pool per warp
         with_stack(c->kmax, [&](auto STACK) {
-            const size_t tables = ((size_t(P.n_searches) * P.len + (size_t(P.n_searches) * P.len * kRunE + 3) / 4) * 4 + 7) & ~size_t{7};
+            const size_t tables = (size_t(P.n_searches) * P.len * 4 + run_table_bytes(P.n_searches * P.len) + 7) & ~size_t{7};
             // warps per block: as many resident warps per SM as shared memory (227 KB, 1 KB reserved per block) and
             // registers (48 per thread: 42 warps) allow; measured on the headline workload: 36 warps 8.4 ms, 30 warps
             // 9.2 ms, 24 warps 10.2 ms
@@ -823,18 +823,19 @@ bool locate_bucketed(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries) {
     CUDA_TRY(cudaMemsetAsync(c->d_lc.p, 0, LC_COUNT * 4, c->stream));
     uint64_t total_rows = 0;
     if (n_cursors > 0) {
+        CUDA_TRY(cudaMemsetAsync(c->d_counters.get<unsigned long long>() + CT_TOTAL_ROWS, 0, sizeof(unsigned long long), c->stream));
         hit_count_kernel<<<grid_for(n_cursors), 256, 0, c->stream>>>(c->d_cursors.get<uint4>(), static_cast<uint32_t>(n_cursors),
-                                                                    c->d_qpos.get<uint32_t>());
+                                                                    c->d_qpos.get<uint32_t>(),
+                                                                    c->d_counters.get<unsigned long long>() + CT_TOTAL_ROWS);
         launch_check(c);
         size_t tmp_bytes = 0;
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->d_qpos.get<uint32_t>(), c->d_qpos.get<uint32_t>(), n_queries + 1, c->stream));
         c->d_tmp.reserve(tmp_bytes);
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_tmp.p, tmp_bytes, c->d_qpos.get<uint32_t>(), c->d_qpos.get<uint32_t>(), n_queries + 1, c->stream));
         c->ct.kernel_launches += 2;
-        mirror_u32_kernel<<<1, 32, 0, c->stream>>>(c->d_qpos.get<uint32_t>() + n_queries, c->h_counters_dev + CT_COUNT, 1);
-        launch_check(c);
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        read_back_words(c, c->d_counters.get<unsigned long long>() + CT_TOTAL_ROWS, 1, CT_COUNT);
         total_rows = c->h_counters[CT_COUNT];
+        if (total_rows >= (1ull << 32)) throw Error("more than 2^32 hits in one call; split the batch");
     }
     c->fused_shift = 0;
     c->sorted_keys = 0;
@@ -1611,8 +1612,9 @@ int sb200_set_scheme(sb200_ctx* c, uint32_t n_searches, uint32_t len, const uint
         if (kmax > 4) throw Error("search schemes with more than 4 errors are not supported by the GPU kernel yet");
         c->d_steps.reserve(steps.size() * 4);
         CUDA_TRY(cudaMemcpyAsync(c->d_steps.p, steps.data(), steps.size() * 4, cudaMemcpyHostToDevice, c->stream));
-        std::vector<uint8_t> runs(steps.size() * kRunE + 4, 0);
+        std::vector<uint8_t> runs(run_table_bytes(static_cast<uint32_t>(steps.size())) + 4, 0);  // run lengths, then state flags
         build_runs(n_searches, len, steps.data(), runs.data());
+        build_state_flags(n_searches, len, steps.data(), runs.data());
         c->d_runs.reserve(runs.size());
         CUDA_TRY(cudaMemcpyAsync(c->d_runs.p, runs.data(), runs.size(), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));

@@ -164,11 +164,23 @@ struct BucketParams {
     unsigned long long* counters;  // [4] LF steps
 };
 
-__global__ void __launch_bounds__(256) hit_count_kernel(const uint4* cursors, uint32_t n_cursors, uint32_t* qcount) {
+// hits per query (u32: a wrap is caught through *total, the exact 64-bit number of hits)
+__global__ void __launch_bounds__(256) hit_count_kernel(const uint4* cursors, uint32_t n_cursors, uint32_t* qcount, unsigned long long* total) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cursors) return;
-    const uint4 c = cursors[i];
-    if (c.z != 0) atomicAdd(&qcount[c.x], c.z);
+    unsigned long long rows = 0;
+    if (i < n_cursors) {
+        const uint4 c = cursors[i];
+        if (c.z != 0) atomicAdd(&qcount[c.x], c.z);
+        rows = c.z;
+    }
+    // one atomic per block on the single total (one per warp costs 0.35 ms at 16 M cursors)
+    __shared__ unsigned long long block_rows;
+    if (threadIdx.x == 0) block_rows = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);
+    if ((threadIdx.x & 31) == 0 && rows) atomicAdd(&block_rows, rows);
+    __syncthreads();
+    if (threadIdx.x == 0 && block_rows) atomicAdd(total, block_rows);
 }
 
 template <int SIGMA>

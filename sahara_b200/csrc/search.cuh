@@ -74,6 +74,45 @@ inline void build_runs(uint32_t n_searches, uint32_t len, const uint32_t* steps,
             }
 }
 
+// State flags.  What a state (step, e) of the in-text verification may do depends on the scheme tables only; the
+// conditions are evaluated once per scheme instead of once per expanded state (text_states).  The table sits behind
+// the run table: flags(step, e) = runs[state_flags_offset(n_steps) + step * kRunE + e].
+enum : uint32_t {
+    SF_MATCH = 1,     // l <= e <= u: the matching symbol may be taken
+    SF_MISMATCH = 2,  // l <= e + 1 <= u: an error may be added
+    SF_M_ALIVE = 4,   // not the last step and the match child survives the next lower bound
+    SF_SUB_ALIVE = 8, // not the last step and a child with e + 1 errors survives the next lower bound
+    SF_PAIR = 16,     // SF_SUB_ALIVE and the next step extends the same end: deletion + substitution share a frame
+    SF_RUN_M = 32,    // the match child (step + 1, e) starts a match-only run
+    SF_RUN_D = 64,    // the deletion child (step, e + 1) starts a match-only run
+    SF_RUN_S = 128    // the substitution child (step + 1, e + 1) starts a match-only run
+};
+__host__ __device__ inline uint32_t state_flags_offset(uint32_t n_steps) { return (n_steps * kRunE + 3u) & ~3u; }
+__host__ __device__ inline uint32_t run_table_bytes(uint32_t n_steps) { return 2u * state_flags_offset(n_steps); }
+inline void build_state_flags(uint32_t n_searches, uint32_t len, const uint32_t* steps, uint8_t* runs) {
+    uint8_t* flags = runs + state_flags_offset(n_searches * len);
+    for (uint32_t j = 0; j < n_searches; ++j)
+        for (uint32_t i = 0; i < len; ++i)
+            for (uint32_t e = 0; e < kRunE; ++e) {
+                const uint32_t st = steps[j * len + i];
+                const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu, right = (st >> 24) & 1u;
+                const bool last = i + 1 == len;
+                const uint32_t sn = last ? 0u : steps[j * len + i + 1];
+                const uint32_t lnext = (sn >> 16) & 0xfu;
+                auto run = [&](uint32_t ii, uint32_t ee) { return ii < len && ee < kRunE && runs[((j * len) + ii) * kRunE + ee] != 0; };
+                uint32_t f = 0;
+                if (l <= e && e <= u) f |= SF_MATCH;
+                if (l <= e + 1 && e + 1 <= u) f |= SF_MISMATCH;
+                if (!last && lnext <= e + 1) f |= SF_M_ALIVE;
+                if (!last && lnext <= e + 2) f |= SF_SUB_ALIVE;
+                if (!last && lnext <= e + 2 && ((sn >> 24) & 1u) == right) f |= SF_PAIR;
+                if (run(i + 1, e)) f |= SF_RUN_M;
+                if (run(i, e + 1)) f |= SF_RUN_D;
+                if (run(i + 1, e + 1)) f |= SF_RUN_S;
+                flags[((j * len) + i) * kRunE + e] = static_cast<uint8_t>(f);
+            }
+}
+
 // counters (unsigned long long each)
 enum : int {
     CT_NEXT_QUERY = 0,   // work distribution of fm_kernel
@@ -89,6 +128,7 @@ enum : int {
     CT_BAD_QUERY = 10,   // 1 + offset of a query symbol outside the alphabet (0 = none)
     CT_NODES_TEXT = 11,  // states expanded by text_kernel (subset of CT_NODES)
     CT_NEXT_ITEM = 12,   // work distribution of fm_items_kernel
+    CT_TOTAL_ROWS = 13,  // (locate) rows of all cursors = hits
     CT_COUNT = 16
 };
 
@@ -950,6 +990,25 @@ __device__ __forceinline__ void stack_push(const FrameStack& st, uint32_t a, uin
         ls.overflow = true;
     }
 }
+// push onto the run stack (run) or the state stack of the pool: pool_carve lays the run stack right behind the state
+// stack (frames, slots, tops, spill), so the choice is an offset instead of a select over five pointers
+__device__ __forceinline__ void pool_push_to(const TextPool& pool, bool run, uint32_t a, uint32_t meta, uint32_t slot, PoolLane& ls) {
+#if defined(SB200_HOST_EMU)
+    const uint32_t idx = pool.S.top[run ? 1 : 0]++;
+#else
+    const uint32_t idx = atomicAdd(pool.S.top + (run ? 1 : 0), 1u);
+#endif
+    const uint32_t cap = run ? kPoolCapR : kPoolCapS;
+    if (idx < cap) {
+        const uint32_t at = idx + (run ? kPoolCapS : 0u);
+        pool.S.frames[at] = make_uint2(a, meta);
+        pool.S.slots[at] = static_cast<uint8_t>(slot);
+    } else if (idx - cap < kSpillCap) {
+        pool.S.spill[idx - cap + (run ? kSpillCap : 0u)] = make_uint4(a, meta, slot, 0);
+    } else {
+        ls.overflow = true;
+    }
+}
 // frame idx of the stack -> (a, meta), slot
 __device__ __forceinline__ uint2 stack_get(const FrameStack& st, uint32_t idx, uint32_t& slot) {
     if (idx < st.cap) {
@@ -972,6 +1031,7 @@ struct SeedCtx {
     const uint32_t* q;
     const uint32_t* tbl;
     const uint8_t* runs;
+    const uint8_t* flags;  // state flags of the search (build_state_flags)
     uint32_t qid, W;
     __device__ __forceinline__ uint32_t qsym(uint32_t pos) const { return (q[pos >> 3] >> ((pos & 7u) * 4u)) & 0xfu; }
     // the 8 query symbols that start at position pos; positions behind the query read as 0xF
@@ -985,7 +1045,9 @@ struct SeedCtx {
 __device__ __forceinline__ SeedCtx seed_ctx(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, const TextPool& pool,
                                             uint32_t slot) {
     const uint32_t sid = pool.ctx_search[slot];
-    return SeedCtx{pool.query + slot * pool.Wp, s_steps + sid * P.len, s_runs + sid * P.len * kRunE, pool.ctx_qid[slot], packed_words(P.len)};
+    const uint8_t* runs = s_runs + sid * P.len * kRunE;
+    return SeedCtx{pool.query + slot * pool.Wp, s_steps + sid * P.len, runs, runs + state_flags_offset(P.n_searches * P.len), pool.ctx_qid[slot],
+                   packed_words(P.len)};
 }
 __device__ __forceinline__ void pool_emit(const SearchParams& P, PoolLane& ls, uint32_t qid, uint32_t a, uint32_t e) {
     ls.outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], P.textpos_out ? make_uint4(qid, a, 1, e | kCursorTextPosFlag) : make_uint4(qid, P.isa32[a], 1, e));
@@ -1062,8 +1124,8 @@ __device__ __forceinline__ uint32_t text_run(const SearchParams& P, const uint32
     return 1;
 }
 
-// STATE frame: the states on its cursor (pair halves, insertion chain), exactly like text_thread; returns the
-// number of frames pushed
+// STATE frame: the states on its cursor (pair halves, insertion chain), exactly like text_thread (the conditions
+// that depend on the scheme tables only come from the state flags); returns the number of frames pushed
 template <bool EDIT>
 __device__ __forceinline__ uint32_t text_states(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, const TextPool& pool,
                                                 const uint2 f, const uint32_t slot, PoolLane& ls) {
@@ -1071,8 +1133,8 @@ __device__ __forceinline__ uint32_t text_states(const SearchParams& P, const uin
     const uint32_t qlen = P.len;
     const uint32_t* tbl = cx.tbl;
     uint32_t pushed = 0;
-    auto push = [&](uint32_t a, uint32_t m) {
-        pool_push(pool, cx.runs, a, m, slot, ls);
+    auto push = [&](uint32_t a, uint32_t m, bool run) {
+        pool_push_to(pool, run, a, m, slot, ls);
         ++pushed;
     };
     const uint32_t a = f.x;
@@ -1089,47 +1151,42 @@ __device__ __forceinline__ uint32_t text_states(const SearchParams& P, const uin
     uint32_t tL = 0;
     if (a != 0) tL = (P.text4[(a - 1) >> 3] >> (((a - 1) & 7u) * 4u)) & 0xfu;
     const uint32_t tR = (P.text4[b >> 3] >> ((b & 7u) * 4u)) & 0xfu;
+    const uint32_t tlenNext = (tlen + 1) << META_TLEN_SHIFT;
 
     bool second = false;
     while (true) {
         ++nodes;
         const uint32_t st = tbl[step];
-        const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
+        const uint32_t fl = cx.flags[step * kRunE + e];
         const bool right = (st >> 24) & 1u;
         const uint32_t c = cx.qsym(st & 0xffffu);
         const bool last = step + 1 == qlen;
-        const uint32_t stn = last ? 0u : tbl[step + 1];
-        const uint32_t lnext = (stn >> 16) & 0xfu;
-        const bool sameDirNext = !last && ((((stn >> 24) & 1u) != 0) == right);
-        const bool matchOK = l <= e && e <= u;
-        const bool mmOK = l <= e + 1 && e + 1 <= u;
+        const bool mmOK = (fl & SF_MISMATCH) != 0;
         const uint32_t T = right ? Rinfo : Linfo;
         const uint32_t O = right ? Linfo : Rinfo;
         const bool otherEndOK = !EDIT || (O & 1u) == 0;
         const uint32_t t = right ? tR : tL;    // the only symbol whose child cursor is not empty
         const uint32_t na = right ? a : a - 1;  // child occurrence T[na, na + tlen + 1)
-        const uint32_t keepL = right ? Linfo : 0u, keepR = right ? 0u : Rinfo;
         const uint32_t sideShift = right ? 16u : 14u;
-        const uint32_t metaBase = (keepL << 14) | (keepR << 16) | ((tlen + 1) << META_TLEN_SHIFT);
+        const uint32_t metaBase = ((right ? Linfo : 0u) << 14) | ((right ? 0u : Rinfo) << 16) | tlenNext;
         if (t != 0) {
             if (t == c) {
-                if (matchOK) {
+                if (fl & SF_MATCH) {
                     if (last) {
                         if (otherEndOK) pool_emit(P, ls, cx.qid, na, e);
-                    } else if (lnext <= e + 1) {
-                        push(na, metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift));
+                    } else if (fl & SF_M_ALIVE) {
+                        push(na, metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift), (fl & SF_RUN_M) != 0);
                     }
                 }
             } else if (mmOK) {
                 const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
-                const bool subAlive = !last && lnext <= e + 2;
                 const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift);
                 const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift);
                 // a pair only when both halves extend the same end (as in fm_kernel)
-                if (delOK && subAlive && sameDirNext) push(na, mD | META_PAIR);
+                if (delOK && (fl & SF_PAIR)) push(na, mD | META_PAIR, false);
                 else {
-                    if (delOK) push(na, mD);
-                    if (subAlive) push(na, mS);
+                    if (delOK) push(na, mD, (fl & SF_RUN_D) != 0);
+                    if (fl & SF_SUB_ALIVE) push(na, mS, (fl & SF_RUN_S) != 0);
                 }
                 if (!EDIT && last) pool_emit(P, ls, cx.qid, na, e + 1);
             }
@@ -1148,7 +1205,7 @@ __device__ __forceinline__ uint32_t text_states(const SearchParams& P, const uin
             if (otherEndOK) pool_emit(P, ls, cx.qid, a, e + 1);
             break;
         }
-        if (lnext > e + 2) break;
+        if (!(fl & SF_SUB_ALIVE)) break;  // dead at the next step
         step += 1;
         e += 1;
         if (right) Rinfo = INFO_I; else Linfo = INFO_I;
@@ -1240,7 +1297,7 @@ template <bool EDIT, int STACK>
 __global__ void __launch_bounds__(kPoolThreads, 3) text_pool_kernel(const SearchParams P, const uint32_t maxpush, const uint32_t run_rounds, uint4* spill) {
     extern __shared__ uint32_t s_steps[];
     const uint32_t n_steps = P.n_searches * P.len;
-    const uint32_t n_run_words = (n_steps * kRunE + 3) / 4;
+    const uint32_t n_run_words = run_table_bytes(n_steps) / 4;  // run lengths + state flags
     uint32_t* s_runs = s_steps + n_steps;
     for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) s_steps[i] = P.steps[i];
     for (uint32_t i = threadIdx.x; i < n_run_words; i += blockDim.x) s_runs[i] = reinterpret_cast<const uint32_t*>(P.runs)[i];

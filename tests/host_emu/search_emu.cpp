@@ -117,8 +117,9 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
             if (u[k] > kmax) kmax = u[k];
         }
     if (kmax > 4) return 2;
-    std::vector<uint8_t> runs(steps.size() * kRunE + 4, 0);
+    std::vector<uint8_t> runs(run_table_bytes(static_cast<uint32_t>(steps.size())) + 4, 0);
     build_runs(n_searches, len, steps.data(), runs.data());
+    build_state_flags(n_searches, len, steps.data(), runs.data());
     // optional in-text verification tables
     std::vector<uint32_t> isa, text4;
     if (sa32 && text) {
