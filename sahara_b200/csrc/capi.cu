@@ -611,7 +611,7 @@ void launch_search(sb200_ctx* c, const SearchParams& P) {
         launch_check(c);
         const size_t ismem = size_t(P.n_searches) * P.len * 4;
         if (ismem > 48 * 1024) throw Error("search scheme table does not fit shared memory (query too long)");
-        unsigned igrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_BLOCKS_PER_SM", 4);
+        unsigned igrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_BLOCKS_PER_SM", SB200_FM_ITEMS_BLOCKS);
         igrid = std::max(1u, std::min(igrid, grid_for(P.n_queries)));
         with_sigma(c->idx.sigma, [&](auto S) {
             with_stack(c->kmax, [&](auto STACK) {
@@ -833,9 +833,12 @@ bool locate_bucketed(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries) {
         c->d_tmp.reserve(tmp_bytes);
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_tmp.p, tmp_bytes, c->d_qpos.get<uint32_t>(), c->d_qpos.get<uint32_t>(), n_queries + 1, c->stream));
         c->ct.kernel_launches += 2;
-        read_back_words(c, c->d_counters.get<unsigned long long>() + CT_TOTAL_ROWS, 1, CT_COUNT);
+        mirror_u32_kernel<<<1, 32, 0, c->stream>>>(c->d_qpos.get<uint32_t>() + n_queries, c->h_counters_dev + CT_COUNT, 1);
+        launch_check(c);
+        read_back_words(c, c->d_counters.get<unsigned long long>() + CT_TOTAL_ROWS, 1, CT_COUNT + 1);
         total_rows = c->h_counters[CT_COUNT];
-        if (total_rows >= (1ull << 32)) throw Error("more than 2^32 hits in one call; split the batch");
+        // (the scan is u32: n_cursors + rows beyond the first of every cursor bounds the true number of hits)
+        if (n_cursors + c->h_counters[CT_COUNT + 1] >= (1ull << 32)) throw Error("more than 2^32 hits in one call; split the batch");
     }
     c->fused_shift = 0;
     c->sorted_keys = 0;

@@ -164,23 +164,21 @@ struct BucketParams {
     unsigned long long* counters;  // [4] LF steps
 };
 
-// hits per query (u32: a wrap is caught through *total, the exact 64-bit number of hits)
-__global__ void __launch_bounds__(256) hit_count_kernel(const uint4* cursors, uint32_t n_cursors, uint32_t* qcount, unsigned long long* total) {
+// hits per query.  The counts and their scan are u32; *extra accumulates the rows beyond the first of every cursor
+// (64 bit, touched only by warps that see a cursor with several rows), so that n_cursors + *extra bounds the number of
+// hits and the host can refuse a call whose scan might have wrapped.
+__global__ void __launch_bounds__(256) hit_count_kernel(const uint4* cursors, uint32_t n_cursors, uint32_t* qcount, unsigned long long* extra) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long rows = 0;
+    unsigned long long more = 0;
     if (i < n_cursors) {
         const uint4 c = cursors[i];
         if (c.z != 0) atomicAdd(&qcount[c.x], c.z);
-        rows = c.z;
+        if (c.z > 1) more = c.z - 1;
     }
-    // one atomic per block on the single total (one per warp costs 0.35 ms at 16 M cursors)
-    __shared__ unsigned long long block_rows;
-    if (threadIdx.x == 0) block_rows = 0;
-    __syncthreads();
-    for (int o = 16; o > 0; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);
-    if ((threadIdx.x & 31) == 0 && rows) atomicAdd(&block_rows, rows);
-    __syncthreads();
-    if (threadIdx.x == 0 && block_rows) atomicAdd(total, block_rows);
+    if (__any_sync(0xffffffffu, more != 0)) {
+        for (int o = 16; o > 0; o >>= 1) more += __shfl_xor_sync(0xffffffffu, more, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(extra, more);
+    }
 }
 
 template <int SIGMA>

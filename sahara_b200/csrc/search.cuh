@@ -128,7 +128,7 @@ enum : int {
     CT_BAD_QUERY = 10,   // 1 + offset of a query symbol outside the alphabet (0 = none)
     CT_NODES_TEXT = 11,  // states expanded by text_kernel (subset of CT_NODES)
     CT_NEXT_ITEM = 12,   // work distribution of fm_items_kernel
-    CT_TOTAL_ROWS = 13,  // (locate) rows of all cursors = hits
+    CT_TOTAL_ROWS = 13,  // (locate) rows beyond the first of every cursor (overflow guard of the u32 hit scan)
     CT_COUNT = 16
 };
 
@@ -915,7 +915,7 @@ constexpr uint32_t kSpillCap = 512;   // frames per warp and stack that spill to
 constexpr uint32_t kPoolSlots = SB200_POOL_SLOTS;
 constexpr uint32_t kPoolThreads = SB200_POOL_THREADS;
 #else
-constexpr uint32_t kPoolSlots = 56;   // seeds a warp works on at a time
+constexpr uint32_t kPoolSlots = 52;   // seeds a warp works on at a time (52: 36 warps per SM still fit next to the tables of a 4-search scheme at 150 bp)
 constexpr uint32_t kPoolThreads = 384;  // at most 12 warps per block: three blocks (36 warps) fit the shared memory of an SM at 150 bp
 #endif
 constexpr uint32_t kRunRounds = 2;    // rounds of 8 symbols per pop (measured: 1 -> 6.47 ms, 2 -> 6.39, 3 -> 6.42, 6 -> 6.73)
@@ -1273,7 +1273,14 @@ __global__ void __launch_bounds__(256) fm_roots_kernel(const SearchParams P) {
 }
 
 template <int SIGMA, bool EDIT, int STACK>
-__global__ void __launch_bounds__(256, 4) fm_items_kernel(const SearchParams P) {
+// Two blocks of 256 threads per SM: the walk saturates the random-access rate of the memory system with 512 threads
+// per SM already, more threads only thrash L1 with their stacks (measured at 3.1 Gbp, fm phase of 2 M queries:
+// 4 blocks / 64 registers 1.13 ms, 3 blocks 1.01, 2 blocks / 102 registers and no spills 0.94, 1 block 0.87; at
+// 100 Mbp: 0.80 / - / 0.62 / 0.71).
+#if !defined(SB200_FM_ITEMS_BLOCKS)
+#define SB200_FM_ITEMS_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, SB200_FM_ITEMS_BLOCKS) fm_items_kernel(const SearchParams P) {
     extern __shared__ uint32_t s_steps[];
     const uint32_t n_steps = P.n_searches * P.len;
     for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) s_steps[i] = P.steps[i];
