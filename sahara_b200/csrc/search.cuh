@@ -907,8 +907,12 @@ constexpr uint32_t kPoolCapS = SB200_POOL_CAP;     // (tests: tiny pools exercis
 constexpr uint32_t kPoolCapR = SB200_POOL_CAP;
 constexpr uint32_t kSpillCap = SB200_SPILL_CAP;
 #else
-constexpr uint32_t kPoolCapS = 64;    // state frames per warp held in shared memory
-constexpr uint32_t kPoolCapR = 48;    // run frames per warp held in shared memory
+#if !defined(SB200_CAP_S)
+#define SB200_CAP_S 64
+#define SB200_CAP_R 48
+#endif
+constexpr uint32_t kPoolCapS = SB200_CAP_S;    // state frames per warp held in shared memory
+constexpr uint32_t kPoolCapR = SB200_CAP_R;    // run frames per warp held in shared memory
 constexpr uint32_t kSpillCap = 512;   // frames per warp and stack that spill to global memory behind them (rare)
 #endif
 #if defined(SB200_POOL_SLOTS)
