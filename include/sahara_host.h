@@ -53,6 +53,12 @@ int sbh_idx_save(const char* path, const sb200_index_view* view);
  * with_revcomp != 0: every record is followed by its reverse complement (the query order of
  * src/sahara/search.cpp:121-123).  Invalid characters fail with the reference's message. */
 int sbh_fasta_load_ranks(const char* path, uint64_t sigma, int with_revcomp, uint8_t** ranks, uint64_t** lens, uint64_t* n_seqs);
+/* the read set of `sahara search` (src/sahara/search.cpp:115-124) converted to ranks by `threads` host threads: all
+ * records must have the length of the first one; fails with the reference's message on an invalid character
+ * ("query '<id>' (<n>) has invalid character at position <p> '<c>'(<hex>)", n = 1-based record number) and with a
+ * clear message on a record of another length — whichever comes first in the file.  ranks: n_reads * len bytes,
+ * released with sbh_free. */
+int sbh_fasta_load_reads(const char* path, uint64_t sigma, uint32_t threads, uint8_t** ranks, uint64_t* n_reads, uint64_t* len);
 int sbh_revcomp_ranks(const uint8_t* in, uint64_t n, uint8_t* out);
 
 void sbh_free(void* p);

@@ -114,6 +114,7 @@ SBH_SYMBOLS = {
     "sbh_idx_free": (None, [C.c_void_p]),
     "sbh_idx_save": (C.c_int, [C.c_char_p, C.POINTER(IndexView)]),
     "sbh_fasta_load_ranks": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p]),
+    "sbh_fasta_load_reads": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p), u64p, u64p]),
     "sbh_revcomp_ranks": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "sbh_free": (None, [C.c_void_p]),
 }

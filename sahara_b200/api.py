@@ -96,6 +96,18 @@ class SearchScheme:
         return a.value, b.value
 
 
+def load_fasta_reads(path, sigma=6, threads=4):
+    """read set of `sahara search` -> uint8 array [n_reads, len] of ranks (parallel reader of the CLI)"""
+    pr, n, ln = C.c_void_p(), C.c_uint64(), C.c_uint64()
+    check_host(host.sbh_fasta_load_reads(str(path).encode(), sigma, threads, C.byref(pr), C.byref(n), C.byref(ln)))
+    try:
+        total = n.value * ln.value
+        a = np.ctypeslib.as_array(C.cast(pr, C.POINTER(C.c_uint8)), shape=(max(1, total),))[:total].copy()
+    finally:
+        host.sbh_free(pr)
+    return a.reshape(n.value, ln.value)
+
+
 def load_fasta_ranks(path, sigma=6, with_revcomp=False):
     """FASTA -> list of uint8 rank arrays (0='$', 1..4=ACGT, 5=N)."""
     pr, pl, n = C.c_void_p(), C.c_void_p(), C.c_uint64()

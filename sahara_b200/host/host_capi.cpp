@@ -191,4 +191,24 @@ int sbh_revcomp_ranks(const uint8_t* in, uint64_t n, uint8_t* out) {
 
 void sbh_free(void* p) { std::free(p); }
 
+int sbh_fasta_load_reads(const char* path, uint64_t sigma, uint32_t threads, uint8_t** ranks, uint64_t* n_reads, uint64_t* len) {
+    return guard([&] {
+        if (sigma != 5 && sigma != 6) throw std::runtime_error("unknown index with " + std::to_string(sigma) + " letters");
+        auto rs = sahara::fasta::readRanksParallel(path, sigma == 5 ? sahara::d_dna4::table : sahara::d_dna5::table, threads);
+        if (rs.problem == 1) {
+            char buf[64];
+            snprintf(buf, sizeof buf, "%x", static_cast<unsigned>(static_cast<uint8_t>(rs.ch)));
+            throw std::runtime_error("query '" + rs.id + "' (" + std::to_string(rs.record + 1) + ") has invalid character at position " +
+                                     std::to_string(rs.pos) + " '" + rs.ch + "'(" + buf + ")");
+        }
+        if (rs.problem == 2)
+            throw std::runtime_error("query '" + rs.id + "' has length " + std::to_string(rs.length) +
+                                     ", the search scheme is expanded for the length of the first query (" + std::to_string(rs.len) + ")");
+        *ranks = static_cast<uint8_t*>(std::malloc(std::max<size_t>(1, rs.ranks.size())));
+        std::memcpy(*ranks, rs.ranks.data(), rs.ranks.size());
+        *n_reads = rs.count;
+        *len = rs.len;
+    });
+}
+
 }  // extern "C"

@@ -201,34 +201,25 @@ void runSearch(Args const& a) {
     std::vector<std::pair<std::string, double>> timing;
     StopWatch sw;
 
-    // load fasta file: queries[2i] = read i, queries[2i+1] = its reverse complement (search.cpp:115-124)
-    std::vector<uint8_t> queries;
-    size_t nQueries = 0, qlen = 0, count = 0;
-    sahara::fasta::read(queryPath, [&](sahara::fasta::Record& rec) {
-        ++count;
-        auto r = sahara::convert_char_to_rank<Alphabet>(rec.seq);
-        if (auto pos = sahara::verify_rank(r); pos) {
-            char buf[256];
-            snprintf(buf, sizeof buf, "query '%s' (%zu) has invalid character at position %zu '%c'(%x)", rec.id.c_str(), nQueries + 1, *pos,
-                     rec.seq[*pos], static_cast<unsigned>(static_cast<uint8_t>(rec.seq[*pos])));
-            fail(buf);
-        }
-        if (nQueries == 0) qlen = r.size();
-        if (r.size() != qlen)
-            fail("query '" + rec.id + "' has length " + std::to_string(r.size()) + ", the search scheme is expanded for the length of the first query (" +
-                 std::to_string(qlen) + ")");
-        queries.insert(queries.end(), r.begin(), r.end());
-        ++nQueries;
-        if (!noReverse) {
-            auto rc = sahara::reverse_complement_rank<Alphabet>(r);
-            queries.insert(queries.end(), rc.begin(), rc.end());
-            ++nQueries;
-        }
-    });
-    if (limitQueries) {
-        nQueries = std::min(limitQueries, nQueries);
-        queries.resize(nQueries * qlen);
+    // load fasta file (search.cpp:115-124): the reads as ranks; queries[2i] = read i, queries[2i+1] = its reverse
+    // complement — the second strand is made on the device (sb200_search_reads), or here for -m besthits
+    const unsigned hostThreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const size_t per = noReverse ? 1 : 2;  // queries per read
+    sahara::fasta::ReadSet rs = sahara::fasta::readRanksParallel(queryPath, Alphabet::table, hostThreads);
+    if (rs.problem == 1) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "query '%s' (%zu) has invalid character at position %zu '%c'(%x)", rs.id.c_str(), rs.record * per + 1, rs.pos,
+                 rs.ch, static_cast<unsigned>(static_cast<uint8_t>(rs.ch)));
+        fail(buf);
     }
+    if (rs.problem == 2)
+        fail("query '" + rs.id + "' has length " + std::to_string(rs.length) + ", the search scheme is expanded for the length of the first query (" +
+             std::to_string(rs.len) + ")");
+    std::vector<uint8_t>& reads = rs.ranks;
+    size_t qlen = rs.len;
+    size_t nQueries = rs.count * per;
+    if (limitQueries) nQueries = std::min(limitQueries, nQueries);
+    const size_t nReads = (nQueries + per - 1) / per;  // (an odd limit keeps the forward strand of the last read only)
     if (nQueries == 0) fail("query file " + queryPath + " was empty - abort\n");
     timing.emplace_back("ld queries", sw.reset());
 
@@ -318,17 +309,39 @@ void runSearch(Args const& a) {
     };
     timing.emplace_back("searchScheme", sw.reset());
 
-    // search + locate: contiguous shards of reads per GPU, batches inside a shard
+    // search + locate: contiguous shards of reads per GPU, batches inside a shard.  Hits stay in the buffers the
+    // library hands out (16-byte records, query ids local to the call) until they are written.
+    struct HitBlock {
+        sb200_hit32* hits;
+        uint64_t n;
+        uint64_t firstQuery;  // added to the query ids of the block
+        bool owned;           // allocated here (besthits), not by the library
+    };
     size_t batch = std::stoul(a.get("--batch", "2000000"));
     batch += batch & 1;  // keep both strands of a read together
-    std::vector<std::vector<sb200_hit>> results(nGpus);
+    const size_t batchReads = std::max<size_t>(1, batch / per);
+    std::vector<std::vector<HitBlock>> results(nGpus);
     std::vector<std::string> errors(nGpus);
     std::vector<double> msSearch(nGpus, 0), msLocate(nGpus, 0);
-    size_t perGpu = ((nQueries / (noReverse ? 1 : 2) + nGpus - 1) / nGpus) * (noReverse ? 1 : 2);
+    const size_t readsPerGpu = (nReads + nGpus - 1) / nGpus;
+    // -m besthits works on single queries: both strands materialised on the host
+    std::vector<uint8_t> queries;
+    if (bestHits) {
+        queries.resize(nQueries * qlen);
+        for (size_t q = 0; q < nQueries; ++q) {
+            const uint8_t* r = reads.data() + (q / per) * qlen;
+            uint8_t* dst = queries.data() + q * qlen;
+            if (per == 2 && (q & 1)) {
+                for (size_t i = 0; i < qlen; ++i) dst[i] = Alphabet::complement_rank(r[qlen - 1 - i]);
+            } else {
+                std::memcpy(dst, r, qlen);
+            }
+        }
+    }
     std::vector<std::thread> threads;
     for (int g = 0; g < nGpus; ++g) {
         threads.emplace_back([&, g] {
-            size_t q0 = std::min(nQueries, perGpu * g), q1 = std::min(nQueries, perGpu * (g + 1));
+            const size_t r0 = std::min(nReads, readsPerGpu * g), r1 = std::min(nReads, readsPerGpu * (g + 1));
             try {
                 auto account = [&] {
                     sb200_counters ct{};
@@ -338,22 +351,19 @@ void runSearch(Args const& a) {
                 };
                 if (!bestHits) {
                     setScheme(ctxs[g], schemes[0]);
-                    for (size_t b = q0; b < q1; b += batch) {
-                        size_t n = std::min(batch, q1 - b);
-                        sb200_hit* hits = nullptr;
+                    for (size_t b = r0; b < r1; b += batchReads) {
+                        const size_t n = std::min(batchReads, r1 - b);
+                        sb200_hit32* hits = nullptr;
                         uint64_t nHits = 0;
-                        check(sb200_search(ctxs[g], queries.data() + b * qlen, n, static_cast<uint32_t>(qlen), &hits, &nHits));
-                        size_t old = results[g].size();
-                        results[g].resize(old + nHits);
-                        for (uint64_t i = 0; i < nHits; ++i) {
-                            results[g][old + i] = hits[i];
-                            results[g][old + i].query_id += b;  // batch-local -> global query id
-                        }
-                        sb200_free(hits);
+                        check(sb200_search_reads(ctxs[g], reads.data() + b * qlen, n, static_cast<uint32_t>(qlen), noReverse ? 0 : 1, &hits,
+                                                 &nHits));
+                        results[g].push_back(HitBlock{hits, nHits, b * per, false});
                         account();
                     }
                 } else {
                     // strata of exactly j errors; queries that found a hit leave the pool
+                    const size_t q0 = std::min(nQueries, r0 * per), q1 = std::min(nQueries, r1 * per);
+                    std::vector<sb200_hit> found_hits;
                     std::vector<uint64_t> active(q1 - q0);
                     for (size_t i = 0; i < active.size(); ++i) active[i] = q0 + i;
                     std::vector<uint8_t> dense;
@@ -367,12 +377,12 @@ void runSearch(Args const& a) {
                             sb200_hit* hits = nullptr;
                             uint64_t nHits = 0;
                             check(sb200_search(ctxs[g], dense.data(), n, static_cast<uint32_t>(qlen), &hits, &nHits));
-                            size_t old = results[g].size();
-                            results[g].resize(old + nHits);
+                            size_t old = found_hits.size();
+                            found_hits.resize(old + nHits);
                             for (uint64_t i = 0; i < nHits; ++i) {
                                 found[b + hits[i].query_id] = 1;
-                                results[g][old + i] = hits[i];
-                                results[g][old + i].query_id = active[b + hits[i].query_id];
+                                found_hits[old + i] = hits[i];
+                                found_hits[old + i].query_id = active[b + hits[i].query_id];
                             }
                             sb200_free(hits);
                             account();
@@ -382,12 +392,17 @@ void runSearch(Args const& a) {
                             if (!found[i]) rest.push_back(active[i]);
                         active.swap(rest);
                     }
-                    std::sort(results[g].begin(), results[g].end(), [](sb200_hit const& x, sb200_hit const& y) {
+                    std::sort(found_hits.begin(), found_hits.end(), [](sb200_hit const& x, sb200_hit const& y) {
                         if (x.query_id != y.query_id) return x.query_id < y.query_id;
                         if (x.seq_id != y.seq_id) return x.seq_id < y.seq_id;
                         if (x.pos != y.pos) return x.pos < y.pos;
                         return x.errors < y.errors;
                     });
+                    auto* block = new sb200_hit32[std::max<size_t>(1, found_hits.size())];
+                    for (size_t i = 0; i < found_hits.size(); ++i)
+                        block[i] = sb200_hit32{static_cast<uint32_t>(found_hits[i].query_id), static_cast<uint32_t>(found_hits[i].seq_id),
+                                               static_cast<uint32_t>(found_hits[i].pos), static_cast<uint32_t>(found_hits[i].errors)};
+                    results[g].push_back(HitBlock{block, found_hits.size(), 0, true});
                 }
             } catch (std::exception const& ex) {
                 errors[g] = ex.what();
@@ -412,29 +427,54 @@ void runSearch(Args const& a) {
     {
         FILE* ofs = fopen(outPath.c_str(), "w");
         if (!ofs) fail("cannot open " + outPath + " for writing");
-        // "{queryId} {seqId} {pos}\n" (search.cpp:257-259) formatted by hand into large blocks
-        std::vector<char> buf(1 << 24);
-        size_t used = 0;
-        auto putNum = [&](uint64_t v, char sep) {
-            char tmp[24];
-            int n = 0;
-            do { tmp[n++] = static_cast<char>('0' + v % 10); v /= 10; } while (v);
-            while (n) buf[used++] = tmp[--n];
-            buf[used++] = sep;
-        };
-        for (int g = 0; g < nGpus; ++g) {
-            for (auto const& h : results[g]) {
-                if (used + 80 > buf.size()) {
-                    fwrite(buf.data(), 1, used, ofs);
-                    used = 0;
-                }
-                putNum(h.query_id, ' ');
-                putNum(h.seq_id, ' ');
-                putNum(h.pos, '\n');
+        // "{queryId} {seqId} {pos}\n" (search.cpp:257-259), formatted by hand: every host thread formats its slice of a
+        // block of hits into its own buffer, the buffers are written in order
+        constexpr size_t kSlice = 1 << 18;  // hits per thread and round
+        std::vector<std::vector<char>> bufs(hostThreads);
+        std::vector<size_t> kept(hostThreads, 0);
+        auto format = [&](HitBlock const& hb, size_t from, size_t to, std::vector<char>& buf, size_t& nKept) {
+            buf.resize((to - from) * 33 + 1);  // 3 numbers of at most 10 digits + separators
+            char* out = buf.data();
+            nKept = 0;
+            auto putNum = [&](uint64_t v, char sep) {
+                char tmp[24];
+                int n = 0;
+                do { tmp[n++] = static_cast<char>('0' + v % 10); v /= 10; } while (v);
+                while (n) *out++ = tmp[--n];
+                *out++ = sep;
+            };
+            for (size_t i = from; i < to; ++i) {
+                const uint64_t q = hb.firstQuery + hb.hits[i].query_id;
+                if (q >= nQueries) continue;  // (the reverse strand of the last read when --limit_queries is odd)
+                putNum(q, ' ');
+                putNum(hb.hits[i].seq_id, ' ');
+                putNum(hb.hits[i].pos, '\n');
+                ++nKept;
             }
-            nHitsTotal += results[g].size();
-        }
-        fwrite(buf.data(), 1, used, ofs);
+            buf.resize(static_cast<size_t>(out - buf.data()));
+        };
+        for (int g = 0; g < nGpus; ++g)
+            for (auto const& hb : results[g]) {
+                for (size_t base = 0; base < hb.n; base += kSlice * hostThreads) {
+                    std::vector<std::thread> pool;
+                    unsigned used = 0;
+                    for (unsigned t = 0; t < hostThreads; ++t) {
+                        const size_t from = base + t * kSlice, to = std::min<size_t>(hb.n, from + kSlice);
+                        if (from >= to) break;
+                        ++used;
+                        if (t == 0) continue;  // slice 0 is formatted by this thread
+                        pool.emplace_back(format, std::cref(hb), from, to, std::ref(bufs[t]), std::ref(kept[t]));
+                    }
+                    if (used) format(hb, base, std::min<size_t>(hb.n, base + kSlice), bufs[0], kept[0]);
+                    for (auto& th : pool) th.join();
+                    for (unsigned t = 0; t < used; ++t) {
+                        fwrite(bufs[t].data(), 1, bufs[t].size(), ofs);
+                        nHitsTotal += kept[t];
+                    }
+                }
+                if (hb.owned) delete[] hb.hits;
+                else sb200_free(hb.hits);
+            }
         fclose(ofs);
     }
     timing.emplace_back("result", sw.reset());

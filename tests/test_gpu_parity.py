@@ -246,6 +246,15 @@ def test_cli_index_and_search_roundtrip(sb, cases, tmp_path):
             sch = sb.SearchScheme.generate("h2-k2", 0, k, m, limit_to_hamming=not edit)
         want = sorted((int(a), int(b), int(c)) for a, b, c, d in ix.locate(ix.search(q, sch, edit)))
         assert got == want
+    # --no-reverse and an odd --limit_queries (the forward strand of the last read only)
+    for extra, keep in ((["--no-reverse"], q[0::2]), (["--limit_queries", "51"], q[:51])):
+        res = subprocess.run([exe, "search", "-q", qa, "-i", fa + ".idx", "-e", str(k), "-o", out, "--batch", "64"] + extra,
+                             capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        got = sorted(tuple(int(x) for x in line.split()) for line in open(out))
+        sch = sb.SearchScheme.generate("h2-k2", 0, k, m)
+        want = sorted((int(a), int(b), int(c)) for a, b, c, d in ix.locate(ix.search(np.ascontiguousarray(keep), sch, True)))
+        assert got == want, extra
     # error behaviour of the reference CLI: message + exit code 1
     res = subprocess.run([exe, "search", "-q", qa, "-i", os.path.join(tmp_path, "missing.idx")], capture_output=True, text=True)
     assert res.returncode == 1 and "no valid index path" in res.stderr

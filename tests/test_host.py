@@ -78,6 +78,49 @@ def test_fasta_alphabet_and_revcomp(tmp_path):
         sb.load_fasta_ranks(p, sigma=6)
 
 
+def test_parallel_read_set_loader_matches_sequential_reader(tmp_path):
+    """`sahara search` loads its reads with a reader that cuts the file into one piece per thread
+    (host/fasta.hpp readRanksParallel): same ranks as the sequential reader for every thread count and line layout,
+    and the first problem in file order is the one reported."""
+    rng = np.random.default_rng(11)
+    n, m = 257, 37
+    reads = rng.integers(1, 6, size=(n, m))
+    p = os.path.join(tmp_path, "reads.fa")
+    with open(p, "w", newline="") as f:
+        f.write("\n\n")
+        for i in range(n):
+            txt = "".join("$ACGTN"[c] for c in reads[i])
+            eol = "\r\n" if i % 5 == 0 else "\n"
+            if i % 3 == 0:  # sequence over several lines, a blank line in between
+                f.write(f">r{i} x{eol}{txt[:10]}{eol}{eol}{txt[10:]}{eol}")
+            else:
+                f.write(f">r{i}{eol}{txt}{eol}")
+    want = np.stack(sb.load_fasta_ranks(p, sigma=6))
+    for threads in (1, 2, 3, 7, 16, 64):
+        got = sb.load_fasta_reads(p, sigma=6, threads=threads)
+        assert got.shape == (n, m) and np.array_equal(got, want)
+    lines = open(p, newline="").read()
+    # an invalid character in record 200, a short record 100 and a short record 230: record 100 is reported
+    bad = lines.replace(">r200\r\n", ">r200\r\nX", 1)
+    i100 = bad.index(">r100")
+    j100 = bad.index("\n", bad.index("\n", i100) + 1)
+    bad = bad[:j100 - 2] + bad[j100 - 1:]  # drop the last base (the line ends with \r\n)
+    open(p, "w", newline="").write(bad)
+    for threads in (1, 4, 16):
+        with pytest.raises(sb.SaharaError, match=r"query 'r100' has length 36, .* first query \(37\)"):
+            sb.load_fasta_reads(p, sigma=6, threads=threads)
+    # only the invalid character: reference message with the 1-based record number
+    open(p, "w", newline="").write(lines.replace(">r200\r\n", ">r200\r\nX", 1))
+    for threads in (1, 4, 16):
+        with pytest.raises(sb.SaharaError, match=r"query 'r200' \(201\) has invalid character at position 0 'X'\(58\)"):
+            sb.load_fasta_reads(p, sigma=6, threads=threads)
+    open(p, "w").write("ACGT\n>r\nACGT\n")
+    with pytest.raises(sb.SaharaError, match="does not start with a '>' header"):
+        sb.load_fasta_reads(p, sigma=6, threads=3)
+    open(p, "w").write("")
+    assert sb.load_fasta_reads(p, sigma=6, threads=3).shape[0] == 0
+
+
 def test_index_file_reader_agrees_with_oracle_and_rejects_garbage(tmp_path):
     rng = np.random.default_rng(3)
     seqs = [W.random_genome(rng, 5000, with_n=True), W.random_genome(rng, 100)]
