@@ -162,6 +162,49 @@ struct SearchParams {
 __host__ __device__ inline uint32_t packed_words(uint32_t len) { return (len + 7) / 8; }
 
 #if !defined(SB200_HOST_EMU)
+// the 8 bytes that start at byte `addr` of buffer q (total bytes; q 4-byte aligned): three aligned word loads instead
+// of eight byte loads; bytes behind the buffer read as 0
+__device__ __forceinline__ uint2 load8_aligned(const uint8_t* q, uint64_t addr, uint64_t total) {
+    const uint64_t a0 = addr & ~uint64_t{3};
+    const uint32_t sh = static_cast<uint32_t>(addr & 3u) * 8u;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(q + a0);
+    const uint64_t end = (total + 3u) & ~uint64_t{3};
+    const uint32_t w0 = p[0];
+    const uint32_t w1 = a0 + 4 < end ? p[1] : 0u;
+    const uint32_t w2 = (sh != 0 && a0 + 8 < end) ? p[2] : 0u;
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+__device__ __forceinline__ uint2 load8_bytes(const uint8_t* q, uint64_t addr, uint64_t total) {
+    uint32_t lo = 0, hi = 0;
+    for (uint32_t k = 0; k < 4; ++k) {
+        if (addr + k < total) lo |= static_cast<uint32_t>(q[addr + k]) << (8 * k);
+        if (addr + 4 + k < total) hi |= static_cast<uint32_t>(q[addr + 4 + k]) << (8 * k);
+    }
+    return make_uint2(lo, hi);
+}
+// low nibbles of 4 bytes -> 16 bits (byte k in nibble k)
+__device__ __forceinline__ uint32_t nibbles4(uint32_t x) {
+    x &= 0x0f0f0f0fu;
+    x = (x | (x >> 4)) & 0x00ff00ffu;
+    return (x | (x >> 8)) & 0xffffu;
+}
+// packs the n (<= 8) symbols in bytes (lo, hi) into one word (unused nibbles 0xF) and reports symbols >= sigma
+// (offset of symbol 0 in the query array = first)
+__device__ __forceinline__ uint32_t pack8(uint32_t lo, uint32_t hi, uint32_t n, uint32_t sigma, uint64_t first, unsigned long long* counters) {
+    const uint32_t lim = sigma * 0x01010101u;
+    uint32_t badLo = __vcmpgeu4(lo, lim), badHi = __vcmpgeu4(hi, lim);
+    if (n < 4) badLo &= (1u << (8 * n)) - 1u;
+    if (n < 8) badHi &= n > 4 ? (1u << (8 * (n - 4))) - 1u : 0u;
+    if (badLo | badHi) {  // verify_rank (/root/reference/src/sahara/search.cpp:118-120): the offset of the last bad symbol
+        const uint32_t k = badHi ? 4u + (31u - static_cast<uint32_t>(__clz(static_cast<int>(badHi)))) / 8u
+                                 : (31u - static_cast<uint32_t>(__clz(static_cast<int>(badLo)))) / 8u;
+        atomicMax(&counters[CT_BAD_QUERY], static_cast<unsigned long long>(first + k + 1));
+    }
+    uint32_t v = nibbles4(lo) | (nibbles4(hi) << 16);
+    if (n < 8) v |= ~((1u << (4 * n)) - 1u);
+    return v;
+}
+
 // packs the queries 8 symbols per word and verifies them (verify_rank of /root/reference/src/sahara/search.cpp:118-120)
 __global__ void pack_queries_kernel(const uint8_t* q, uint64_t n_queries, uint32_t len, uint32_t sigma, uint32_t* out,
                                     unsigned long long* counters) {
@@ -170,13 +213,11 @@ __global__ void pack_queries_kernel(const uint8_t* q, uint64_t n_queries, uint32
     if (i >= n_queries * W) return;
     uint64_t qi = i / W;
     uint32_t w = static_cast<uint32_t>(i % W);
-    const uint8_t* src = q + qi * len + w * 8;
-    uint32_t v = 0xffffffffu;  // unused nibbles stay 0xF (never a valid symbol)
-    for (uint32_t k = 0; k < 8 && w * 8 + k < len; ++k) {
-        if (src[k] >= sigma) atomicMax(&counters[CT_BAD_QUERY], static_cast<unsigned long long>(qi * len + w * 8 + k + 1));
-        v = (v & ~(0xfu << (4 * k))) | (static_cast<uint32_t>(src[k] & 0xfu) << (4 * k));
-    }
-    out[i] = v;
+    const uint64_t addr = qi * len + w * 8, total = n_queries * len;
+    const bool aligned = (reinterpret_cast<uintptr_t>(q) & 3u) == 0;
+    const uint2 b = aligned ? load8_aligned(q, addr, total) : load8_bytes(q, addr, total);
+    const uint32_t n = len - w * 8 < 8u ? len - w * 8 : 8u;
+    out[i] = pack8(b.x, b.y, n, sigma, addr, counters);
 }
 
 // the same from the reads alone: query 2r = read r, query 2r + 1 = its reverse complement (A<->T, C<->G on ranks 1..4,
@@ -188,17 +229,25 @@ __global__ void pack_reads_kernel(const uint8_t* reads, uint64_t n_queries, uint
     if (i >= n_queries * W) return;
     uint64_t qi = i / W;
     uint32_t w = static_cast<uint32_t>(i % W);
-    const uint8_t* src = reads + (qi >> 1) * len;
     const bool rc = qi & 1u;
-    uint32_t v = 0xffffffffu;
-    for (uint32_t k = 0; k < 8 && w * 8 + k < len; ++k) {
-        const uint32_t p = w * 8 + k;
-        uint8_t c = rc ? src[len - 1 - p] : src[p];
-        if (rc && c >= 1 && c <= 4) c = static_cast<uint8_t>(5 - c);
-        if (c >= sigma) atomicMax(&counters[CT_BAD_QUERY], static_cast<unsigned long long>(qi * len + p + 1));
-        v = (v & ~(0xfu << (4 * k))) | (static_cast<uint32_t>(c & 0xfu) << (4 * k));
+    const uint32_t n = len - w * 8 < 8u ? len - w * 8 : 8u;
+    const uint64_t total = ((n_queries + 1) >> 1) * len;
+    // symbols w*8 .. w*8+n-1 of the query: of the read itself, or (reverse strand) the n bytes that end at len-1-w*8, reversed
+    const uint64_t addr = (qi >> 1) * len + (rc ? len - w * 8 - n : w * 8);
+    const bool aligned = (reinterpret_cast<uintptr_t>(reads) & 3u) == 0;
+    uint2 b = aligned ? load8_aligned(reads, addr, total) : load8_bytes(reads, addr, total);
+    if (rc) {
+        // byte j of the reversed 8 bytes = byte 7-j; the n valid ones move down to byte 0
+        unsigned long long x = (static_cast<unsigned long long>(__byte_perm(b.x, 0, 0x0123)) << 32) | __byte_perm(b.y, 0, 0x0123);
+        x >>= 8 * (8 - n);
+        b = make_uint2(static_cast<uint32_t>(x), static_cast<uint32_t>(x >> 32));
+        // complement of ranks 1..4
+        const uint32_t mLo = __vcmpgeu4(b.x, 0x01010101u) & __vcmpleu4(b.x, 0x04040404u);
+        const uint32_t mHi = __vcmpgeu4(b.y, 0x01010101u) & __vcmpleu4(b.y, 0x04040404u);
+        b.x = (b.x & ~mLo) | (__vsub4(0x05050505u, b.x) & mLo);
+        b.y = (b.y & ~mHi) | (__vsub4(0x05050505u, b.y) & mHi);
     }
-    out[i] = v;
+    out[i] = pack8(b.x, b.y, n, sigma, qi * len + w * 8, counters);
 }
 #endif
 

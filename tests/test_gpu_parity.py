@@ -452,3 +452,28 @@ def test_bucketed_locate_sort_all_segment_sizes(sb, ctx, monkeypatch):
                         assert np.array_equal(got32, want), (text, bucket, textpos)
     finally:
         ctx.enable_text(False)
+
+
+@pytest.mark.parametrize("m", [19, 20, 21, 24, 33])
+def test_query_validation_reports_the_last_bad_symbol(sb, ctx, cases, m):
+    """pack_queries_kernel / pack_reads_kernel verify the ranks while packing them 8 per word (verify_rank,
+    search.cpp:118-120); the error names the offset inside the query and the query (lengths around the word size,
+    both strands, unaligned query starts)."""
+    rng, seqs, ix, path = cases[("random", 5)]  # dna4: rank 5 (N) is invalid
+    ctx.load_index(path)
+    sch = sb.SearchScheme.generate("h2-k2", 0, 1, m)
+    ctx.set_scheme(sch, True)
+    q = W.sample_reads(rng, seqs, 6, m, 1, True)
+    for qi, pos in ((0, 0), (3, m - 1), (5, 7), (8, 8), (11, m // 2)):
+        bad = q.copy()
+        bad[qi, pos] = 5
+        with pytest.raises(sb.SaharaError, match=f"invalid character at offset {pos} of query {qi}$"):
+            ctx.search(bad)
+    # the reads call: a bad symbol of read r shows up in query 2r (offset pos) and 2r+1 (offset m-1-pos); the larger one is named
+    reads = np.ascontiguousarray(q[0::2])
+    for r, pos in ((0, 0), (2, m - 1), (5, 9)):
+        bad = reads.copy()
+        bad[r, pos] = 5
+        with pytest.raises(sb.SaharaError, match=f"invalid character at offset {m - 1 - pos} of query {2 * r + 1}$"):
+            ctx.search_reads(bad)
+    assert np.array_equal(ctx.search_reads(reads).astype(np.uint64), ctx.search(q))
