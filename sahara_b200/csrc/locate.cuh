@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(256) locate_kernel(const LocateParams P) {
 constexpr uint32_t kInlineRows = 8;      // rows a thread of locate_scatter_kernel locates itself
 constexpr uint32_t kTaskRows = 1024;     // rows per task of locate_tasks_kernel
 constexpr uint32_t kWarpSeg = 256;       // keys a warp of segment_sort_kernel sorts
+constexpr uint32_t kRankSortMax = 20;    // ... by counting ranks instead of a sorting network
 constexpr uint32_t kBigSeg = 2048;       // keys a block of segment_sort_big_kernel sorts
 enum : int { LC_TASKS = 0, LC_BIG_SEGS = 1, LC_HUGE = 2, LC_COUNT = 4 };
 
@@ -253,7 +254,17 @@ __global__ void __launch_bounds__(256) segment_sort_kernel(const BucketParams P)
         todo &= todo - 1;
         const uint32_t s = __shfl_sync(0xffffffffu, s_l, src), n = __shfl_sync(0xffffffffu, n_l, src);
         uint64_t* k = P.keys + s;
-        if (n <= 32u) {
+        if (n <= kRankSortMax) {
+            // few keys: every lane counts the keys that precede its own (n broadcasts), cheaper than the 15 stages
+            // of the 32-key network
+            const uint64_t v = lane < n ? k[lane] : ~uint64_t{0};
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint64_t o = __shfl_sync(0xffffffffu, v, static_cast<int>(j));
+                rank += (o < v || (o == v && j < lane)) ? 1u : 0u;
+            }
+            if (lane < n) k[rank] = v;
+        } else if (n <= 32u) {
             uint64_t v = lane < n ? k[lane] : ~uint64_t{0};
 #pragma unroll
             for (uint32_t size = 2; size <= 32u; size <<= 1)
