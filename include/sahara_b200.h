@@ -114,6 +114,14 @@ int sb200_index_build_qgram(sb200_ctx* ctx, uint32_t q);
 int sb200_set_scheme(sb200_ctx* ctx, uint32_t n_searches, uint32_t len, const uint16_t* pi, const uint8_t* l,
                      const uint8_t* u, int edit);
 
+/* replaces the maxHits argument of fmc::search_ng24::search_n<Edit>(index, queries, scheme, maxHits, res_cb)
+ * (src/sahara/search.cpp:228,231; `--max_hits`, src/sahara/search.cpp:91-96).  max_hits > 0: every following search
+ * call delivers at most max_hits suffix-array rows per query — the first ones in the order of the reference's
+ * recursion (searches in scheme order; match, then the symbols ascending with deletion before substitution,
+ * then insertion); the cursor that crosses the limit is cut to its first rows.  0 (default) = unlimited,
+ * the plain search<Edit>. */
+int sb200_set_max_hits(sb200_ctx* ctx, uint64_t max_hits);
+
 /* ---- search + locate ------------------------------------------------------------------------------- */
 
 /* mirrors std::tuple<size_t, fmc::LeftBiFMIndexCursor, size_t> (src/sahara/search.cpp:214-220) */

@@ -460,13 +460,26 @@ struct Searcher {
     u64 qid;
     std::vector<RawCursor>& out;
     Counters& ct;
+    // search_n (src/sahara/search.cpp:228,231): at most maxHits suffix-array rows are delivered per query, in the
+    // order of the recursion; the cursor that crosses the limit is cut to its first rows and the query ends
+    // (0 = unlimited).  *taken = rows delivered for this query so far, shared by the searches of the scheme.
+    u64 maxHits{0};
+    u64* taken{nullptr};
+
+    bool stopped() const { return maxHits != 0 && *taken >= maxHits; }
 
     template <char LInfo, char RInfo>
     void next(Cursor const& cur, int e, size_t i) {
         if (cur.len == 0) return;
+        if (stopped()) return;
         if (i == steps.size()) {
             if constexpr (!Edit || ((LInfo == 'M' || LInfo == 'I') && (RInfo == 'M' || RInfo == 'I'))) {
-                out.push_back(RawCursor{qid, cur.lb, cur.len, static_cast<u64>(e)});
+                u64 len = cur.len;
+                if (maxHits != 0) {
+                    if (*taken + len > maxHits) len = maxHits - *taken;
+                    *taken += len;
+                }
+                out.push_back(RawCursor{qid, cur.lb, len, static_cast<u64>(e)});
                 ct.cursors += 1;
             }
             return;
@@ -525,19 +538,20 @@ static Scheme make_scheme(u64 nSearches, u64 m, u16 const* pi, u8 const* l, u8 c
 
 template <int S>
 static void run_search(Index<S> const& ix, u8 const* queries, u64 nq, u64 m, Scheme const& sch, bool edit, int threads,
-                       std::vector<RawCursor>& out, Counters& total) {
+                       std::vector<RawCursor>& out, Counters& total, u64 maxHits = 0) {
     if (threads < 1) threads = 1;
     std::vector<std::vector<RawCursor>> outs(threads);
     std::vector<Counters> cts(threads);
     auto body = [&](int t, u64 q0, u64 q1) {
         for (u64 q = q0; q < q1; ++q) {
+            u64 taken = 0;
             for (auto const& st : sch.searches) {
                 Cursor root{0, 0, ix.size()};
                 if (edit) {
-                    Searcher<S, true> s{ix, st, queries + q * m, q, outs[t], cts[t]};
+                    Searcher<S, true> s{ix, st, queries + q * m, q, outs[t], cts[t], maxHits, &taken};
                     s.template next<'M', 'M'>(root, 0, 0);
                 } else {
-                    Searcher<S, false> s{ix, st, queries + q * m, q, outs[t], cts[t]};
+                    Searcher<S, false> s{ix, st, queries + q * m, q, outs[t], cts[t], maxHits, &taken};
                     s.template next<'M', 'M'>(root, 0, 0);
                 }
             }
@@ -747,8 +761,8 @@ int orc_index_samples(void* h, u64* marksOut /* rows/64+1 words */, u64* ssaOut)
 
 // search_ng24::search<Edit> over dense queries[nq][m]; scheme tables pi/l/u are [nSearches][m].
 // counters[0..4] = nodes, rankOps, cursors, lfSteps, hits (accumulated).
-int orc_search(void* h, u8 const* queries, u64 nq, u64 m, u64 nSearches, u16 const* pi, u8 const* l, u8 const* u, int edit,
-               int threads, u64** cursorsOut, u64* nOut, u64* counters) {
+static int search_entry(void* h, u8 const* queries, u64 nq, u64 m, u64 nSearches, u16 const* pi, u8 const* l, u8 const* u, int edit,
+                        int threads, u64 maxHits, u64** cursorsOut, u64* nOut, u64* counters) {
     return guard([&] {
         if (nq == 0) throw std::runtime_error("query file was empty - abort");
         for (u64 j = 0; j < nSearches; ++j)
@@ -760,7 +774,7 @@ int orc_search(void* h, u8 const* queries, u64 nq, u64 m, u64 nSearches, u16 con
         dispatch(static_cast<IndexBase*>(h), [&](auto& ix) {
             for (u64 i = 0; i < nq * m; ++i)
                 if (queries[i] >= ix.sigma) throw std::runtime_error("query has invalid character");  // rank 0 ('$') is a valid character of the alphabet
-            run_search(ix, queries, nq, m, sch, edit != 0, threads, out, ct);
+            run_search(ix, queries, nq, m, sch, edit != 0, threads, out, ct, maxHits);
             return 0;
         });
         u64* buf = static_cast<u64*>(std::malloc(std::max<size_t>(1, out.size()) * sizeof(RawCursor)));
@@ -773,6 +787,19 @@ int orc_search(void* h, u8 const* queries, u64 nq, u64 m, u64 nSearches, u16 con
             counters[2] += ct.cursors;
         }
     });
+}
+
+int orc_search(void* h, u8 const* queries, u64 nq, u64 m, u64 nSearches, u16 const* pi, u8 const* l, u8 const* u, int edit,
+               int threads, u64** cursorsOut, u64* nOut, u64* counters) {
+    return search_entry(h, queries, nq, m, nSearches, pi, l, u, edit, threads, 0, cursorsOut, nOut, counters);
+}
+
+// search_ng24::search_n<Edit>(index, queries, scheme, maxHits, cb) (src/sahara/search.cpp:228,231): as orc_search, but a
+// query ends once maxHits suffix-array rows were delivered (the last cursor is cut to its first rows).  The
+// recursion order decides which hits those are.  [RECALL low: SURVEY.md 9.4]
+int orc_search_n(void* h, u8 const* queries, u64 nq, u64 m, u64 nSearches, u16 const* pi, u8 const* l, u8 const* u, int edit,
+                 int threads, u64 maxHits, u64** cursorsOut, u64* nOut, u64* counters) {
+    return search_entry(h, queries, nq, m, nSearches, pi, l, u, edit, threads, maxHits, cursorsOut, nOut, counters);
 }
 
 // LocateLinear over cursors (qid, lb, len, e) -> hits (qid, seqId, pos, e), in cursor order then row order.

@@ -74,6 +74,7 @@ SB200_SYMBOLS = {
     "sb200_index_build_qgram": (C.c_int, [C.c_void_p, C.c_uint32]),
     "sb200_index_enable_text": (C.c_int, [C.c_void_p, C.c_int]),
     "sb200_set_scheme": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "sb200_set_max_hits": (C.c_int, [C.c_void_p, C.c_uint64]),
     "sb200_search_cursors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p), u64p]),
     "sb200_locate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), u64p]),
     "sb200_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p), u64p]),

@@ -215,6 +215,11 @@ class Context:
         check(cuda.sb200_set_scheme(self._h, scheme.n_searches, scheme.n_entries, _ptr(scheme.pi), _ptr(scheme.l), _ptr(scheme.u),
                                     int(edit)))
 
+    def set_max_hits(self, max_hits):
+        """search_n (src/sahara/search.cpp:228,231): at most max_hits rows per query, the first ones in the order
+        of the reference recursion; 0 = unlimited"""
+        check(cuda.sb200_set_max_hits(self._h, int(max_hits)))
+
     # ---- search ----
     @staticmethod
     def _take4(p, n):

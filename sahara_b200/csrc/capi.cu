@@ -168,10 +168,11 @@ struct sb200_ctx {
     DevBuf d_steps, d_runs;
     uint32_t n_searches{}, qlen{}, kmax{};
     bool edit{}, have_scheme{};
+    uint32_t max_hits{0};  // > 0: search_n (fm_ordered_kernel), at most this many rows per query
     // work buffers
     uint32_t fused_shift{0};  // hit keys of the last locate carry the query id above this bit (0: separate array)
     int sorted_keys{0};       // d_keys[] buffer that holds the sorted hits
-    DevBuf d_qpos, d_tasks, d_bigsegs, d_lc, d_items, d_item_tags, d_seeds, d_spill, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
+    DevBuf d_qpos, d_tasks, d_bigsegs, d_lc, d_items, d_item_tags, d_ostack, d_seeds, d_spill, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
     uint64_t cursor_cap{}, seed_cap{};
     uint64_t last_cursors{}, last_real_cursors{}, last_hits{};
     uint64_t nodes_text{};
@@ -606,6 +607,25 @@ void launch_search(sb200_ctx* c, const SearchParams& P) {
     unsigned need = grid_for((uint64_t(P.n_queries) + kQueryBatch - 1) / kQueryBatch);
     if (need < grid) grid = std::max(1u, need);
     CUDA_TRY(cudaEventRecord(c->ev[8], c->stream));
+    if (P.max_hits) {  // search_n: the ordered walk, one thread per query with its stack in global memory
+        const size_t osmem = size_t(P.n_searches) * P.len * 4;
+        if (osmem > 48 * 1024) throw Error("search scheme table does not fit shared memory (query too long)");
+        unsigned ogrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_BLOCKS_PER_SM", P.len > 300 ? 1 : 2);
+        ogrid = std::max(1u, std::min(ogrid, grid_for(P.n_queries)));
+        SearchParams Q = P;
+        Q.ostack_frames = ordered_stack_frames(P.len, c->idx.sigma);
+        c->d_ostack.reserve(size_t(ogrid) * 256 * Q.ostack_frames * sizeof(uint4));
+        Q.ostack = c->d_ostack.get<uint4>();
+        with_sigma(c->idx.sigma, [&](auto S) {
+            if (c->edit) fm_ordered_kernel<S(), true><<<ogrid, 256, osmem, c->stream>>>(Q);
+            else fm_ordered_kernel<S(), false><<<ogrid, 256, osmem, c->stream>>>(Q);
+            return 0;
+        });
+        launch_check(c);
+        CUDA_TRY(cudaEventRecord(c->ev[9], c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev[10], c->stream));
+        return;
+    }
     if (P.items) {  // root frames of all (query, search) in one pass, then the warp-synchronous walk over the live ones
         fm_roots_kernel<<<grid_for(P.n_queries), 256, 0, c->stream>>>(P);
         launch_check(c);
@@ -752,6 +772,13 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         // cursors that go straight to the locate step carry the text position of a verified occurrence instead of its row
         P.textpos_out = (for_locate && ix.text_mode && !(std::getenv("SB200_TEXTPOS") && std::atoi(std::getenv("SB200_TEXTPOS")) == 0)) ? 1u : 0u;
         if (const char* dbg = std::getenv("SB200_DEBUG")) P.debug_flags = static_cast<uint32_t>(std::atoi(dbg));
+        if (c->max_hits) {  // search_n: rows come from the ordered walk alone
+            P.max_hits = c->max_hits;
+            P.items = nullptr, P.item_tags = nullptr;
+            P.qgram = nullptr, P.qgram_q = 0;
+            P.sa32 = P.isa32 = P.text4 = nullptr;
+            P.textpos_out = 0;
+        }
         launch_search(c, P);
         read_back_words(c, c->d_counters.p, CT_COUNT);
         if (std::getenv("SB200_DEBUG"))
@@ -1626,6 +1653,14 @@ int sb200_set_scheme(sb200_ctx* c, uint32_t n_searches, uint32_t len, const uint
         c->kmax = kmax;
         c->edit = edit != 0;
         c->have_scheme = true;
+    });
+}
+
+int sb200_set_max_hits(sb200_ctx* c, uint64_t max_hits) {
+    return guard([&] {
+        use(c);
+        if (max_hits > 0xfffffffeull) throw Error("--max_hits above 2^32 - 2 is not supported");
+        c->max_hits = static_cast<uint32_t>(max_hits);
     });
 }
 

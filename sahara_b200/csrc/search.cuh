@@ -157,6 +157,10 @@ struct SearchParams {
     uint4* items;
     uint2* item_tags;
     uint32_t textpos_out;    // 1: verified occurrences are reported as (qid, text position, 1, e | kCursorTextPos) for the locate step
+    // ordered walk with a hit limit (fm_ordered_kernel): rows per query, the threads' stacks
+    uint32_t max_hits;
+    uint4* ostack;
+    uint32_t ostack_frames;  // frames per thread
 };
 
 __host__ __device__ inline uint32_t packed_words(uint32_t len) { return (len + 7) / 8; }
@@ -545,6 +549,143 @@ __device__ __forceinline__ void fm_thread(const SearchParams& P, const uint32_t*
     atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxsp));
     if (emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(emitted));
     if (seeded) atomicAdd(&P.counters[CT_SEEDS], static_cast<unsigned long long>(seeded));
+}
+
+// ================================================================================================
+// Ordered walk with a hit limit (fm_ordered_kernel): fmc::search_ng24::search_n<Edit>(index, queries, scheme, maxHits, cb)
+// as called at /root/reference/src/sahara/search.cpp:228,231.  A query ends as soon as maxHits suffix-array rows were
+// delivered, the cursor that crosses the limit is cut to its first rows — WHICH hits those are is decided by the order
+// of the reference recursion (searches in scheme order; at a node the match child, then the symbols in
+// ascending order with the deletion before the substitution, then the insertion).  The other kernels expand the same
+// states in another order, so this path has its own walk: one thread per query, an explicit stack (global memory,
+// frame i of a thread at stack[i * stride]) onto which the children of a node are pushed in REVERSE recursion order,
+// so that they are popped in recursion order.  A frame is one call of the recursion with a non-empty cursor:
+// (lb, lbRev, len, step | e | LInfo | RInfo); step == query length reports.  Every popped frame with step < length is
+// one cursor extension of the reference ("node").  No q-gram table, no in-text verification here: the limit ends most
+// queries after one root-to-leaf path.
+// ================================================================================================
+template <int SIGMA>
+__device__ __forceinline__ void probe_children(const SearchParams& P, bool right, uint32_t lb, uint32_t lbRev, uint32_t len, uint32_t* klb,
+                                               uint32_t* klbRev, uint32_t* cnt) {
+    const OccTable& tab = right ? P.bwtRev : P.bwt;
+    const uint32_t lo = right ? lbRev : lb;
+    const uint32_t hi = lo + len;
+    OccBlk b1 = load_blk(tab.blk + (lo >> kBlkShift));
+    OccSup s1 = load_sup(tab.sup + (lo >> kSupShift));
+    OccBlk b2 = b1;
+    OccSup s2 = s1;
+    if ((lo >> kBlkShift) != (hi >> kBlkShift)) {
+        b2 = load_blk(tab.blk + (hi >> kBlkShift));
+        if ((lo >> kSupShift) != (hi >> kSupShift)) s2 = load_sup(tab.sup + (hi >> kSupShift));
+    }
+    uint32_t own[SIGMA];
+    uint32_t sum1 = 0, sumc = 0;
+#pragma unroll
+    for (int s = 1; s < SIGMA; ++s) {
+        const uint32_t a = s1.c[s] + blk_ctr(b1, s) + blk_count(b1, lo & 63u, s);
+        const uint32_t b = s2.c[s] + blk_ctr(b2, s) + blk_count(b2, hi & 63u, s);
+        own[s] = P.C[s] + a;
+        cnt[s] = b - a;
+        sum1 += a;
+        sumc += b - a;
+    }
+    own[0] = lo - sum1;  // C[0] == 0
+    cnt[0] = len - sumc;
+    uint32_t other = right ? lb : lbRev;  // interval start on the side that is not probed
+#pragma unroll
+    for (int s = 0; s < SIGMA; ++s) {
+        klb[s] = right ? other : own[s];
+        klbRev[s] = right ? own[s] : other;
+        other += cnt[s];
+    }
+}
+
+// frames a thread's stack must hold: a node pushes at most 2 (SIGMA - 2) + 2 children and a path has at most
+// length + kmax nodes (a deletion stays on its step)
+__host__ __device__ inline uint32_t ordered_stack_frames(uint32_t len, uint32_t sigma) { return (len + 6u) * (2u * sigma - 2u) + 2u; }
+
+template <int SIGMA, bool EDIT>
+__device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const uint32_t* s_steps, uint4* stack, uint32_t stride, uint32_t cap) {
+    const uint32_t qlen = P.len;
+    const uint32_t W = packed_words(qlen);
+    const uint32_t max_hits = P.max_hits;
+    uint32_t nodes = 0, emitted = 0, maxsp = 0;
+    bool overflow = false;
+    ChunkWriter outW;
+    while (true) {
+        const unsigned long long w = atomicAdd(&P.counters[CT_NEXT_QUERY], 1ull);
+        if (w >= P.n_queries) break;
+        const uint32_t qid = static_cast<uint32_t>(w);
+        const uint32_t* q = P.packed + static_cast<uint64_t>(qid) * W;
+        auto qsym = [&](uint32_t pos) -> uint32_t { return (ldg32(q + (pos >> 3)) >> ((pos & 7u) * 4u)) & 0xfu; };
+        uint32_t taken = 0;  // rows delivered for this query
+        for (uint32_t j = 0; j < P.n_searches && taken < max_hits; ++j) {
+            const uint32_t* tbl = s_steps + j * qlen;
+            uint32_t sp = 0;
+            auto push = [&](uint32_t nlb, uint32_t nlbRev, uint32_t nlen, uint32_t m) {
+                if (sp < cap) stack[static_cast<uint64_t>(sp) * stride] = make_uint4(nlb, nlbRev, nlen, m);
+                else overflow = true;
+                ++sp;
+            };
+            push(0, 0, P.n_rows, pack_meta(0, 0, INFO_M, INFO_M));
+            while (sp != 0 && taken < max_hits) {
+                maxsp = sp > maxsp ? sp : maxsp;
+                --sp;
+                if (sp >= cap) continue;  // (frame lost to an overflow: the call fails)
+                const uint4 f = stack[static_cast<uint64_t>(sp) * stride];
+                const uint32_t lb = f.x, lbRev = f.y, len = f.z, meta = f.w;
+                const uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
+                const uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
+                if (step == qlen) {  // the end of the query: report (edit distance: not behind a substitution or deletion at either end)
+                    if (!EDIT || (((Linfo | Rinfo) & 1u) == 0)) {
+                        const uint32_t n = len < max_hits - taken ? len : max_hits - taken;
+                        taken += n;
+                        outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], make_uint4(qid, lb, n, e));
+                        ++emitted;
+                    }
+                    continue;
+                }
+                const uint32_t st = tbl[step];
+                const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
+                const bool right = (st >> 24) & 1u;
+                const bool matchOK = l <= e && e <= u;
+                const bool mmOK = l <= e + 1 && e + 1 <= u;
+                if (!matchOK && !mmOK) continue;
+                const uint32_t c = qsym(st & 0xffffu);
+                uint32_t klb[SIGMA], klbRev[SIGMA], cnt[SIGMA];
+                probe_children<SIGMA>(P, right, lb, lbRev, len, klb, klbRev, cnt);
+                ++nodes;
+                const uint32_t T = right ? Rinfo : Linfo;
+                const uint32_t sideShift = right ? 16u : 14u;
+                const uint32_t metaBase = ((right ? Linfo : 0u) << 14) | ((right ? 0u : Rinfo) << 16);
+                if (mmOK) {
+                    const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift);
+                    const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift);
+                    const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift);
+                    const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
+                    if (EDIT && (T == INFO_M || T == INFO_I)) push(lb, lbRev, len, mI);  // popped last
+#pragma unroll
+                    for (int s = SIGMA - 1; s >= 1; --s) {
+                        if (static_cast<uint32_t>(s) == c || cnt[s] == 0) continue;
+                        push(klb[s], klbRev[s], cnt[s], mS);
+                        if (delOK) push(klb[s], klbRev[s], cnt[s], mD);  // the deletion is tried before the substitution
+                    }
+                }
+                if (matchOK) {  // popped first
+                    uint32_t mc = 0, nlb = 0, nlbRev = 0;
+#pragma unroll
+                    for (int s = 0; s < SIGMA; ++s)
+                        if (static_cast<uint32_t>(s) == c) { mc = cnt[s]; nlb = klb[s]; nlbRev = klbRev[s]; }
+                    if (mc != 0) push(nlb, nlbRev, mc, metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift));
+                }
+            }
+        }
+    }
+    outW.finish(P.out, P.out_cap);
+    if (nodes) atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(nodes));
+    if (overflow) atomicExch(&P.counters[CT_OVERFLOW], 1ull);
+    atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxsp));
+    if (emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(emitted));
 }
 
 // ================================================================================================
@@ -1317,6 +1458,17 @@ __global__ void __launch_bounds__(256, 4) fm_kernel(const SearchParams P) {
     __syncthreads();
     // word w of this thread's query lives at s_query[w * blockDim.x]: every lane stays in its own bank
     fm_thread<SIGMA, EDIT, STACK>(P, s_steps, s_steps + n_steps + threadIdx.x, blockDim.x);
+}
+
+// search_n: one thread per query, children visited in the order of the reference recursion (fm_ordered_thread)
+template <int SIGMA, bool EDIT>
+__global__ void __launch_bounds__(256) fm_ordered_kernel(const SearchParams P) {
+    extern __shared__ uint32_t s_steps[];
+    const uint32_t n_steps = P.n_searches * P.len;
+    for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) s_steps[i] = P.steps[i];
+    __syncthreads();
+    const uint32_t stride = gridDim.x * blockDim.x;
+    fm_ordered_thread<SIGMA, EDIT>(P, s_steps, P.ostack + (blockIdx.x * blockDim.x + threadIdx.x), stride, P.ostack_frames);
 }
 
 // one thread per query: its live root frames become the work items of fm_items_kernel

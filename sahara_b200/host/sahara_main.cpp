@@ -12,9 +12,10 @@
 // -m besthits follows fmc::search_ng21::search_best (search.cpp:233-240): per query the strata of exactly
 // 0, 1, ..., k errors are searched in turn (schemes generator(j, j)) and the first stratum with a hit ends the
 // query; as in the reference this mode always uses edit distance.
-// Not implemented on the GPU path (fails with a clear message): --max_hits > 0 (its result depends on the
-// reference's recursion order; SURVEY.md §8f "next" row).  --dynamic_generator follows a reconstruction of
-// optimizeByWNCTopDown (host/scheme.hpp).
+// --max_hits n follows search_ng24::search_n / search_ng21::search_best_n (search.cpp:228,231,240): a query ends after n
+// suffix-array rows, taken in the order of the reference's recursion (sb200_set_max_hits -> fm_ordered_kernel); with
+// -m besthits the limit applies inside the first stratum that has a hit.  --dynamic_generator follows a
+// reconstruction of optimizeByWNCTopDown (host/scheme.hpp).
 #include <algorithm>
 #include <chrono>
 #include <cinttypes>
@@ -194,7 +195,7 @@ void runSearch(Args const& a) {
     if (mode != "all" && mode != "besthits") fail("unknown search mode \"" + mode + "\"");
     if (metric != "ham" && metric != "lev") fail("unknown distance metric \"" + metric + "\"");
     const bool bestHits = mode == "besthits";
-    if (maxHits != 0) fail("--max_hits is not available on the GPU path yet");
+    if (maxHits < 0) fail("--max_hits must not be negative");
     const bool dynGenerator = a.has("--dynamic_generator");
     bool edit = metric == "lev" || bestHits;  // search_best has no Hamming variant (search.cpp:239)
 
@@ -243,6 +244,7 @@ void runSearch(Args const& a) {
     for (int g = 0; g < nGpus; ++g) {
         check(sb200_create(g, &ctxs[g]));
         check(sb200_index_upload(ctxs[g], &view));
+        check(sb200_set_max_hits(ctxs[g], static_cast<uint64_t>(maxHits)));  // search_n / search_best_n (search.cpp:228,231,240)
         if (a.has("--device-sa-rate")) check(sb200_index_densify(ctxs[g], std::stoul(a.get("--device-sa-rate"))));
         // in-text verification (17 more bytes per row on the device) and the q-gram jump table are on by default
         if (!a.has("--no-text")) check(sb200_index_enable_text(ctxs[g], 1));

@@ -20,6 +20,8 @@ def _load(name, flags):
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.emu_free.argtypes = [C.c_void_p]
+    lib.emu_set_max_hits.argtypes = [C.c_uint32]
+    lib.emu_ordered_max_depth.restype = C.c_uint32
     return lib
 
 
@@ -51,9 +53,10 @@ def text_tables(oracle_index, seqs):
     return np.ascontiguousarray(sa), np.ascontiguousarray(text)
 
 
-def search(oracle_index, queries, scheme, edit, debug_flags=0, text=None, small_pool=False):
+def search(oracle_index, queries, scheme, edit, debug_flags=0, text=None, small_pool=False, max_hits=0):
     """runs the kernel body on the host over the oracle index's BWTs -> (sorted cursors uint64 [n,4], nodes).
-    text = (sa32, text symbols) from text_tables() enables the in-text verification mode."""
+    text = (sa32, text symbols) from text_tables() enables the in-text verification mode.
+    max_hits > 0 runs the ordered walk of search_n (fm_ordered_kernel) instead."""
     info = oracle_index.info()
     bwt = np.ascontiguousarray(oracle_index.bwt(0))
     rev = np.ascontiguousarray(oracle_index.bwt(1))
@@ -61,6 +64,7 @@ def search(oracle_index, queries, scheme, edit, debug_flags=0, text=None, small_
     q = np.ascontiguousarray(queries, dtype=np.uint8)
     out, n, nodes = C.c_void_p(), C.c_uint64(), C.c_uint64()
     lib = _lib_small_pool if small_pool else _lib
+    lib.emu_set_max_hits(int(max_hits))
     rc = lib.emu_search(_p(bwt), _p(rev), info["n_rows"], info["sigma"], _p(Carr), _p(q), q.shape[0], q.shape[1], scheme.n_searches,
                          _p(scheme.pi), _p(scheme.l), _p(scheme.u), int(edit), debug_flags,
                          _p(text[0]) if text else None, _p(text[1]) if text else None, C.byref(out), C.byref(n), C.byref(nodes))

@@ -97,7 +97,13 @@ void run_text_pool(const SearchParams& P, const uint32_t* steps, const uint8_t* 
 }
 }  // namespace
 
+uint32_t g_max_hits = 0;  // > 0: emu_search runs the ordered walk with a hit limit (fm_ordered_kernel)
+uint32_t g_ordered_maxsp = 0;
+
 extern "C" {
+
+void emu_set_max_hits(uint32_t n) { g_max_hits = n; }
+uint32_t emu_ordered_max_depth() { return g_ordered_maxsp; }
 
 // bwt / bwtRev: symbols per row; C: sigma+1 entries; scheme tables as for sb200_set_scheme.
 // out: library-allocated (qid, lb, len, e) u32 quadruples, release with emu_free.
@@ -193,7 +199,22 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
         P.sa32 = isa.empty() ? nullptr : sa32;
         P.isa32 = isa.empty() ? nullptr : isa.data();
         P.text4 = isa.empty() ? nullptr : text4.data();
-        if (debug_flags & 16u) {  // item-based walk: fm_roots_kernel as a host loop, then fm_items_kernel as a one-lane warp
+        if (g_max_hits) {  // search_n: fm_ordered_kernel as a single thread
+            P.max_hits = g_max_hits;
+            P.qgram = nullptr, P.qgram_q = 0;
+            P.sa32 = P.isa32 = P.text4 = nullptr;
+            std::vector<uint4> ostack(ordered_stack_frames(len, static_cast<uint32_t>(sigma)));
+            P.ostack = ostack.data();
+            P.ostack_frames = static_cast<uint32_t>(ostack.size());
+            if (sigma == 6) {
+                if (edit) fm_ordered_thread<6, true>(P, steps.data(), ostack.data(), 1, P.ostack_frames);
+                else fm_ordered_thread<6, false>(P, steps.data(), ostack.data(), 1, P.ostack_frames);
+            } else if (sigma == 5) {
+                if (edit) fm_ordered_thread<5, true>(P, steps.data(), ostack.data(), 1, P.ostack_frames);
+                else fm_ordered_thread<5, false>(P, steps.data(), ostack.data(), 1, P.ostack_frames);
+            } else return 3;
+            g_ordered_maxsp = static_cast<uint32_t>(counters[CT_MAX_SP]);
+        } else if (debug_flags & 16u) {  // item-based walk: fm_roots_kernel as a host loop, then fm_items_kernel as a one-lane warp
             if (P.qgram_q >= len) P.qgram = nullptr, P.qgram_q = 0;
             P.items = items.data();
             P.item_tags = item_tags.data();

@@ -23,6 +23,8 @@ _lib.orc_locate_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
 _lib.orc_index_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
 _lib.orc_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                             C.c_int, C.POINTER(C.c_void_p), u64p, C.c_void_p]
+_lib.orc_search_n.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                              C.c_int, C.c_uint64, C.POINTER(C.c_void_p), u64p, C.c_void_p]
 _lib.orc_locate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), u64p, C.c_void_p]
 _lib.orc_free.argtypes = [C.c_void_p]
 _lib.orc_bf_hamming.restype = C.c_uint64
@@ -109,13 +111,14 @@ class OracleIndex:
         _check(_lib.orc_locate_rows(self._h, _ptr(rows), rows.size, _ptr(out)))
         return out
 
-    def search(self, queries, scheme, edit, threads=1):
-        """scheme: object with pi (uint16 [S, m]), l, u (uint8).  -> cursors uint64 [n, 4] in reference order."""
+    def search(self, queries, scheme, edit, threads=1, max_hits=0):
+        """scheme: object with pi (uint16 [S, m]), l, u (uint8).  -> cursors uint64 [n, 4] in reference order.
+        max_hits > 0: search_n (a query ends after max_hits suffix-array rows)."""
         q = np.ascontiguousarray(queries, dtype=np.uint8)
         assert q.ndim == 2 and q.shape[1] == scheme.pi.shape[1]
         p, n = C.c_void_p(), C.c_uint64()
-        _check(_lib.orc_search(self._h, _ptr(q), q.shape[0], q.shape[1], scheme.pi.shape[0], _ptr(scheme.pi), _ptr(scheme.l),
-                               _ptr(scheme.u), int(edit), threads, C.byref(p), C.byref(n), _ptr(self.counters)))
+        _check(_lib.orc_search_n(self._h, _ptr(q), q.shape[0], q.shape[1], scheme.pi.shape[0], _ptr(scheme.pi), _ptr(scheme.l),
+                                 _ptr(scheme.u), int(edit), threads, int(max_hits), C.byref(p), C.byref(n), _ptr(self.counters)))
         try:
             if n.value == 0:
                 return np.zeros((0, 4), dtype=np.uint64)

@@ -331,8 +331,96 @@ def test_cli_besthits_follows_search_best(sb, cases, tmp_path):
             want.append((active[int(a)], int(b), int(c)))
         active = [x for i, x in enumerate(active) if i not in found]
     assert got == sorted(want)
-    res = subprocess.run([exe, "search", "-q", qa, "-i", path, "--max_hits", "3"], capture_output=True, text=True)
+    # search_best_n (search.cpp:240): the limit applies inside the first stratum with a hit
+    res = subprocess.run([exe, "search", "-q", qa, "-i", path, "-e", str(k), "-o", out, "-m", "besthits", "--max_hits", "2"],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    got = sorted(tuple(int(x) for x in line.split()) for line in open(out))
+    want = []
+    active = list(range(q.shape[0]))
+    for j in range(k + 1):
+        if not active:
+            break
+        sch = sb.SearchScheme.generate("h2-k2", j, j, m)
+        hits = ix.locate(ix.search(q[active], sch, True, max_hits=2))
+        found = set(int(a) for a in hits[:, 0])
+        want += [(active[int(a)], int(b), int(c)) for a, b, c, d in hits]
+        active = [x for i, x in enumerate(active) if i not in found]
+    assert got == sorted(want)
+    res = subprocess.run([exe, "search", "-q", qa, "-i", path, "--max_hits", "-3"], capture_output=True, text=True)
     assert res.returncode == 1 and "max_hits" in res.stderr
+
+
+@pytest.mark.parametrize("key", [("random", 6), ("multi", 6), ("repeats", 6), ("random", 5)])
+@pytest.mark.parametrize("edit,k", [(False, 0), (False, 2), (True, 1), (True, 2), (True, 3)])
+def test_max_hits_matches_search_n(sb, ctx, cases, key, edit, k):
+    """sb200_set_max_hits (fm_ordered_kernel) against the oracle's search_n (search_ng24::search_n as called at
+    /root/reference/src/sahara/search.cpp:228,231): the first n rows of every query in recursion order, the same number
+    of cursor extensions; with and without the in-text verification tables / q-gram table loaded (not used here)."""
+    rng, seqs, ix, path = cases[key]
+    ctx.load_index(path)
+    if k == 2:
+        ctx.enable_text(True)
+        ctx.build_qgram(5)
+    m = 44
+    q = W.sample_reads(rng, seqs, 400, m, k, edit)
+    q[5, 7] = 0  # a query with the delimiter
+    try:
+        for gen in ("h2-k2", "01*0"):
+            sch = sb.SearchScheme.generate(gen, 0, k, m, limit_to_hamming=not edit)
+            ctx.set_scheme(sch, edit)
+            for n in (1, 3, 40, 10**9):
+                ctx.set_max_hits(n)
+                before = int(ix.counters[0])
+                want_cur = O.sort_rows(ix.search(q, sch, edit, max_hits=n))
+                nodes_oracle = int(ix.counters[0]) - before
+                ctx.reset_counters()
+                got_cur = ctx.search_cursors(q)
+                assert got_cur.shape == want_cur.shape and np.array_equal(got_cur, want_cur)
+                assert ctx.counters()["nodes"] == nodes_oracle
+                want_hits = O.sort_rows(ix.locate(want_cur))
+                assert np.array_equal(ctx.search(q), want_hits)
+                per_query = np.bincount(want_hits[:, 0].astype(np.int64), minlength=q.shape[0])
+                assert per_query.max() <= n
+                if n == 3:  # the reads-in / compact-hits-out call (both strands made on the device)
+                    reads = q[0::2]
+                    both = np.empty((2 * reads.shape[0], m), np.uint8)
+                    both[0::2] = reads
+                    both[1::2] = sb.revcomp_ranks(reads)
+                    want2 = O.sort_rows(ix.locate(ix.search(both, sch, edit, max_hits=n)))
+                    assert np.array_equal(ctx.search_reads(reads).astype(np.uint64), want2)
+            ctx.set_max_hits(0)
+            assert np.array_equal(ctx.search_cursors(q), O.sort_rows(ix.search(q, sch, edit)))
+    finally:
+        ctx.set_max_hits(0)
+
+
+def test_cli_max_hits(sb, cases, tmp_path):
+    """sahara search --max_hits n (src/sahara/search.cpp:91-96, 228, 231), Hamming and edit distance, 2 batches"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "sahara_b200", "sahara")
+    rng, seqs, ix, path = cases[("repeats", 6)]
+    m, k = 36, 2
+    q = W.sample_reads(rng, seqs, 120, m, k, True)
+    qa = os.path.join(tmp_path, "reads.fa")
+    with open(qa, "w") as f:
+        for i in range(0, q.shape[0], 2):
+            f.write(f">r{i // 2}\n" + "".join("$ACGTN"[c] for c in q[i]) + "\n")
+    reads = q[0::2]
+    both = np.empty((2 * reads.shape[0], m), np.uint8)
+    both[0::2] = reads
+    both[1::2] = sb.revcomp_ranks(reads)
+    out = os.path.join(tmp_path, "n.txt")
+    for metric, edit in (("lev", True), ("ham", False)):
+        for n in (1, 4):
+            res = subprocess.run([exe, "search", "-q", qa, "-i", path, "-e", str(k), "-o", out, "-d", metric, "--max_hits", str(n),
+                                  "--batch", "100"], capture_output=True, text=True)
+            assert res.returncode == 0, res.stderr
+            got = sorted(tuple(int(x) for x in line.split()) for line in open(out))
+            sch = sb.SearchScheme.generate("h2-k2", 0, k, m, limit_to_hamming=not edit)
+            hits = ix.locate(ix.search(both, sch, edit, max_hits=n))
+            assert got == sorted((int(a), int(b), int(c)) for a, b, c, d in hits)
 
 
 def test_search_reads_compact_matches_full_call(sb, ctx, cases, monkeypatch):

@@ -74,3 +74,26 @@ def test_qgram_covers_whole_query(indexes):
     for flags in (emu.QGRAM(5), emu.ITEMS | emu.QGRAM(5), emu.QGRAM(6), emu.ITEMS | emu.QGRAM(6)):
         got, _ = emu.search(ix, q, sch, False, flags)
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("key", ["repeats", "multi", "dna4"])
+@pytest.mark.parametrize("edit,k", [(False, 0), (False, 2), (True, 1), (True, 2), (True, 3)])
+def test_ordered_walk_matches_search_n(indexes, key, edit, k):
+    """fm_ordered_kernel's source against the oracle's search_n: the same cursors (cut at the limit) and the same
+    number of cursor extensions, for limits below, around and above the number of hits of a query"""
+    rng, seqs, ix, tt = indexes[key]
+    m = 36
+    q = W.sample_reads(rng, seqs, 40, m, k, edit)
+    q[3, 9] = 0
+    for gen in ("h2-k2", "pigeon_opt", "backtracking"):
+        sch = sb.SearchScheme.generate(gen, 0, k, m, limit_to_hamming=not edit)
+        full = O.sort_rows(ix.search(q, sch, edit))
+        for n in (1, 2, 5, 17, 10**9):
+            before = int(ix.counters[0])
+            want = O.sort_rows(ix.search(q, sch, edit, max_hits=n))
+            nodes_oracle = int(ix.counters[0]) - before
+            got, nodes = emu.search(ix, q, sch, edit, max_hits=n)
+            assert got.shape == want.shape and np.array_equal(got, want)
+            assert nodes == nodes_oracle
+            if n == 10**9:  # a limit nobody reaches: the plain search
+                assert np.array_equal(got, full)

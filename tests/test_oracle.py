@@ -125,3 +125,24 @@ def test_search_rejects_bad_input():
         ix.search(np.full((2, 8), 7, np.uint8), sch, True)  # invalid rank
     with pytest.raises(O.OracleError):
         ix.search(np.zeros((0, 8), np.uint8), sch, True)  # empty query set
+
+
+def test_search_n_is_a_prefix_of_the_recursion_order():
+    """search_n (src/sahara/search.cpp:228,231): per query the rows of the plain search in recursion order, cut
+    after max_hits rows"""
+    rng = np.random.default_rng(5)
+    seqs = [W.repetitive_genome(rng, 12000)]
+    ix = O.OracleIndex.build(seqs, 6, 16)
+    m, k = 30, 2
+    q = W.sample_reads(rng, seqs, 50, m, k, True)
+    sch = sb.SearchScheme.generate("h2-k2", 0, k, m)
+    full = ix.search(q, sch, True)  # reference order: query, search, recursion
+    for n in (1, 3, 8):
+        got = ix.search(q, sch, True, max_hits=n)
+        for qid in range(q.shape[0]):
+            f = full[full[:, 0] == qid]
+            g = got[got[:, 0] == qid]
+            rows = np.concatenate([np.arange(lb, lb + ln) for _, lb, ln, _ in f] or [np.zeros(0, np.uint64)])
+            rows_n = np.concatenate([np.arange(lb, lb + ln) for _, lb, ln, _ in g] or [np.zeros(0, np.uint64)])
+            assert len(rows_n) == min(n, len(rows))
+            assert np.array_equal(rows_n, rows[: len(rows_n)])

@@ -20,6 +20,7 @@ ap.add_argument("--densify", type=int, default=0)
 ap.add_argument("--text", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--rank-bench", type=int, default=1)
+ap.add_argument("--max-hits", default="", help="comma list of --max_hits limits to time after the plain search (search_n, fm_ordered_kernel)")
 a = ap.parse_args()
 
 ctx = sb.Context(0)
@@ -51,3 +52,15 @@ for rep in range(a.reps):
                           nodes=c["nodes"], lf=c["lf_steps"], ms_search=round(c["ms_search"], 2), ms_locate=round(c["ms_locate"], 2),
                           ms_sort=round(c["ms_sort"], 2), Gnodes_s=round(c["nodes"] / c["ms_search"] / 1e6, 2),
                           nodes_per_read=round(c["nodes"] / a.reads, 1))), flush=True)
+for n in [int(x) for x in a.max_hits.split(",") if x]:
+    ctx.set_max_hits(n)
+    for rep in range(2):
+        ctx.reset_counters()
+        t = time.time()
+        nc, nh = ctx.search_device(dq, 2 * a.reads, a.len)
+        dt = time.time() - t
+        c = ctx.counters()
+        print(json.dumps(dict(max_hits=n, rep=rep, wall_s=round(dt, 4), reads_per_s=round(a.reads / dt), cursors=nc, hits=nh, nodes=c["nodes"],
+                              ms_search=round(c["ms_search"], 2), ms_locate=round(c["ms_locate"], 2), ms_sort=round(c["ms_sort"], 2),
+                              nodes_per_read=round(c["nodes"] / a.reads, 1))), flush=True)
+ctx.set_max_hits(0)
