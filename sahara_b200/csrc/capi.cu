@@ -172,7 +172,7 @@ struct sb200_ctx {
     // work buffers
     uint32_t fused_shift{0};  // hit keys of the last locate carry the query id above this bit (0: separate array)
     int sorted_keys{0};       // d_keys[] buffer that holds the sorted hits
-    DevBuf d_qpos, d_tasks, d_bigsegs, d_lc, d_items, d_item_tags, d_ostack, d_seeds, d_spill, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
+    DevBuf d_qpos, d_tasks, d_bigsegs, d_lc, d_items, d_item_tags, d_ostack, d_rows, d_redo, d_seeds, d_spill, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
     uint64_t cursor_cap{}, seed_cap{};
     uint64_t last_cursors{}, last_real_cursors{}, last_hits{};
     uint64_t nodes_text{};
@@ -599,6 +599,70 @@ void read_back_words(sb200_ctx* c, const void* d_src, int n, int at = 0) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
 }
 
+// search_n: the ordered walk (fm_ordered_kernel), one thread per query with its stack in global memory
+unsigned ordered_grid(sb200_ctx* c, uint32_t len, uint64_t n_queries) {
+    unsigned g = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_BLOCKS_PER_SM", len > 300 ? 1 : 2);
+    return std::max(1u, std::min(g, grid_for(n_queries)));
+}
+void launch_ordered(sb200_ctx* c, const SearchParams& P) {
+    const size_t osmem = size_t(P.n_searches) * P.len * 4;
+    if (osmem > 48 * 1024) throw Error("search scheme table does not fit shared memory (query too long)");
+    const unsigned ogrid = ordered_grid(c, P.len, P.n_queries);
+    SearchParams Q = P;
+    Q.ostack_frames = ordered_stack_frames(P.len, c->idx.sigma);
+    c->d_ostack.reserve(size_t(ogrid) * 256 * Q.ostack_frames * sizeof(uint4));
+    Q.ostack = c->d_ostack.get<uint4>();
+    with_sigma(c->idx.sigma, [&](auto S) {
+        if (c->edit) fm_ordered_kernel<S(), true><<<ogrid, 256, osmem, c->stream>>>(Q);
+        else fm_ordered_kernel<S(), false><<<ogrid, 256, osmem, c->stream>>>(Q);
+        return 0;
+    });
+    launch_check(c);
+}
+
+// search_n after the plain search: a query with at most max_hits rows is complete; the others (they end early by
+// definition) are walked again in the reference's recursion order and their cursors of the first pass are dropped.
+// P: the parameters of the first pass, n_slots: its output slots.  false = the cursor buffer is too small (cursor_cap was
+// raised, the caller starts over).
+bool refine_max_hits(sb200_ctx* c, const SearchParams& P, uint64_t n_slots) {
+    const uint32_t nq = P.n_queries;
+    c->d_rows.reserve((size_t(nq) + 4) * sizeof(unsigned long long));
+    c->d_redo.reserve(size_t(nq) * sizeof(uint32_t));
+    unsigned long long* rows = c->d_rows.get<unsigned long long>();
+    unsigned long long* tally = rows + nq;  // queries to redo, bound on their cursors, cursors dropped
+    CUDA_TRY(cudaMemsetAsync(rows, 0, (size_t(nq) + 4) * sizeof(unsigned long long), c->stream));
+    if (n_slots) cursor_rows_kernel<<<grid_for(n_slots), 256, 0, c->stream>>>(P.out, n_slots, rows);
+    redo_list_kernel<<<grid_for(nq), 256, 0, c->stream>>>(rows, nq, c->max_hits, c->d_redo.get<uint32_t>(), tally);
+    launch_check(c);
+    read_back_words(c, tally, 2, CT_COUNT);
+    const uint64_t n_redo = c->h_counters[CT_COUNT], bound = c->h_counters[CT_COUNT + 1];
+    if (n_redo == 0) return true;
+    const uint64_t need = n_slots + bound + uint64_t(ordered_grid(c, P.len, n_redo)) * 256 * kEmitChunk;
+    if (need >= 0xfffffffeull) throw Error("more than 2^32 cursors in one call; split the batch");
+    if (need > c->cursor_cap) {
+        c->cursor_cap = need + need / 8;
+        return false;
+    }
+    drop_cursors_kernel<<<grid_for(n_slots), 256, 0, c->stream>>>(P.out, n_slots, rows, c->max_hits, tally);
+    CUDA_TRY(cudaMemsetAsync(P.counters + CT_NEXT_QUERY, 0, sizeof(unsigned long long), c->stream));
+    SearchParams Q = P;
+    Q.max_hits = c->max_hits;
+    Q.redo = c->d_redo.get<uint32_t>();
+    Q.n_queries = static_cast<uint32_t>(n_redo);
+    Q.items = nullptr, Q.item_tags = nullptr;
+    Q.qgram = nullptr, Q.qgram_q = 0;
+    Q.sa32 = Q.isa32 = Q.text4 = nullptr;
+    Q.textpos_out = 0;
+    launch_ordered(c, Q);
+    read_back_words(c, tally + 2, 1, CT_COUNT);
+    const uint64_t dropped = c->h_counters[CT_COUNT];
+    read_back_words(c, c->d_counters.p, CT_COUNT);
+    if (c->h_counters[CT_OVERFLOW]) throw Error("internal error: search stack overflow");
+    if (c->h_counters[CT_OUT_SLOTS] > c->cursor_cap) throw Error("internal error: cursor buffer of the ordered walk too small");
+    c->h_counters[CT_CURSORS] -= dropped;
+    return true;
+}
+
 void launch_search(sb200_ctx* c, const SearchParams& P) {
     // shared memory: scheme table + one staged packed query per thread
     size_t smem = (size_t(P.n_searches) * P.len + (size_t(P.n_searches) * P.len * kRunE + 3) / 4 + size_t(packed_words(P.len)) * 256) * 4;
@@ -607,21 +671,8 @@ void launch_search(sb200_ctx* c, const SearchParams& P) {
     unsigned need = grid_for((uint64_t(P.n_queries) + kQueryBatch - 1) / kQueryBatch);
     if (need < grid) grid = std::max(1u, need);
     CUDA_TRY(cudaEventRecord(c->ev[8], c->stream));
-    if (P.max_hits) {  // search_n: the ordered walk, one thread per query with its stack in global memory
-        const size_t osmem = size_t(P.n_searches) * P.len * 4;
-        if (osmem > 48 * 1024) throw Error("search scheme table does not fit shared memory (query too long)");
-        unsigned ogrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_BLOCKS_PER_SM", P.len > 300 ? 1 : 2);
-        ogrid = std::max(1u, std::min(ogrid, grid_for(P.n_queries)));
-        SearchParams Q = P;
-        Q.ostack_frames = ordered_stack_frames(P.len, c->idx.sigma);
-        c->d_ostack.reserve(size_t(ogrid) * 256 * Q.ostack_frames * sizeof(uint4));
-        Q.ostack = c->d_ostack.get<uint4>();
-        with_sigma(c->idx.sigma, [&](auto S) {
-            if (c->edit) fm_ordered_kernel<S(), true><<<ogrid, 256, osmem, c->stream>>>(Q);
-            else fm_ordered_kernel<S(), false><<<ogrid, 256, osmem, c->stream>>>(Q);
-            return 0;
-        });
-        launch_check(c);
+    if (P.max_hits) {  // search_n by the ordered walk alone (SB200_ORDERED_ONLY=1)
+        launch_ordered(c, P);
         CUDA_TRY(cudaEventRecord(c->ev[9], c->stream));
         CUDA_TRY(cudaEventRecord(c->ev[10], c->stream));
         return;
@@ -772,7 +823,10 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         // cursors that go straight to the locate step carry the text position of a verified occurrence instead of its row
         P.textpos_out = (for_locate && ix.text_mode && !(std::getenv("SB200_TEXTPOS") && std::atoi(std::getenv("SB200_TEXTPOS")) == 0)) ? 1u : 0u;
         if (const char* dbg = std::getenv("SB200_DEBUG")) P.debug_flags = static_cast<uint32_t>(std::atoi(dbg));
-        if (c->max_hits) {  // search_n: rows come from the ordered walk alone
+        // search_n: the plain search first, then the queries above the limit again in recursion order (refine_max_hits);
+        // SB200_ORDERED_ONLY=1 walks every query in order instead
+        const bool ordered_only = c->max_hits && std::getenv("SB200_ORDERED_ONLY") && std::atoi(std::getenv("SB200_ORDERED_ONLY")) != 0;
+        if (ordered_only) {
             P.max_hits = c->max_hits;
             P.items = nullptr, P.item_tags = nullptr;
             P.qgram = nullptr, P.qgram_q = 0;
@@ -800,6 +854,10 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         if (n_cursors > c->cursor_cap) {
             c->cursor_cap = n_cursors + n_cursors / 4;
             fits = false;
+        }
+        if (fits && c->max_hits && !ordered_only) {
+            if (!refine_max_hits(c, P, n_cursors)) continue;
+            n_cursors = c->h_counters[CT_OUT_SLOTS];
         }
         if (fits) break;
     }

@@ -161,6 +161,7 @@ struct SearchParams {
     uint32_t max_hits;
     uint4* ostack;
     uint32_t ostack_frames;  // frames per thread
+    const uint32_t* redo;    // optional: the queries to walk (n_queries = their number); nullptr = all queries
 };
 
 __host__ __device__ inline uint32_t packed_words(uint32_t len) { return (len + 7) / 8; }
@@ -561,8 +562,11 @@ __device__ __forceinline__ void fm_thread(const SearchParams& P, const uint32_t*
 // frame i of a thread at stack[i * stride]) onto which the children of a node are pushed in REVERSE recursion order,
 // so that they are popped in recursion order.  A frame is one call of the recursion with a non-empty cursor:
 // (lb, lbRev, len, step | e | LInfo | RInfo); step == query length reports.  Every popped frame with step < length is
-// one cursor extension of the reference ("node").  No q-gram table, no in-text verification here: the limit ends most
-// queries after one root-to-leaf path.
+// one cursor extension of the reference ("node").  No q-gram table, no in-text verification here: a query that
+// reaches the limit ends early by definition.  That is also how the work is split (capi.cu, search_only): the
+// throughput kernels search everything first; a query with at most maxHits rows is complete and identical to its
+// search_n result, only the queries with MORE rows (`redo` list, found by the kernels below) are walked again in
+// order, and their cursors from the first pass are dropped.
 // ================================================================================================
 template <int SIGMA>
 __device__ __forceinline__ void probe_children(const SearchParams& P, bool right, uint32_t lb, uint32_t lbRev, uint32_t len, uint32_t* klb,
@@ -615,7 +619,7 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
     while (true) {
         const unsigned long long w = atomicAdd(&P.counters[CT_NEXT_QUERY], 1ull);
         if (w >= P.n_queries) break;
-        const uint32_t qid = static_cast<uint32_t>(w);
+        const uint32_t qid = P.redo ? ldg32(P.redo + w) : static_cast<uint32_t>(w);
         const uint32_t* q = P.packed + static_cast<uint64_t>(qid) * W;
         auto qsym = [&](uint32_t pos) -> uint32_t { return (ldg32(q + (pos >> 3)) >> ((pos & 7u) * 4u)) & 0xfu; };
         uint32_t taken = 0;  // rows delivered for this query
@@ -1458,6 +1462,33 @@ __global__ void __launch_bounds__(256, 4) fm_kernel(const SearchParams P) {
     __syncthreads();
     // word w of this thread's query lives at s_query[w * blockDim.x]: every lane stays in its own bank
     fm_thread<SIGMA, EDIT, STACK>(P, s_steps, s_steps + n_steps + threadIdx.x, blockDim.x);
+}
+
+// ---- search_n, selection of the queries that exceed the limit -----------------------------------------
+// rows[q] += rows of every cursor of query q (cursors: the output slots of the first pass)
+__global__ void __launch_bounds__(256) cursor_rows_kernel(const uint4* cursors, uint64_t n, unsigned long long* rows) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const uint4 cu = cursors[i];
+    if (cu.x != kInvalidQid && cu.z != 0) atomicAdd(&rows[cu.x], static_cast<unsigned long long>(cu.z));
+}
+// queries with more rows than the limit -> redo[0 .. tally[0]); tally[1] = cursors the ordered walk can report for them
+__global__ void __launch_bounds__(256) redo_list_kernel(const unsigned long long* rows, uint32_t n_queries, uint32_t max_hits, uint32_t* redo,
+                                                        unsigned long long* tally) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queries || rows[q] <= max_hits) return;
+    redo[atomicAdd(&tally[0], 1ull)] = q;
+    atomicAdd(&tally[1], static_cast<unsigned long long>(max_hits));
+}
+// cursors of those queries become empty entries; tally[2] = how many were dropped
+__global__ void __launch_bounds__(256) drop_cursors_kernel(uint4* cursors, uint64_t n, const unsigned long long* rows, uint32_t max_hits,
+                                                           unsigned long long* tally) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const uint4 cu = cursors[i];
+    if (cu.x == kInvalidQid || rows[cu.x] <= max_hits) return;
+    cursors[i] = make_uint4(kInvalidQid, 0, 0, 0);
+    atomicAdd(&tally[2], 1ull);
 }
 
 // search_n: one thread per query, children visited in the order of the reference recursion (fm_ordered_thread)

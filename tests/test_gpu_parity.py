@@ -353,7 +353,7 @@ def test_cli_besthits_follows_search_best(sb, cases, tmp_path):
 
 @pytest.mark.parametrize("key", [("random", 6), ("multi", 6), ("repeats", 6), ("random", 5)])
 @pytest.mark.parametrize("edit,k", [(False, 0), (False, 2), (True, 1), (True, 2), (True, 3)])
-def test_max_hits_matches_search_n(sb, ctx, cases, key, edit, k):
+def test_max_hits_matches_search_n(sb, ctx, cases, key, edit, k, monkeypatch):
     """sb200_set_max_hits (fm_ordered_kernel) against the oracle's search_n (search_ng24::search_n as called at
     /root/reference/src/sahara/search.cpp:228,231): the first n rows of every query in recursion order, the same number
     of cursor extensions; with and without the in-text verification tables / q-gram table loaded (not used here)."""
@@ -374,10 +374,16 @@ def test_max_hits_matches_search_n(sb, ctx, cases, key, edit, k):
                 before = int(ix.counters[0])
                 want_cur = O.sort_rows(ix.search(q, sch, edit, max_hits=n))
                 nodes_oracle = int(ix.counters[0]) - before
+                # the plain search + the ordered walk over the queries above the limit (what runs by default)
+                got_cur = ctx.search_cursors(q)
+                assert got_cur.shape == want_cur.shape and np.array_equal(got_cur, want_cur)
+                # the ordered walk over every query: the extensions of the reference's search_n, one by one
+                monkeypatch.setenv("SB200_ORDERED_ONLY", "1")
                 ctx.reset_counters()
                 got_cur = ctx.search_cursors(q)
                 assert got_cur.shape == want_cur.shape and np.array_equal(got_cur, want_cur)
                 assert ctx.counters()["nodes"] == nodes_oracle
+                monkeypatch.delenv("SB200_ORDERED_ONLY")
                 want_hits = O.sort_rows(ix.locate(want_cur))
                 assert np.array_equal(ctx.search(q), want_hits)
                 per_query = np.bincount(want_hits[:, 0].astype(np.int64), minlength=q.shape[0])
@@ -386,7 +392,7 @@ def test_max_hits_matches_search_n(sb, ctx, cases, key, edit, k):
                     reads = q[0::2]
                     both = np.empty((2 * reads.shape[0], m), np.uint8)
                     both[0::2] = reads
-                    both[1::2] = sb.revcomp_ranks(reads)
+                    both[1::2] = np.stack([W.revcomp(r) for r in reads])
                     want2 = O.sort_rows(ix.locate(ix.search(both, sch, edit, max_hits=n)))
                     assert np.array_equal(ctx.search_reads(reads).astype(np.uint64), want2)
             ctx.set_max_hits(0)
@@ -410,7 +416,7 @@ def test_cli_max_hits(sb, cases, tmp_path):
     reads = q[0::2]
     both = np.empty((2 * reads.shape[0], m), np.uint8)
     both[0::2] = reads
-    both[1::2] = sb.revcomp_ranks(reads)
+    both[1::2] = np.stack([W.revcomp(r) for r in reads])
     out = os.path.join(tmp_path, "n.txt")
     for metric, edit in (("lev", True), ("ham", False)):
         for n in (1, 4):
