@@ -601,7 +601,7 @@ void read_back_words(sb200_ctx* c, const void* d_src, int n, int at = 0) {
 
 // search_n: the ordered walk (fm_ordered_kernel), one thread per query with its stack in global memory
 unsigned ordered_grid(sb200_ctx* c, uint32_t len, uint64_t n_queries) {
-    unsigned g = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_BLOCKS_PER_SM", len > 300 ? 1 : 2);
+    unsigned g = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_ORDERED_BLOCKS_PER_SM", len > 300 ? 1 : 4);  // (the stacks: 16 B x frames per thread)
     return std::max(1u, std::min(g, grid_for(n_queries)));
 }
 void launch_ordered(sb200_ctx* c, const SearchParams& P) {
@@ -651,8 +651,6 @@ bool refine_max_hits(sb200_ctx* c, const SearchParams& P, uint64_t n_slots) {
     Q.n_queries = static_cast<uint32_t>(n_redo);
     Q.items = nullptr, Q.item_tags = nullptr;
     Q.qgram = nullptr, Q.qgram_q = 0;
-    Q.sa32 = Q.isa32 = Q.text4 = nullptr;
-    Q.textpos_out = 0;
     launch_ordered(c, Q);
     read_back_words(c, tally + 2, 1, CT_COUNT);
     const uint64_t dropped = c->h_counters[CT_COUNT];
@@ -830,8 +828,6 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
             P.max_hits = c->max_hits;
             P.items = nullptr, P.item_tags = nullptr;
             P.qgram = nullptr, P.qgram_q = 0;
-            P.sa32 = P.isa32 = P.text4 = nullptr;
-            P.textpos_out = 0;
         }
         launch_search(c, P);
         read_back_words(c, c->d_counters.p, CT_COUNT);

@@ -562,8 +562,9 @@ __device__ __forceinline__ void fm_thread(const SearchParams& P, const uint32_t*
 // frame i of a thread at stack[i * stride]) onto which the children of a node are pushed in REVERSE recursion order,
 // so that they are popped in recursion order.  A frame is one call of the recursion with a non-empty cursor:
 // (lb, lbRev, len, step | e | LInfo | RInfo); step == query length reports.  Every popped frame with step < length is
-// one cursor extension of the reference ("node").  No q-gram table, no in-text verification here: a query that
-// reaches the limit ends early by definition.  That is also how the work is split (capi.cu, search_only): the
+// one cursor extension of the reference ("node").  A cursor that holds one row continues as a text frame when the
+// verification tables are loaded (one text symbol instead of two rank probes per node).  No q-gram table here: a
+// query that reaches the limit ends early by definition.  That is also how the work is split (capi.cu, search_only): the
 // throughput kernels search everything first; a query with at most maxHits rows is complete and identical to its
 // search_n result, only the queries with MORE rows (`redo` list, found by the kernels below) are walked again in
 // order, and their cursors from the first pass are dropped.
@@ -608,6 +609,10 @@ __device__ __forceinline__ void probe_children(const SearchParams& P, bool right
 // length + kmax nodes (a deletion stays on its step)
 __host__ __device__ inline uint32_t ordered_stack_frames(uint32_t len, uint32_t sigma) { return (len + 6u) * (2u * sigma - 2u) + 2u; }
 
+// ordered walk: the frame is (a, -, 1, meta) — a cursor with ONE row whose occurrence is T[a, a + tlen): its children
+// follow from one text symbol (in-text verification as in text_kernel) instead of two rank probes
+constexpr uint32_t META_OTEXT = META_PAIR;
+
 template <int SIGMA, bool EDIT>
 __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const uint32_t* s_steps, uint4* stack, uint32_t stride, uint32_t cap) {
     const uint32_t qlen = P.len;
@@ -616,35 +621,80 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
     uint32_t nodes = 0, emitted = 0, maxsp = 0;
     bool overflow = false;
     ChunkWriter outW;
-    while (true) {
-        const unsigned long long w = atomicAdd(&P.counters[CT_NEXT_QUERY], 1ull);
-        if (w >= P.n_queries) break;
-        const uint32_t qid = P.redo ? ldg32(P.redo + w) : static_cast<uint32_t>(w);
-        const uint32_t* q = P.packed + static_cast<uint64_t>(qid) * W;
-        auto qsym = [&](uint32_t pos) -> uint32_t { return (ldg32(q + (pos >> 3)) >> ((pos & 7u) * 4u)) & 0xfu; };
-        uint32_t taken = 0;  // rows delivered for this query
-        for (uint32_t j = 0; j < P.n_searches && taken < max_hits; ++j) {
-            const uint32_t* tbl = s_steps + j * qlen;
-            uint32_t sp = 0;
-            auto push = [&](uint32_t nlb, uint32_t nlbRev, uint32_t nlen, uint32_t m) {
-                if (sp < cap) stack[static_cast<uint64_t>(sp) * stride] = make_uint4(nlb, nlbRev, nlen, m);
-                else overflow = true;
-                ++sp;
-            };
-            push(0, 0, P.n_rows, pack_meta(0, 0, INFO_M, INFO_M));
-            while (sp != 0 && taken < max_hits) {
-                maxsp = sp > maxsp ? sp : maxsp;
-                --sp;
-                if (sp >= cap) continue;  // (frame lost to an overflow: the call fails)
-                const uint4 f = stack[static_cast<uint64_t>(sp) * stride];
+    // ONE loop for "next query / next search / next frame" (as in fm_thread): with nested loops the lanes of a warp
+    // would wait for the slowest search of the 32 before any of them starts its next one
+    uint32_t qid = 0;
+    const uint32_t* q = P.packed;
+    bool toText = false;
+    uint32_t taken = 0;               // rows delivered for the current query
+    uint32_t j = P.n_searches;        // next search of the current query (forces the first claim)
+    const uint32_t* tbl = s_steps;
+    // the stack: frames 0 .. sp-1 in global memory, the newest frame in registers (`top`) — the child that is
+    // visited next (mostly the match child) never makes the round trip through memory
+    uint32_t sp = 0;
+    uint4 top = make_uint4(0, 0, 0, 0);
+    bool haveTop = false;
+    auto qsym = [&](uint32_t pos) -> uint32_t { return (ldg32(q + (pos >> 3)) >> ((pos & 7u) * 4u)) & 0xfu; };
+    auto push = [&](uint32_t nlb, uint32_t nlbRev, uint32_t nlen, uint32_t m) {
+        if (toText && nlen == 1 && !(m & META_OTEXT)) {  // a unique cursor: continue at its text position SA[lb]
+            nlb = ldg32(P.sa32 + nlb);
+            m |= META_OTEXT;
+        }
+        if (haveTop) {
+            if (sp < cap) stack[static_cast<uint64_t>(sp) * stride] = top;
+            else overflow = true;
+            ++sp;
+        }
+        top = make_uint4(nlb, nlbRev, nlen, m);
+        haveTop = true;
+    };
+    {
+        while (true) {
+            {
+                if (taken >= max_hits) {  // the limit is reached: the query ends
+                    sp = 0;
+                    haveTop = false;
+                    j = P.n_searches;
+                }
+                if (!haveTop && sp == 0) {  // next search of the query, or the next query
+                    if (j == P.n_searches) {
+                        const unsigned long long w = atomicAdd(&P.counters[CT_NEXT_QUERY], 1ull);
+                        if (w >= P.n_queries) break;
+                        qid = P.redo ? ldg32(P.redo + w) : static_cast<uint32_t>(w);
+                        q = P.packed + static_cast<uint64_t>(qid) * W;
+                        // unique cursors are verified in the text, unless the query contains the delimiter (as in fm_kernel)
+                        toText = P.sa32 != nullptr;
+                        for (uint32_t i = 0; toText && i < W; ++i) {
+                            const uint32_t v = ldg32(q + i);
+                            toText = ((v - 0x11111111u) & ~v & 0x88888888u) == 0;  // no nibble is 0
+                        }
+                        taken = 0;
+                        j = 0;
+                    }
+                    tbl = s_steps + j * qlen;
+                    ++j;
+                    push(0, 0, P.n_rows, pack_meta(0, 0, INFO_M, INFO_M));
+                }
+                maxsp = sp + 1 > maxsp ? sp + 1 : maxsp;
+                uint4 f = top;
+                if (!haveTop) {
+                    --sp;
+                    if (sp >= cap) continue;  // (frame lost to an overflow: the call fails)
+                    f = stack[static_cast<uint64_t>(sp) * stride];
+                }
+                haveTop = false;
                 const uint32_t lb = f.x, lbRev = f.y, len = f.z, meta = f.w;
                 const uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
                 const uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
+                const bool inText = (meta & META_OTEXT) != 0;
+                const uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
                 if (step == qlen) {  // the end of the query: report (edit distance: not behind a substitution or deletion at either end)
                     if (!EDIT || (((Linfo | Rinfo) & 1u) == 0)) {
                         const uint32_t n = len < max_hits - taken ? len : max_hits - taken;
                         taken += n;
-                        outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], make_uint4(qid, lb, n, e));
+                        uint4 cu = make_uint4(qid, lb, n, e);
+                        if (inText) cu = P.textpos_out ? make_uint4(qid, lb, 1, e | kCursorTextPosFlag) : make_uint4(qid, ldg32(P.isa32 + lb), 1, e);
+                        outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], cu);
                         ++emitted;
                     }
                     continue;
@@ -656,23 +706,49 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
                 const bool mmOK = l <= e + 1 && e + 1 <= u;
                 if (!matchOK && !mmOK) continue;
                 const uint32_t c = qsym(st & 0xffffu);
-                uint32_t klb[SIGMA], klbRev[SIGMA], cnt[SIGMA];
-                probe_children<SIGMA>(P, right, lb, lbRev, len, klb, klbRev, cnt);
                 ++nodes;
                 const uint32_t T = right ? Rinfo : Linfo;
                 const uint32_t sideShift = right ? 16u : 14u;
-                const uint32_t metaBase = ((right ? Linfo : 0u) << 14) | ((right ? 0u : Rinfo) << 16);
+                const uint32_t metaBase = ((right ? Linfo : 0u) << 14) | ((right ? 0u : Rinfo) << 16) | (meta & META_OTEXT);
+                const uint32_t tlenSame = tlen << META_TLEN_SHIFT, tlenNext = (tlen + 1) << META_TLEN_SHIFT;
+                const uint32_t mM = metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift) | tlenNext;
+                const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift) | tlenNext;
+                const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift) | tlenNext;
+                const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift) | tlenSame;
+                const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
+                const bool insOK = EDIT && (T == INFO_M || T == INFO_I);
+                if (inText) {
+                    // the occurrence is T[a, a + tlen): the only non-empty child is the one of the text symbol next to it
+                    const uint32_t a = lb;
+                    uint32_t t = 0;  // (the delimiter before position 0)
+                    if (right) t = (ldg32(P.text4 + ((a + tlen) >> 3)) >> (((a + tlen) & 7u) * 4u)) & 0xfu;
+                    else if (a != 0) t = (ldg32(P.text4 + ((a - 1) >> 3)) >> (((a - 1) & 7u) * 4u)) & 0xfu;
+                    const uint32_t na = right ? a : a - 1;
+                    if (mmOK) {
+                        if (insOK) push(a, 0, 1, mI);  // popped last
+                        if (t != c && t != 0) {
+                            push(na, 0, 1, mS);
+                            if (delOK) push(na, 0, 1, mD);  // the deletion is tried before the substitution
+                        }
+                    }
+                    if (matchOK && t == c) push(na, 0, 1, mM);  // popped first
+                    continue;
+                }
+                uint32_t klb[SIGMA], klbRev[SIGMA], cnt[SIGMA];
+                probe_children<SIGMA>(P, right, lb, lbRev, len, klb, klbRev, cnt);
                 if (mmOK) {
-                    const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift);
-                    const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift);
-                    const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift);
-                    const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
-                    if (EDIT && (T == INFO_M || T == INFO_I)) push(lb, lbRev, len, mI);  // popped last
+                    if (insOK) push(lb, lbRev, len, mI);  // popped last
 #pragma unroll
                     for (int s = SIGMA - 1; s >= 1; --s) {
                         if (static_cast<uint32_t>(s) == c || cnt[s] == 0) continue;
-                        push(klb[s], klbRev[s], cnt[s], mS);
-                        if (delOK) push(klb[s], klbRev[s], cnt[s], mD);  // the deletion is tried before the substitution
+                        if (toText && cnt[s] == 1) {  // (one load of the text position for both frames)
+                            const uint32_t a = ldg32(P.sa32 + klb[s]);
+                            push(a, 0, 1, mS | META_OTEXT);
+                            if (delOK) push(a, 0, 1, mD | META_OTEXT);
+                        } else {
+                            push(klb[s], klbRev[s], cnt[s], mS);
+                            if (delOK) push(klb[s], klbRev[s], cnt[s], mD);  // the deletion is tried before the substitution
+                        }
                     }
                 }
                 if (matchOK) {  // popped first
@@ -680,7 +756,7 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
 #pragma unroll
                     for (int s = 0; s < SIGMA; ++s)
                         if (static_cast<uint32_t>(s) == c) { mc = cnt[s]; nlb = klb[s]; nlbRev = klbRev[s]; }
-                    if (mc != 0) push(nlb, nlbRev, mc, metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift));
+                    if (mc != 0) push(nlb, nlbRev, mc, mM);
                 }
             }
         }
@@ -1493,7 +1569,7 @@ __global__ void __launch_bounds__(256) drop_cursors_kernel(uint4* cursors, uint6
 
 // search_n: one thread per query, children visited in the order of the reference recursion (fm_ordered_thread)
 template <int SIGMA, bool EDIT>
-__global__ void __launch_bounds__(256) fm_ordered_kernel(const SearchParams P) {
+__global__ void __launch_bounds__(256, 4) fm_ordered_kernel(const SearchParams P) {
     extern __shared__ uint32_t s_steps[];
     const uint32_t n_steps = P.n_searches * P.len;
     for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) s_steps[i] = P.steps[i];

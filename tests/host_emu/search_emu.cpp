@@ -202,7 +202,6 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
         if (g_max_hits) {  // search_n: fm_ordered_kernel as a single thread
             P.max_hits = g_max_hits;
             P.qgram = nullptr, P.qgram_q = 0;
-            P.sa32 = P.isa32 = P.text4 = nullptr;
             std::vector<uint4> ostack(ordered_stack_frames(len, static_cast<uint32_t>(sigma)));
             P.ostack = ostack.data();
             P.ostack_frames = static_cast<uint32_t>(ostack.size());
@@ -214,6 +213,7 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
                 else fm_ordered_thread<5, false>(P, steps.data(), ostack.data(), 1, P.ostack_frames);
             } else return 3;
             g_ordered_maxsp = static_cast<uint32_t>(counters[CT_MAX_SP]);
+            P.sa32 = nullptr;  // (no second kernel)
         } else if (debug_flags & 16u) {  // item-based walk: fm_roots_kernel as a host loop, then fm_items_kernel as a one-lane warp
             if (P.qgram_q >= len) P.qgram = nullptr, P.qgram_q = 0;
             P.items = items.data();

@@ -92,8 +92,9 @@ def test_ordered_walk_matches_search_n(indexes, key, edit, k):
             before = int(ix.counters[0])
             want = O.sort_rows(ix.search(q, sch, edit, max_hits=n))
             nodes_oracle = int(ix.counters[0]) - before
-            got, nodes = emu.search(ix, q, sch, edit, max_hits=n)
-            assert got.shape == want.shape and np.array_equal(got, want)
-            assert nodes == nodes_oracle
+            for text in (None, tt):  # probes only / unique cursors verified in the text
+                got, nodes = emu.search(ix, q, sch, edit, text=text, max_hits=n)
+                assert got.shape == want.shape and np.array_equal(got, want)
+                assert nodes == nodes_oracle
             if n == 10**9:  # a limit nobody reaches: the plain search
                 assert np.array_equal(got, full)
