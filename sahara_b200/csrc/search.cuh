@@ -648,117 +648,113 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
         top = make_uint4(nlb, nlbRev, nlen, m);
         haveTop = true;
     };
-    {
-        while (true) {
-            {
-                if (taken >= max_hits) {  // the limit is reached: the query ends
-                    sp = 0;
-                    haveTop = false;
-                    j = P.n_searches;
+    while (true) {
+        if (taken >= max_hits) {  // the limit is reached: the query ends
+            sp = 0;
+            haveTop = false;
+            j = P.n_searches;
+        }
+        if (!haveTop && sp == 0) {  // next search of the query, or the next query
+            if (j == P.n_searches) {
+                const unsigned long long w = atomicAdd(&P.counters[CT_NEXT_QUERY], 1ull);
+                if (w >= P.n_queries) break;
+                qid = P.redo ? ldg32(P.redo + w) : static_cast<uint32_t>(w);
+                q = P.packed + static_cast<uint64_t>(qid) * W;
+                // unique cursors are verified in the text, unless the query contains the delimiter (as in fm_kernel)
+                toText = P.sa32 != nullptr;
+                for (uint32_t i = 0; toText && i < W; ++i) {
+                    const uint32_t v = ldg32(q + i);
+                    toText = ((v - 0x11111111u) & ~v & 0x88888888u) == 0;  // no nibble is 0
                 }
-                if (!haveTop && sp == 0) {  // next search of the query, or the next query
-                    if (j == P.n_searches) {
-                        const unsigned long long w = atomicAdd(&P.counters[CT_NEXT_QUERY], 1ull);
-                        if (w >= P.n_queries) break;
-                        qid = P.redo ? ldg32(P.redo + w) : static_cast<uint32_t>(w);
-                        q = P.packed + static_cast<uint64_t>(qid) * W;
-                        // unique cursors are verified in the text, unless the query contains the delimiter (as in fm_kernel)
-                        toText = P.sa32 != nullptr;
-                        for (uint32_t i = 0; toText && i < W; ++i) {
-                            const uint32_t v = ldg32(q + i);
-                            toText = ((v - 0x11111111u) & ~v & 0x88888888u) == 0;  // no nibble is 0
-                        }
-                        taken = 0;
-                        j = 0;
-                    }
-                    tbl = s_steps + j * qlen;
-                    ++j;
-                    push(0, 0, P.n_rows, pack_meta(0, 0, INFO_M, INFO_M));
-                }
-                maxsp = sp + 1 > maxsp ? sp + 1 : maxsp;
-                uint4 f = top;
-                if (!haveTop) {
-                    --sp;
-                    if (sp >= cap) continue;  // (frame lost to an overflow: the call fails)
-                    f = stack[static_cast<uint64_t>(sp) * stride];
-                }
-                haveTop = false;
-                const uint32_t lb = f.x, lbRev = f.y, len = f.z, meta = f.w;
-                const uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
-                const uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
-                const bool inText = (meta & META_OTEXT) != 0;
-                const uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
-                if (step == qlen) {  // the end of the query: report (edit distance: not behind a substitution or deletion at either end)
-                    if (!EDIT || (((Linfo | Rinfo) & 1u) == 0)) {
-                        const uint32_t n = len < max_hits - taken ? len : max_hits - taken;
-                        taken += n;
-                        uint4 cu = make_uint4(qid, lb, n, e);
-                        if (inText) cu = P.textpos_out ? make_uint4(qid, lb, 1, e | kCursorTextPosFlag) : make_uint4(qid, ldg32(P.isa32 + lb), 1, e);
-                        outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], cu);
-                        ++emitted;
-                    }
-                    continue;
-                }
-                const uint32_t st = tbl[step];
-                const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
-                const bool right = (st >> 24) & 1u;
-                const bool matchOK = l <= e && e <= u;
-                const bool mmOK = l <= e + 1 && e + 1 <= u;
-                if (!matchOK && !mmOK) continue;
-                const uint32_t c = qsym(st & 0xffffu);
-                ++nodes;
-                const uint32_t T = right ? Rinfo : Linfo;
-                const uint32_t sideShift = right ? 16u : 14u;
-                const uint32_t metaBase = ((right ? Linfo : 0u) << 14) | ((right ? 0u : Rinfo) << 16) | (meta & META_OTEXT);
-                const uint32_t tlenSame = tlen << META_TLEN_SHIFT, tlenNext = (tlen + 1) << META_TLEN_SHIFT;
-                const uint32_t mM = metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift) | tlenNext;
-                const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift) | tlenNext;
-                const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift) | tlenNext;
-                const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift) | tlenSame;
-                const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
-                const bool insOK = EDIT && (T == INFO_M || T == INFO_I);
-                if (inText) {
-                    // the occurrence is T[a, a + tlen): the only non-empty child is the one of the text symbol next to it
-                    const uint32_t a = lb;
-                    uint32_t t = 0;  // (the delimiter before position 0)
-                    if (right) t = (ldg32(P.text4 + ((a + tlen) >> 3)) >> (((a + tlen) & 7u) * 4u)) & 0xfu;
-                    else if (a != 0) t = (ldg32(P.text4 + ((a - 1) >> 3)) >> (((a - 1) & 7u) * 4u)) & 0xfu;
-                    const uint32_t na = right ? a : a - 1;
-                    if (mmOK) {
-                        if (insOK) push(a, 0, 1, mI);  // popped last
-                        if (t != c && t != 0) {
-                            push(na, 0, 1, mS);
-                            if (delOK) push(na, 0, 1, mD);  // the deletion is tried before the substitution
-                        }
-                    }
-                    if (matchOK && t == c) push(na, 0, 1, mM);  // popped first
-                    continue;
-                }
-                uint32_t klb[SIGMA], klbRev[SIGMA], cnt[SIGMA];
-                probe_children<SIGMA>(P, right, lb, lbRev, len, klb, klbRev, cnt);
-                if (mmOK) {
-                    if (insOK) push(lb, lbRev, len, mI);  // popped last
-#pragma unroll
-                    for (int s = SIGMA - 1; s >= 1; --s) {
-                        if (static_cast<uint32_t>(s) == c || cnt[s] == 0) continue;
-                        if (toText && cnt[s] == 1) {  // (one load of the text position for both frames)
-                            const uint32_t a = ldg32(P.sa32 + klb[s]);
-                            push(a, 0, 1, mS | META_OTEXT);
-                            if (delOK) push(a, 0, 1, mD | META_OTEXT);
-                        } else {
-                            push(klb[s], klbRev[s], cnt[s], mS);
-                            if (delOK) push(klb[s], klbRev[s], cnt[s], mD);  // the deletion is tried before the substitution
-                        }
-                    }
-                }
-                if (matchOK) {  // popped first
-                    uint32_t mc = 0, nlb = 0, nlbRev = 0;
-#pragma unroll
-                    for (int s = 0; s < SIGMA; ++s)
-                        if (static_cast<uint32_t>(s) == c) { mc = cnt[s]; nlb = klb[s]; nlbRev = klbRev[s]; }
-                    if (mc != 0) push(nlb, nlbRev, mc, mM);
+                taken = 0;
+                j = 0;
+            }
+            tbl = s_steps + j * qlen;
+            ++j;
+            push(0, 0, P.n_rows, pack_meta(0, 0, INFO_M, INFO_M));
+        }
+        maxsp = sp + 1 > maxsp ? sp + 1 : maxsp;
+        uint4 f = top;
+        if (!haveTop) {
+            --sp;
+            if (sp >= cap) continue;  // (frame lost to an overflow: the call fails)
+            f = stack[static_cast<uint64_t>(sp) * stride];
+        }
+        haveTop = false;
+        const uint32_t lb = f.x, lbRev = f.y, len = f.z, meta = f.w;
+        const uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
+        const uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
+        const bool inText = (meta & META_OTEXT) != 0;
+        const uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
+        if (step == qlen) {  // the end of the query: report (edit distance: not behind a substitution or deletion at either end)
+            if (!EDIT || (((Linfo | Rinfo) & 1u) == 0)) {
+                const uint32_t n = len < max_hits - taken ? len : max_hits - taken;
+                taken += n;
+                uint4 cu = make_uint4(qid, lb, n, e);
+                if (inText) cu = P.textpos_out ? make_uint4(qid, lb, 1, e | kCursorTextPosFlag) : make_uint4(qid, ldg32(P.isa32 + lb), 1, e);
+                outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], cu);
+                ++emitted;
+            }
+            continue;
+        }
+        const uint32_t st = tbl[step];
+        const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
+        const bool right = (st >> 24) & 1u;
+        const bool matchOK = l <= e && e <= u;
+        const bool mmOK = l <= e + 1 && e + 1 <= u;
+        if (!matchOK && !mmOK) continue;
+        const uint32_t c = qsym(st & 0xffffu);
+        ++nodes;
+        const uint32_t T = right ? Rinfo : Linfo;
+        const uint32_t sideShift = right ? 16u : 14u;
+        const uint32_t metaBase = ((right ? Linfo : 0u) << 14) | ((right ? 0u : Rinfo) << 16) | (meta & META_OTEXT);
+        const uint32_t tlenSame = tlen << META_TLEN_SHIFT, tlenNext = (tlen + 1) << META_TLEN_SHIFT;
+        const uint32_t mM = metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift) | tlenNext;
+        const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift) | tlenNext;
+        const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift) | tlenNext;
+        const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift) | tlenSame;
+        const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
+        const bool insOK = EDIT && (T == INFO_M || T == INFO_I);
+        if (inText) {
+            // the occurrence is T[a, a + tlen): the only non-empty child is the one of the text symbol next to it
+            const uint32_t a = lb;
+            uint32_t t = 0;  // (the delimiter before position 0)
+            if (right) t = (ldg32(P.text4 + ((a + tlen) >> 3)) >> (((a + tlen) & 7u) * 4u)) & 0xfu;
+            else if (a != 0) t = (ldg32(P.text4 + ((a - 1) >> 3)) >> (((a - 1) & 7u) * 4u)) & 0xfu;
+            const uint32_t na = right ? a : a - 1;
+            if (mmOK) {
+                if (insOK) push(a, 0, 1, mI);  // popped last
+                if (t != c && t != 0) {
+                    push(na, 0, 1, mS);
+                    if (delOK) push(na, 0, 1, mD);  // the deletion is tried before the substitution
                 }
             }
+            if (matchOK && t == c) push(na, 0, 1, mM);  // popped first
+            continue;
+        }
+        uint32_t klb[SIGMA], klbRev[SIGMA], cnt[SIGMA];
+        probe_children<SIGMA>(P, right, lb, lbRev, len, klb, klbRev, cnt);
+        if (mmOK) {
+            if (insOK) push(lb, lbRev, len, mI);  // popped last
+#pragma unroll
+            for (int s = SIGMA - 1; s >= 1; --s) {
+                if (static_cast<uint32_t>(s) == c || cnt[s] == 0) continue;
+                if (toText && cnt[s] == 1) {  // (one load of the text position for both frames)
+                    const uint32_t a = ldg32(P.sa32 + klb[s]);
+                    push(a, 0, 1, mS | META_OTEXT);
+                    if (delOK) push(a, 0, 1, mD | META_OTEXT);
+                } else {
+                    push(klb[s], klbRev[s], cnt[s], mS);
+                    if (delOK) push(klb[s], klbRev[s], cnt[s], mD);  // the deletion is tried before the substitution
+                }
+            }
+        }
+        if (matchOK) {  // popped first
+            uint32_t mc = 0, nlb = 0, nlbRev = 0;
+#pragma unroll
+            for (int s = 0; s < SIGMA; ++s)
+                if (static_cast<uint32_t>(s) == c) { mc = cnt[s]; nlb = klb[s]; nlbRev = klbRev[s]; }
+            if (mc != 0) push(nlb, nlbRev, mc, mM);
         }
     }
     outW.finish(P.out, P.out_cap);
