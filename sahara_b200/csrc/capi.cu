@@ -650,7 +650,8 @@ bool refine_max_hits(sb200_ctx* c, const SearchParams& P, uint64_t n_slots) {
     Q.redo = c->d_redo.get<uint32_t>();
     Q.n_queries = static_cast<uint32_t>(n_redo);
     Q.items = nullptr, Q.item_tags = nullptr;
-    Q.qgram = nullptr, Q.qgram_q = 0;
+    Q.qgram = c->idx.qgram_q && c->idx.qgram_q < P.len ? c->idx.qgram.get<uint4>() : nullptr;  // (not a table that covers the whole query)
+    Q.qgram_q = Q.qgram ? c->idx.qgram_q : 0;
     launch_ordered(c, Q);
     read_back_words(c, tally + 2, 1, CT_COUNT);
     const uint64_t dropped = c->h_counters[CT_COUNT];
@@ -827,7 +828,7 @@ void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uin
         if (ordered_only) {
             P.max_hits = c->max_hits;
             P.items = nullptr, P.item_tags = nullptr;
-            P.qgram = nullptr, P.qgram_q = 0;
+            if (P.qgram_q >= len) P.qgram = nullptr, P.qgram_q = 0;  // (a table that covers the whole query: plain walk)
         }
         launch_search(c, P);
         read_back_words(c, c->d_counters.p, CT_COUNT);

@@ -563,8 +563,8 @@ __device__ __forceinline__ void fm_thread(const SearchParams& P, const uint32_t*
 // so that they are popped in recursion order.  A frame is one call of the recursion with a non-empty cursor:
 // (lb, lbRev, len, step | e | LInfo | RInfo); step == query length reports.  Every popped frame with step < length is
 // one cursor extension of the reference ("node").  A cursor that holds one row continues as a text frame when the
-// verification tables are loaded (one text symbol instead of two rank probes per node).  No q-gram table here: a
-// query that reaches the limit ends early by definition.  That is also how the work is split (capi.cu, search_only): the
+// verification tables are loaded (one text symbol instead of two rank probes per node), and a search starts from the
+// q-gram table like the other walks.  A query that reaches the limit ends early by definition.  That is also how the work is split (capi.cu, search_only): the
 // throughput kernels search everything first; a query with at most maxHits rows is complete and identical to its
 // search_n result, only the queries with MORE rows (`redo` list, found by the kernels below) are walked again in
 // order, and their cursors from the first pass are dropped.
@@ -671,7 +671,11 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
             }
             tbl = s_steps + j * qlen;
             ++j;
-            push(0, 0, P.n_rows, pack_meta(0, 0, INFO_M, INFO_M));
+            // the root: the q-gram entry when the leading steps allow no error (their only child is the match
+            // child, so the jump keeps the order)
+            uint4 root;
+            if (fm_root(P, tbl, qsym, root) == 1) push(root.x, root.y, root.z, root.w);
+            if (!haveTop) continue;  // the search cannot start
         }
         maxsp = sp + 1 > maxsp ? sp + 1 : maxsp;
         uint4 f = top;

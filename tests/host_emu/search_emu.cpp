@@ -201,7 +201,7 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
         P.text4 = isa.empty() ? nullptr : text4.data();
         if (g_max_hits) {  // search_n: fm_ordered_kernel as a single thread
             P.max_hits = g_max_hits;
-            P.qgram = nullptr, P.qgram_q = 0;
+            if (P.qgram_q >= len) P.qgram = nullptr, P.qgram_q = 0;
             std::vector<uint4> ostack(ordered_stack_frames(len, static_cast<uint32_t>(sigma)));
             P.ostack = ostack.data();
             P.ostack_frames = static_cast<uint32_t>(ostack.size());

@@ -382,7 +382,10 @@ def test_max_hits_matches_search_n(sb, ctx, cases, key, edit, k, monkeypatch):
                 ctx.reset_counters()
                 got_cur = ctx.search_cursors(q)
                 assert got_cur.shape == want_cur.shape and np.array_equal(got_cur, want_cur)
-                assert ctx.counters()["nodes"] == nodes_oracle
+                if k == 2:  # (started from the q-gram table: the leading extensions are skipped)
+                    assert ctx.counters()["nodes"] <= nodes_oracle
+                else:
+                    assert ctx.counters()["nodes"] == nodes_oracle
                 monkeypatch.delenv("SB200_ORDERED_ONLY")
                 want_hits = O.sort_rows(ix.locate(want_cur))
                 assert np.array_equal(ctx.search(q), want_hits)

@@ -96,5 +96,9 @@ def test_ordered_walk_matches_search_n(indexes, key, edit, k):
                 got, nodes = emu.search(ix, q, sch, edit, text=text, max_hits=n)
                 assert got.shape == want.shape and np.array_equal(got, want)
                 assert nodes == nodes_oracle
+                # started from a q-gram table: the same cursors, the leading extensions skipped
+                got, nodes = emu.search(ix, q, sch, edit, emu.QGRAM(4), text=text, max_hits=n)
+                assert got.shape == want.shape and np.array_equal(got, want)
+                assert nodes <= nodes_oracle
             if n == 10**9:  # a limit nobody reaches: the plain search
                 assert np.array_equal(got, full)
