@@ -1,5 +1,5 @@
 """Randomised parity sweep (GPU): random genomes, read lengths, error counts, generators, alphabets and device
-options (in-text verification, q-gram table, densified suffix array) against the oracle, bit-exact."""
+options (in-text verification, q-gram table, densified suffix array, --max_hits limits) against the oracle, bit-exact."""
 import numpy as np
 import pytest
 
@@ -35,7 +35,7 @@ def test_random_configuration(seed):
             ctx.densify(int(rng.choice([r for r in (1, 2, 4, 8, 16) if r <= rate])))
         if rng.random() < 0.5:
             ctx.build_qgram(int(rng.integers(1, 8)))
-        for _ in range(3):
+        for it in range(3):
             edit = bool(rng.random() < 0.65)
             k = int(rng.integers(0, 5 if edit else 4))
             m = int(rng.integers(max(8, k + 3), 40 if k == 4 else 160))
@@ -57,3 +57,13 @@ def test_random_configuration(seed):
             if ctx.info()["device_bytes"] and not ctx.counters()["nodes"] > nodes:  # the q-gram table only removes nodes
                 assert ctx.counters()["nodes"] <= nodes
             assert np.array_equal(ctx.search(q), O.sort_rows(ix.locate(want_cur))), (seed, gen, k, m, edit)
+            # search_n with a random limit: the first rows of every query in the reference's recursion order
+            n = (1, 2, 3, 7, 50)[(seed + it) % 5]  # (not drawn from rng: the configurations stay what they were)
+            ctx.set_max_hits(n)
+            try:
+                want_n = O.sort_rows(ix.search(q, sch, edit, max_hits=n))
+                got_n = ctx.search_cursors(q)
+                assert got_n.shape == want_n.shape and np.array_equal(got_n, want_n), (seed, gen, k, m, edit, n)
+                assert np.array_equal(ctx.search(q), O.sort_rows(ix.locate(want_n))), (seed, gen, k, m, edit, n)
+            finally:
+                ctx.set_max_hits(0)
