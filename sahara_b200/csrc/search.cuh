@@ -553,222 +553,6 @@ __device__ __forceinline__ void fm_thread(const SearchParams& P, const uint32_t*
 }
 
 // ================================================================================================
-// Ordered walk with a hit limit (fm_ordered_kernel): fmc::search_ng24::search_n<Edit>(index, queries, scheme, maxHits, cb)
-// as called at /root/reference/src/sahara/search.cpp:228,231.  A query ends as soon as maxHits suffix-array rows were
-// delivered, the cursor that crosses the limit is cut to its first rows — WHICH hits those are is decided by the order
-// of the reference recursion (SURVEY.md 9.4: searches in scheme order; at a node the match child, then the symbols in
-// ascending order with the deletion before the substitution, then the insertion).  The other kernels expand the same
-// states in another order, so this path has its own walk: one thread per query, an explicit stack (global memory,
-// frame i of a thread at stack[i * stride]) onto which the children of a node are pushed in REVERSE recursion order,
-// so that they are popped in recursion order.  A frame is one call of the recursion with a non-empty cursor:
-// (lb, lbRev, len, step | e | LInfo | RInfo); step == query length reports.  Every popped frame with step < length is
-// one cursor extension of the reference ("node").  A cursor that holds one row continues as a text frame when the
-// verification tables are loaded (one text symbol instead of two rank probes per node), and a search starts from the
-// q-gram table like the other walks.  A query that reaches the limit ends early by definition.  That is also how the work is split (capi.cu, search_only): the
-// throughput kernels search everything first; a query with at most maxHits rows is complete and identical to its
-// search_n result, only the queries with MORE rows (`redo` list, found by the kernels below) are walked again in
-// order, and their cursors from the first pass are dropped.
-// ================================================================================================
-template <int SIGMA>
-__device__ __forceinline__ void probe_children(const SearchParams& P, bool right, uint32_t lb, uint32_t lbRev, uint32_t len, uint32_t* klb,
-                                               uint32_t* klbRev, uint32_t* cnt) {
-    const OccTable& tab = right ? P.bwtRev : P.bwt;
-    const uint32_t lo = right ? lbRev : lb;
-    const uint32_t hi = lo + len;
-    OccBlk b1 = load_blk(tab.blk + (lo >> kBlkShift));
-    OccSup s1 = load_sup(tab.sup + (lo >> kSupShift));
-    OccBlk b2 = b1;
-    OccSup s2 = s1;
-    if ((lo >> kBlkShift) != (hi >> kBlkShift)) {
-        b2 = load_blk(tab.blk + (hi >> kBlkShift));
-        if ((lo >> kSupShift) != (hi >> kSupShift)) s2 = load_sup(tab.sup + (hi >> kSupShift));
-    }
-    uint32_t own[SIGMA];
-    uint32_t sum1 = 0, sumc = 0;
-#pragma unroll
-    for (int s = 1; s < SIGMA; ++s) {
-        const uint32_t a = s1.c[s] + blk_ctr(b1, s) + blk_count(b1, lo & 63u, s);
-        const uint32_t b = s2.c[s] + blk_ctr(b2, s) + blk_count(b2, hi & 63u, s);
-        own[s] = P.C[s] + a;
-        cnt[s] = b - a;
-        sum1 += a;
-        sumc += b - a;
-    }
-    own[0] = lo - sum1;  // C[0] == 0
-    cnt[0] = len - sumc;
-    uint32_t other = right ? lb : lbRev;  // interval start on the side that is not probed
-#pragma unroll
-    for (int s = 0; s < SIGMA; ++s) {
-        klb[s] = right ? other : own[s];
-        klbRev[s] = right ? own[s] : other;
-        other += cnt[s];
-    }
-}
-
-// frames a thread's stack must hold: a node pushes at most 2 (SIGMA - 2) + 2 children and a path has at most
-// length + kmax nodes (a deletion stays on its step)
-__host__ __device__ inline uint32_t ordered_stack_frames(uint32_t len, uint32_t sigma) { return (len + 6u) * (2u * sigma - 2u) + 2u; }
-
-// ordered walk: the frame is (a, -, 1, meta) — a cursor with ONE row whose occurrence is T[a, a + tlen): its children
-// follow from one text symbol (in-text verification as in text_kernel) instead of two rank probes
-constexpr uint32_t META_OTEXT = META_PAIR;
-
-template <int SIGMA, bool EDIT>
-__device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const uint32_t* s_steps, uint4* stack, uint32_t stride, uint32_t cap) {
-    const uint32_t qlen = P.len;
-    const uint32_t W = packed_words(qlen);
-    const uint32_t max_hits = P.max_hits;
-    uint32_t nodes = 0, emitted = 0, maxsp = 0;
-    bool overflow = false;
-    ChunkWriter outW;
-    // ONE loop for "next query / next search / next frame" (as in fm_thread): with nested loops the lanes of a warp
-    // would wait for the slowest search of the 32 before any of them starts its next one
-    uint32_t qid = 0;
-    const uint32_t* q = P.packed;
-    bool toText = false;
-    uint32_t taken = 0;               // rows delivered for the current query
-    uint32_t j = P.n_searches;        // next search of the current query (forces the first claim)
-    const uint32_t* tbl = s_steps;
-    // the stack: frames 0 .. sp-1 in global memory, the newest frame in registers (`top`) — the child that is
-    // visited next (mostly the match child) never makes the round trip through memory
-    uint32_t sp = 0;
-    uint4 top = make_uint4(0, 0, 0, 0);
-    bool haveTop = false;
-    auto qsym = [&](uint32_t pos) -> uint32_t { return (ldg32(q + (pos >> 3)) >> ((pos & 7u) * 4u)) & 0xfu; };
-    auto push = [&](uint32_t nlb, uint32_t nlbRev, uint32_t nlen, uint32_t m) {
-        if (toText && nlen == 1 && !(m & META_OTEXT)) {  // a unique cursor: continue at its text position SA[lb]
-            nlb = ldg32(P.sa32 + nlb);
-            m |= META_OTEXT;
-        }
-        if (haveTop) {
-            if (sp < cap) stack[static_cast<uint64_t>(sp) * stride] = top;
-            else overflow = true;
-            ++sp;
-        }
-        top = make_uint4(nlb, nlbRev, nlen, m);
-        haveTop = true;
-    };
-    while (true) {
-        if (taken >= max_hits) {  // the limit is reached: the query ends
-            sp = 0;
-            haveTop = false;
-            j = P.n_searches;
-        }
-        if (!haveTop && sp == 0) {  // next search of the query, or the next query
-            if (j == P.n_searches) {
-                const unsigned long long w = atomicAdd(&P.counters[CT_NEXT_QUERY], 1ull);
-                if (w >= P.n_queries) break;
-                qid = P.redo ? ldg32(P.redo + w) : static_cast<uint32_t>(w);
-                q = P.packed + static_cast<uint64_t>(qid) * W;
-                // unique cursors are verified in the text, unless the query contains the delimiter (as in fm_kernel)
-                toText = P.sa32 != nullptr;
-                for (uint32_t i = 0; toText && i < W; ++i) {
-                    const uint32_t v = ldg32(q + i);
-                    toText = ((v - 0x11111111u) & ~v & 0x88888888u) == 0;  // no nibble is 0
-                }
-                taken = 0;
-                j = 0;
-            }
-            tbl = s_steps + j * qlen;
-            ++j;
-            // the root: the q-gram entry when the leading steps allow no error (their only child is the match
-            // child, so the jump keeps the order)
-            uint4 root;
-            if (fm_root(P, tbl, qsym, root) == 1) push(root.x, root.y, root.z, root.w);
-            if (!haveTop) continue;  // the search cannot start
-        }
-        maxsp = sp + 1 > maxsp ? sp + 1 : maxsp;
-        uint4 f = top;
-        if (!haveTop) {
-            --sp;
-            if (sp >= cap) continue;  // (frame lost to an overflow: the call fails)
-            f = stack[static_cast<uint64_t>(sp) * stride];
-        }
-        haveTop = false;
-        const uint32_t lb = f.x, lbRev = f.y, len = f.z, meta = f.w;
-        const uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
-        const uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
-        const bool inText = (meta & META_OTEXT) != 0;
-        const uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
-        if (step == qlen) {  // the end of the query: report (edit distance: not behind a substitution or deletion at either end)
-            if (!EDIT || (((Linfo | Rinfo) & 1u) == 0)) {
-                const uint32_t n = len < max_hits - taken ? len : max_hits - taken;
-                taken += n;
-                uint4 cu = make_uint4(qid, lb, n, e);
-                if (inText) cu = P.textpos_out ? make_uint4(qid, lb, 1, e | kCursorTextPosFlag) : make_uint4(qid, ldg32(P.isa32 + lb), 1, e);
-                outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], cu);
-                ++emitted;
-            }
-            continue;
-        }
-        const uint32_t st = tbl[step];
-        const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
-        const bool right = (st >> 24) & 1u;
-        const bool matchOK = l <= e && e <= u;
-        const bool mmOK = l <= e + 1 && e + 1 <= u;
-        if (!matchOK && !mmOK) continue;
-        const uint32_t c = qsym(st & 0xffffu);
-        ++nodes;
-        const uint32_t T = right ? Rinfo : Linfo;
-        const uint32_t sideShift = right ? 16u : 14u;
-        const uint32_t metaBase = ((right ? Linfo : 0u) << 14) | ((right ? 0u : Rinfo) << 16) | (meta & META_OTEXT);
-        const uint32_t tlenSame = tlen << META_TLEN_SHIFT, tlenNext = (tlen + 1) << META_TLEN_SHIFT;
-        const uint32_t mM = metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift) | tlenNext;
-        const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift) | tlenNext;
-        const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift) | tlenNext;
-        const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift) | tlenSame;
-        const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
-        const bool insOK = EDIT && (T == INFO_M || T == INFO_I);
-        if (inText) {
-            // the occurrence is T[a, a + tlen): the only non-empty child is the one of the text symbol next to it
-            const uint32_t a = lb;
-            uint32_t t = 0;  // (the delimiter before position 0)
-            if (right) t = (ldg32(P.text4 + ((a + tlen) >> 3)) >> (((a + tlen) & 7u) * 4u)) & 0xfu;
-            else if (a != 0) t = (ldg32(P.text4 + ((a - 1) >> 3)) >> (((a - 1) & 7u) * 4u)) & 0xfu;
-            const uint32_t na = right ? a : a - 1;
-            if (mmOK) {
-                if (insOK) push(a, 0, 1, mI);  // popped last
-                if (t != c && t != 0) {
-                    push(na, 0, 1, mS);
-                    if (delOK) push(na, 0, 1, mD);  // the deletion is tried before the substitution
-                }
-            }
-            if (matchOK && t == c) push(na, 0, 1, mM);  // popped first
-            continue;
-        }
-        uint32_t klb[SIGMA], klbRev[SIGMA], cnt[SIGMA];
-        probe_children<SIGMA>(P, right, lb, lbRev, len, klb, klbRev, cnt);
-        if (mmOK) {
-            if (insOK) push(lb, lbRev, len, mI);  // popped last
-#pragma unroll
-            for (int s = SIGMA - 1; s >= 1; --s) {
-                if (static_cast<uint32_t>(s) == c || cnt[s] == 0) continue;
-                if (toText && cnt[s] == 1) {  // (one load of the text position for both frames)
-                    const uint32_t a = ldg32(P.sa32 + klb[s]);
-                    push(a, 0, 1, mS | META_OTEXT);
-                    if (delOK) push(a, 0, 1, mD | META_OTEXT);
-                } else {
-                    push(klb[s], klbRev[s], cnt[s], mS);
-                    if (delOK) push(klb[s], klbRev[s], cnt[s], mD);  // the deletion is tried before the substitution
-                }
-            }
-        }
-        if (matchOK) {  // popped first
-            uint32_t mc = 0, nlb = 0, nlbRev = 0;
-#pragma unroll
-            for (int s = 0; s < SIGMA; ++s)
-                if (static_cast<uint32_t>(s) == c) { mc = cnt[s]; nlb = klb[s]; nlbRev = klbRev[s]; }
-            if (mc != 0) push(nlb, nlbRev, mc, mM);
-        }
-    }
-    outW.finish(P.out, P.out_cap);
-    if (nodes) atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(nodes));
-    if (overflow) atomicExch(&P.counters[CT_OVERFLOW], 1ull);
-    atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxsp));
-    if (emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(emitted));
-}
-
-// ================================================================================================
 // Item-based walk (fm_roots_kernel + fm_items_kernel).
 // In fm_thread a lane that runs out of frames fetches its next query (work atomic, staging, q-gram entries of up
 // to n_searches dead searches in a row) while the other 31 lanes of the warp wait at the reconvergence point in
@@ -951,6 +735,275 @@ __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t 
 __device__ __forceinline__ uint32_t text8(const uint32_t* text4, uint32_t pos) {
     const uint32_t w = pos >> 3;
     return funnel_r(text4[w], text4[w + 1], (pos & 7u) * 4u);
+}
+
+// ================================================================================================
+// Ordered walk with a hit limit (fm_ordered_kernel): fmc::search_ng24::search_n<Edit>(index, queries, scheme, maxHits, cb)
+// as called at /root/reference/src/sahara/search.cpp:228,231.  A query ends as soon as maxHits suffix-array rows were
+// delivered, the cursor that crosses the limit is cut to its first rows — WHICH hits those are is decided by the order
+// of the reference recursion (SURVEY.md 9.4: searches in scheme order; at a node the match child, then the symbols in
+// ascending order with the deletion before the substitution, then the insertion).  The other kernels expand the same
+// states in another order, so this path has its own walk: one thread per query, an explicit stack (global memory,
+// frame i of a thread at stack[i * stride]) onto which the children of a node are pushed in REVERSE recursion order,
+// so that they are popped in recursion order.  A frame is one call of the recursion with a non-empty cursor:
+// (lb, lbRev, len, step | e | LInfo | RInfo); step == query length reports.  Every popped frame with step < length is
+// one cursor extension of the reference ("node").  A cursor that holds one row continues as a text frame when the
+// verification tables are loaded (one text symbol instead of two rank probes per node), and a search starts from the
+// q-gram table like the other walks.  A query that reaches the limit ends early by definition.  That is also how the work is split (capi.cu, search_only): the
+// throughput kernels search everything first; a query with at most maxHits rows is complete and identical to its
+// search_n result, only the queries with MORE rows (`redo` list, found by the kernels below) are walked again in
+// order, and their cursors from the first pass are dropped.
+// ================================================================================================
+template <int SIGMA>
+__device__ __forceinline__ void probe_children(const SearchParams& P, bool right, uint32_t lb, uint32_t lbRev, uint32_t len, uint32_t* klb,
+                                               uint32_t* klbRev, uint32_t* cnt) {
+    const OccTable& tab = right ? P.bwtRev : P.bwt;
+    const uint32_t lo = right ? lbRev : lb;
+    const uint32_t hi = lo + len;
+    OccBlk b1 = load_blk(tab.blk + (lo >> kBlkShift));
+    OccSup s1 = load_sup(tab.sup + (lo >> kSupShift));
+    OccBlk b2 = b1;
+    OccSup s2 = s1;
+    if ((lo >> kBlkShift) != (hi >> kBlkShift)) {
+        b2 = load_blk(tab.blk + (hi >> kBlkShift));
+        if ((lo >> kSupShift) != (hi >> kSupShift)) s2 = load_sup(tab.sup + (hi >> kSupShift));
+    }
+    uint32_t own[SIGMA];
+    uint32_t sum1 = 0, sumc = 0;
+#pragma unroll
+    for (int s = 1; s < SIGMA; ++s) {
+        const uint32_t a = s1.c[s] + blk_ctr(b1, s) + blk_count(b1, lo & 63u, s);
+        const uint32_t b = s2.c[s] + blk_ctr(b2, s) + blk_count(b2, hi & 63u, s);
+        own[s] = P.C[s] + a;
+        cnt[s] = b - a;
+        sum1 += a;
+        sumc += b - a;
+    }
+    own[0] = lo - sum1;  // C[0] == 0
+    cnt[0] = len - sumc;
+    uint32_t other = right ? lb : lbRev;  // interval start on the side that is not probed
+#pragma unroll
+    for (int s = 0; s < SIGMA; ++s) {
+        klb[s] = right ? other : own[s];
+        klbRev[s] = right ? own[s] : other;
+        other += cnt[s];
+    }
+}
+
+// frames a thread's stack must hold: a node pushes at most 2 (SIGMA - 2) + 2 children and a path has at most
+// length + kmax nodes (a deletion stays on its step)
+__host__ __device__ inline uint32_t ordered_stack_frames(uint32_t len, uint32_t sigma) { return (len + 6u) * (2u * sigma - 2u) + 2u; }
+
+// ordered walk: the frame is (a, -, 1, meta) — a cursor with ONE row whose occurrence is T[a, a + tlen): its children
+// follow from one text symbol (in-text verification as in text_kernel) instead of two rank probes
+constexpr uint32_t META_OTEXT = META_PAIR;
+
+template <int SIGMA, bool EDIT>
+__device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const uint32_t* s_steps, uint4* stack, uint32_t stride, uint32_t cap) {
+    const uint32_t qlen = P.len;
+    const uint32_t W = packed_words(qlen);
+    const uint32_t max_hits = P.max_hits;
+    uint32_t nodes = 0, emitted = 0, maxsp = 0;
+    bool overflow = false;
+    ChunkWriter outW;
+    // ONE loop for "next query / next search / next frame" (as in fm_thread): with nested loops the lanes of a warp
+    // would wait for the slowest search of the 32 before any of them starts its next one
+    uint32_t qid = 0;
+    const uint32_t* q = P.packed;
+    bool toText = false;
+    uint32_t taken = 0;               // rows delivered for the current query
+    uint32_t j = P.n_searches;        // next search of the current query (forces the first claim)
+    const uint32_t* tbl = s_steps;
+    // the stack: frames 0 .. sp-1 in global memory, the newest frame in registers (`top`) — the child that is
+    // visited next (mostly the match child) never makes the round trip through memory
+    uint32_t sp = 0;
+    uint4 top = make_uint4(0, 0, 0, 0);
+    bool haveTop = false;
+    auto qsym = [&](uint32_t pos) -> uint32_t { return (ldg32(q + (pos >> 3)) >> ((pos & 7u) * 4u)) & 0xfu; };
+    auto push = [&](uint32_t nlb, uint32_t nlbRev, uint32_t nlen, uint32_t m) {
+        if (toText && nlen == 1 && !(m & META_OTEXT)) {  // a unique cursor: continue at its text position SA[lb]
+            nlb = ldg32(P.sa32 + nlb);
+            m |= META_OTEXT;
+        }
+        if (haveTop) {
+            if (sp < cap) stack[static_cast<uint64_t>(sp) * stride] = top;
+            else overflow = true;
+            ++sp;
+        }
+        top = make_uint4(nlb, nlbRev, nlen, m);
+        haveTop = true;
+    };
+    while (true) {
+        if (taken >= max_hits) {  // the limit is reached: the query ends
+            sp = 0;
+            haveTop = false;
+            j = P.n_searches;
+        }
+        if (!haveTop && sp == 0) {  // next search of the query, or the next query
+            if (j == P.n_searches) {
+                const unsigned long long w = atomicAdd(&P.counters[CT_NEXT_QUERY], 1ull);
+                if (w >= P.n_queries) break;
+                qid = P.redo ? ldg32(P.redo + w) : static_cast<uint32_t>(w);
+                q = P.packed + static_cast<uint64_t>(qid) * W;
+                // unique cursors are verified in the text, unless the query contains the delimiter (as in fm_kernel)
+                toText = P.sa32 != nullptr;
+                for (uint32_t i = 0; toText && i < W; ++i) {
+                    const uint32_t v = ldg32(q + i);
+                    toText = ((v - 0x11111111u) & ~v & 0x88888888u) == 0;  // no nibble is 0
+                }
+                taken = 0;
+                j = 0;
+            }
+            tbl = s_steps + j * qlen;
+            ++j;
+            // the root: the q-gram entry when the leading steps allow no error (their only child is the match
+            // child, so the jump keeps the order)
+            uint4 root;
+            if (fm_root(P, tbl, qsym, root) == 1) push(root.x, root.y, root.z, root.w);
+            if (!haveTop) continue;  // the search cannot start
+        }
+        maxsp = sp + 1 > maxsp ? sp + 1 : maxsp;
+        uint4 f = top;
+        if (!haveTop) {
+            --sp;
+            if (sp >= cap) continue;  // (frame lost to an overflow: the call fails)
+            f = stack[static_cast<uint64_t>(sp) * stride];
+        }
+        haveTop = false;
+        const uint32_t lbRev = f.y, len = f.z, meta = f.w;
+        uint32_t lb = f.x;  // (text frames: the text position a)
+        uint32_t step = meta & 0x3ffu;
+        const uint32_t e = (meta >> 10) & 0xfu;
+        uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
+        const bool inText = (meta & META_OTEXT) != 0;
+        uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
+        // match-only run of a text frame (steps with u == e: the match child is the only child, so walking them in
+        // one go keeps the order): query and text compared 8 symbols per round on the packed words, as in text_kernel
+        if (inText && step != qlen) {
+            const uint8_t* runs = P.runs + static_cast<size_t>(j - 1) * qlen * kRunE;
+            auto query8 = [&](uint32_t pos) -> uint32_t {  // the 8 query symbols from position pos; behind the query: 0xF
+                const uint32_t w = pos >> 3;
+                const uint32_t lo = ldg32(q + w);
+                const uint32_t hi = w + 1 < W ? ldg32(q + w + 1) : 0xffffffffu;
+                return funnel_r(lo, hi, (pos & 7u) * 4u);
+            };
+            bool dead = false;
+            uint32_t R = runs[step * kRunE + e];
+            while (R != 0) {
+                const uint32_t st = tbl[step];
+                const bool right = (st >> 24) & 1u;
+                const uint32_t p0 = st & 0xffffu;
+                uint32_t r = 0;
+                if (right) {
+                    while (r < R) {
+                        const uint32_t n = R - r < 8u ? R - r : 8u;
+                        const uint32_t x = (text8(P.text4, lb + tlen + r) ^ query8(p0 + r)) & nib_mask(n);
+                        if (x != 0) { r += (ctz32(x) >> 2); break; }
+                        r += n;
+                    }
+                } else {
+                    while (r < R) {
+                        if (lb < r + 1) break;  // the delimiter before position 0
+                        const uint32_t endT = lb - 1 - r, endQ = p0 - r;  // compare the symbols ending here, downwards
+                        uint32_t n = R - r < 8u ? R - r : 8u;
+                        if (n > endT + 1) n = endT + 1;
+                        const uint32_t x = (text8(P.text4, endT + 1 - n) ^ query8(endQ + 1 - n)) & nib_mask(n);
+                        if (x != 0) { r += n - 1 - ((31u - clz32(x)) >> 2); break; }
+                        r += n;
+                    }
+                }
+                if (r < R) {  // a symbol differs: the state at step + r has no child
+                    nodes += r + 1;
+                    dead = true;
+                    break;
+                }
+                nodes += R;
+                step += R;
+                tlen += R;
+                if (right) Rinfo = INFO_M;
+                else { Linfo = INFO_M; lb -= R; }
+                if (step == qlen) break;  // reported below
+                if (((tbl[step] >> 16) & 0xfu) > e + 1) { dead = true; break; }  // dead at the next step
+                R = runs[step * kRunE + e];
+            }
+            if (dead) continue;
+        }
+        if (step == qlen) {  // the end of the query: report (edit distance: not behind a substitution or deletion at either end)
+            if (!EDIT || (((Linfo | Rinfo) & 1u) == 0)) {
+                const uint32_t n = len < max_hits - taken ? len : max_hits - taken;
+                taken += n;
+                uint4 cu = make_uint4(qid, lb, n, e);
+                if (inText) cu = P.textpos_out ? make_uint4(qid, lb, 1, e | kCursorTextPosFlag) : make_uint4(qid, ldg32(P.isa32 + lb), 1, e);
+                outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], cu);
+                ++emitted;
+            }
+            continue;
+        }
+        const uint32_t st = tbl[step];
+        const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
+        const bool right = (st >> 24) & 1u;
+        const bool matchOK = l <= e && e <= u;
+        const bool mmOK = l <= e + 1 && e + 1 <= u;
+        if (!matchOK && !mmOK) continue;
+        const uint32_t c = qsym(st & 0xffffu);
+        ++nodes;
+        const uint32_t T = right ? Rinfo : Linfo;
+        const uint32_t sideShift = right ? 16u : 14u;
+        const uint32_t metaBase = ((right ? Linfo : 0u) << 14) | ((right ? 0u : Rinfo) << 16) | (meta & META_OTEXT);
+        const uint32_t tlenSame = tlen << META_TLEN_SHIFT, tlenNext = (tlen + 1) << META_TLEN_SHIFT;
+        const uint32_t mM = metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift) | tlenNext;
+        const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift) | tlenNext;
+        const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift) | tlenNext;
+        const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift) | tlenSame;
+        const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
+        const bool insOK = EDIT && (T == INFO_M || T == INFO_I);
+        if (inText) {
+            // the occurrence is T[a, a + tlen): the only non-empty child is the one of the text symbol next to it
+            const uint32_t a = lb;
+            uint32_t t = 0;  // (the delimiter before position 0)
+            if (right) t = (ldg32(P.text4 + ((a + tlen) >> 3)) >> (((a + tlen) & 7u) * 4u)) & 0xfu;
+            else if (a != 0) t = (ldg32(P.text4 + ((a - 1) >> 3)) >> (((a - 1) & 7u) * 4u)) & 0xfu;
+            const uint32_t na = right ? a : a - 1;
+            if (mmOK) {
+                if (insOK) push(a, 0, 1, mI);  // popped last
+                if (t != c && t != 0) {
+                    push(na, 0, 1, mS);
+                    if (delOK) push(na, 0, 1, mD);  // the deletion is tried before the substitution
+                }
+            }
+            if (matchOK && t == c) push(na, 0, 1, mM);  // popped first
+            continue;
+        }
+        uint32_t klb[SIGMA], klbRev[SIGMA], cnt[SIGMA];
+        probe_children<SIGMA>(P, right, lb, lbRev, len, klb, klbRev, cnt);
+        if (mmOK) {
+            if (insOK) push(lb, lbRev, len, mI);  // popped last
+#pragma unroll
+            for (int s = SIGMA - 1; s >= 1; --s) {
+                if (static_cast<uint32_t>(s) == c || cnt[s] == 0) continue;
+                if (toText && cnt[s] == 1) {  // (one load of the text position for both frames)
+                    const uint32_t a = ldg32(P.sa32 + klb[s]);
+                    push(a, 0, 1, mS | META_OTEXT);
+                    if (delOK) push(a, 0, 1, mD | META_OTEXT);
+                } else {
+                    push(klb[s], klbRev[s], cnt[s], mS);
+                    if (delOK) push(klb[s], klbRev[s], cnt[s], mD);  // the deletion is tried before the substitution
+                }
+            }
+        }
+        if (matchOK) {  // popped first
+            uint32_t mc = 0, nlb = 0, nlbRev = 0;
+#pragma unroll
+            for (int s = 0; s < SIGMA; ++s)
+                if (static_cast<uint32_t>(s) == c) { mc = cnt[s]; nlb = klb[s]; nlbRev = klbRev[s]; }
+            if (mc != 0) push(nlb, nlbRev, mc, mM);
+        }
+    }
+    outW.finish(P.out, P.out_cap);
+    if (nodes) atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(nodes));
+    if (overflow) atomicExch(&P.counters[CT_OVERFLOW], 1ull);
+    atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxsp));
+    if (emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(emitted));
 }
 
 constexpr uint32_t kSeedClaim = 1;  // seeds a thread takes per atomic (larger claims lose more to the tail than they save)
