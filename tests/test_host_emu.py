@@ -102,3 +102,44 @@ def test_ordered_walk_matches_search_n(indexes, key, edit, k):
                 assert nodes <= nodes_oracle
             if n == 10**9:  # a limit nobody reaches: the plain search
                 assert np.array_equal(got, full)
+
+
+GENERATORS = ["h2-k2", "h2-k1", "h2-k3", "pigeon", "pigeon_opt", "suffix", "01*0", "01*0_opt", "optimum", "kianfar", "kucherov-k1",
+              "kucherov-k2", "backtracking"]
+
+
+@pytest.mark.parametrize("seed", range(64))
+def test_ordered_walk_random_configurations(seed):
+    """the CPU twin of the GPU fuzz sweep for search_n: random genomes, read lengths, error counts, generators, limits;
+    the ordered walk with and without the text tables and the q-gram start against the oracle's search_n"""
+    rng = np.random.default_rng(7000 + seed)
+    sigma = 6 if rng.random() < 0.7 else 5
+    kind = rng.integers(0, 3)
+    if kind == 0:
+        seqs = [W.random_genome(rng, int(rng.integers(2000, 20000)), with_n=(sigma == 6))]
+    elif kind == 1:
+        seqs = [W.repetitive_genome(rng, int(rng.integers(3000, 10000))) for _ in range(int(rng.integers(1, 4)))]
+    else:
+        seqs = [W.random_genome(rng, int(n), with_n=(sigma == 6)) for n in rng.integers(1, 2000, size=int(rng.integers(2, 20)))]
+        seqs.append(W.random_genome(rng, 5000))
+    ix = O.OracleIndex.build(seqs, sigma, 16)
+    tt = emu.text_tables(ix, seqs)
+    for it in range(3):
+        edit = bool(rng.random() < 0.65)
+        k = int(rng.integers(0, 5 if edit else 4))
+        m = int(rng.integers(max(8, k + 3), 40 if k == 4 else 120))
+        gen = str(rng.choice(GENERATORS))
+        if gen == "backtracking" and (k > 2 or m > 40):
+            gen = "h2-k2"
+        q = W.sample_reads(rng, seqs, 12 if k >= 3 else 40, m, k, edit)
+        if rng.random() < 0.3:
+            q[int(rng.integers(0, q.shape[0])), int(rng.integers(0, m))] = 0  # a delimiter inside a query
+        sch = sb.SearchScheme.generate(gen, 0, k, m, limit_to_hamming=not edit)
+        n = (1, 2, 3, 7, 50)[(seed + it) % 5]
+        before = int(ix.counters[0])
+        want = O.sort_rows(ix.search(q, sch, edit, max_hits=n))
+        nodes_oracle = int(ix.counters[0]) - before
+        for text, flags in ((None, 0), (tt, 0), (tt, emu.QGRAM(int(rng.integers(1, 7))))):
+            got, nodes = emu.search(ix, q, sch, edit, flags, text=text, max_hits=n)
+            assert got.shape == want.shape and np.array_equal(got, want), (seed, gen, k, m, edit, n, flags)
+            assert nodes == nodes_oracle if flags == 0 else nodes <= nodes_oracle
