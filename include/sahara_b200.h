@@ -14,6 +14,14 @@
  *   - a context owns one GPU.  There is no CPU fallback: without a usable CUDA device
  *     sb200_create() fails.
  *   - ranks: 0 = '$' delimiter, 1..4 = A,C,G,T, 5 = N (only when sigma == 6).
+ *
+ * Limits the reference does not have (it computes in size_t, src/sahara/search.cpp:63-68); each is refused with a
+ * clear error, none is silently truncated:
+ *   - the index has fewer than 2^32 - 8192 rows (text + delimiters; a 3.1 Gbp genome has 3.1e9) — rows are u32 on the GPU;
+ *   - at most 4 errors (search schemes with u <= 4), queries of at most 1000 characters, at most 255 searches per scheme;
+ *   - fewer than 2^32 (query, search) pairs, cursors and hits per call (split the batch);
+ *   - the 16-byte and packed hit formats (sb200_search_reads, sb200_submit_reads) need bits_for_position <= 32;
+ *     sb200_search returns the reference's full 64-bit tuples.
  */
 #ifndef SAHARA_B200_H
 #define SAHARA_B200_H
@@ -21,11 +29,13 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "sahara_policy.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define SB200_ABI_VERSION 1
+#define SB200_ABI_VERSION 2
 
 typedef struct sb200_ctx sb200_ctx;
 
@@ -114,6 +124,19 @@ int sb200_index_build_qgram(sb200_ctx* ctx, uint32_t q);
 int sb200_set_scheme(sb200_ctx* ctx, uint32_t n_searches, uint32_t len, const uint16_t* pi, const uint8_t* l,
                      const uint8_t* u, int edit);
 
+/* The rules of the recursion that are reconstructions of fmindex-collection's behaviour (which operation may follow
+ * which, what may be reported, order of the children, expansion of the lower bounds) live in ONE table,
+ * include/sahara_policy.h; this call replaces the table in force (default: SB200_POLICY_DEFAULT).  The CPU oracle
+ * consumes the same struct.  Meant for pinning against a real sahara binary (tools/pin_against_sahara.sh). */
+int sb200_set_policy(sb200_ctx* ctx, const sb200_policy* policy);
+int sb200_get_policy(sb200_ctx* ctx, sb200_policy* out);
+
+/* knobs of the host orchestration; none of them changes results (they select between equivalent kernels / sort paths
+ * or tune launch geometry and chunking; tests use them to reach every path).  Names: bucket_sort, fused_sort, textpos,
+ * ordered_only, debug, chunk, edge_div, pool_blocks_per_sm, pool_threads, run_rounds, items_blocks_per_sm,
+ * ordered_blocks_per_sm.  The library reads no environment variables. */
+int sb200_set_option(sb200_ctx* ctx, const char* name, int64_t value);
+
 /* replaces the maxHits argument of fmc::search_ng24::search_n<Edit>(index, queries, scheme, maxHits, res_cb)
  * (src/sahara/search.cpp:228,231; `--max_hits`, src/sahara/search.cpp:91-96).  max_hits > 0: every following search
  * call delivers at most max_hits suffix-array rows per query — the first ones in the order of the reference's
@@ -160,6 +183,41 @@ typedef struct sb200_hit32 {
 int sb200_search_reads(sb200_ctx* ctx, const uint8_t* reads, uint64_t n_reads, uint32_t len, int with_reverse,
                        sb200_hit32** hits, uint64_t* n_hits);
 
+/* ---- asynchronous batches ---------------------------------------------------------------------------------
+ * The same search + locate as sb200_search_reads, split into submit and wait so that consecutive batches overlap: while
+ * batch i computes, the reads of batch i+1 travel to the GPU and the hits of batch i-1 travel back; nothing inside a
+ * batch waits for the host.  Up to SB200_MAX_IN_FLIGHT batches may be submitted before the oldest is waited for.
+ *
+ *   reads   host memory (page-locked memory from sb200_host_alloc makes the copy a single DMA); it must stay valid until
+ *           sb200_wait_batch returned.  format SB200_READS_RANKS: n_reads * len ranks, one byte each (the reference's
+ *           std::vector<uint8_t> per read, src/sahara/search.cpp:115-124).  SB200_READS_PACKED4: 4 bits per base, 8 bases
+ *           per little-endian 32-bit word, (len + 7) / 8 words per read (what sbh_pack_reads4 of the host library and the
+ *           CLI's FASTA reader produce): half the PCIe bytes.
+ *   result  hits in CSR form: the hits of query q are records [q ? hit_end[q-1] : 0, hit_end[q]); a record is
+ *           record_bytes little-endian bytes holding ((seq_id << bits_for_position | pos) << 4) | errors, sorted by that
+ *           value within a query.  query ids count as in the reference (2i = read i, 2i+1 = its reverse complement when
+ *           with_reverse != 0).  5 bytes per hit for a human-sized genome instead of the reference's 32-byte tuple.
+ *           The arrays belong to the batch and stay valid until sb200_release_batch(ticket). */
+#define SB200_MAX_IN_FLIGHT 3
+#define SB200_READS_RANKS 0
+#define SB200_READS_PACKED4 1
+typedef struct sb200_batch_result {
+    uint64_t n_queries, n_hits, n_cursors;
+    const uint32_t* hit_end;   /* [n_queries] */
+    const uint8_t* records;    /* n_hits * record_bytes */
+    uint32_t record_bytes, bits_for_position;
+    uint64_t h2d_bytes, d2h_bytes;          /* bytes this batch moved over PCIe */
+    float ms_search, ms_locate, ms_sort;    /* CUDA-event times of the batch's kernels */
+} sb200_batch_result;
+int sb200_submit_reads(sb200_ctx* ctx, const void* reads, uint64_t n_reads, uint32_t len, int format, int with_reverse,
+                       uint64_t* ticket);
+/* the same for queries that already sit in HBM (both strands, one byte per rank; device pointer) */
+int sb200_submit_device(sb200_ctx* ctx, const uint8_t* d_queries, uint64_t n_queries, uint32_t len, uint64_t* ticket);
+/* blocks until the batch is finished; copy_to_host != 0 also brings hit_end / records to page-locked host memory
+ * (0: counts only, the hits stay in HBM) */
+int sb200_wait_batch(sb200_ctx* ctx, uint64_t ticket, int copy_to_host, sb200_batch_result* out);
+int sb200_release_batch(sb200_ctx* ctx, uint64_t ticket);
+
 /* same pipeline with the queries already in HBM (d_queries = device pointer) and the hits left on the
  * GPU; returns only the counts.  Used to time the kernels without PCIe transfers. */
 int sb200_search_device(sb200_ctx* ctx, const uint8_t* d_queries, uint64_t n_queries, uint32_t len,
@@ -194,6 +252,7 @@ typedef struct sb200_counters {
     float ms_search, ms_locate, ms_sort, ms_h2d, ms_d2h; /* last call, CUDA events */
     float ms_fm, ms_text;     /* last call: the walk over the occurrence tables (fm_roots_kernel + fm_items_kernel), the in-text verification (text_pool_kernel) */
     uint64_t nodes_text;      /* extensions verified in the text instead of the occurrence tables (subset of nodes) */
+    uint64_t batch_restarts;  /* batches started over because a work buffer was too small (buffers grow, then stay) */
 } sb200_counters;
 int sb200_get_counters(sb200_ctx* ctx, sb200_counters* out);
 int sb200_reset_counters(sb200_ctx* ctx);

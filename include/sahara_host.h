@@ -60,6 +60,12 @@ int sbh_fasta_load_ranks(const char* path, uint64_t sigma, int with_revcomp, uin
  * released with sbh_free. */
 int sbh_fasta_load_reads(const char* path, uint64_t sigma, uint32_t threads, uint8_t** ranks, uint64_t* n_reads, uint64_t* len);
 int sbh_revcomp_ranks(const uint8_t* in, uint64_t n, uint8_t* out);
+/* ranks (one byte per base, values 0..15) -> SB200_READS_PACKED4 (include/sahara_b200.h): 4 bits per base, 8 bases per
+ * little-endian 32-bit word, (len + 7) / 8 words per read, unused nibbles of a read's last word 0xF.  out: n_reads *
+ * ((len + 7) / 8) words (page-locked memory from sb200_host_alloc makes the copy to the GPU a single DMA). */
+int sbh_pack_reads4(const uint8_t* ranks, uint64_t n_reads, uint32_t len, uint32_t threads, uint32_t* out);
+/* rule `expand_lower` of the policy table (include/sahara_policy.h) used by every expansion that follows (default 0) */
+int sbh_set_expand_rule(uint32_t rule);
 
 void sbh_free(void* p);
 

@@ -37,7 +37,14 @@
 #include <parallel/algorithm>
 #endif
 
+// the ONE table of reconstructed rules of the recursion, shared with the CUDA kernels (a header of data, no code of the
+// product): which operation may follow which, what may be reported, the order of the children
+#include "../include/sahara_policy.h"
+
 namespace {
+
+sb200_policy g_policy = SB200_POLICY_DEFAULT;  // orc_set_policy()
+
 
 using u8 = uint8_t;
 using u16 = uint16_t;
@@ -468,12 +475,15 @@ struct Searcher {
 
     bool stopped() const { return maxHits != 0 && *taken >= maxHits; }
 
+    static constexpr unsigned info_code(char c) { return c == 'M' ? SB200_INFO_M : c == 'S' ? SB200_INFO_S : c == 'I' ? SB200_INFO_I : SB200_INFO_D; }
+
     template <char LInfo, char RInfo>
     void next(Cursor const& cur, int e, size_t i) {
         if (cur.len == 0) return;
         if (stopped()) return;
         if (i == steps.size()) {
-            if constexpr (!Edit || ((LInfo == 'M' || LInfo == 'I') && (RInfo == 'M' || RInfo == 'I'))) {
+            // end filter (policy): by default not behind a substitution or a deletion at either end
+            if (!Edit || sb200_pol_end(&g_policy, info_code(LInfo), info_code(RInfo))) {
                 u64 len = cur.len;
                 if (maxHits != 0) {
                     if (*taken + len > maxHits) len = maxHits - *taken;
@@ -491,8 +501,11 @@ struct Searcher {
     template <char LInfo, char RInfo, bool Right>
     void dir(Cursor const& cur, int e, size_t i) {
         constexpr char T = Right ? RInfo : LInfo;
-        constexpr bool DelOK = Edit && (T == 'M' || T == 'D');
-        constexpr bool InsOK = Edit && (T == 'M' || T == 'I');
+        // which operation may follow T at the end that is extended (policy)
+        const bool DelOK = Edit && sb200_pol_del(&g_policy, info_code(T));
+        const bool InsOK = Edit && sb200_pol_ins(&g_policy, info_code(T));
+        const bool subFirst = (g_policy.child_order & SB200_CHILD_SUB_BEFORE_DEL) != 0;
+        const bool insEarly = (g_policy.child_order & SB200_CHILD_INS_BEFORE_SYMBOLS) != 0;
         constexpr char ML = Right ? LInfo : 'M', MR = Right ? 'M' : RInfo;
         constexpr char SL = Right ? LInfo : 'S', SR = Right ? 'S' : RInfo;
         constexpr char DL = Right ? LInfo : 'D', DR = Right ? 'D' : RInfo;
@@ -504,13 +517,16 @@ struct Searcher {
         if (mismatchOK) {
             Cursor kids[S];
             extend_all<S, Right>(ix, cur, kids, ct);
+            // order of the children (policy): match; then per symbol deletion and substitution; the insertion last
             if (matchOK) next<ML, MR>(kids[c], e, i + 1);
+            if (InsOK && insEarly) next<IL, IR>(cur, e + 1, i + 1);
             for (int s = 1; s < S; ++s) {
                 if (s == c) continue;
-                if constexpr (DelOK) next<DL, DR>(kids[s], e + 1, i);
-                next<SL, SR>(kids[s], e + 1, i + 1);
+                if (subFirst) next<SL, SR>(kids[s], e + 1, i + 1);
+                if (DelOK) next<DL, DR>(kids[s], e + 1, i);
+                if (!subFirst) next<SL, SR>(kids[s], e + 1, i + 1);
             }
-            if constexpr (InsOK) next<IL, IR>(cur, e + 1, i + 1);
+            if (InsOK && !insEarly) next<IL, IR>(cur, e + 1, i + 1);
         } else if (matchOK) {
             next<ML, MR>(extend_one<S, Right>(ix, cur, c, ct), e, i + 1);
         }
@@ -823,6 +839,15 @@ int orc_locate(void* h, u64 const* cursors, u64 n, int threads, u64** hitsOut, u
 }
 
 void orc_free(void* p) { std::free(p); }
+
+// replaces the policy table in force (include/sahara_policy.h); nullptr restores the default
+int orc_set_policy(sb200_policy const* p) {
+    return guard([&] {
+        sb200_policy def = SB200_POLICY_DEFAULT;
+        if (p && !sb200_pol_valid(p)) throw std::runtime_error("invalid search policy");
+        g_policy = p ? *p : def;
+    });
+}
 
 // ---------------------------------------------------------------------------------------------
 // Brute-force checkers (implementation-independent ground truth for tests).

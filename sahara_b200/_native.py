@@ -52,6 +52,25 @@ class Counters(C.Structure):
         ("hits", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("ms_search", C.c_float), ("ms_locate", C.c_float), ("ms_sort", C.c_float), ("ms_h2d", C.c_float),
         ("ms_d2h", C.c_float), ("ms_fm", C.c_float), ("ms_text", C.c_float), ("nodes_text", C.c_uint64),
+        ("batch_restarts", C.c_uint64),
+    ]
+
+
+class Policy(C.Structure):
+    """sb200_policy (include/sahara_policy.h): the reconstructed rules of the recursion"""
+    _fields_ = [
+        ("del_after", C.c_uint32), ("ins_after", C.c_uint32), ("end_ok", C.c_uint32), ("child_order", C.c_uint32),
+        ("expand_lower", C.c_uint32), ("reserved", C.c_uint32 * 3),
+    ]
+
+
+class BatchResult(C.Structure):
+    _fields_ = [
+        ("n_queries", C.c_uint64), ("n_hits", C.c_uint64), ("n_cursors", C.c_uint64),
+        ("hit_end", C.c_void_p), ("records", C.c_void_p),
+        ("record_bytes", C.c_uint32), ("bits_for_position", C.c_uint32),
+        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+        ("ms_search", C.c_float), ("ms_locate", C.c_float), ("ms_sort", C.c_float),
     ]
 
 
@@ -75,6 +94,13 @@ SB200_SYMBOLS = {
     "sb200_index_enable_text": (C.c_int, [C.c_void_p, C.c_int]),
     "sb200_set_scheme": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "sb200_set_max_hits": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "sb200_set_policy": (C.c_int, [C.c_void_p, C.POINTER(Policy)]),
+    "sb200_get_policy": (C.c_int, [C.c_void_p, C.POINTER(Policy)]),
+    "sb200_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "sb200_submit_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, u64p]),
+    "sb200_submit_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, u64p]),
+    "sb200_wait_batch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(BatchResult)]),
+    "sb200_release_batch": (C.c_int, [C.c_void_p, C.c_uint64]),
     "sb200_search_cursors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p), u64p]),
     "sb200_locate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), u64p]),
     "sb200_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p), u64p]),
@@ -117,6 +143,8 @@ SBH_SYMBOLS = {
     "sbh_fasta_load_ranks": (C.c_int, [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p]),
     "sbh_fasta_load_reads": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p), u64p, u64p]),
     "sbh_revcomp_ranks": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "sbh_pack_reads4": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "sbh_set_expand_rule": (C.c_int, [C.c_uint32]),
     "sbh_free": (None, [C.c_void_p]),
 }
 

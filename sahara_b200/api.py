@@ -126,6 +126,48 @@ def load_fasta_ranks(path, sigma=6, with_revcomp=False):
     return out
 
 
+def pack_reads4(reads, threads=4, out=None):
+    """ranks [n_reads, len] -> SB200_READS_PACKED4 words [n_reads, (len + 7) // 8] (uint32)"""
+    r = np.ascontiguousarray(reads, dtype=np.uint8)
+    if r.ndim != 2:
+        raise ValueError("reads must be a dense [n_reads, length] array of ranks")
+    W = (r.shape[1] + 7) // 8
+    if out is None:
+        out = np.empty((r.shape[0], W), dtype=np.uint32)
+    check_host(host.sbh_pack_reads4(_ptr(r), r.shape[0], r.shape[1], threads, C.c_void_p(out.ctypes.data)))
+    return out
+
+
+def default_policy():
+    """SB200_POLICY_DEFAULT of include/sahara_policy.h"""
+    return N.Policy(del_after=0b1001, ins_after=0b0101, end_ok=0b0101, child_order=0, expand_lower=0)
+
+
+def set_expand_rule(rule):
+    """rule `expand_lower` of the policy table for every SearchScheme.generate() that follows"""
+    check_host(host.sbh_set_expand_rule(int(rule)))
+
+
+def decode_batch(res, first_query=0):
+    """sb200_batch_result -> uint64 [n_hits, 4] = (queryId, seqId, pos, errors) in the order of the records"""
+    nq, nh, rb, bits = res.n_queries, res.n_hits, res.record_bytes, res.bits_for_position
+    if nh == 0:
+        return np.zeros((0, 4), dtype=np.uint64)
+    ends = np.ctypeslib.as_array(C.cast(res.hit_end, N.u32p), shape=(nq,)).astype(np.int64)
+    raw = np.ctypeslib.as_array(C.cast(res.records, N.u8p), shape=(nh * rb,)).reshape(nh, rb)
+    key = np.zeros(nh, dtype=np.uint64)
+    for b in range(rb):
+        key |= raw[:, b].astype(np.uint64) << np.uint64(8 * b)
+    counts = np.diff(np.concatenate([[0], ends]))
+    out = np.empty((nh, 4), dtype=np.uint64)
+    out[:, 0] = np.repeat(np.arange(nq, dtype=np.uint64) + np.uint64(first_query), counts)
+    v = key >> np.uint64(4)
+    out[:, 1] = v >> np.uint64(bits)
+    out[:, 2] = v & np.uint64((1 << bits) - 1)
+    out[:, 3] = key & np.uint64(15)
+    return out
+
+
 def revcomp_ranks(r):
     r = np.ascontiguousarray(r, dtype=np.uint8)
     out = np.empty_like(r)
@@ -215,6 +257,20 @@ class Context:
         check(cuda.sb200_set_scheme(self._h, scheme.n_searches, scheme.n_entries, _ptr(scheme.pi), _ptr(scheme.l), _ptr(scheme.u),
                                     int(edit)))
 
+    def set_policy(self, policy=None):
+        """replaces the table of reconstructed rules (include/sahara_policy.h); None = the default"""
+        p = policy if policy is not None else default_policy()
+        check(cuda.sb200_set_policy(self._h, C.byref(p)))
+
+    def get_policy(self):
+        p = N.Policy()
+        check(cuda.sb200_get_policy(self._h, C.byref(p)))
+        return p
+
+    def set_option(self, name, value):
+        """knobs of the host orchestration (sb200_set_option); results never depend on them"""
+        check(cuda.sb200_set_option(self._h, name.encode(), int(value)))
+
     def set_max_hits(self, max_hits):
         """search_n (src/sahara/search.cpp:228,231): at most max_hits rows per query, the first ones in the order
         of the reference recursion; 0 = unlimited"""
@@ -256,6 +312,58 @@ class Context:
             return np.ctypeslib.as_array(C.cast(p, N.u32p), shape=(n.value * 4,)).copy().reshape(-1, 4)
         finally:
             cuda.sb200_free(p)
+
+    # ---- asynchronous batches (sb200_submit_reads / sb200_wait_batch / sb200_release_batch) ----
+    def submit_reads(self, reads, length=None, packed4=False, with_reverse=True):
+        """reads: ranks [n, len] (uint8), or with packed4 the words of pack_reads4 [n, (len + 7) // 8] (uint32) — or an
+        int address of such a (page-locked) buffer together with (n_reads, length) in `length`.  Returns a ticket; the
+        buffer must stay alive until wait_batch."""
+        if isinstance(reads, tuple):
+            addr, n_reads, ln = reads
+        else:
+            a = np.ascontiguousarray(reads)
+            n_reads = a.shape[0]
+            ln = length if length is not None else a.shape[1]
+            addr = a.ctypes.data
+            self._keep = getattr(self, "_keep", {})
+        t = C.c_uint64()
+        check(cuda.sb200_submit_reads(self._h, C.c_void_p(addr), n_reads, ln, 1 if packed4 else 0, int(with_reverse), C.byref(t)))
+        if not isinstance(reads, tuple):
+            self._keep[t.value] = a
+        return t.value
+
+    def submit_device(self, d_queries, n_queries, length):
+        t = C.c_uint64()
+        check(cuda.sb200_submit_device(self._h, C.c_void_p(d_queries), n_queries, length, C.byref(t)))
+        return t.value
+
+    def wait_batch(self, ticket, copy_to_host=True):
+        res = N.BatchResult()
+        check(cuda.sb200_wait_batch(self._h, ticket, int(copy_to_host), C.byref(res)))
+        return res
+
+    def release_batch(self, ticket):
+        check(cuda.sb200_release_batch(self._h, ticket))
+        getattr(self, "_keep", {}).pop(ticket, None)
+
+    def search_reads_async(self, reads, packed4=False, with_reverse=True, batch=None, depth=2):
+        """the reads cut into batches that are submitted `depth` deep -> uint64 [n_hits, 4] like search()"""
+        r = self._queries(reads)
+        n, m = r.shape
+        batch = batch or n
+        per = 2 if with_reverse else 1
+        pieces = [(o, min(n, o + batch)) for o in range(0, n, batch)]
+        bufs = [pack_reads4(r[a:b]) if packed4 else np.ascontiguousarray(r[a:b]) for a, b in pieces]
+        out, tickets = [], []
+        for i in range(len(pieces) + depth):
+            if i >= depth:
+                j = i - depth
+                res = self.wait_batch(tickets[j])
+                out.append(decode_batch(res, first_query=pieces[j][0] * per))
+                self.release_batch(tickets[j])
+            if i < len(pieces):
+                tickets.append(self.submit_reads(bufs[i], length=m, packed4=packed4, with_reverse=with_reverse))
+        return np.concatenate(out) if out else np.zeros((0, 4), dtype=np.uint64)
 
     def search_cursors(self, queries):
         """-> uint64 [n, 4] = (queryId, lb, len, errors), sorted."""

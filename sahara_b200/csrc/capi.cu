@@ -56,9 +56,25 @@ int guard(F&& f) {
     }
 }
 
+// device allocation that grows on demand; owning and move-only (released on scope exit, also when an error unwinds)
 struct DevBuf {
     void* p{};
     size_t cap{};
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            cap = o.cap;
+            o.p = nullptr;
+            o.cap = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }
     template <typename T = void>
     T* get() const { return static_cast<T*>(p); }
     void reserve(size_t bytes) {
@@ -158,6 +174,60 @@ struct DeviceIndex {
     }
 };
 
+// knobs of the host orchestration (sb200_set_option); none of them changes results
+struct Options {
+    int bucket_sort{1};        // locate + sort through per-query buckets (0: global radix sort)
+    int fused_sort{-1};        // global radix sort with the query id fused into the key (-1: when it saves a pass)
+    int textpos{1};            // verified occurrences go to the locate step as text positions (0: as suffix-array rows)
+    int ordered_only{0};       // search_n by the ordered walk over every query (0: plain search first, ordered walk for the queries above the limit)
+    int debug{0};              // bits 0..7: SearchParams::debug_flags; any bit: progress lines on stderr
+    uint64_t chunk{2000000};   // host-buffer calls: queries per middle chunk
+    uint64_t edge_div{5};      // ... first and last chunk = 1 / edge_div of the batch
+    int pool_blocks_per_sm{0}, pool_threads{0}, run_rounds{0};  // text_pool_kernel geometry (0 = default)
+    int items_blocks_per_sm{0}, ordered_blocks_per_sm{0};       // fm_items_kernel / fm_ordered_kernel blocks per SM (0 = default)
+};
+
+enum : int { IN_QUERIES_RANKS = 0, IN_READS_RANKS = 1, IN_READS_PACKED4 = 2 };
+enum : int { OUT_NONE = 0, OUT_HIT64 = 1, OUT_HIT32 = 2, OUT_CSR = 3 };
+constexpr int kSlots = 3;
+
+// one work slot: the buffers, stream and events of one batch in flight
+struct Work {
+    int id{};
+    bool busy{};              // handed out by submit, not yet released
+    uint64_t ticket{};
+    cudaStream_t own_stream{}, stream{};
+    cudaEvent_t ev[12]{};     // timing: 0 start, 11 search end, 8..10 fm / text, 1..3 locate / sort
+    cudaEvent_t ev_in{}, ev_done{}, ev_ready{}, ev_out{}, ev_fork{};
+    DevBuf d_in, d_packed, d_items, d_item_tags, d_seeds, d_spill, d_cursors, d_counters, d_qpos, d_lc, d_tasks, d_bigsegs, d_keys[2], d_qids[2],
+        d_offsets, d_tmp, d_scratch, d_rows, d_redo, d_ostack, d_out;
+    uint64_t cursor_cap{}, seed_cap{}, hit_cap{};
+    uint32_t task_cap{};
+    unsigned long long* h_status{};      // pinned + mapped status block (publish_status_kernel)
+    unsigned long long* h_status_dev{};
+    // pinned result buffers of the asynchronous calls (owned by the slot, recycled)
+    void* h_out{};
+    size_t h_out_cap{};
+    uint32_t* h_ends{};
+    size_t h_ends_cap{};
+    // the batch
+    const uint8_t* d_src{};
+    uint64_t n_queries{}, first_query{};
+    uint32_t len{};
+    int in_fmt{}, out_fmt{};
+    bool with_reverse{}, do_locate{}, packed_ready{}, located{};
+    uint32_t fused_shift{0};  // hit keys of a global sort carry the query id above this bit (0: separate array)
+    int sorted_keys{0};       // d_keys[] buffer that holds the sorted hits
+    uint64_t n_cursor_slots{}, n_real_cursors{}, n_hits{};
+    uint64_t h2d_bytes{}, d2h_bytes{};
+    float ms_search{}, ms_locate{}, ms_sort{}, ms_fm{}, ms_text{};
+    void release_buffers() {
+        for (DevBuf* b : {&d_in, &d_packed, &d_items, &d_item_tags, &d_seeds, &d_spill, &d_cursors, &d_counters, &d_qpos, &d_lc, &d_tasks, &d_bigsegs,
+                          &d_keys[0], &d_keys[1], &d_qids[0], &d_qids[1], &d_offsets, &d_tmp, &d_scratch, &d_rows, &d_redo, &d_ostack, &d_out})
+            b->release();
+    }
+};
+
 }  // namespace
 
 struct sb200_ctx {
@@ -168,25 +238,23 @@ struct sb200_ctx {
     DevBuf d_steps, d_runs;
     uint32_t n_searches{}, qlen{}, kmax{};
     bool edit{}, have_scheme{};
+    std::vector<uint32_t> h_steps;  // the packed steps as set (the state flags are rebuilt when the policy changes)
+    sb200_policy policy = SB200_POLICY_DEFAULT;
     uint32_t max_hits{0};  // > 0: search_n (fm_ordered_kernel), at most this many rows per query
-    // work buffers
-    uint32_t fused_shift{0};  // hit keys of the last locate carry the query id above this bit (0: separate array)
-    int sorted_keys{0};       // d_keys[] buffer that holds the sorted hits
-    DevBuf d_qpos, d_tasks, d_bigsegs, d_lc, d_items, d_item_tags, d_ostack, d_rows, d_redo, d_seeds, d_spill, d_packed, d_queries, d_cursors, d_counters, d_offsets, d_keys[2], d_qids[2], d_tmp, d_scratch;
-    uint64_t cursor_cap{}, seed_cap{};
-    uint64_t last_cursors{}, last_real_cursors{}, last_hits{};
+    Options opt;
+    // work slots; synchronous calls use slot 0 on `stream`
+    Work work[kSlots];
+    Work* last{};          // slot that holds the result of the last synchronous search (sb200_fetch_hits, sb200_search_cursors)
+    uint64_t next_ticket{1};
+    DevBuf d_tmp, d_scratch, d_counters;  // index construction, rank benchmark
     uint64_t nodes_text{};
     float ms_fm{}, ms_text{};
-    bool hits_in_second{};  // which of the double buffers holds the sorted hits
     unsigned long long* h_counters{};  // pinned + mapped, CT_COUNT entries + 8 scratch words
     unsigned long long* h_counters_dev{};  // its device alias
     sb200_counters ct{};
     cudaEvent_t ev[12]{};
     int sms{};
-    // pipelined host-buffer search: copy streams, double buffers
-    cudaStream_t s_in{}, s_out{};
-    DevBuf d_qchunk[2], d_hitchunk[2];
-    cudaEvent_t ev_in[2]{}, ev_free_q[2]{}, ev_expanded[2]{}, ev_out[2]{};
+    cudaStream_t s_in{}, s_out{};  // copy streams of the pipelined calls
 };
 
 namespace {
@@ -571,6 +639,17 @@ void build_index_device(sb200_ctx* c, const uint8_t* d_src, const uint64_t* seq_
 }
 
 // ---- search pipeline ---------------------------------------------------------------------------------
+//
+// A BATCH (contiguous range of queries) runs as one fixed sequence of launches on the stream of its work slot, with no
+// host round trip in between: pack -> fm_roots -> fm_items -> text_pool -> hit_count -> scan -> locate_scatter ->
+// locate_tasks -> segment_sort (+ big) -> output formatting -> publish.  Every size the next kernel needs (cursor slots,
+// seeds, hits) stays in device memory; buffers are sized from capacities that grow when a batch did not fit (the kernels
+// never write out of bounds, they raise flags; finish_batch() then starts the batch over with larger buffers).  The
+// host reads the published status block once, when it waits for the batch.
+//
+// Slots make batches overlap: while slot A computes, the reads of the next batch are copied into slot B and the hits of
+// the previous one leave slot C (copy streams s_in / s_out).  The public asynchronous pair sb200_submit_reads /
+// sb200_wait_reads and the synchronous host-buffer calls (which cut their batch into chunks) share this code.
 
 // worst-case stack depth of the pair/chain traversal (search.cuh): D(k) = 2, D(e) = F(e) - 1 + D(e + 1) with
 // F(e) <= 9 (k - e) + 2 frames pushed per iteration
@@ -584,299 +663,161 @@ void with_stack(uint32_t k, F&& f) {
     else throw Error("search schemes with more than 4 errors are not supported by the GPU kernel yet");
 }
 
-unsigned blocks_per_sm(const char* env, unsigned def) {
-    if (const char* e = std::getenv(env)) return static_cast<unsigned>(std::max(1, std::atoi(e)));
-    return def;
-}
-
 __global__ void mirror_words_kernel(const unsigned long long* src, unsigned long long* dst, int n) {
     if (threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
 }
 // n (<= CT_COUNT + 1) device words -> c->h_counters[at ...], then waits for the stream
-void read_back_words(sb200_ctx* c, const void* d_src, int n, int at = 0) {
-    mirror_words_kernel<<<1, 32, 0, c->stream>>>(static_cast<const unsigned long long*>(d_src), c->h_counters_dev + at, n);
+void read_back_words(sb200_ctx* c, cudaStream_t s, const void* d_src, int n, int at = 0) {
+    mirror_words_kernel<<<1, 32, 0, s>>>(static_cast<const unsigned long long*>(d_src), c->h_counters_dev + at, n);
     launch_check(c);
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaStreamSynchronize(s));
+}
+
+// status block a batch publishes into mapped host memory (one kernel at its end)
+enum : int { ST_COUNTERS = 0, ST_LC = CT_COUNT, ST_HITS = CT_COUNT + LC_COUNT, ST_COUNT = CT_COUNT + LC_COUNT + 2 };
+__global__ void publish_status_kernel(const unsigned long long* counters, const unsigned int* lc, const uint32_t* total_hits,
+                                      unsigned long long* dst) {
+    const int t = threadIdx.x;
+    if (t < CT_COUNT) dst[ST_COUNTERS + t] = counters[t];
+    else if (t < CT_COUNT + LC_COUNT) dst[t] = lc ? lc[t - CT_COUNT] : 0u;
+    else if (t == ST_HITS) dst[t] = total_hits ? *total_hits : 0u;
+}
+
+SearchParams search_params(sb200_ctx* c, Work& w) {
+    auto& ix = c->idx;
+    SearchParams P{};
+    P.bwt = ix.bwt();
+    P.bwtRev = ix.rev();
+    for (int i = 0; i < 8; ++i) P.C[i] = ix.C[i];
+    P.n_rows = static_cast<uint32_t>(ix.n_rows);
+    P.packed = w.d_packed.get<uint32_t>();
+    P.seeds = w.d_seeds.get<uint4>();
+    P.seed_cap = static_cast<uint32_t>(std::min<uint64_t>(w.seed_cap, 0xfffffffeull));
+    P.n_queries = static_cast<uint32_t>(w.n_queries);
+    P.len = w.len;
+    P.n_searches = c->n_searches;
+    P.steps = c->d_steps.get<uint32_t>();
+    P.runs = c->d_runs.get<uint8_t>();
+    P.out = w.d_cursors.get<uint4>();
+    P.out_cap = static_cast<uint32_t>(std::min<uint64_t>(w.cursor_cap, 0xfffffffeull));
+    P.counters = w.d_counters.get<unsigned long long>();
+    P.qgram = ix.qgram_q ? ix.qgram.get<uint4>() : nullptr;
+    P.qgram_q = ix.qgram_q;
+    if (P.qgram_q >= w.len) P.qgram = nullptr, P.qgram_q = 0;  // (a table that covers the whole query: plain walk)
+    P.sa32 = ix.text_mode ? ix.sa32.get<uint32_t>() : nullptr;
+    P.isa32 = ix.text_mode ? ix.isa32.get<uint32_t>() : nullptr;
+    P.text4 = ix.text_mode ? ix.text4.get<uint32_t>() : nullptr;
+    // cursors that go straight to the locate step carry the text position of a verified occurrence instead of its row
+    P.textpos_out = (w.do_locate && ix.text_mode && c->opt.textpos) ? 1u : 0u;
+    P.debug_flags = static_cast<uint32_t>(c->opt.debug) & 0xffu;
+    P.pol = c->policy;
+    return P;
 }
 
 // search_n: the ordered walk (fm_ordered_kernel), one thread per query with its stack in global memory
 unsigned ordered_grid(sb200_ctx* c, uint32_t len, uint64_t n_queries) {
-    unsigned g = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_ORDERED_BLOCKS_PER_SM", len > 300 ? 1 : 4);  // (the stacks: 16 B x frames per thread)
+    const unsigned per_sm = c->opt.ordered_blocks_per_sm > 0 ? static_cast<unsigned>(c->opt.ordered_blocks_per_sm) : (len > 300 ? 1u : 4u);
+    unsigned g = static_cast<unsigned>(c->sms) * per_sm;  // (the stacks: 16 B x frames per thread)
     return std::max(1u, std::min(g, grid_for(n_queries)));
 }
-void launch_ordered(sb200_ctx* c, const SearchParams& P) {
+void launch_ordered(sb200_ctx* c, Work& w, const SearchParams& P) {
     const size_t osmem = size_t(P.n_searches) * P.len * 4;
     if (osmem > 48 * 1024) throw Error("search scheme table does not fit shared memory (query too long)");
     const unsigned ogrid = ordered_grid(c, P.len, P.n_queries);
     SearchParams Q = P;
     Q.ostack_frames = ordered_stack_frames(P.len, c->idx.sigma);
-    c->d_ostack.reserve(size_t(ogrid) * 256 * Q.ostack_frames * sizeof(uint4));
-    Q.ostack = c->d_ostack.get<uint4>();
+    w.d_ostack.reserve(size_t(ogrid) * 256 * Q.ostack_frames * sizeof(uint4));
+    Q.ostack = w.d_ostack.get<uint4>();
     with_sigma(c->idx.sigma, [&](auto S) {
-        if (c->edit) fm_ordered_kernel<S(), true><<<ogrid, 256, osmem, c->stream>>>(Q);
-        else fm_ordered_kernel<S(), false><<<ogrid, 256, osmem, c->stream>>>(Q);
+        if (c->edit) fm_ordered_kernel<S(), true><<<ogrid, 256, osmem, w.stream>>>(Q);
+        else fm_ordered_kernel<S(), false><<<ogrid, 256, osmem, w.stream>>>(Q);
         return 0;
     });
     launch_check(c);
 }
 
-// search_n after the plain search: a query with at most max_hits rows is complete; the others (they end early by
-// definition) are walked again in the reference's recursion order and their cursors of the first pass are dropped.
-// P: the parameters of the first pass, n_slots: its output slots.  false = the cursor buffer is too small (cursor_cap was
-// raised, the caller starts over).
-bool refine_max_hits(sb200_ctx* c, const SearchParams& P, uint64_t n_slots) {
-    const uint32_t nq = P.n_queries;
-    c->d_rows.reserve((size_t(nq) + 4) * sizeof(unsigned long long));
-    c->d_redo.reserve(size_t(nq) * sizeof(uint32_t));
-    unsigned long long* rows = c->d_rows.get<unsigned long long>();
-    unsigned long long* tally = rows + nq;  // queries to redo, bound on their cursors, cursors dropped
-    CUDA_TRY(cudaMemsetAsync(rows, 0, (size_t(nq) + 4) * sizeof(unsigned long long), c->stream));
-    if (n_slots) cursor_rows_kernel<<<grid_for(n_slots), 256, 0, c->stream>>>(P.out, n_slots, rows);
-    redo_list_kernel<<<grid_for(nq), 256, 0, c->stream>>>(rows, nq, c->max_hits, c->d_redo.get<uint32_t>(), tally);
-    launch_check(c);
-    read_back_words(c, tally, 2, CT_COUNT);
-    const uint64_t n_redo = c->h_counters[CT_COUNT], bound = c->h_counters[CT_COUNT + 1];
-    if (n_redo == 0) return true;
-    const uint64_t need = n_slots + bound + uint64_t(ordered_grid(c, P.len, n_redo)) * 256 * kEmitChunk;
-    if (need >= 0xfffffffeull) throw Error("more than 2^32 cursors in one call; split the batch");
-    if (need > c->cursor_cap) {
-        c->cursor_cap = need + need / 8;
-        return false;
+// launch geometry of text_pool_kernel for this scheme: as many resident warps per SM as shared memory (227 KB, 1 KB
+// reserved per block) and registers allow; measured on the headline workload: 36 warps 8.4 ms, 30 warps 9.2 ms, 24 warps
+// 10.2 ms
+struct PoolGeometry { unsigned threads, per_sm; size_t smem; };
+PoolGeometry pool_geometry(sb200_ctx* c, uint32_t n_searches, uint32_t len) {
+    const size_t tables = (size_t(n_searches) * len * 4 + run_table_bytes(n_searches * len) + 7) & ~size_t{7};
+    PoolGeometry g{0, 1, 0};
+    for (unsigned wps = kPoolThreads / 32; wps >= 4; --wps) {
+        const size_t bytes = tables + wps * size_t(pool_bytes(len));
+        const unsigned blocks = static_cast<unsigned>(std::min<size_t>((227 * 1024) / (bytes + 1024), 42 / wps));
+        if (blocks * wps > g.per_sm * (g.threads / 32)) g = PoolGeometry{wps * 32, blocks, bytes};
     }
-    drop_cursors_kernel<<<grid_for(n_slots), 256, 0, c->stream>>>(P.out, n_slots, rows, c->max_hits, tally);
-    CUDA_TRY(cudaMemsetAsync(P.counters + CT_NEXT_QUERY, 0, sizeof(unsigned long long), c->stream));
-    SearchParams Q = P;
-    Q.max_hits = c->max_hits;
-    Q.redo = c->d_redo.get<uint32_t>();
-    Q.n_queries = static_cast<uint32_t>(n_redo);
-    Q.items = nullptr, Q.item_tags = nullptr;
-    Q.qgram = c->idx.qgram_q && c->idx.qgram_q < P.len ? c->idx.qgram.get<uint4>() : nullptr;  // (not a table that covers the whole query)
-    Q.qgram_q = Q.qgram ? c->idx.qgram_q : 0;
-    launch_ordered(c, Q);
-    read_back_words(c, tally + 2, 1, CT_COUNT);
-    const uint64_t dropped = c->h_counters[CT_COUNT];
-    read_back_words(c, c->d_counters.p, CT_COUNT);
-    if (c->h_counters[CT_OVERFLOW]) throw Error("internal error: search stack overflow");
-    if (c->h_counters[CT_OUT_SLOTS] > c->cursor_cap) throw Error("internal error: cursor buffer of the ordered walk too small");
-    c->h_counters[CT_CURSORS] -= dropped;
-    return true;
+    if (c->opt.pool_threads > 0) {
+        g.threads = std::min<unsigned>(kPoolThreads, std::max(32, c->opt.pool_threads)) & ~31u;
+        g.smem = tables + (g.threads / 32) * size_t(pool_bytes(len));
+        g.per_sm = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(42 / (g.threads / 32), (227 * 1024) / (g.smem + 1024))));
+    }
+    if (c->opt.pool_blocks_per_sm > 0) g.per_sm = static_cast<unsigned>(c->opt.pool_blocks_per_sm);
+    if (g.threads == 0 || g.smem > 226 * 1024) throw Error("search scheme table and frame pools do not fit shared memory (query too long)");
+    return g;
 }
 
-void launch_search(sb200_ctx* c, const SearchParams& P) {
-    // shared memory: scheme table + one staged packed query per thread
-    size_t smem = (size_t(P.n_searches) * P.len + (size_t(P.n_searches) * P.len * kRunE + 3) / 4 + size_t(packed_words(P.len)) * 256) * 4;
-    if (smem > 100 * 1024) throw Error("search scheme table and staged queries do not fit shared memory (query too long)");
-    unsigned grid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_BLOCKS_PER_SM", 4);
-    unsigned need = grid_for((uint64_t(P.n_queries) + kQueryBatch - 1) / kQueryBatch);
-    if (need < grid) grid = std::max(1u, need);
-    CUDA_TRY(cudaEventRecord(c->ev[8], c->stream));
-    if (P.max_hits) {  // search_n by the ordered walk alone (SB200_ORDERED_ONLY=1)
-        launch_ordered(c, P);
-        CUDA_TRY(cudaEventRecord(c->ev[9], c->stream));
-        CUDA_TRY(cudaEventRecord(c->ev[10], c->stream));
+// the search kernels of a batch (queries already packed in w.d_packed); nothing waits for the device
+void enqueue_search_kernels(sb200_ctx* c, Work& w) {
+    auto& ix = c->idx;
+    const uint64_t n_queries = w.n_queries;
+    const uint32_t len = w.len;
+    w.d_cursors.reserve((w.cursor_cap + 1) * sizeof(uint4));
+    if (ix.text_mode) w.d_seeds.reserve((w.seed_cap + 1) * sizeof(uint4));
+    unsigned long long* ctr = w.d_counters.get<unsigned long long>();
+    CUDA_TRY(cudaMemsetAsync(ctr, 0, CT_BAD_QUERY * sizeof(unsigned long long), w.stream));  // keeps CT_BAD_QUERY
+    CUDA_TRY(cudaMemsetAsync(ctr + CT_NODES_TEXT, 0, (CT_COUNT - CT_NODES_TEXT) * sizeof(unsigned long long), w.stream));
+    SearchParams P = search_params(c, w);
+    CUDA_TRY(cudaEventRecord(w.ev[8], w.stream));
+    // search_n by the ordered walk alone (option ordered_only); the default is the plain search first, then the queries
+    // above the limit again in recursion order (refine_max_hits)
+    if (c->max_hits && c->opt.ordered_only) {
+        P.max_hits = c->max_hits;
+        launch_ordered(c, w, P);
+        CUDA_TRY(cudaEventRecord(w.ev[9], w.stream));
+        CUDA_TRY(cudaEventRecord(w.ev[10], w.stream));
         return;
     }
-    if (P.items) {  // root frames of all (query, search) in one pass, then the warp-synchronous walk over the live ones
-        fm_roots_kernel<<<grid_for(P.n_queries), 256, 0, c->stream>>>(P);
-        launch_check(c);
-        const size_t ismem = size_t(P.n_searches) * P.len * 4;
-        if (ismem > 48 * 1024) throw Error("search scheme table does not fit shared memory (query too long)");
-        unsigned igrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_BLOCKS_PER_SM", SB200_FM_ITEMS_BLOCKS);
-        igrid = std::max(1u, std::min(igrid, grid_for(P.n_queries)));
-        with_sigma(c->idx.sigma, [&](auto S) {
-            with_stack(c->kmax, [&](auto STACK) {
-                if (c->edit) fm_items_kernel<S(), true, STACK()><<<igrid, 256, ismem, c->stream>>>(P);
-                else fm_items_kernel<S(), false, STACK()><<<igrid, 256, ismem, c->stream>>>(P);
-            });
-            return 0;
+    // root frames of all (query, search) in one pass, then the warp-synchronous walk over the live ones
+    const uint64_t total = n_queries * uint64_t(c->n_searches);
+    w.d_items.reserve(total * sizeof(uint4));
+    w.d_item_tags.reserve(total * sizeof(uint2));
+    P.items = w.d_items.get<uint4>();
+    P.item_tags = w.d_item_tags.get<uint2>();
+    fm_roots_kernel<<<grid_for(n_queries), 256, 0, w.stream>>>(P);
+    launch_check(c);
+    const size_t ismem = size_t(P.n_searches) * P.len * 4;
+    if (ismem > 48 * 1024) throw Error("search scheme table does not fit shared memory (query too long)");
+    const unsigned iper = c->opt.items_blocks_per_sm > 0 ? static_cast<unsigned>(c->opt.items_blocks_per_sm) : SB200_FM_ITEMS_BLOCKS;
+    const unsigned igrid = std::max(1u, std::min(static_cast<unsigned>(c->sms) * iper, grid_for(n_queries)));
+    // (a policy without PAIR frames pushes the deletion and the substitution children separately: one level more)
+    const uint32_t stack_k = std::min<uint32_t>(4, c->kmax + (sb200_pol_pairs(&c->policy) ? 0u : 1u));
+    with_sigma(ix.sigma, [&](auto S) {
+        with_stack(stack_k, [&](auto STACK) {
+            if (c->edit) fm_items_kernel<S(), true, STACK()><<<igrid, 256, ismem, w.stream>>>(P);
+            else fm_items_kernel<S(), false, STACK()><<<igrid, 256, ismem, w.stream>>>(P);
         });
-        launch_check(c);
-    } else {
-        with_sigma(c->idx.sigma, [&](auto S) {
-            with_stack(c->kmax, [&](auto STACK) {
-                auto go = [&](auto kern) {
-                    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                    kern<<<grid, 256, smem, c->stream>>>(P);
-                };
-                if (c->edit) go(fm_kernel<S(), true, STACK()>);
-                else go(fm_kernel<S(), false, STACK()>);
-            });
-            return 0;
-        });
-        launch_check(c);
-    }
-    CUDA_TRY(cudaEventRecord(c->ev[9], c->stream));
-    const bool use_pool = !(std::getenv("SB200_TEXT_POOL") && std::atoi(std::getenv("SB200_TEXT_POOL")) == 0);
-    if (P.sa32 && use_pool) {  // in-text verification, one frame pool per warp
-        with_stack(c->kmax, [&](auto STACK) {
-            const size_t tables = (size_t(P.n_searches) * P.len * 4 + run_table_bytes(P.n_searches * P.len) + 7) & ~size_t{7};
-            // warps per block: as many resident warps per SM as shared memory (227 KB, 1 KB reserved per block) and
-            // registers (48 per thread: 42 warps) allow; measured on the headline workload: 36 warps 8.4 ms, 30 warps
-            // 9.2 ms, 24 warps 10.2 ms
-            unsigned threads = 0, per_sm = 1;
-            size_t psmem = 0;
-            for (unsigned w = kPoolThreads / 32; w >= 4; --w) {
-                const size_t bytes = tables + w * size_t(pool_bytes(P.len));
-                const unsigned blocks = static_cast<unsigned>(std::min<size_t>((227 * 1024) / (bytes + 1024), 42 / w));
-                if (blocks * w > per_sm * (threads / 32)) {
-                    threads = w * 32;
-                    per_sm = blocks;
-                    psmem = bytes;
-                }
-            }
-            if (const char* e = std::getenv("SB200_POOL_THREADS")) {
-                threads = std::min<unsigned>(kPoolThreads, std::max(32, std::atoi(e))) & ~31u;
-                psmem = tables + (threads / 32) * size_t(pool_bytes(P.len));
-                per_sm = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(42 / (threads / 32), (227 * 1024) / (psmem + 1024))));
-            }
-            if (threads == 0 || psmem > 226 * 1024) throw Error("search scheme table and frame pools do not fit shared memory (query too long)");
-            unsigned tgrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_POOL_BLOCKS_PER_SM", per_sm);
+        return 0;
+    });
+    launch_check(c);
+    CUDA_TRY(cudaEventRecord(w.ev[9], w.stream));
+    if (P.sa32) {  // in-text verification, one frame pool per warp (reads the seed count from device memory)
+        const PoolGeometry g = pool_geometry(c, P.n_searches, P.len);
+        const unsigned tgrid = static_cast<unsigned>(c->sms) * g.per_sm;
+        w.d_spill.reserve(size_t(tgrid) * (g.threads / 32) * 2 * kSpillCap * sizeof(uint4));
+        const uint32_t run_rounds = c->opt.run_rounds > 0 ? static_cast<uint32_t>(c->opt.run_rounds) : kRunRounds;
+        with_stack(stack_k, [&](auto STACK) {
             auto go = [&](auto kern) {
-                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(psmem)));
-                c->d_spill.reserve(size_t(tgrid) * (threads / 32) * 2 * kSpillCap * sizeof(uint4));
-                kern<<<tgrid, threads, psmem, c->stream>>>(P, 2 * (c->kmax + 1), blocks_per_sm("SB200_RUN_ROUNDS", kRunRounds),
-                                                           c->d_spill.get<uint4>());
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem)));
+                kern<<<tgrid, g.threads, g.smem, w.stream>>>(P, 2 * (c->kmax + 1), run_rounds, w.d_spill.get<uint4>());
             };
             if (c->edit) go(text_pool_kernel<true, STACK()>);
             else go(text_pool_kernel<false, STACK()>);
         });
         launch_check(c);
-    } else if (P.sa32) {  // in-text verification of the seeds (reads the seed count from device memory: no host sync)
-        unsigned tgrid = static_cast<unsigned>(c->sms) * blocks_per_sm("SB200_TEXT_BLOCKS_PER_SM", 6);
-        with_stack(c->kmax, [&](auto STACK) {
-            auto go = [&](auto kern) {
-                if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                kern<<<tgrid, 256, smem, c->stream>>>(P);
-            };
-            if (c->edit) go(text_kernel<true, STACK()>);
-            else go(text_kernel<false, STACK()>);
-        });
-        launch_check(c);
     }
-    CUDA_TRY(cudaEventRecord(c->ev[10], c->stream));
-}
-
-// kernel 2 on device-resident queries; cursors stay in c->d_cursors
-// d_queries: the queries (both strands), or with from_reads the n_queries / 2 reads (the reverse complements are made while packing)
-void search_only(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uint32_t len, bool for_locate = false, bool from_reads = false) {
-    auto& ix = c->idx;
-    if (!ix.loaded) throw Error("no index loaded");
-    if (!c->have_scheme) throw Error("no search scheme set");
-    if (len != c->qlen) throw Error("query length " + std::to_string(len) + " does not match the expanded search scheme (" +
-                                    std::to_string(c->qlen) + ")");
-    if (n_queries == 0) throw Error("query file was empty - abort");
-    if (n_queries * uint64_t(c->n_searches) >= (1ull << 32)) throw Error("too many (query, search) pairs for one call; split the batch");
-
-    if (c->cursor_cap < n_queries * 16) c->cursor_cap = std::max<uint64_t>(1 << 20, n_queries * 16);
-    if (c->seed_cap < n_queries * 4) c->seed_cap = std::max<uint64_t>(1 << 20, n_queries * 4);
-    c->d_counters.reserve(CT_COUNT * sizeof(unsigned long long));
-    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    const uint32_t W = packed_words(len);
-    c->d_packed.reserve(n_queries * W * 4);
-    CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, CT_COUNT * sizeof(unsigned long long), c->stream));
-    if (from_reads)
-        pack_reads_kernel<<<grid_for(n_queries * W), 256, 0, c->stream>>>(d_queries, n_queries, len, ix.sigma, c->d_packed.get<uint32_t>(),
-                                                                          c->d_counters.get<unsigned long long>());
-    else
-        pack_queries_kernel<<<grid_for(n_queries * W), 256, 0, c->stream>>>(d_queries, n_queries, len, ix.sigma, c->d_packed.get<uint32_t>(),
-                                                                            c->d_counters.get<unsigned long long>());
-    launch_check(c);
-    uint64_t n_cursors = 0;
-    while (true) {
-        c->d_cursors.reserve((c->cursor_cap + 1) * sizeof(uint4));
-        if (ix.text_mode) c->d_seeds.reserve((c->seed_cap + 1) * sizeof(uint4));
-        CUDA_TRY(cudaMemsetAsync(c->d_counters.p, 0, CT_BAD_QUERY * sizeof(unsigned long long), c->stream));  // keeps CT_BAD_QUERY
-        CUDA_TRY(cudaMemsetAsync(c->d_counters.get<unsigned long long>() + CT_NODES_TEXT, 0, (CT_NEXT_ITEM + 1 - CT_NODES_TEXT) * sizeof(unsigned long long),
-                                 c->stream));
-        SearchParams P{};
-        P.bwt = ix.bwt();
-        P.bwtRev = ix.rev();
-        for (int i = 0; i < 8; ++i) P.C[i] = ix.C[i];
-        P.n_rows = static_cast<uint32_t>(ix.n_rows);
-        P.packed = c->d_packed.get<uint32_t>();
-        P.seeds = c->d_seeds.get<uint4>();
-        P.seed_cap = static_cast<uint32_t>(std::min<uint64_t>(c->seed_cap, 0xfffffffeull));
-        P.n_queries = static_cast<uint32_t>(n_queries);
-        P.len = len;
-        P.n_searches = c->n_searches;
-        P.steps = c->d_steps.get<uint32_t>();
-        P.runs = c->d_runs.get<uint8_t>();
-        P.out = c->d_cursors.get<uint4>();
-        P.out_cap = static_cast<uint32_t>(std::min<uint64_t>(c->cursor_cap, 0xfffffffeull));
-        P.counters = c->d_counters.get<unsigned long long>();
-        P.qgram = ix.qgram_q ? ix.qgram.get<uint4>() : nullptr;
-        P.qgram_q = ix.qgram_q;
-        // item-based walk (fm_roots_kernel + fm_items_kernel); SB200_FM_ITEMS=0 keeps the query-owning fm_kernel
-        const bool use_items = !(std::getenv("SB200_FM_ITEMS") && std::atoi(std::getenv("SB200_FM_ITEMS")) == 0);
-        if (use_items && c->n_searches <= 255) {  // (search index and slot count share a tag word)
-            if (P.qgram_q >= len) P.qgram = nullptr, P.qgram_q = 0;  // (a table that covers the whole query: plain walk)
-            const uint64_t total = n_queries * uint64_t(c->n_searches);
-            c->d_items.reserve(total * sizeof(uint4));
-            c->d_item_tags.reserve(total * sizeof(uint2));
-            P.items = c->d_items.get<uint4>();
-            P.item_tags = c->d_item_tags.get<uint2>();
-        }
-        P.sa32 = ix.text_mode ? ix.sa32.get<uint32_t>() : nullptr;
-        P.isa32 = ix.text_mode ? ix.isa32.get<uint32_t>() : nullptr;
-        P.text4 = ix.text_mode ? ix.text4.get<uint32_t>() : nullptr;
-        // cursors that go straight to the locate step carry the text position of a verified occurrence instead of its row
-        P.textpos_out = (for_locate && ix.text_mode && !(std::getenv("SB200_TEXTPOS") && std::atoi(std::getenv("SB200_TEXTPOS")) == 0)) ? 1u : 0u;
-        if (const char* dbg = std::getenv("SB200_DEBUG")) P.debug_flags = static_cast<uint32_t>(std::atoi(dbg));
-        // search_n: the plain search first, then the queries above the limit again in recursion order (refine_max_hits);
-        // SB200_ORDERED_ONLY=1 walks every query in order instead
-        const bool ordered_only = c->max_hits && std::getenv("SB200_ORDERED_ONLY") && std::atoi(std::getenv("SB200_ORDERED_ONLY")) != 0;
-        if (ordered_only) {
-            P.max_hits = c->max_hits;
-            P.items = nullptr, P.item_tags = nullptr;
-            if (P.qgram_q >= len) P.qgram = nullptr, P.qgram_q = 0;  // (a table that covers the whole query: plain walk)
-        }
-        launch_search(c, P);
-        read_back_words(c, c->d_counters.p, CT_COUNT);
-        if (std::getenv("SB200_DEBUG"))
-            fprintf(stderr, "[sb200 debug] max stack depth %llu overflow %llu seeds %llu\n", c->h_counters[CT_MAX_SP], c->h_counters[CT_OVERFLOW],
-                    c->h_counters[CT_SEEDS]);
-        if (c->h_counters[CT_BAD_QUERY]) {
-            uint64_t off = c->h_counters[CT_BAD_QUERY] - 1;
-            throw Error("query has invalid character at offset " + std::to_string(off % len) + " of query " + std::to_string(off / len));
-        }
-        if (c->h_counters[CT_OVERFLOW]) throw Error("internal error: search stack overflow");
-        n_cursors = c->h_counters[CT_OUT_SLOTS];
-        uint64_t n_seed_slots = c->h_counters[CT_SEED_SLOTS];
-        if (n_cursors >= 0xfffffffeull || n_seed_slots >= 0xfffffffeull) throw Error("more than 2^32 cursors in one call; split the batch");
-        bool fits = true;
-        if (n_seed_slots > c->seed_cap) {  // the text kernel saw a truncated seed list: rerun with a buffer that fits
-            c->seed_cap = n_seed_slots + n_seed_slots / 4;
-            fits = false;
-        }
-        if (n_cursors > c->cursor_cap) {
-            c->cursor_cap = n_cursors + n_cursors / 4;
-            fits = false;
-        }
-        if (fits && c->max_hits && !ordered_only) {
-            if (!refine_max_hits(c, P, n_cursors)) continue;
-            n_cursors = c->h_counters[CT_OUT_SLOTS];
-        }
-        if (fits) break;
-    }
-    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-    CUDA_TRY(cudaEventSynchronize(c->ev[1]));
-    CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_search, c->ev[0], c->ev[1]));
-    CUDA_TRY(cudaEventElapsedTime(&c->ms_fm, c->ev[8], c->ev[9]));
-    CUDA_TRY(cudaEventElapsedTime(&c->ms_text, c->ev[9], c->ev[10]));
-    c->ct.ms_locate = c->ct.ms_sort = 0;
-    c->ct.nodes += c->h_counters[CT_NODES];
-    c->nodes_text += c->h_counters[CT_NODES_TEXT];
-    c->ct.rank_ops += 2 * (c->h_counters[CT_NODES] - c->h_counters[CT_NODES_TEXT]);
-    c->ct.cursors += c->h_counters[CT_CURSORS];
-    c->last_cursors = n_cursors;  // reserved output slots; unused ones are empty entries (qid 0xffffffff, len 0)
-    c->last_real_cursors = c->h_counters[CT_CURSORS];
-    c->last_hits = 0;
-}
-
-static_assert(kCursorTextPosFlag == kCursorTextPos, "search.cuh and locate.cuh agree on the flag");
-
-__global__ void mirror_u32_kernel(const uint32_t* src, unsigned long long* dst, int n) {
-    if (threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+    CUDA_TRY(cudaEventRecord(w.ev[10], w.stream));
 }
 
 LocateIndex locate_index(sb200_ctx* c) {
@@ -892,114 +833,204 @@ LocateIndex locate_index(sb200_ctx* c) {
     return L;
 }
 
-// Locate + sort through per-query buckets (locate.cuh) for the cursors of a search over queries 0 .. n_queries-1.
-// Returns false when some query has more hits than a block sorts (the caller then takes the global radix sort).
-bool locate_bucketed(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries) {
+// Locate + sort through per-query buckets (locate.cuh) for the cursors the search kernels of this batch leave in
+// w.d_cursors.  The cursor count is read on the device (CT_OUT_SLOTS); hits land in w.d_keys[0] (+ w.d_qids[0] when the
+// output format needs the query of every hit), per-query ends in w.d_qpos.
+void enqueue_locate_bucketed(sb200_ctx* c, Work& w) {
     auto& ix = c->idx;
-    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-    c->d_counters.reserve(CT_COUNT * sizeof(unsigned long long));
-    CUDA_TRY(cudaMemsetAsync(c->d_counters.get<unsigned long long>() + CT_LF_STEPS, 0, sizeof(unsigned long long), c->stream));
-    c->d_qpos.reserve((n_queries + 1) * 4);
-    c->d_lc.reserve(LC_COUNT * 4);
-    CUDA_TRY(cudaMemsetAsync(c->d_qpos.p, 0, (n_queries + 1) * 4, c->stream));
-    CUDA_TRY(cudaMemsetAsync(c->d_lc.p, 0, LC_COUNT * 4, c->stream));
-    uint64_t total_rows = 0;
-    if (n_cursors > 0) {
-        CUDA_TRY(cudaMemsetAsync(c->d_counters.get<unsigned long long>() + CT_TOTAL_ROWS, 0, sizeof(unsigned long long), c->stream));
-        hit_count_kernel<<<grid_for(n_cursors), 256, 0, c->stream>>>(c->d_cursors.get<uint4>(), static_cast<uint32_t>(n_cursors),
-                                                                    c->d_qpos.get<uint32_t>(),
-                                                                    c->d_counters.get<unsigned long long>() + CT_TOTAL_ROWS);
+    const uint64_t n_queries = w.n_queries;
+    unsigned long long* ctr = w.d_counters.get<unsigned long long>();
+    CUDA_TRY(cudaEventRecord(w.ev[1], w.stream));
+    w.d_qpos.reserve((n_queries + 1) * 4);
+    w.d_lc.reserve(LC_COUNT * 4);
+    CUDA_TRY(cudaMemsetAsync(w.d_qpos.p, 0, (n_queries + 1) * 4, w.stream));
+    CUDA_TRY(cudaMemsetAsync(w.d_lc.p, 0, LC_COUNT * 4, w.stream));
+    const uint32_t cur_cap = static_cast<uint32_t>(std::min<uint64_t>(w.cursor_cap, 0xfffffffeull));
+    const unsigned wide = static_cast<unsigned>(c->sms) * 8;
+    hit_count_kernel<<<wide, 256, 0, w.stream>>>(w.d_cursors.get<uint4>(), cur_cap, ctr + CT_OUT_SLOTS, w.d_qpos.get<uint32_t>(), ctr + CT_TOTAL_ROWS);
+    launch_check(c);
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, w.d_qpos.get<uint32_t>(), w.d_qpos.get<uint32_t>(), n_queries + 1, w.stream));
+    w.d_tmp.reserve(tmp_bytes);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(w.d_tmp.p, tmp_bytes, w.d_qpos.get<uint32_t>(), w.d_qpos.get<uint32_t>(), n_queries + 1, w.stream));
+    c->ct.kernel_launches += 2;
+    const bool want_qids = w.out_fmt != OUT_CSR;
+    w.d_keys[0].reserve(std::max<uint64_t>(1, w.hit_cap) * 8);
+    if (want_qids) w.d_qids[0].reserve(std::max<uint64_t>(1, w.hit_cap) * 4);
+    // the scan leaves the total behind the last query; the scatter turns qpos[q] into the END of segment q, so the total
+    // is kept aside for the kernels that follow
+    w.d_scratch.reserve(64);
+    CUDA_TRY(cudaMemcpyAsync(w.d_scratch.p, w.d_qpos.get<uint32_t>() + n_queries, 4, cudaMemcpyDeviceToDevice, w.stream));
+    BucketParams B{};
+    B.index = locate_index(c);
+    B.cursors = w.d_cursors.get<uint4>();
+    B.n_cursors = cur_cap;
+    B.n_cursors_dev = ctr + CT_OUT_SLOTS;
+    B.n_queries = static_cast<uint32_t>(n_queries);
+    B.qpos = w.d_qpos.get<uint32_t>();
+    B.keys = w.d_keys[0].get<uint64_t>();
+    B.qids = want_qids ? w.d_qids[0].get<uint32_t>() : nullptr;
+    B.key_cap = static_cast<uint32_t>(std::min<uint64_t>(w.hit_cap, 0xfffffff0ull));
+    B.task_cap = static_cast<uint32_t>(std::min<uint64_t>(w.hit_cap / kInlineRows + 1024, 0xfffffff0ull));
+    B.big_cap = static_cast<uint32_t>(w.hit_cap / kWarpSeg + 16);
+    w.d_tasks.reserve(uint64_t(B.task_cap) * sizeof(uint4));
+    w.d_bigsegs.reserve(uint64_t(B.big_cap) * 4);
+    B.tasks = w.d_tasks.get<uint4>();
+    B.big_segs = w.d_bigsegs.get<uint32_t>();
+    B.lc = w.d_lc.get<unsigned int>();
+    B.counters = ctr;
+    w.task_cap = B.task_cap;
+    with_sigma(ix.sigma, [&](auto S) {
+        locate_scatter_kernel<S()><<<wide, 256, 0, w.stream>>>(B);
         launch_check(c);
-        size_t tmp_bytes = 0;
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->d_qpos.get<uint32_t>(), c->d_qpos.get<uint32_t>(), n_queries + 1, c->stream));
-        c->d_tmp.reserve(tmp_bytes);
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_tmp.p, tmp_bytes, c->d_qpos.get<uint32_t>(), c->d_qpos.get<uint32_t>(), n_queries + 1, c->stream));
-        c->ct.kernel_launches += 2;
-        mirror_u32_kernel<<<1, 32, 0, c->stream>>>(c->d_qpos.get<uint32_t>() + n_queries, c->h_counters_dev + CT_COUNT, 1);
+        locate_tasks_kernel<S()><<<static_cast<unsigned>(c->sms) * 4, 256, 0, w.stream>>>(B);
+        return 0;
+    });
+    launch_check(c);
+    CUDA_TRY(cudaEventRecord(w.ev[2], w.stream));
+    segment_sort_kernel<<<grid_for((n_queries + 31) / 32 * 32), 256, 0, w.stream>>>(B);  // one lane per query
+    launch_check(c);
+    segment_sort_big_kernel<<<static_cast<unsigned>(c->sms) * 4, 256, 0, w.stream>>>(B);
+    launch_check(c);
+    CUDA_TRY(cudaEventRecord(w.ev[3], w.stream));
+    w.fused_shift = 0;
+    w.sorted_keys = 0;
+}
+
+size_t out_record_bytes(sb200_ctx* c, int fmt) {
+    if (fmt == OUT_HIT64) return sizeof(sb200_hit);
+    if (fmt == OUT_HIT32) return sizeof(sb200_hit32);
+    if (fmt == OUT_CSR) return (c->idx.key_bits + 4 + 7) / 8;
+    return 0;
+}
+
+// sorted hits of the batch (w.d_keys[w.sorted_keys], w.d_qids[0]) -> w.d_out in the wanted format; n = capacity (count read
+// on the device) or, with n_dev == nullptr, the exact number
+void enqueue_output(sb200_ctx* c, Work& w, uint64_t n, const uint32_t* n_dev) {
+    if (w.out_fmt == OUT_NONE) return;
+    auto& ix = c->idx;
+    const size_t rec = out_record_bytes(c, w.out_fmt);
+    w.d_out.reserve((std::max<uint64_t>(1, n) + 4) * rec + 64);
+    const uint64_t* keys = w.d_keys[w.sorted_keys].get<uint64_t>();
+    const unsigned grid = n_dev ? static_cast<unsigned>(c->sms) * 8 : std::max(1u, grid_for(n));
+    if (w.out_fmt == OUT_HIT32)
+        compact_hits_kernel<<<grid, 256, 0, w.stream>>>(keys, w.d_qids[0].get<uint32_t>(), n, n_dev, static_cast<uint32_t>(ix.bits_for_position),
+                                                       static_cast<uint32_t>(w.first_query), w.fused_shift, w.d_out.get<uint4>());
+    else if (w.out_fmt == OUT_HIT64)
+        expand_hits_kernel<<<grid, 256, 0, w.stream>>>(keys, w.d_qids[0].get<uint32_t>(), n, n_dev, static_cast<uint32_t>(ix.bits_for_position),
+                                                      w.first_query, w.fused_shift, w.d_out.get<uint64_t>());
+    else
+        pack_records_kernel<<<grid, 256, 0, w.stream>>>(keys, n, n_dev, w.fused_shift, static_cast<uint32_t>(rec), w.d_out.get<uint8_t>());
+    launch_check(c);
+}
+
+void enqueue_publish(sb200_ctx* c, Work& w, bool located) {
+    publish_status_kernel<<<1, 64, 0, w.stream>>>(w.d_counters.get<unsigned long long>(), located ? w.d_lc.get<unsigned int>() : nullptr,
+                                                  located ? w.d_scratch.get<uint32_t>() : nullptr, w.h_status_dev);
+    launch_check(c);
+    CUDA_TRY(cudaEventRecord(w.ev_done, w.stream));
+}
+
+// everything of a batch that can be queued without looking at device results: pack, search, locate, sort, output
+void enqueue_compute(sb200_ctx* c, Work& w) {
+    auto& ix = c->idx;
+    const uint64_t n_queries = w.n_queries;
+    const uint32_t len = w.len, W = packed_words(len);
+    if (w.cursor_cap < n_queries * 16) w.cursor_cap = std::max<uint64_t>(1 << 20, n_queries * 16);
+    if (w.seed_cap < n_queries * 4) w.seed_cap = std::max<uint64_t>(1 << 20, n_queries * 4);
+    if (w.hit_cap < n_queries * 12) w.hit_cap = std::max<uint64_t>(1 << 20, n_queries * 12);
+    w.d_counters.reserve(CT_COUNT * sizeof(unsigned long long));
+    w.d_packed.reserve(n_queries * W * 4);
+    unsigned long long* ctr = w.d_counters.get<unsigned long long>();
+    CUDA_TRY(cudaEventRecord(w.ev[0], w.stream));
+    if (!w.packed_ready) {
+        CUDA_TRY(cudaMemsetAsync(ctr, 0, CT_COUNT * sizeof(unsigned long long), w.stream));
+        const uint8_t* in = w.d_src;
+        const unsigned grid = grid_for(n_queries * W);
+        if (w.in_fmt == IN_READS_PACKED4)
+            pack_packed4_kernel<<<grid, 256, 0, w.stream>>>(reinterpret_cast<const uint32_t*>(in), n_queries, len, ix.sigma, w.with_reverse ? 1u : 0u,
+                                                           w.d_packed.get<uint32_t>(), ctr);
+        else if (w.in_fmt == IN_READS_RANKS && w.with_reverse)
+            pack_reads_kernel<<<grid, 256, 0, w.stream>>>(in, n_queries, len, ix.sigma, w.d_packed.get<uint32_t>(), ctr);
+        else
+            pack_queries_kernel<<<grid, 256, 0, w.stream>>>(in, n_queries, len, ix.sigma, w.d_packed.get<uint32_t>(), ctr);
         launch_check(c);
-        read_back_words(c, c->d_counters.get<unsigned long long>() + CT_TOTAL_ROWS, 1, CT_COUNT + 1);
-        total_rows = c->h_counters[CT_COUNT];
-        // (the scan is u32: n_cursors + rows beyond the first of every cursor bounds the true number of hits)
-        if (n_cursors + c->h_counters[CT_COUNT + 1] >= (1ull << 32)) throw Error("more than 2^32 hits in one call; split the batch");
+        w.packed_ready = true;
     }
-    c->fused_shift = 0;
-    c->sorted_keys = 0;
-    c->d_keys[0].reserve(std::max<uint64_t>(1, total_rows) * 8);
-    c->d_qids[0].reserve(std::max<uint64_t>(1, total_rows) * 4);
-    bool ok = true;
-    if (total_rows > 0) {
-        BucketParams B{};
-        B.index = locate_index(c);
-        B.cursors = c->d_cursors.get<uint4>();
-        B.n_cursors = static_cast<uint32_t>(n_cursors);
-        B.n_queries = static_cast<uint32_t>(n_queries);
-        B.qpos = c->d_qpos.get<uint32_t>();
-        B.keys = c->d_keys[0].get<uint64_t>();
-        B.qids = c->d_qids[0].get<uint32_t>();
-        B.task_cap = static_cast<uint32_t>(std::min<uint64_t>(total_rows / kInlineRows + 1024, 0xfffffff0ull));
-        B.big_cap = static_cast<uint32_t>(total_rows / kWarpSeg + 16);
-        c->d_tasks.reserve(uint64_t(B.task_cap) * sizeof(uint4));
-        c->d_bigsegs.reserve(uint64_t(B.big_cap) * 4);
-        B.tasks = c->d_tasks.get<uint4>();
-        B.big_segs = c->d_bigsegs.get<uint32_t>();
-        B.lc = c->d_lc.get<unsigned int>();
-        B.counters = c->d_counters.get<unsigned long long>();
-        const unsigned wide = static_cast<unsigned>(c->sms) * 4;
-        with_sigma(ix.sigma, [&](auto S) {
-            locate_scatter_kernel<S()><<<grid_for(n_cursors), 256, 0, c->stream>>>(B);
-            launch_check(c);
-            locate_tasks_kernel<S()><<<wide, 256, 0, c->stream>>>(B);
-            return 0;
-        });
-        launch_check(c);
-        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-        segment_sort_kernel<<<grid_for((n_queries + 31) / 32 * 32), 256, 0, c->stream>>>(B);  // one lane per query
-        launch_check(c);
-        segment_sort_big_kernel<<<wide, 256, 0, c->stream>>>(B);
-        launch_check(c);
-        CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
-        mirror_u32_kernel<<<1, 32, 0, c->stream>>>(c->d_lc.get<uint32_t>(), c->h_counters_dev + CT_COUNT, LC_COUNT);
-        launch_check(c);
-        read_back_words(c, c->d_counters.p, CT_COUNT);
-        ok = c->h_counters[CT_COUNT + LC_HUGE] == 0 && c->h_counters[CT_COUNT + LC_TASKS] <= B.task_cap;
-    } else {
-        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-        CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
-        read_back_words(c, c->d_counters.p, CT_COUNT);
+    enqueue_search_kernels(c, w);
+    CUDA_TRY(cudaEventRecord(w.ev[11], w.stream));
+    // search_n needs the host between search and locate (which queries exceed the limit); foreign cursor lists and the
+    // option bucket_sort = 0 take the global radix sort: both are finished synchronously in finish_batch
+    w.located = w.do_locate && c->max_hits == 0 && c->opt.bucket_sort;
+    if (w.located) {
+        enqueue_locate_bucketed(c, w);
+        enqueue_output(c, w, w.hit_cap, w.d_scratch.get<uint32_t>());
     }
-    if (!ok) return false;
-    c->ct.lf_steps += c->h_counters[CT_LF_STEPS];
-    c->ct.hits += total_rows;
-    c->last_hits = total_rows;
-    CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_locate, c->ev[1], c->ev[2]));
-    CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_sort, c->ev[2], c->ev[3]));
+    enqueue_publish(c, w, w.located);
+}
+
+// search_n after the plain search: a query with at most max_hits rows is complete; the others (they end early by
+// definition) are walked again in the reference's recursion order and their cursors of the first pass are dropped.
+// n_slots: output slots of the first pass.  false = the cursor buffer is too small (cursor_cap was raised, the caller
+// starts over).
+bool refine_max_hits(sb200_ctx* c, Work& w, uint64_t n_slots) {
+    SearchParams P = search_params(c, w);
+    const uint32_t nq = P.n_queries;
+    w.d_rows.reserve((size_t(nq) + 4) * sizeof(unsigned long long));
+    w.d_redo.reserve(size_t(nq) * sizeof(uint32_t));
+    unsigned long long* rows = w.d_rows.get<unsigned long long>();
+    unsigned long long* tally = rows + nq;  // queries to redo, bound on their cursors, cursors dropped
+    CUDA_TRY(cudaMemsetAsync(rows, 0, (size_t(nq) + 4) * sizeof(unsigned long long), w.stream));
+    if (n_slots) cursor_rows_kernel<<<grid_for(n_slots), 256, 0, w.stream>>>(P.out, n_slots, rows);
+    redo_list_kernel<<<grid_for(nq), 256, 0, w.stream>>>(rows, nq, c->max_hits, w.d_redo.get<uint32_t>(), tally);
+    launch_check(c);
+    read_back_words(c, w.stream, tally, 2, CT_COUNT);
+    const uint64_t n_redo = c->h_counters[CT_COUNT], bound = c->h_counters[CT_COUNT + 1];
+    if (n_redo == 0) return true;
+    const uint64_t need = n_slots + bound + uint64_t(ordered_grid(c, P.len, n_redo)) * 256 * kEmitChunk;
+    if (need >= 0xfffffffeull) throw Error("more than 2^32 cursors in one call; split the batch");
+    if (need > w.cursor_cap) {
+        w.cursor_cap = need + need / 8;
+        return false;
+    }
+    drop_cursors_kernel<<<grid_for(n_slots), 256, 0, w.stream>>>(P.out, n_slots, rows, c->max_hits, tally);
+    CUDA_TRY(cudaMemsetAsync(P.counters + CT_NEXT_QUERY, 0, sizeof(unsigned long long), w.stream));
+    SearchParams Q = P;
+    Q.max_hits = c->max_hits;
+    Q.redo = w.d_redo.get<uint32_t>();
+    Q.n_queries = static_cast<uint32_t>(n_redo);
+    launch_ordered(c, w, Q);
+    read_back_words(c, w.stream, tally + 2, 1, CT_COUNT);
+    const uint64_t dropped = c->h_counters[CT_COUNT];
+    read_back_words(c, w.stream, w.d_counters.p, CT_COUNT);
+    if (c->h_counters[CT_OVERFLOW]) throw Error("internal error: search stack overflow");
+    if (c->h_counters[CT_OUT_SLOTS] > w.cursor_cap) throw Error("internal error: cursor buffer of the ordered walk too small");
+    for (int i = 0; i < CT_COUNT; ++i) w.h_status[ST_COUNTERS + i] = c->h_counters[i];
+    w.h_status[ST_COUNTERS + CT_CURSORS] -= dropped;
     return true;
 }
 
-// kernel 3 over the n_cursors cursors in c->d_cursors (room for one extra slot), then sort by
-// (qid, seq/pos, e).  Sorted hits end in d_keys[sorted_keys] (fused keys) or d_keys[0] / d_qids[0].
-void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
+// kernel 3 over the n_cursors cursors in w.d_cursors (room for one extra slot) with a global sort by (qid, seq/pos, e):
+// cursors with arbitrary query ids (sb200_locate), queries with thousands of hits, option bucket_sort = 0.  Synchronous.
+// Sorted hits end in w.d_keys[w.sorted_keys] (fused keys) or w.d_keys[0] / w.d_qids[0].
+void locate_radix(sb200_ctx* c, Work& w, uint64_t n_cursors, uint64_t n_queries_hint) {
     auto& ix = c->idx;
-    // cursors of our own search (query ids 0 .. n_queries_hint-1): per-query buckets; SB200_BUCKET_SORT=0 or a query with
-    // thousands of hits: global radix sort
-    const bool bucketed = n_queries_hint > 0 && n_queries_hint < 0xffffffffull && n_cursors < 0xffffffffull &&
-                          !(std::getenv("SB200_BUCKET_SORT") && std::atoi(std::getenv("SB200_BUCKET_SORT")) == 0);
-    if (bucketed && locate_bucketed(c, n_cursors, n_queries_hint)) return;
-    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-    c->d_counters.reserve(CT_COUNT * sizeof(unsigned long long));
-    CUDA_TRY(cudaMemsetAsync(c->d_counters.get<unsigned long long>() + CT_LF_STEPS, 0, sizeof(unsigned long long), c->stream));
+    CUDA_TRY(cudaEventRecord(w.ev[1], w.stream));
+    w.d_counters.reserve(CT_COUNT * sizeof(unsigned long long));
+    unsigned long long* ctr = w.d_counters.get<unsigned long long>();
+    CUDA_TRY(cudaMemsetAsync(ctr + CT_LF_STEPS, 0, sizeof(unsigned long long), w.stream));
     uint64_t total_rows = 0;
     if (n_cursors > 0) {
-        c->d_offsets.reserve((n_cursors + 1) * 8);
-        auto lens = cub::TransformInputIterator<uint64_t, CursorLen, const uint4*>(c->d_cursors.get<uint4>(), CursorLen{});
+        w.d_offsets.reserve((n_cursors + 1) * 8);
+        auto lens = cub::TransformInputIterator<uint64_t, CursorLen, const uint4*>(w.d_cursors.get<uint4>(), CursorLen{});
         size_t tmp_bytes = 0;
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, lens, c->d_offsets.get<uint64_t>(), n_cursors + 1, c->stream));
-        c->d_tmp.reserve(tmp_bytes);
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, lens, w.d_offsets.get<uint64_t>(), n_cursors + 1, w.stream));
+        w.d_tmp.reserve(tmp_bytes);
         // n_cursors + 1 items are scanned: zero the slot behind the last cursor
-        CUDA_TRY(cudaMemsetAsync(c->d_cursors.get<uint4>() + n_cursors, 0, sizeof(uint4), c->stream));
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->d_tmp.p, tmp_bytes, lens, c->d_offsets.get<uint64_t>(), n_cursors + 1, c->stream));
+        CUDA_TRY(cudaMemsetAsync(w.d_cursors.get<uint4>() + n_cursors, 0, sizeof(uint4), w.stream));
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(w.d_tmp.p, tmp_bytes, lens, w.d_offsets.get<uint64_t>(), n_cursors + 1, w.stream));
         c->ct.kernel_launches += 1;
-        read_back_words(c, c->d_offsets.get<uint64_t>() + n_cursors, 1, CT_COUNT);
+        read_back_words(c, w.stream, w.d_offsets.get<uint64_t>() + n_cursors, 1, CT_COUNT);
         total_rows = c->h_counters[CT_COUNT];
     }
     if (total_rows >= (1ull << 32)) throw Error("more than 2^32 hits in one call; split the batch");
@@ -1009,123 +1040,299 @@ void locate_only(sb200_ctx* c, uint64_t n_cursors, uint64_t n_queries_hint) {
     // (measured at equal pass counts, 16 M hits: two pair sorts 1.19 ms, one 64-bit keys-only sort 1.38 ms — so only
     // when it saves a radix pass)
     const bool fewer_passes = (key_bits + qid_bits + 7) / 8 < (key_bits + 7) / 8 + (qid_bits + 7) / 8;
-    const char* force = std::getenv("SB200_FUSED_SORT");
-    const bool fused = key_bits + qid_bits <= 64 && (force ? std::atoi(force) != 0 : fewer_passes);
-    c->fused_shift = fused ? static_cast<uint32_t>(key_bits) : 0u;
-    c->sorted_keys = 0;
+    const bool fused = key_bits + qid_bits <= 64 && (c->opt.fused_sort >= 0 ? c->opt.fused_sort != 0 : fewer_passes);
+    w.fused_shift = fused ? static_cast<uint32_t>(key_bits) : 0u;
+    w.sorted_keys = 0;
     for (int i = 0; i < 2; ++i) {
-        c->d_keys[i].reserve(std::max<uint64_t>(1, total_rows) * 8);
-        if (!fused) c->d_qids[i].reserve(std::max<uint64_t>(1, total_rows) * 4);
+        w.d_keys[i].reserve(std::max<uint64_t>(1, total_rows) * 8);
+        if (!fused) w.d_qids[i].reserve(std::max<uint64_t>(1, total_rows) * 4);
     }
     if (total_rows > 0) {
         LocateParams L{};
         L.index = locate_index(c);
-        L.cursors = c->d_cursors.get<uint4>();
-        L.offsets = c->d_offsets.get<uint64_t>();
+        L.cursors = w.d_cursors.get<uint4>();
+        L.offsets = w.d_offsets.get<uint64_t>();
         L.n_cursors = static_cast<uint32_t>(n_cursors);
         L.n_rows_total = total_rows;
-        L.out_key = c->d_keys[0].get<uint64_t>();
-        L.out_qid = fused ? nullptr : c->d_qids[0].get<uint32_t>();
-        L.fused_shift = c->fused_shift;
-        L.counters = c->d_counters.get<unsigned long long>();
+        L.out_key = w.d_keys[0].get<uint64_t>();
+        L.out_qid = fused ? nullptr : w.d_qids[0].get<uint32_t>();
+        L.fused_shift = w.fused_shift;
+        L.counters = ctr;
         with_sigma(ix.sigma, [&](auto S) {
-            locate_kernel<S()><<<grid_for(total_rows), 256, 0, c->stream>>>(L);
+            locate_kernel<S()><<<grid_for(total_rows), 256, 0, w.stream>>>(L);
             return 0;
         });
         launch_check(c);
     }
-    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    CUDA_TRY(cudaEventRecord(w.ev[2], w.stream));
     if (total_rows > 1 && fused) {
         size_t t1 = 0;
-        CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, t1, c->d_keys[0].get<uint64_t>(), c->d_keys[1].get<uint64_t>(), total_rows, 0,
-                                                key_bits + qid_bits, c->stream));
-        c->d_tmp.reserve(t1);
-        CUDA_TRY(cub::DeviceRadixSort::SortKeys(c->d_tmp.p, t1, c->d_keys[0].get<uint64_t>(), c->d_keys[1].get<uint64_t>(), total_rows, 0,
-                                                key_bits + qid_bits, c->stream));
-        c->sorted_keys = 1;
+        CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, t1, w.d_keys[0].get<uint64_t>(), w.d_keys[1].get<uint64_t>(), total_rows, 0,
+                                                key_bits + qid_bits, w.stream));
+        w.d_tmp.reserve(t1);
+        CUDA_TRY(cub::DeviceRadixSort::SortKeys(w.d_tmp.p, t1, w.d_keys[0].get<uint64_t>(), w.d_keys[1].get<uint64_t>(), total_rows, 0,
+                                                key_bits + qid_bits, w.stream));
+        w.sorted_keys = 1;
         c->ct.kernel_launches += (key_bits + qid_bits + 7) / 8 + 2;
     } else if (total_rows > 1) {
         size_t t1 = 0, t2 = 0;
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t1, c->d_keys[0].get<uint64_t>(), c->d_keys[1].get<uint64_t>(),
-                                                 c->d_qids[0].get<uint32_t>(), c->d_qids[1].get<uint32_t>(), total_rows, 0, key_bits,
-                                                 c->stream));
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t2, c->d_qids[1].get<uint32_t>(), c->d_qids[0].get<uint32_t>(),
-                                                 c->d_keys[1].get<uint64_t>(), c->d_keys[0].get<uint64_t>(), total_rows, 0, qid_bits,
-                                                 c->stream));
-        c->d_tmp.reserve(std::max(t1, t2));
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_tmp.p, t1, c->d_keys[0].get<uint64_t>(), c->d_keys[1].get<uint64_t>(),
-                                                 c->d_qids[0].get<uint32_t>(), c->d_qids[1].get<uint32_t>(), total_rows, 0, key_bits,
-                                                 c->stream));
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_tmp.p, t2, c->d_qids[1].get<uint32_t>(), c->d_qids[0].get<uint32_t>(),
-                                                 c->d_keys[1].get<uint64_t>(), c->d_keys[0].get<uint64_t>(), total_rows, 0, qid_bits,
-                                                 c->stream));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t1, w.d_keys[0].get<uint64_t>(), w.d_keys[1].get<uint64_t>(),
+                                                 w.d_qids[0].get<uint32_t>(), w.d_qids[1].get<uint32_t>(), total_rows, 0, key_bits, w.stream));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t2, w.d_qids[1].get<uint32_t>(), w.d_qids[0].get<uint32_t>(),
+                                                 w.d_keys[1].get<uint64_t>(), w.d_keys[0].get<uint64_t>(), total_rows, 0, qid_bits, w.stream));
+        w.d_tmp.reserve(std::max(t1, t2));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.d_tmp.p, t1, w.d_keys[0].get<uint64_t>(), w.d_keys[1].get<uint64_t>(),
+                                                 w.d_qids[0].get<uint32_t>(), w.d_qids[1].get<uint32_t>(), total_rows, 0, key_bits, w.stream));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.d_tmp.p, t2, w.d_qids[1].get<uint32_t>(), w.d_qids[0].get<uint32_t>(),
+                                                 w.d_keys[1].get<uint64_t>(), w.d_keys[0].get<uint64_t>(), total_rows, 0, qid_bits, w.stream));
         c->ct.kernel_launches += 2 * ((key_bits + 7) / 8 + 1) + 2 * ((qid_bits + 7) / 8 + 1);
     }
-    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
-    read_back_words(c, c->d_counters.p, CT_COUNT);
-    c->ct.lf_steps += c->h_counters[CT_LF_STEPS];
-    c->ct.hits += total_rows;
-    c->last_hits = total_rows;
-    CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_locate, c->ev[1], c->ev[2]));
-    CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_sort, c->ev[2], c->ev[3]));
+    CUDA_TRY(cudaEventRecord(w.ev[3], w.stream));
+    if (w.out_fmt == OUT_CSR) {  // per-query ends of the sorted list
+        if (n_queries_hint == 0) throw Error("internal error: CSR output needs the number of queries");
+        w.d_qpos.reserve((n_queries_hint + 1) * 4);
+        csr_ends_kernel<<<std::max(1u, std::min(grid_for(total_rows + 1), static_cast<unsigned>(c->sms) * 8)), 256, 0, w.stream>>>(
+            w.d_keys[w.sorted_keys].get<uint64_t>(), w.d_qids[0].get<uint32_t>(), total_rows, w.fused_shift, static_cast<uint32_t>(n_queries_hint),
+            w.d_qpos.get<uint32_t>());
+        launch_check(c);
+    }
+    enqueue_output(c, w, total_rows, nullptr);
+    read_back_words(c, w.stream, ctr, CT_COUNT);
+    w.h_status[ST_COUNTERS + CT_LF_STEPS] = c->h_counters[CT_LF_STEPS];
+    w.n_hits = total_rows;
 }
 
-void run_pipeline(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uint32_t len, bool do_locate, bool from_reads = false) {
-    search_only(c, d_queries, n_queries, len, do_locate, from_reads);
-    if (do_locate) locate_only(c, c->last_cursors, n_queries);
+// waits for the batch, grows buffers and starts over when something did not fit, finishes the parts that need the host
+// (search_n, global sort).  Afterwards: w.n_cursor_slots / w.n_real_cursors / w.n_hits are valid, hits sit in w.d_out.
+void finish_batch(sb200_ctx* c, Work& w) {
+    const uint32_t len = w.len;
+    for (int attempt = 0;; ++attempt) {
+        if (attempt > 8) throw Error("internal error: work buffers do not converge");
+        CUDA_TRY(cudaEventSynchronize(w.ev_done));
+        const unsigned long long* st = w.h_status;
+        if (st[ST_COUNTERS + CT_BAD_QUERY]) {
+            const uint64_t off = st[ST_COUNTERS + CT_BAD_QUERY] - 1 + w.first_query * len;
+            throw Error("query has invalid character at offset " + std::to_string(off % len) + " of query " + std::to_string(off / len));
+        }
+        if (c->opt.debug)
+            fprintf(stderr, "[sb200 debug] slot %d: max stack depth %llu overflow %llu seeds %llu cursors %llu hits %llu\n", w.id,
+                    st[ST_COUNTERS + CT_MAX_SP], st[ST_COUNTERS + CT_OVERFLOW], st[ST_COUNTERS + CT_SEEDS], st[ST_COUNTERS + CT_OUT_SLOTS], st[ST_HITS]);
+        if (st[ST_COUNTERS + CT_OVERFLOW]) throw Error("internal error: search stack overflow");
+        const uint64_t n_slots = st[ST_COUNTERS + CT_OUT_SLOTS], n_seed_slots = st[ST_COUNTERS + CT_SEED_SLOTS];
+        if (n_slots >= 0xfffffffeull || n_seed_slots >= 0xfffffffeull) throw Error("more than 2^32 cursors in one call; split the batch");
+        bool fits = true;
+        if (n_seed_slots > w.seed_cap) {  // the text kernel saw a truncated seed list
+            w.seed_cap = n_seed_slots + n_seed_slots / 4;
+            fits = false;
+        }
+        if (n_slots > w.cursor_cap) {
+            w.cursor_cap = n_slots + n_slots / 4;
+            fits = false;
+        }
+        bool radix = false;
+        if (fits && w.located) {
+            const uint64_t total = st[ST_HITS];
+            // (the scan is u32: n_slots + rows beyond the first of every cursor bounds the true number of hits)
+            if (n_slots + st[ST_COUNTERS + CT_TOTAL_ROWS] >= (1ull << 32)) throw Error("more than 2^32 hits in one call; split the batch");
+            if (total > w.hit_cap || st[ST_LC + LC_KEY_OVERFLOW]) {
+                w.hit_cap = total + total / 4 + 1024;
+                fits = false;
+            } else if (st[ST_LC + LC_TASKS] > w.task_cap) {
+                w.hit_cap = std::max<uint64_t>(w.hit_cap * 2, uint64_t(st[ST_LC + LC_TASKS]) * kInlineRows);
+                fits = false;
+            } else {
+                radix = st[ST_LC + LC_HUGE] != 0;  // a query with more hits than a block sorts
+                w.n_hits = total;
+            }
+        }
+        if (!fits) {
+            c->ct.batch_restarts += 1;
+            enqueue_compute(c, w);
+            continue;
+        }
+        w.n_cursor_slots = n_slots;
+        if (c->max_hits && !c->opt.ordered_only) {
+            if (!refine_max_hits(c, w, n_slots)) {
+                c->ct.batch_restarts += 1;
+                enqueue_compute(c, w);
+                continue;
+            }
+            w.n_cursor_slots = w.h_status[ST_COUNTERS + CT_OUT_SLOTS];
+        }
+        if (w.do_locate && (!w.located || radix)) {
+            // (cursors of our own search carry query ids 0 .. n_queries - 1: per-query buckets unless switched off)
+            if (!w.located && c->opt.bucket_sort) {  // search_n: the bucketed path, now that the cursor list is final
+                unsigned long long* ctr = w.d_counters.get<unsigned long long>();
+                CUDA_TRY(cudaMemcpyAsync(ctr + CT_OUT_SLOTS, &w.n_cursor_slots, 8, cudaMemcpyHostToDevice, w.stream));
+                CUDA_TRY(cudaMemsetAsync(ctr + CT_LF_STEPS, 0, sizeof(unsigned long long), w.stream));
+                CUDA_TRY(cudaMemsetAsync(ctr + CT_TOTAL_ROWS, 0, sizeof(unsigned long long), w.stream));
+                const unsigned long long keep_cursors = w.h_status[ST_COUNTERS + CT_CURSORS], keep_nodes = w.h_status[ST_COUNTERS + CT_NODES],
+                                         keep_text = w.h_status[ST_COUNTERS + CT_NODES_TEXT];
+                bool again = true;
+                while (again) {
+                    enqueue_locate_bucketed(c, w);
+                    enqueue_output(c, w, w.hit_cap, w.d_scratch.get<uint32_t>());
+                    enqueue_publish(c, w, true);
+                    CUDA_TRY(cudaEventSynchronize(w.ev_done));
+                    const uint64_t total = w.h_status[ST_HITS];
+                    again = false;
+                    if (total > w.hit_cap || w.h_status[ST_LC + LC_KEY_OVERFLOW]) {
+                        w.hit_cap = total + total / 4 + 1024;
+                        again = true;
+                    } else if (w.h_status[ST_LC + LC_TASKS] > w.task_cap) {
+                        w.hit_cap = std::max<uint64_t>(w.hit_cap * 2, uint64_t(w.h_status[ST_LC + LC_TASKS]) * kInlineRows);
+                        again = true;
+                    } else {
+                        radix = w.h_status[ST_LC + LC_HUGE] != 0;
+                        w.n_hits = total;
+                    }
+                }
+                w.h_status[ST_COUNTERS + CT_CURSORS] = keep_cursors;
+                w.h_status[ST_COUNTERS + CT_NODES] = keep_nodes;
+                w.h_status[ST_COUNTERS + CT_NODES_TEXT] = keep_text;
+                w.located = true;
+            } else {
+                radix = true;
+            }
+            if (radix) locate_radix(c, w, w.n_cursor_slots, w.n_queries);
+        }
+        break;
+    }
+    const unsigned long long* st = w.h_status;
+    w.n_real_cursors = st[ST_COUNTERS + CT_CURSORS];
+    if (!w.do_locate) w.n_hits = 0;
+    // accounting
+    CUDA_TRY(cudaStreamSynchronize(w.stream));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, w.ev[0], w.ev[11]));
+    w.ms_search = ms;
+    CUDA_TRY(cudaEventElapsedTime(&w.ms_fm, w.ev[8], w.ev[9]));
+    CUDA_TRY(cudaEventElapsedTime(&w.ms_text, w.ev[9], w.ev[10]));
+    w.ms_locate = w.ms_sort = 0;
+    if (w.do_locate) {
+        CUDA_TRY(cudaEventElapsedTime(&w.ms_locate, w.ev[1], w.ev[2]));
+        CUDA_TRY(cudaEventElapsedTime(&w.ms_sort, w.ev[2], w.ev[3]));
+    }
+    c->ct.nodes += st[ST_COUNTERS + CT_NODES];
+    c->nodes_text += st[ST_COUNTERS + CT_NODES_TEXT];
+    c->ct.rank_ops += 2 * (st[ST_COUNTERS + CT_NODES] - st[ST_COUNTERS + CT_NODES_TEXT]);
+    c->ct.cursors += st[ST_COUNTERS + CT_CURSORS];
+    if (w.do_locate) {
+        c->ct.lf_steps += st[ST_COUNTERS + CT_LF_STEPS];
+        c->ct.hits += w.n_hits;
+    }
+    c->ct.ms_search = w.ms_search;
+    c->ct.ms_locate = w.ms_locate;
+    c->ct.ms_sort = w.ms_sort;
+    c->ms_fm = w.ms_fm;
+    c->ms_text = w.ms_text;
+}
+
+// describes a batch in slot w; src = host pointer (copied on the input stream) or device pointer
+void setup_batch(sb200_ctx* c, Work& w, const void* src, bool src_on_device, int in_fmt, bool with_reverse, uint64_t n_queries, uint32_t len,
+                 bool do_locate, int out_fmt, uint64_t first_query, cudaStream_t stream) {
+    auto& ix = c->idx;
+    if (!ix.loaded) throw Error("no index loaded");
+    if (!c->have_scheme) throw Error("no search scheme set");
+    if (len != c->qlen) throw Error("query length " + std::to_string(len) + " does not match the expanded search scheme (" +
+                                    std::to_string(c->qlen) + ")");
+    if (!src || n_queries == 0) throw Error("query file was empty - abort");
+    if (n_queries * uint64_t(c->n_searches) >= (1ull << 32)) throw Error("too many (query, search) pairs for one call; split the batch");
+    if (c->n_searches > 255) throw Error("search schemes with more than 255 searches are not supported");
+    w.stream = stream;
+    w.n_queries = n_queries;
+    w.len = len;
+    w.in_fmt = in_fmt;
+    w.with_reverse = with_reverse;
+    w.do_locate = do_locate;
+    w.out_fmt = do_locate ? out_fmt : OUT_NONE;
+    w.first_query = first_query;
+    w.packed_ready = false;
+    w.located = false;
+    w.n_hits = w.n_cursor_slots = w.n_real_cursors = 0;
+    const uint64_t n_items = (with_reverse && in_fmt != IN_QUERIES_RANKS) ? n_queries / 2 : n_queries;
+    const uint64_t bytes = in_fmt == IN_READS_PACKED4 ? n_items * packed_words(len) * 4 : n_items * len;
+    if (src_on_device) {
+        w.d_src = static_cast<const uint8_t*>(src);
+    } else {
+        w.d_in.reserve(bytes + 16);
+        // the slot's previous batch is finished (slots are handed out only after finish_batch): the buffer is free
+        CUDA_TRY(cudaMemcpyAsync(w.d_in.p, src, bytes, cudaMemcpyHostToDevice, c->s_in));
+        CUDA_TRY(cudaEventRecord(w.ev_in, c->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(w.stream, w.ev_in, 0));
+        w.d_src = w.d_in.get<uint8_t>();
+        w.h2d_bytes = bytes;
+    }
+}
+
+// copies the formatted hits of a finished batch (w.d_out) and, for CSR, the per-query ends to host memory on the output
+// stream; returns without waiting (w.ev_out marks the end)
+void enqueue_copy_out(sb200_ctx* c, Work& w, void* dst_records, uint32_t* dst_ends) {
+    const size_t rec = out_record_bytes(c, w.out_fmt);
+    CUDA_TRY(cudaEventRecord(w.ev_ready, w.stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->s_out, w.ev_ready, 0));
+    if (w.n_hits) CUDA_TRY(cudaMemcpyAsync(dst_records, w.d_out.p, w.n_hits * rec, cudaMemcpyDeviceToHost, c->s_out));
+    if (dst_ends) CUDA_TRY(cudaMemcpyAsync(dst_ends, w.d_qpos.p, w.n_queries * 4, cudaMemcpyDeviceToHost, c->s_out));
+    CUDA_TRY(cudaEventRecord(w.ev_out, c->s_out));
+    w.d2h_bytes = w.n_hits * rec + (dst_ends ? w.n_queries * 4 : 0);
+}
+
+// the synchronous entry points run on slot 0 and the caller's stream
+void run_pipeline(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uint32_t len, bool do_locate, int in_fmt = IN_QUERIES_RANKS,
+                  bool with_reverse = false, int out_fmt = OUT_NONE) {
+    Work& w = c->work[0];
+    if (w.busy) throw Error("a submitted batch is still in flight in slot 0: wait for it first");
+    setup_batch(c, w, d_queries, true, in_fmt, with_reverse, n_queries, len, do_locate, out_fmt, 0, c->stream);
+    enqueue_compute(c, w);
+    finish_batch(c, w);
+    c->last = &w;
 }
 
 void fetch_hits(sb200_ctx* c, sb200_hit** hits, uint64_t* n_hits) {
-    uint64_t n = c->last_hits;
-    auto& ix = c->idx;
+    Work* wp = c->last;
+    if (!wp) throw Error("no search result to fetch");
+    Work& w = *wp;
+    const uint64_t n = w.n_hits;
     sb200_hit* out = static_cast<sb200_hit*>(g_pinned.alloc(std::max<uint64_t>(1, n) * sizeof(sb200_hit)));
     if (n) {
         // expand to the reference tuple on the device, then one pinned copy
-        c->d_scratch.reserve(n * sizeof(sb200_hit));
-        expand_hits_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->d_keys[c->sorted_keys].get<uint64_t>(), c->d_qids[0].get<uint32_t>(), n,
-                                                               static_cast<uint32_t>(ix.bits_for_position), 0, c->fused_shift,
-                                                               c->d_scratch.get<uint64_t>());
-        launch_check(c);
-        CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
-        CUDA_TRY(cudaMemcpyAsync(out, c->d_scratch.p, n * sizeof(sb200_hit), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        const int keep = w.out_fmt;
+        w.out_fmt = OUT_HIT64;
+        enqueue_output(c, w, n, nullptr);
+        w.out_fmt = keep;
+        CUDA_TRY(cudaEventRecord(c->ev[4], w.stream));
+        CUDA_TRY(cudaMemcpyAsync(out, w.d_out.p, n * sizeof(sb200_hit), cudaMemcpyDeviceToHost, w.stream));
+        CUDA_TRY(cudaEventRecord(c->ev[5], w.stream));
+        CUDA_TRY(cudaStreamSynchronize(w.stream));
         CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_d2h, c->ev[4], c->ev[5]));
     }
     *hits = out;
     *n_hits = n;
 }
 
-const uint8_t* stage_queries(sb200_ctx* c, const uint8_t* queries, uint64_t n_queries, uint32_t len) {
-    if (!c->idx.loaded) throw Error("no index loaded");
-    if (!queries || n_queries == 0) throw Error("query file was empty - abort");
-    c->d_queries.reserve(n_queries * len);
-    CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->d_queries.p, queries, n_queries * len, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaEventRecord(c->ev[7], c->stream));
-    return c->d_queries.get<uint8_t>();
-}
-
-// search + locate from host buffers, pipelined: the batch is cut into chunks of reads; the host->device copy of
-// chunk i+1 and the device->host copy of the hits of chunk i-1 run on their own streams while chunk i computes.
+// search + locate from host buffers, pipelined over the work slots: the batch is cut into chunks of reads; the
+// host->device copy of chunk i+1 and the device->host copy of the hits of chunk i-1 run on their own streams while chunk
+// i computes, and the kernels of chunk i+1 are queued behind those of chunk i before the host looks at chunk i.
 // Chunks are contiguous query ranges, so concatenating their sorted hit lists keeps the global order.
-//   make_rc : the host buffer holds only the reads; the reverse complements are made on the device
-//             (queries[2i] = read i, queries[2i+1] = its reverse complement, search.cpp:121-123)
-//   compact : hits are returned as sb200_hit32 (16 bytes) instead of the reference's 32-byte tuple
-void search_host_pipelined(sb200_ctx* c, const uint8_t* src, uint64_t n_items, uint32_t len, bool make_rc, bool compact, void** hits,
-                           uint64_t* n_hits) {
+//   in_fmt / with_reverse : what the host buffer holds (sb200.h); the reverse complements are made on the device
+//                           (queries[2i] = read i, queries[2i+1] = its reverse complement, search.cpp:121-123)
+//   out_fmt               : OUT_HIT64 (the reference's 32-byte tuple) or OUT_HIT32 (16 bytes)
+void search_host_pipelined(sb200_ctx* c, const uint8_t* src, uint64_t n_items, uint32_t len, int in_fmt, bool with_reverse, int out_fmt,
+                           void** hits, uint64_t* n_hits) {
     auto& ix = c->idx;
     if (!ix.loaded) throw Error("no index loaded");
     if (!src || n_items == 0) throw Error("query file was empty - abort");
-    const uint64_t per_item = make_rc ? 2 : 1;  // queries per host item
+    for (auto& w : c->work)
+        if (w.busy) throw Error("submitted batches are still in flight: wait for them first");
+    const uint64_t per_item = (with_reverse && in_fmt != IN_QUERIES_RANKS) ? 2 : 1;  // queries per host item
     const uint64_t n_queries = n_items * per_item;
-    const size_t hit_bytes = compact ? sizeof(sb200_hit32) : sizeof(sb200_hit);
-    // Chunk boundaries (in queries).  Every chunk costs ~0.9 ms of kernel drain (the longest single seed), so few
-    // chunks: a short first one (its copy-in cannot be hidden), a short last one (its copy-out cannot be hidden),
-    // and the rest in pieces of at most `chunk` queries whose copies hide behind the neighbours' kernels.
-    uint64_t chunk = 2000000, edge_div = 5;
-    if (const char* e = std::getenv("SB200_CHUNK")) chunk = std::max<uint64_t>(2, std::strtoull(e, nullptr, 10));
-    if (const char* e = std::getenv("SB200_EDGE_DIV")) edge_div = std::max<uint64_t>(2, std::strtoull(e, nullptr, 10));
+    const size_t hit_bytes = out_record_bytes(c, out_fmt);
+    const size_t item_bytes = in_fmt == IN_READS_PACKED4 ? size_t(packed_words(len)) * 4 : len;
+    // Chunk boundaries (in queries).  Every chunk costs a kernel drain (the longest single seed), so few chunks: a short
+    // first one (its copy-in cannot be hidden), a short last one (its copy-out cannot be hidden), and the rest in pieces
+    // of at most `chunk` queries whose copies hide behind the neighbours' kernels.
+    uint64_t chunk = std::max<uint64_t>(2, c->opt.chunk);
+    const uint64_t edge_div = std::max<uint64_t>(2, c->opt.edge_div);
     chunk += chunk & 1;  // both strands of a read stay together
     std::vector<uint64_t> bounds{0};
     {
@@ -1142,46 +1349,36 @@ void search_host_pipelined(sb200_ctx* c, const uint8_t* src, uint64_t n_items, u
         bounds.push_back(n_queries);
     }
     const uint64_t n_chunks = bounds.size() - 1;
-    uint64_t max_chunk = 0;
-    for (uint64_t k = 0; k < n_chunks; ++k) max_chunk = std::max(max_chunk, bounds[k + 1] - bounds[k]);
-    for (int i = 0; i < 2; ++i) c->d_qchunk[i].reserve(max_chunk * len);
-    // wait until earlier work on the caller's stream is done before the copy streams touch the buffers
+    // wait until earlier work on the caller's stream is done before the slot streams touch anything
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    auto copy_in = [&](uint64_t k) {
-        const uint64_t q0 = bounds[k], n = bounds[k + 1] - q0;
-        const int b = static_cast<int>(k & 1);
-        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->ev_free_q[b], 0));  // chunk k-2 no longer reads this buffer
-        CUDA_TRY(cudaMemcpyAsync(c->d_qchunk[b].p, src + (q0 / per_item) * len, (n / per_item) * len, cudaMemcpyHostToDevice, c->s_in));
-        CUDA_TRY(cudaEventRecord(c->ev_in[b], c->s_in));
-    };
     uint8_t* out = nullptr;
     uint64_t out_cap = 0, total = 0;
-    auto t0 = std::chrono::steady_clock::now();
-    copy_in(0);
     float ms_search = 0, ms_locate = 0, ms_sort = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    auto submit = [&](uint64_t k) {
+        Work& w = c->work[k % kSlots];
+        const uint64_t q0 = bounds[k], n = bounds[k + 1] - q0;
+        setup_batch(c, w, src + (q0 / per_item) * item_bytes, false, in_fmt, with_reverse, n, len, true, out_fmt, q0, w.own_stream);
+        enqueue_compute(c, w);
+        w.busy = true;
+    };
     try {
+        const uint64_t depth = std::min<uint64_t>(kSlots - 1, n_chunks);  // one slot stays free for the copy-out of the oldest chunk
+        for (uint64_t k = 0; k < depth; ++k) submit(k);
         for (uint64_t k = 0; k < n_chunks; ++k) {
-            const uint64_t q0 = bounds[k], n = bounds[k + 1] - q0;
-            const int b = static_cast<int>(k & 1);
-            if (k + 1 < n_chunks) copy_in(k + 1);
-            CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
-            const uint8_t* dq = c->d_qchunk[b].get<uint8_t>();
-            auto tc0 = std::chrono::steady_clock::now();
-            run_pipeline(c, dq, n, len, true, make_rc);  // search + locate + sort of this chunk (make_rc: dq holds the reads only)
-            if (std::getenv("SB200_DEBUG"))
-                fprintf(stderr,
-                        "[sb200 debug] chunk %llu: %llu queries, host wall %.3f ms, device search %.3f (fm %.3f text %.3f) locate %.3f sort %.3f ms\n",
-                        (unsigned long long)k, (unsigned long long)n,
-                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count(), c->ct.ms_search, c->ms_fm,
-                        c->ms_text, c->ct.ms_locate, c->ct.ms_sort);
-            CUDA_TRY(cudaEventRecord(c->ev_free_q[b], c->stream));
-            ms_search += c->ct.ms_search;
-            ms_locate += c->ct.ms_locate;
-            ms_sort += c->ct.ms_sort;
-            const uint64_t nh = c->last_hits;
+            Work& w = c->work[k % kSlots];
+            finish_batch(c, w);
+            if (c->opt.debug)
+                fprintf(stderr, "[sb200 debug] chunk %llu: %llu queries, device search %.3f (fm %.3f text %.3f) locate %.3f sort %.3f ms\n",
+                        (unsigned long long)k, (unsigned long long)w.n_queries, w.ms_search, w.ms_fm, w.ms_text, w.ms_locate, w.ms_sort);
+            ms_search += w.ms_search;
+            ms_locate += w.ms_locate;
+            ms_sort += w.ms_sort;
+            const uint64_t nh = w.n_hits;
             // output buffer: sized from the first chunk, grown (rarely) when the estimate was too small
             if (total + nh > out_cap) {
                 // first estimate: the hit density of the first chunk over the whole batch
+                const uint64_t n = w.n_queries;
                 uint64_t want = k == 0 ? nh * ((n_queries + n - 1) / n) + nh / 4 + 1024 : (total + nh) * 2;
                 uint8_t* bigger = static_cast<uint8_t*>(g_pinned.alloc(std::max<uint64_t>(1, want) * hit_bytes));
                 if (out) {
@@ -1192,46 +1389,51 @@ void search_host_pipelined(sb200_ctx* c, const uint8_t* src, uint64_t n_items, u
                 out = bigger;
                 out_cap = want;
             }
-            if (nh) {
-                if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_out[b], 0));  // hits of chunk k-2 have left this buffer
-                c->d_hitchunk[b].reserve(nh * hit_bytes);
-                if (compact)
-                    compact_hits_kernel<<<grid_for(nh), 256, 0, c->stream>>>(c->d_keys[c->sorted_keys].get<uint64_t>(),
-                                                                             c->d_qids[0].get<uint32_t>(), nh,
-                                                                             static_cast<uint32_t>(ix.bits_for_position),
-                                                                             static_cast<uint32_t>(q0), c->fused_shift,
-                                                                             c->d_hitchunk[b].get<uint4>());
-                else
-                    expand_hits_kernel<<<grid_for(nh), 256, 0, c->stream>>>(c->d_keys[c->sorted_keys].get<uint64_t>(),
-                                                                            c->d_qids[0].get<uint32_t>(), nh,
-                                                                            static_cast<uint32_t>(ix.bits_for_position), q0, c->fused_shift,
-                                                                            c->d_hitchunk[b].get<uint64_t>());
-                launch_check(c);
-                CUDA_TRY(cudaEventRecord(c->ev_expanded[b], c->stream));
-                CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->ev_expanded[b], 0));
-                CUDA_TRY(cudaMemcpyAsync(out + total * hit_bytes, c->d_hitchunk[b].p, nh * hit_bytes, cudaMemcpyDeviceToHost, c->s_out));
-            }
-            CUDA_TRY(cudaEventRecord(c->ev_out[b], c->s_out));
+            enqueue_copy_out(c, w, out + total * hit_bytes, nullptr);
             total += nh;
+            // the slot of chunk k + depth is the one whose copy-out (chunk k + depth - kSlots) was queued one round ago
+            if (k + depth < n_chunks) {
+                Work& nw = c->work[(k + depth) % kSlots];
+                if (nw.busy) {
+                    CUDA_TRY(cudaEventSynchronize(nw.ev_out));
+                    nw.busy = false;
+                }
+                submit(k + depth);
+            }
         }
         CUDA_TRY(cudaStreamSynchronize(c->s_out));
         CUDA_TRY(cudaStreamSynchronize(c->s_in));
+        for (auto& w : c->work) w.busy = false;
     } catch (...) {
-        cudaStreamSynchronize(c->s_out);
-        cudaStreamSynchronize(c->s_in);
+        cudaDeviceSynchronize();
+        for (auto& w : c->work) w.busy = false;
         if (out) g_pinned.free(out);
         throw;
     }
     if (!out) out = static_cast<uint8_t*>(g_pinned.alloc(hit_bytes));
-    if (std::getenv("SB200_DEBUG"))
+    if (c->opt.debug)
         fprintf(stderr, "[sb200 debug] host-buffer search total host wall %.3f ms\n",
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     c->ct.ms_search = ms_search;
     c->ct.ms_locate = ms_locate;
     c->ct.ms_sort = ms_sort;
     c->ct.ms_h2d = c->ct.ms_d2h = 0;  // overlapped with the kernels
+    c->last = nullptr;
     *hits = out;
     *n_hits = total;
+}
+
+// scheme tables of the context -> device: packed steps, run lengths and the state flags (which depend on the policy)
+void upload_scheme_tables(sb200_ctx* c) {
+    const std::vector<uint32_t>& steps = c->h_steps;
+    c->d_steps.reserve(steps.size() * 4);
+    CUDA_TRY(cudaMemcpyAsync(c->d_steps.p, steps.data(), steps.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    std::vector<uint8_t> runs(run_table_bytes(static_cast<uint32_t>(steps.size())) + 4, 0);  // run lengths, then state flags
+    build_runs(c->n_searches, c->qlen, steps.data(), runs.data());
+    build_state_flags(c->n_searches, c->qlen, steps.data(), runs.data(), c->policy);
+    c->d_runs.reserve(runs.size());
+    CUDA_TRY(cudaMemcpyAsync(c->d_runs.p, runs.data(), runs.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
 }
 
 }  // namespace
@@ -1272,11 +1474,14 @@ int sb200_create(int device, sb200_ctx** out) {
         for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
         CUDA_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_free_q[i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_expanded[i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+        for (int i = 0; i < kSlots; ++i) {
+            Work& w = c->work[i];
+            w.id = i;
+            CUDA_TRY(cudaStreamCreateWithFlags(&w.own_stream, cudaStreamNonBlocking));
+            for (auto& ev : w.ev) CUDA_TRY(cudaEventCreate(&ev));
+            for (cudaEvent_t* ev : {&w.ev_in, &w.ev_done, &w.ev_ready, &w.ev_out, &w.ev_fork}) CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+            CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&w.h_status), ST_COUNT * sizeof(unsigned long long), cudaHostAllocMapped));
+            CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&w.h_status_dev), w.h_status, 0));
         }
         // mapped: small read-backs are written by a kernel straight into host memory, so they never queue behind
         // a large hit transfer on the copy engine
@@ -1294,18 +1499,18 @@ int sb200_destroy(sb200_ctx* c) {
         if (!c) return;
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
+        cudaDeviceSynchronize();
         c->idx.release();
-        for (DevBuf* b : {&c->d_steps, &c->d_runs, &c->d_qpos, &c->d_tasks, &c->d_bigsegs, &c->d_lc, &c->d_items, &c->d_item_tags, &c->d_seeds, &c->d_spill, &c->d_packed, &c->d_queries, &c->d_cursors, &c->d_counters, &c->d_offsets, &c->d_keys[0], &c->d_keys[1],
-                          &c->d_qids[0], &c->d_qids[1], &c->d_tmp, &c->d_scratch})
-            b->release();
+        for (DevBuf* b : {&c->d_steps, &c->d_runs, &c->d_tmp, &c->d_scratch, &c->d_counters}) b->release();
         for (auto& ev : c->ev) cudaEventDestroy(ev);
-        for (int i = 0; i < 2; ++i) {
-            c->d_qchunk[i].release();
-            c->d_hitchunk[i].release();
-            cudaEventDestroy(c->ev_in[i]);
-            cudaEventDestroy(c->ev_free_q[i]);
-            cudaEventDestroy(c->ev_expanded[i]);
-            cudaEventDestroy(c->ev_out[i]);
+        for (auto& w : c->work) {
+            w.release_buffers();
+            for (auto& ev : w.ev) cudaEventDestroy(ev);
+            for (cudaEvent_t ev : {w.ev_in, w.ev_done, w.ev_ready, w.ev_out, w.ev_fork}) cudaEventDestroy(ev);
+            cudaStreamDestroy(w.own_stream);
+            cudaFreeHost(w.h_status);
+            if (w.h_out) cudaFreeHost(w.h_out);
+            if (w.h_ends) cudaFreeHost(w.h_ends);
         }
         cudaStreamDestroy(c->s_in);
         cudaStreamDestroy(c->s_out);
@@ -1594,15 +1799,13 @@ static void densify_index(sb200_ctx* c, uint32_t rate) {
         });
         launch_check(c);
         if (!ix.ref_ssa.p) {  // keep the reference-rate samples for download
-            ix.ref_ssa = ix.ssa;
-            ix.ssa = DevBuf{};
+            ix.ref_ssa = std::move(ix.ssa);
         } else {
             ix.ssa.release();
         }
         if (rate == 1) {
             CUDA_TRY(cudaStreamSynchronize(c->stream));
-            ix.ssa = row_value;
-            row_value = DevBuf{};
+            ix.ssa = std::move(row_value);
             ix.n_ssa = n;
             ix.full_sa = true;
             ix.marks.release();
@@ -1667,8 +1870,7 @@ int sb200_index_build_qgram(sb200_ctx* c, uint32_t q) {
         }
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         if (cur != &a) throw Error("internal error: q-gram ping-pong");
-        ix.qgram = a;
-        a = DevBuf{};
+        ix.qgram = std::move(a);
         b.release();
         ix.qgram_q = q;
     });
@@ -1695,19 +1897,56 @@ int sb200_set_scheme(sb200_ctx* c, uint32_t n_searches, uint32_t len, const uint
             }
         }
         if (kmax > 4) throw Error("search schemes with more than 4 errors are not supported by the GPU kernel yet");
-        c->d_steps.reserve(steps.size() * 4);
-        CUDA_TRY(cudaMemcpyAsync(c->d_steps.p, steps.data(), steps.size() * 4, cudaMemcpyHostToDevice, c->stream));
-        std::vector<uint8_t> runs(run_table_bytes(static_cast<uint32_t>(steps.size())) + 4, 0);  // run lengths, then state flags
-        build_runs(n_searches, len, steps.data(), runs.data());
-        build_state_flags(n_searches, len, steps.data(), runs.data());
-        c->d_runs.reserve(runs.size());
-        CUDA_TRY(cudaMemcpyAsync(c->d_runs.p, runs.data(), runs.size(), cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (auto& w : c->work)
+            if (w.busy) throw Error("submitted batches are still in flight: wait for them before changing the scheme");
+        CUDA_TRY(cudaDeviceSynchronize());
+        c->h_steps = std::move(steps);
         c->n_searches = n_searches;
         c->qlen = len;
         c->kmax = kmax;
         c->edit = edit != 0;
+        upload_scheme_tables(c);
         c->have_scheme = true;
+    });
+}
+
+int sb200_set_policy(sb200_ctx* c, const sb200_policy* policy) {
+    return guard([&] {
+        use(c);
+        if (!policy || !sb200_pol_valid(policy)) throw Error("invalid search policy");
+        for (auto& w : c->work)
+            if (w.busy) throw Error("submitted batches are still in flight: wait for them before changing the policy");
+        CUDA_TRY(cudaDeviceSynchronize());
+        c->policy = *policy;
+        if (c->have_scheme) upload_scheme_tables(c);  // (the state flags depend on it)
+    });
+}
+
+int sb200_get_policy(sb200_ctx* c, sb200_policy* out) {
+    return guard([&] {
+        if (!c || !out) throw Error("null argument");
+        *out = c->policy;
+    });
+}
+
+int sb200_set_option(sb200_ctx* c, const char* name, int64_t value) {
+    return guard([&] {
+        if (!c || !name) throw Error("null argument");
+        const std::string n(name);
+        auto& o = c->opt;
+        if (n == "bucket_sort") o.bucket_sort = value != 0;
+        else if (n == "fused_sort") o.fused_sort = value < 0 ? -1 : (value != 0);
+        else if (n == "textpos") o.textpos = value != 0;
+        else if (n == "ordered_only") o.ordered_only = value != 0;
+        else if (n == "debug") o.debug = static_cast<int>(value);
+        else if (n == "chunk") o.chunk = value <= 0 ? Options{}.chunk : static_cast<uint64_t>(value);
+        else if (n == "edge_div") o.edge_div = value <= 0 ? Options{}.edge_div : static_cast<uint64_t>(value);
+        else if (n == "pool_blocks_per_sm") o.pool_blocks_per_sm = static_cast<int>(std::max<int64_t>(0, value));
+        else if (n == "pool_threads") o.pool_threads = static_cast<int>(std::max<int64_t>(0, value));
+        else if (n == "run_rounds") o.run_rounds = static_cast<int>(std::max<int64_t>(0, value));
+        else if (n == "items_blocks_per_sm") o.items_blocks_per_sm = static_cast<int>(std::max<int64_t>(0, value));
+        else if (n == "ordered_blocks_per_sm") o.ordered_blocks_per_sm = static_cast<int>(std::max<int64_t>(0, value));
+        else throw Error("unknown option '" + n + "'");
     });
 }
 
@@ -1723,8 +1962,8 @@ int sb200_search_device(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queri
     return guard([&] {
         use(c);
         run_pipeline(c, d_queries, n_queries, len, n_hits != nullptr);
-        if (n_cursors) *n_cursors = c->last_real_cursors;
-        if (n_hits) *n_hits = c->last_hits;
+        if (n_cursors) *n_cursors = c->last->n_real_cursors;
+        if (n_hits) *n_hits = c->last->n_hits;
     });
 }
 
@@ -1735,12 +1974,11 @@ int sb200_fetch_hits(sb200_ctx* c, sb200_hit** hits, uint64_t* n_hits) {
     });
 }
 
-
 int sb200_search(sb200_ctx* c, const uint8_t* queries, uint64_t n_queries, uint32_t len, sb200_hit** hits, uint64_t* n_hits) {
     return guard([&] {
         use(c);
         void* p = nullptr;
-        search_host_pipelined(c, queries, n_queries, len, false, false, &p, n_hits);
+        search_host_pipelined(c, queries, n_queries, len, IN_QUERIES_RANKS, false, OUT_HIT64, &p, n_hits);
         *hits = static_cast<sb200_hit*>(p);
     });
 }
@@ -1751,22 +1989,133 @@ int sb200_search_reads(sb200_ctx* c, const uint8_t* reads, uint64_t n_reads, uin
         use(c);
         if (c->idx.loaded && c->idx.bits_for_position > 32) throw Error("sequences too long for 32-bit positions: use sb200_search");
         void* p = nullptr;
-        search_host_pipelined(c, reads, n_reads, len, with_reverse != 0, true, &p, n_hits);
+        search_host_pipelined(c, reads, n_reads, len, IN_READS_RANKS, with_reverse != 0, OUT_HIT32, &p, n_hits);
         *hits = static_cast<sb200_hit32*>(p);
+    });
+}
+
+// ---- asynchronous batches ------------------------------------------------------------------------------
+
+static Work& slot_of(sb200_ctx* c, uint64_t ticket) {
+    for (auto& w : c->work)
+        if (w.busy && w.ticket == ticket) return w;
+    throw Error("unknown batch ticket");
+}
+
+static uint64_t submit_batch(sb200_ctx* c, const void* src, bool on_device, uint64_t n_items, uint32_t len, int in_fmt, bool with_reverse,
+                             int out_fmt) {
+    Work* free_slot = nullptr;
+    for (auto& w : c->work)
+        if (!w.busy) { free_slot = &w; break; }
+    if (!free_slot) throw Error("too many batches in flight (" + std::to_string(kSlots) + "): wait for one and release it first");
+    Work& w = *free_slot;
+    const uint64_t n_queries = (with_reverse && in_fmt != IN_QUERIES_RANKS) ? 2 * n_items : n_items;
+    // fork from the caller's stream: work queued there before this call happens before the batch
+    CUDA_TRY(cudaEventRecord(w.ev_fork, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(w.own_stream, w.ev_fork, 0));
+    if (!on_device) CUDA_TRY(cudaStreamWaitEvent(c->s_in, w.ev_fork, 0));
+    setup_batch(c, w, src, on_device, in_fmt, with_reverse, n_queries, len, true, out_fmt, 0, w.own_stream);
+    enqueue_compute(c, w);
+    w.busy = true;
+    w.ticket = c->next_ticket++;
+    return w.ticket;
+}
+
+int sb200_submit_reads(sb200_ctx* c, const void* reads, uint64_t n_reads, uint32_t len, int format, int with_reverse, uint64_t* ticket) {
+    return guard([&] {
+        use(c);
+        if (!ticket) throw Error("null argument");
+        if (format != SB200_READS_RANKS && format != SB200_READS_PACKED4) throw Error("unknown read format");
+        if (c->max_hits) throw Error("sb200_submit_reads does not support --max_hits: use sb200_search_reads");
+        *ticket = submit_batch(c, reads, false, n_reads, len, format == SB200_READS_PACKED4 ? IN_READS_PACKED4 : IN_READS_RANKS,
+                               with_reverse != 0, OUT_CSR);
+    });
+}
+
+int sb200_submit_device(sb200_ctx* c, const uint8_t* d_queries, uint64_t n_queries, uint32_t len, uint64_t* ticket) {
+    return guard([&] {
+        use(c);
+        if (!ticket) throw Error("null argument");
+        if (c->max_hits) throw Error("sb200_submit_device does not support --max_hits: use sb200_search_device");
+        *ticket = submit_batch(c, d_queries, true, n_queries, len, IN_QUERIES_RANKS, false, OUT_CSR);
+    });
+}
+
+int sb200_wait_batch(sb200_ctx* c, uint64_t ticket, int copy_to_host, sb200_batch_result* out) {
+    return guard([&] {
+        use(c);
+        if (!out) throw Error("null argument");
+        Work& w = slot_of(c, ticket);
+        std::memset(out, 0, sizeof(*out));
+        try {
+            finish_batch(c, w);
+        } catch (...) {
+            w.busy = false;
+            throw;
+        }
+        const size_t rec = out_record_bytes(c, OUT_CSR);
+        out->n_queries = w.n_queries;
+        out->n_hits = w.n_hits;
+        out->n_cursors = w.n_real_cursors;
+        out->record_bytes = static_cast<uint32_t>(rec);
+        out->bits_for_position = static_cast<uint32_t>(c->idx.bits_for_position);
+        if (copy_to_host) {
+            const size_t need = (w.n_hits + 4) * rec + 64, need_ends = (w.n_queries + 1) * 4;
+            if (need > w.h_out_cap) {
+                if (w.h_out) cudaFreeHost(w.h_out);
+                w.h_out = nullptr;
+                w.h_out_cap = 0;
+                CUDA_TRY(cudaHostAlloc(&w.h_out, need + need / 4, cudaHostAllocDefault));
+                w.h_out_cap = need + need / 4;
+            }
+            if (need_ends > w.h_ends_cap) {
+                if (w.h_ends) cudaFreeHost(w.h_ends);
+                w.h_ends = nullptr;
+                w.h_ends_cap = 0;
+                CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&w.h_ends), need_ends + need_ends / 4, cudaHostAllocDefault));
+                w.h_ends_cap = need_ends + need_ends / 4;
+            }
+            enqueue_copy_out(c, w, w.h_out, w.h_ends);
+            CUDA_TRY(cudaEventSynchronize(w.ev_out));
+            out->hit_end = w.h_ends;
+            out->records = static_cast<const uint8_t*>(w.h_out);
+            out->h2d_bytes = w.h2d_bytes;
+            out->d2h_bytes = w.d2h_bytes;
+            // join: work queued on the caller's stream after this call happens after the batch
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, w.ev_out, 0));
+        } else {
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, w.ev_done, 0));
+        }
+        out->ms_search = w.ms_search;
+        out->ms_locate = w.ms_locate;
+        out->ms_sort = w.ms_sort;
+    });
+}
+
+int sb200_release_batch(sb200_ctx* c, uint64_t ticket) {
+    return guard([&] {
+        if (!c) throw Error("null context");
+        slot_of(c, ticket).busy = false;
     });
 }
 
 int sb200_search_cursors(sb200_ctx* c, const uint8_t* queries, uint64_t n_queries, uint32_t len, sb200_cursor** cursors, uint64_t* n_cursors) {
     return guard([&] {
         use(c);
-        const uint8_t* dq = stage_queries(c, queries, n_queries, len);
-        run_pipeline(c, dq, n_queries, len, false);
-        uint64_t n = c->last_cursors;
+        if (!c->idx.loaded) throw Error("no index loaded");
+        if (!queries || n_queries == 0) throw Error("query file was empty - abort");
+        Work& w = c->work[0];
+        if (w.busy) throw Error("a submitted batch is still in flight in slot 0: wait for it first");
+        setup_batch(c, w, queries, false, IN_QUERIES_RANKS, false, n_queries, len, false, OUT_NONE, 0, c->stream);
+        enqueue_compute(c, w);
+        finish_batch(c, w);
+        c->last = &w;
+        uint64_t n = w.n_cursor_slots;
         std::vector<uint4> tmp(n);
-        CUDA_TRY(cudaMemcpyAsync(tmp.data(), c->d_cursors.p, n * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(tmp.data(), w.d_cursors.p, n * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         tmp.erase(std::remove_if(tmp.begin(), tmp.end(), [](uint4 const& a) { return a.x == kInvalidQid; }), tmp.end());
-        if (tmp.size() != c->last_real_cursors) throw Error("internal error: cursor count mismatch");
+        if (tmp.size() != w.n_real_cursors) throw Error("internal error: cursor count mismatch");
         n = tmp.size();
         std::sort(tmp.begin(), tmp.end(), [](uint4 const& a, uint4 const& b) {
             if (a.x != b.x) return a.x < b.x;
@@ -1790,16 +2139,29 @@ int sb200_locate(sb200_ctx* c, const sb200_cursor* cursors, uint64_t n_cursors, 
         std::vector<uint4> tmp(n_cursors + 1);
         for (uint64_t i = 0; i < n_cursors; ++i) {
             auto const& k = cursors[i];
-            if (k.lb + k.len > ix.n_rows || k.errors > 15 || k.query_id > 0xffffffffull) throw Error("cursor out of range");
+            // (written so that huge values cannot wrap around the check)
+            if (k.len > ix.n_rows || k.lb > ix.n_rows - k.len || k.errors > 15 || k.query_id > 0xffffffffull) throw Error("cursor out of range");
             tmp[i] = make_uint4(static_cast<uint32_t>(k.query_id), static_cast<uint32_t>(k.lb), static_cast<uint32_t>(k.len),
                                 static_cast<uint32_t>(k.errors));
         }
         tmp[n_cursors] = make_uint4(0, 0, 0, 0);
-        c->d_cursors.reserve((n_cursors + 1) * sizeof(uint4));
-        CUDA_TRY(cudaMemcpyAsync(c->d_cursors.p, tmp.data(), (n_cursors + 1) * sizeof(uint4), cudaMemcpyHostToDevice, c->stream));
+        Work& w = c->work[0];
+        if (w.busy) throw Error("a submitted batch is still in flight in slot 0: wait for it first");
+        w.stream = c->stream;
+        w.d_cursors.reserve((n_cursors + 1) * sizeof(uint4));
+        CUDA_TRY(cudaMemcpyAsync(w.d_cursors.p, tmp.data(), (n_cursors + 1) * sizeof(uint4), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        c->last_cursors = n_cursors;
-        locate_only(c, n_cursors, 0);
+        w.out_fmt = OUT_NONE;
+        w.first_query = 0;
+        w.n_queries = 0;
+        w.do_locate = true;
+        locate_radix(c, w, n_cursors, 0);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_locate, w.ev[1], w.ev[2]));
+        CUDA_TRY(cudaEventElapsedTime(&c->ct.ms_sort, w.ev[2], w.ev[3]));
+        c->ct.lf_steps += w.h_status[ST_COUNTERS + CT_LF_STEPS];
+        c->ct.hits += w.n_hits;
+        c->last = &w;
         fetch_hits(c, hits, n_hits);
     });
 }

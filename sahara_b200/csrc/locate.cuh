@@ -147,16 +147,18 @@ constexpr uint32_t kTaskRows = 1024;     // rows per task of locate_tasks_kernel
 constexpr uint32_t kWarpSeg = 256;       // keys a warp of segment_sort_kernel sorts
 constexpr uint32_t kRankSortMax = 20;    // ... by counting ranks instead of a sorting network
 constexpr uint32_t kBigSeg = 2048;       // keys a block of segment_sort_big_kernel sorts
-enum : int { LC_TASKS = 0, LC_BIG_SEGS = 1, LC_HUGE = 2, LC_COUNT = 4 };
+enum : int { LC_TASKS = 0, LC_BIG_SEGS = 1, LC_HUGE = 2, LC_KEY_OVERFLOW = 3, LC_COUNT = 4 };
 
 struct BucketParams {
     LocateIndex index;
     const uint4* cursors;  // (qid, lb or text position, len, e | flags)
-    uint32_t n_cursors;
+    uint32_t n_cursors;    // number of cursor slots; with n_cursors_dev: the capacity of the cursor array
+    const unsigned long long* n_cursors_dev;  // optional: the slot count as the search kernels left it in device memory (no host round trip)
     uint32_t n_queries;
     uint32_t* qpos;        // [n_queries + 1] hits per query -> first slot -> (after the scatter) end of the segment
     uint64_t* keys;        // (value << 4) | e
-    uint32_t* qids;
+    uint32_t* qids;        // query of every hit (nullptr: not wanted — qpos already says it)
+    uint32_t key_cap;      // capacity of keys / qids; a query whose segment does not fit sets lc[LC_KEY_OVERFLOW]
     uint4* tasks;          // (cursor, first row of the task, first slot, -)
     uint32_t task_cap;
     uint32_t* big_segs;    // queries with more than kWarpSeg hits
@@ -168,13 +170,21 @@ struct BucketParams {
 // hits per query.  The counts and their scan are u32; *extra accumulates the rows beyond the first of every cursor
 // (64 bit, touched only by warps that see a cursor with several rows), so that n_cursors + *extra bounds the number of
 // hits and the host can refuse a call whose scan might have wrapped.
-__global__ void __launch_bounds__(256) hit_count_kernel(const uint4* cursors, uint32_t n_cursors, uint32_t* qcount, unsigned long long* extra) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ uint32_t bucket_cursor_count(uint32_t n_cursors, const unsigned long long* n_dev) {
+    if (n_dev == nullptr) return n_cursors;
+    const unsigned long long n = *n_dev;
+    return n < n_cursors ? static_cast<uint32_t>(n) : n_cursors;
+}
+
+__global__ void __launch_bounds__(256) hit_count_kernel(const uint4* cursors, uint32_t n_cursors, const unsigned long long* n_dev, uint32_t* qcount,
+                                                        unsigned long long* extra) {
+    const uint32_t n = bucket_cursor_count(n_cursors, n_dev);
+    const uint32_t stride = gridDim.x * blockDim.x;
     unsigned long long more = 0;
-    if (i < n_cursors) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint4 c = cursors[i];
         if (c.z != 0) atomicAdd(&qcount[c.x], c.z);
-        if (c.z > 1) more = c.z - 1;
+        if (c.z > 1) more += c.z - 1;
     }
     if (__any_sync(0xffffffffu, more != 0)) {
         for (int o = 16; o > 0; o >>= 1) more += __shfl_xor_sync(0xffffffffu, more, o);
@@ -184,28 +194,32 @@ __global__ void __launch_bounds__(256) hit_count_kernel(const uint4* cursors, ui
 
 template <int SIGMA>
 __global__ void __launch_bounds__(256) locate_scatter_kernel(const BucketParams P) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = bucket_cursor_count(P.n_cursors, P.n_cursors_dev);
+    const uint32_t stride = gridDim.x * blockDim.x;
     uint32_t steps = 0;
-    if (i < P.n_cursors) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint4 c = P.cursors[i];
-        if (c.z != 0) {
-            const uint32_t base = atomicAdd(&P.qpos[c.x], c.z);
-            const uint32_t e = c.w & 0xfu;
-            if (c.w & kCursorTextPos) {  // (always a single row)
-                P.keys[base] = (textpos_value(P.index, c.y) << 4) | e;
-                P.qids[base] = c.x;
-            } else if (c.z <= kInlineRows) {
-                for (uint32_t r = 0; r < c.z; ++r) {
-                    uint32_t st = 0;
-                    P.keys[base + r] = (locate_row<SIGMA>(P.index, c.y + r, st) << 4) | e;
-                    P.qids[base + r] = c.x;
-                    steps += st;
-                }
-            } else {
-                for (uint32_t off = 0; off < c.z; off += kTaskRows) {
-                    const uint32_t t = atomicAdd(&P.lc[LC_TASKS], 1u);
-                    if (t < P.task_cap) P.tasks[t] = make_uint4(i, off, base + off, 0);
-                }
+        if (c.z == 0) continue;
+        const uint32_t base = atomicAdd(&P.qpos[c.x], c.z);
+        if (base + c.z > P.key_cap || base + c.z < base) {  // the hit buffer is too small: the host grows it and starts over
+            P.lc[LC_KEY_OVERFLOW] = 1u;
+            continue;
+        }
+        const uint32_t e = c.w & 0xfu;
+        if (c.w & kCursorTextPos) {  // (always a single row)
+            P.keys[base] = (textpos_value(P.index, c.y) << 4) | e;
+            if (P.qids) P.qids[base] = c.x;
+        } else if (c.z <= kInlineRows) {
+            for (uint32_t r = 0; r < c.z; ++r) {
+                uint32_t st = 0;
+                P.keys[base + r] = (locate_row<SIGMA>(P.index, c.y + r, st) << 4) | e;
+                if (P.qids) P.qids[base + r] = c.x;
+                steps += st;
+            }
+        } else {
+            for (uint32_t off = 0; off < c.z; off += kTaskRows) {
+                const uint32_t t = atomicAdd(&P.lc[LC_TASKS], 1u);
+                if (t < P.task_cap) P.tasks[t] = make_uint4(i, off, base + off, 0);
             }
         }
     }
@@ -227,7 +241,7 @@ __global__ void __launch_bounds__(256) locate_tasks_kernel(const BucketParams P)
         for (uint32_t r = task.y + lane; r < end; r += 32u) {
             uint32_t st = 0;
             P.keys[task.z + (r - task.y)] = (locate_row<SIGMA>(P.index, c.y + r, st) << 4) | (c.w & 0xfu);
-            P.qids[task.z + (r - task.y)] = c.x;
+            if (P.qids) P.qids[task.z + (r - task.y)] = c.x;
             steps += st;
         }
     }
@@ -246,6 +260,7 @@ __global__ void __launch_bounds__(256) segment_sort_kernel(const BucketParams P)
     if (q < P.n_queries) {
         s_l = q ? P.qpos[q - 1] : 0u;
         n_l = P.qpos[q] - s_l;
+        if (P.qpos[q] > P.key_cap || P.qpos[q] < s_l) n_l = 0;  // (overflowed hit buffer: the host starts over)
     }
     uint32_t todo = __ballot_sync(0xffffffffu, n_l >= 2);
     uint64_t* buf = sbuf[warp];
@@ -316,6 +331,7 @@ __global__ void __launch_bounds__(256) segment_sort_big_kernel(const BucketParam
     for (uint32_t b = blockIdx.x; b < n_big; b += gridDim.x) {
         const uint32_t q = P.big_segs[b];
         const uint32_t s = q ? P.qpos[q - 1] : 0u, n = P.qpos[q] - s;
+        if (n > kBigSeg) continue;  // (cannot happen: segment_sort_kernel sends only segments that fit)
         uint32_t m = 64;  // power of two >= n
         while (m < n) m <<= 1;
         for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) sk[i] = i < n ? P.keys[s + i] : ~uint64_t{0};
@@ -358,34 +374,82 @@ __device__ __forceinline__ void hit_key(const uint64_t* keys, const uint32_t* qi
     }
 }
 
+// number of hits: given by the host, or read from device memory (n_dev: the last entry of the per-query scan) and
+// clamped to the capacity `n`
+__device__ __forceinline__ uint64_t hit_total(uint64_t n, const uint32_t* n_dev) {
+    if (n_dev == nullptr) return n;
+    const uint64_t t = *n_dev;
+    return t < n ? t : n;
+}
+
 // sorted hits -> the reference's result tuple (queryId, seqId, pos, errors), 4 x u64
-__global__ void expand_hits_kernel(const uint64_t* keys, const uint32_t* qids, uint64_t n, uint32_t bits, uint64_t first_query,
-                                   uint32_t fused_shift, uint64_t* out) {
-    uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (i >= n) return;
-    uint32_t qid;
-    uint64_t k;
-    hit_key(keys, qids, i, fused_shift, qid, k);
-    uint64_t v = k >> 4;
-    ulonglong4 h;
-    h.x = first_query + qid;
-    h.y = v >> bits;
-    h.z = v & ((uint64_t{1} << bits) - 1);
-    h.w = k & 15u;
-    reinterpret_cast<ulonglong4*>(out)[i] = h;
+__global__ void expand_hits_kernel(const uint64_t* keys, const uint32_t* qids, uint64_t n, const uint32_t* n_dev, uint32_t bits,
+                                   uint64_t first_query, uint32_t fused_shift, uint64_t* out) {
+    const uint64_t total = hit_total(n, n_dev), stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total; i += stride) {
+        uint32_t qid;
+        uint64_t k;
+        hit_key(keys, qids, i, fused_shift, qid, k);
+        uint64_t v = k >> 4;
+        ulonglong4 h;
+        h.x = first_query + qid;
+        h.y = v >> bits;
+        h.z = v & ((uint64_t{1} << bits) - 1);
+        h.w = k & 15u;
+        reinterpret_cast<ulonglong4*>(out)[i] = h;
+    }
 }
 
 // sorted hits -> compact hits (query_id, seq_id, pos, errors) as 4 x u32
-__global__ void compact_hits_kernel(const uint64_t* keys, const uint32_t* qids, uint64_t n, uint32_t bits, uint32_t first_query,
-                                    uint32_t fused_shift, uint4* out) {
-    uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (i >= n) return;
-    uint32_t qid;
-    uint64_t k;
-    hit_key(keys, qids, i, fused_shift, qid, k);
-    uint64_t v = k >> 4;
-    out[i] = make_uint4(first_query + qid, static_cast<uint32_t>(v >> bits), static_cast<uint32_t>(v & ((uint64_t{1} << bits) - 1)),
-                        static_cast<uint32_t>(k & 15u));
+__global__ void compact_hits_kernel(const uint64_t* keys, const uint32_t* qids, uint64_t n, const uint32_t* n_dev, uint32_t bits,
+                                    uint32_t first_query, uint32_t fused_shift, uint4* out) {
+    const uint64_t total = hit_total(n, n_dev), stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total; i += stride) {
+        uint32_t qid;
+        uint64_t k;
+        hit_key(keys, qids, i, fused_shift, qid, k);
+        uint64_t v = k >> 4;
+        out[i] = make_uint4(first_query + qid, static_cast<uint32_t>(v >> bits), static_cast<uint32_t>(v & ((uint64_t{1} << bits) - 1)),
+                            static_cast<uint32_t>(k & 15u));
+    }
+}
+
+// sorted hits -> records of rec_bytes bytes, little endian: ((seqId << bits | pos) << 4) | errors.  The query of a record
+// follows from the per-query ends (CSR), so a hit costs rec_bytes (5 for a human-sized genome) instead of 16 or 32 bytes
+// on the way to the host.  One thread per 4 records: whole words are stored.
+__global__ void pack_records_kernel(const uint64_t* keys, uint64_t n, const uint32_t* n_dev, uint32_t fused_shift, uint32_t rec_bytes,
+                                    uint8_t* out) {
+    const uint64_t total = hit_total(n, n_dev), stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    const uint64_t mask = fused_shift ? (uint64_t{1} << fused_shift) - 1 : ~uint64_t{0};
+    const uint64_t recmask = rec_bytes >= 8 ? ~uint64_t{0} : (uint64_t{1} << (8u * rec_bytes)) - 1;
+    for (uint64_t g = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; g * 4 < total; g += stride) {
+        // 4 records = 4 * rec_bytes bytes = rec_bytes aligned words
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (uint32_t r = 0; r < 4; ++r) {
+            const uint64_t i = g * 4 + r;
+            const uint64_t k = i < total ? (keys[i] & mask & recmask) : 0;
+            const uint32_t bit = r * rec_bytes * 8u;  // first bit of the record inside the group
+            const uint32_t wi = bit >> 5, sh = bit & 31u;
+            w[wi] |= static_cast<uint32_t>(k << sh);
+            const uint64_t rest = sh ? (k >> (32u - sh)) : (k >> 16 >> 16);
+            w[wi + 1] |= static_cast<uint32_t>(rest);
+            if (wi + 2 < 8) w[wi + 2] |= static_cast<uint32_t>(rest >> 16 >> 16);
+        }
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out) + g * rec_bytes;  // (out is 16-byte aligned, sized to whole groups)
+        for (uint32_t j = 0; j < rec_bytes; ++j) dst[j] = w[j];
+    }
+}
+
+// per-query ends of a hit list sorted by query (global radix-sort path): ends[q] = number of hits of queries <= q
+__global__ void csr_ends_kernel(const uint64_t* keys, const uint32_t* qids, uint64_t n, uint32_t fused_shift, uint32_t n_queries, uint32_t* ends) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i <= n; i += stride) {
+        // hit i-1 belongs to query a, hit i to query b: every query in [a, b) ends at i
+        uint32_t a = 0, b = n_queries;
+        if (i > 0) a = fused_shift ? static_cast<uint32_t>(keys[i - 1] >> fused_shift) : qids[i - 1];
+        if (i < n) b = fused_shift ? static_cast<uint32_t>(keys[i] >> fused_shift) : qids[i];
+        for (uint32_t q = a; q < b && q < n_queries; ++q) ends[q] = static_cast<uint32_t>(i);
+    }
 }
 
 // ---- densify: re-sample the suffix array at a denser rate ------------------------------------------

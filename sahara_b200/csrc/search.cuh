@@ -3,16 +3,23 @@
 // Replaces fmc::search_ng24::search<Edit>(index, queries, scheme, delegate) as called at
 // /root/reference/src/sahara/search.cpp:227-231 (semantics: SURVEY.md §9.4).
 //
-// Two persistent-thread kernels share one state machine:
+// Three kernels share one state machine:
 //
-//   fm_kernel    walks the search trees while a cursor still covers several suffix-array rows.  One thread owns
-//                one query at a time and explores each search depth first with an explicit stack.  One loop
-//                iteration = ONE probe of one BWT (the rows lb and lb+len; a single 32-byte request when they
-//                share a block) from which the child cursors of all symbols are derived; then every search
-//                state that lives on this cursor is expanded.
-//   text_kernel  takes over as soon as a cursor holds a single row ("seed"): its occurrence T[a, b) is unique,
-//                so whether a child cursor is empty is decided by one text symbol (T[a-1] or T[b]) instead of
-//                two rank probes (in-text verification).  The reported cursor is lb = ISA[a], len = 1.
+//   fm_roots_kernel   makes the root frame of every (query, search): the q-gram table entry of the leading error-free
+//                     steps, or the whole suffix array.
+//   fm_items_kernel   walks the search trees while a cursor still covers several suffix-array rows.  A lane owns one
+//                     query at a time and explores each search depth first with an explicit stack.  One loop
+//                     iteration = ONE probe of one BWT (the rows lb and lb+len; a single 32-byte request when they
+//                     share a block) from which the child cursors of all symbols are derived; then every search
+//                     state that lives on this cursor is expanded (fm_node).
+//   text_pool_kernel  takes over as soon as a cursor holds a single row ("seed"): its occurrence T[a, b) is unique,
+//                     so whether a child cursor is empty is decided by one text symbol (T[a-1] or T[b]) instead of
+//                     two rank probes (in-text verification).  The reported cursor is lb = ISA[a], len = 1.
+//   fm_ordered_kernel the same states in the ORDER of the reference recursion, for search_n (--max_hits).
+//
+// The rules that are reconstructions of upstream behaviour (which operation may follow which, what may be reported,
+// the order of the children) are NOT written into these bodies: they come from the policy table
+// include/sahara_policy.h (SearchParams::pol), which the CPU oracle consumes as well.
 //
 // States.  A frame is a cursor plus a search state (step, e, LInfo, RInfo) — LInfo/RInfo = last operation at the
 // left/right end of the match, as in the reference recursion.  The deletion (step, e+1, D) and the substitution
@@ -26,6 +33,7 @@
 // path keeps siblings only at the nodes it left through an error edge, which bounds the stack (capi.cu).
 #pragma once
 #include <cstdio>
+#include "../../include/sahara_policy.h"
 #include "layout.cuh"
 
 namespace sb200 {
@@ -45,7 +53,6 @@ __host__ __device__ inline uint32_t pack_meta(uint32_t step, uint32_t e, uint32_
 constexpr uint32_t META_PAIR = 1u << 18;
 constexpr uint32_t META_TLEN_SHIFT = 20;
 constexpr uint32_t kEmitChunk = 16;   // output slots a thread reserves per atomic
-constexpr uint32_t kQueryBatch = 2;   // queries a thread takes per atomic
 constexpr uint32_t kInvalidQid = 0xffffffffu;
 constexpr uint32_t kRunE = 5;         // error levels 0..4 in the run table
 constexpr uint32_t kCursorTextPosFlag = 0x10u;  // == kCursorTextPos of locate.cuh
@@ -82,14 +89,16 @@ enum : uint32_t {
     SF_MISMATCH = 2,  // l <= e + 1 <= u: an error may be added
     SF_M_ALIVE = 4,   // not the last step and the match child survives the next lower bound
     SF_SUB_ALIVE = 8, // not the last step and a child with e + 1 errors survives the next lower bound
-    SF_PAIR = 16,     // SF_SUB_ALIVE and the next step extends the same end: deletion + substitution share a frame
+    SF_PAIR = 16,     // SF_SUB_ALIVE, the next step extends the same end and the policy lets no insertion follow a D or an S:
+                      // deletion + substitution share a frame
     SF_RUN_M = 32,    // the match child (step + 1, e) starts a match-only run
     SF_RUN_D = 64,    // the deletion child (step, e + 1) starts a match-only run
     SF_RUN_S = 128    // the substitution child (step + 1, e + 1) starts a match-only run
 };
 __host__ __device__ inline uint32_t state_flags_offset(uint32_t n_steps) { return (n_steps * kRunE + 3u) & ~3u; }
 __host__ __device__ inline uint32_t run_table_bytes(uint32_t n_steps) { return 2u * state_flags_offset(n_steps); }
-inline void build_state_flags(uint32_t n_searches, uint32_t len, const uint32_t* steps, uint8_t* runs) {
+inline void build_state_flags(uint32_t n_searches, uint32_t len, const uint32_t* steps, uint8_t* runs, const sb200_policy& pol) {
+    const bool pairs = sb200_pol_pairs(&pol) != 0;  // (a PAIR frame expands no insertion child of either half)
     uint8_t* flags = runs + state_flags_offset(n_searches * len);
     for (uint32_t j = 0; j < n_searches; ++j)
         for (uint32_t i = 0; i < len; ++i)
@@ -105,7 +114,7 @@ inline void build_state_flags(uint32_t n_searches, uint32_t len, const uint32_t*
                 if (l <= e + 1 && e + 1 <= u) f |= SF_MISMATCH;
                 if (!last && lnext <= e + 1) f |= SF_M_ALIVE;
                 if (!last && lnext <= e + 2) f |= SF_SUB_ALIVE;
-                if (!last && lnext <= e + 2 && ((sn >> 24) & 1u) == right) f |= SF_PAIR;
+                if (pairs && !last && lnext <= e + 2 && ((sn >> 24) & 1u) == right) f |= SF_PAIR;
                 if (run(i + 1, e)) f |= SF_RUN_M;
                 if (run(i, e + 1)) f |= SF_RUN_D;
                 if (run(i + 1, e + 1)) f |= SF_RUN_S;
@@ -115,18 +124,18 @@ inline void build_state_flags(uint32_t n_searches, uint32_t len, const uint32_t*
 
 // counters (unsigned long long each)
 enum : int {
-    CT_NEXT_QUERY = 0,   // work distribution of fm_kernel
+    CT_NEXT_QUERY = 0,   // work distribution of fm_ordered_kernel
     CT_OUT_SLOTS = 1,    // cursor output slots reserved
     CT_NODES = 2,        // states expanded
     CT_OVERFLOW = 3,     // stack overflow flag
     CT_LF_STEPS = 4,     // (locate kernel)
     CT_MAX_SP = 5,       // deepest stack seen
     CT_CURSORS = 6,      // cursors reported
-    CT_SEED_SLOTS = 7,   // seed slots reserved by fm_kernel
-    CT_NEXT_SEED = 8,    // work distribution of text_kernel
+    CT_SEED_SLOTS = 7,   // seed slots reserved by fm_items_kernel
+    CT_NEXT_SEED = 8,    // work distribution of text_pool_kernel
     CT_SEEDS = 9,        // seeds produced
     CT_BAD_QUERY = 10,   // 1 + offset of a query symbol outside the alphabet (0 = none)
-    CT_NODES_TEXT = 11,  // states expanded by text_kernel (subset of CT_NODES)
+    CT_NODES_TEXT = 11,  // states expanded by text_pool_kernel (subset of CT_NODES)
     CT_NEXT_ITEM = 12,   // work distribution of fm_items_kernel
     CT_TOTAL_ROWS = 13,  // (locate) rows beyond the first of every cursor (overflow guard of the u32 hit scan)
     CT_COUNT = 16
@@ -145,12 +154,13 @@ struct SearchParams {
     unsigned long long* counters;
     const uint4* qgram;      // optional q-gram jump table [4^q] (lb, lbRev, len, 0)
     uint32_t qgram_q;
-    uint32_t debug_flags;    // 1: no pair frames, 2: no insertion chains in fm_kernel (diagnostics only)
+    uint32_t debug_flags;    // 1: no pair frames, 2: no insertion chains in fm_node (diagnostics only)
+    sb200_policy pol;        // the reconstructed rules of the recursion (include/sahara_policy.h)
     // in-text verification (nullptr = off): suffix array, its inverse, the text packed 8 symbols per word
     const uint32_t* sa32;
     const uint32_t* isa32;
     const uint32_t* text4;
-    uint4* seeds;            // (qid, lb, search, meta) handed from fm_kernel to text_kernel
+    uint4* seeds;            // (qid, lb, search, meta) handed from fm_items_kernel to text_pool_kernel
     uint32_t seed_cap;
     // work items of fm_items_kernel, n_searches slots per query: root frame (lb, lbRev, len, meta) and
     // (qid, search | toText << 8 | live slots of the query << 16)
@@ -254,6 +264,55 @@ __global__ void pack_reads_kernel(const uint8_t* reads, uint64_t n_queries, uint
     }
     out[i] = pack8(b.x, b.y, n, sigma, qi * len + w * 8, counters);
 }
+
+// the same from reads the host packed already (SB200_READS_PACKED4: 4 bits per base, 8 bases per little-endian word,
+// packed_words(len) words per read — the layout of `out`): half the PCIe bytes of the rank bytes.  Query qi is read qi,
+// or with with_reverse read qi / 2 and, for odd qi, its reverse complement.  Nibbles behind the read are forced to 0xF.
+__global__ void pack_packed4_kernel(const uint32_t* reads, uint64_t n_queries, uint32_t len, uint32_t sigma, uint32_t with_reverse,
+                                    uint32_t* out, unsigned long long* counters) {
+    const uint32_t W = packed_words(len);
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n_queries * W) return;
+    const uint64_t qi = i / W;
+    const uint32_t w = static_cast<uint32_t>(i % W);
+    const bool rc = with_reverse && (qi & 1u);
+    const uint32_t* src = reads + (with_reverse ? (qi >> 1) : qi) * W;
+    const uint32_t n = len - w * 8 < 8u ? len - w * 8 : 8u;
+    uint32_t v;
+    if (!rc) {
+        v = src[w];
+    } else {
+        // symbols w*8 .. w*8+n-1 of the reverse strand = symbols p_hi .. p_hi-n+1 of the read, complemented
+        const uint32_t p_hi = len - 1 - w * 8, p_lo = p_hi + 1 - n;
+        const uint32_t w0 = p_lo >> 3;
+        const uint32_t lo = src[w0], hi = w0 + 1 < W ? src[w0 + 1] : 0u;
+        uint32_t x = __funnelshift_r(lo, hi, (p_lo & 7u) * 4u);  // nibble j = symbol p_lo + j
+        // reverse the 8 nibbles, then move the n valid ones (now at the top) down
+        x = ((x & 0x0f0f0f0fu) << 4) | ((x >> 4) & 0x0f0f0f0fu);
+        x = __byte_perm(x, 0, 0x0123);
+        x >>= 4u * (8u - n);
+        // complement of ranks 1..4 (nibble-wise through the two byte lanes)
+        uint32_t ev = x & 0x0f0f0f0fu, od = (x >> 4) & 0x0f0f0f0fu;
+        const uint32_t me = __vcmpgeu4(ev, 0x01010101u) & __vcmpleu4(ev, 0x04040404u);
+        const uint32_t mo = __vcmpgeu4(od, 0x01010101u) & __vcmpleu4(od, 0x04040404u);
+        ev = (ev & ~me) | (__vsub4(0x05050505u, ev) & me);
+        od = (od & ~mo) | (__vsub4(0x05050505u, od) & mo);
+        v = ev | (od << 4);
+    }
+    // verify_rank (/root/reference/src/sahara/search.cpp:118-120): the offset of the last symbol >= sigma
+    const uint32_t ev = v & 0x0f0f0f0fu, od = (v >> 4) & 0x0f0f0f0fu;
+    const uint32_t lim = sigma * 0x01010101u;
+    uint32_t bad = 0;  // bit j: symbol j is outside the alphabet
+    const uint32_t be = __vcmpgeu4(ev, lim), bo = __vcmpgeu4(od, lim);
+    for (uint32_t j = 0; j < 4; ++j) {
+        bad |= ((be >> (8 * j)) & 1u) << (2 * j);
+        bad |= ((bo >> (8 * j)) & 1u) << (2 * j + 1);
+    }
+    if (n < 8) bad &= (1u << n) - 1u;
+    if (bad) atomicMax(&counters[CT_BAD_QUERY], static_cast<unsigned long long>(qi * len + w * 8 + (31u - static_cast<uint32_t>(__clz(static_cast<int>(bad)))) + 1));
+    if (n < 8) v |= ~((1u << (4 * n)) - 1u);
+    out[i] = v;
+}
 #endif
 
 // chunked append to a global array: one atomic per kEmitChunk entries
@@ -273,18 +332,6 @@ struct ChunkWriter {
             if (pos < cap) buf[pos] = make_uint4(kInvalidQid, 0, 0, 0);
     }
 };
-
-// copies the packed query into this thread's staging words; returns true when it contains the delimiter
-__device__ __forceinline__ bool stage_query(const SearchParams& P, uint32_t qid, uint32_t W, uint32_t* s_query, uint32_t qstride) {
-    const uint32_t* src = P.packed + static_cast<uint64_t>(qid) * W;
-    bool delim = false;
-    for (uint32_t w = 0; w < W; ++w) {
-        uint32_t v = src[w];
-        s_query[w * qstride] = v;
-        delim = delim || (((v - 0x11111111u) & ~v & 0x88888888u) != 0);  // some nibble is 0
-    }
-    return delim;
-}
 
 // ================================================================================================
 // Shared pieces of the FM-index walk.
@@ -419,7 +466,11 @@ __device__ __forceinline__ void fm_node(const SearchParams& P, const uint32_t* t
         const bool mmOK = l <= e + 1 && e + 1 <= u;
         const uint32_t T = right ? Rinfo : Linfo;
         const uint32_t O = right ? Linfo : Rinfo;          // info of the other end
-        const bool otherEndOK = !EDIT || (O & 1u) == 0;    // M or I
+        // end filter of the policy: may a cursor be reported whose moving end carries M / I / S (the other end: O)?
+        const bool otherEndOK = !EDIT || sb200_pol_end1(&P.pol, O);
+        const bool endM = otherEndOK && (!EDIT || sb200_pol_end1(&P.pol, INFO_M));
+        const bool endI = otherEndOK && (!EDIT || sb200_pol_end1(&P.pol, INFO_I));
+        const bool endS = otherEndOK && (!EDIT || sb200_pol_end1(&P.pol, INFO_S));
         // metas of the possible children: the moving side gets the new info
         const uint32_t keepL = right ? Linfo : 0u, keepR = right ? 0u : Rinfo;
         const uint32_t sideShift = right ? 16u : 14u;
@@ -436,22 +487,22 @@ __device__ __forceinline__ void fm_node(const SearchParams& P, const uint32_t* t
                 if (static_cast<uint32_t>(s) == c) { mc = cnt[s]; nlb = klb[s]; nlbRev = klbRev[s]; }
             const bool alive = matchOK && mc != 0;
             if (alive && last) {
-                if (otherEndOK) emit(nlb, mc, e);
+                if (endM) emit(nlb, mc, e);
             } else if (alive && lnext <= e + 1) {
                 push(nlb, nlbRev, mc, mM);
             }
         }
         if (mmOK) {
-            const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
+            const bool delOK = EDIT && sb200_pol_del(&P.pol, T);
             const bool subAlive = !last && lnext <= e + 2;
-            const bool asPair = delOK && subAlive && sameDirNext && !(P.debug_flags & 1u);
+            const bool asPair = delOK && subAlive && sameDirNext && sb200_pol_pairs(&P.pol) && !(P.debug_flags & 1u);
 #pragma unroll
             for (int s = 1; s < SIGMA; ++s) {
                 const bool live = static_cast<uint32_t>(s) != c && cnt[s] != 0;
                 const uint32_t nlb = klb[s], nlbRev = klbRev[s];
                 if (live && (asPair || delOK)) push(nlb, nlbRev, cnt[s], asPair ? (mD | META_PAIR) : mD);
                 if (live && !asPair && subAlive) push(nlb, nlbRev, cnt[s], mS);
-                if (!EDIT && live && last) emit(nlb, cnt[s], e + 1);
+                if (live && last && endS) emit(nlb, cnt[s], e + 1);  // (edit distance: only when the policy reports an S at an end)
             }
         }
         // next state on the same cursor
@@ -463,10 +514,10 @@ __device__ __forceinline__ void fm_node(const SearchParams& P, const uint32_t* t
             if (right) Rinfo = INFO_S; else Linfo = INFO_S;
             continue;
         }
-        const bool insOK = EDIT && mmOK && (T == INFO_M || T == INFO_I);
+        const bool insOK = EDIT && mmOK && sb200_pol_ins(&P.pol, T);
         if (!insOK) break;
         if (last) {
-            if (otherEndOK) emit(lb, len, e + 1);
+            if (endI) emit(lb, len, e + 1);
             break;
         }
         if (lnext > e + 2) break;  // dead at the next step
@@ -478,78 +529,6 @@ __device__ __forceinline__ void fm_node(const SearchParams& P, const uint32_t* t
         e += 1;
         if (right) Rinfo = INFO_I; else Linfo = INFO_I;
     }
-}
-
-// ================================================================================================
-// fm_kernel body (one thread owns one query at a time).  s_steps: scheme table (shared memory); s_query: this
-// thread's staged query, word w at s_query[w * qstride].
-// ================================================================================================
-template <int SIGMA, bool EDIT, int STACK>
-__device__ __forceinline__ void fm_thread(const SearchParams& P, const uint32_t* s_steps, uint32_t* s_query, uint32_t qstride) {
-    uint4 stack[STACK];
-    int sp = 0;
-    const uint32_t* tbl = nullptr;
-    uint32_t qid = 0, qid_end = 0, next_search = P.n_searches;  // forces the first fetch
-    uint32_t nodes = 0, emitted = 0, seeded = 0;
-    ChunkWriter outW, seedW;
-    bool overflow = false;
-    bool toText = false;  // unique cursors of the current query are handed to text_kernel
-    int maxsp = 0;
-    const uint32_t qlen = P.len;
-    const uint32_t W = packed_words(qlen);
-
-    auto qsym = [&](uint32_t pos) -> uint32_t { return (s_query[(pos >> 3) * qstride] >> ((pos & 7u) * 4u)) & 0xfu; };
-    auto emit = [&](uint32_t lb, uint32_t len, uint32_t e) {
-        outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], make_uint4(qid, lb, len, e));
-        ++emitted;
-    };
-    // a child frame: unique cursors go to the text kernel, the others on the stack
-    auto push = [&](uint32_t nlb, uint32_t nlbRev, uint32_t nlen, uint32_t m) {
-        if (toText && nlen == 1) {
-            seedW.put(P.seeds, P.seed_cap, &P.counters[CT_SEED_SLOTS], make_uint4(qid, nlb, next_search - 1, m));
-            ++seeded;
-        } else {
-            if (sp < STACK) stack[sp] = make_uint4(nlb, nlbRev, nlen, m);
-            else overflow = true;
-            ++sp;
-        }
-    };
-
-    bool done = false;
-    while (true) {
-        // ---- make sure there is a frame: next search of the current query, next query, next batch ----
-        while (sp == 0) {
-            if (next_search == P.n_searches) {
-                next_search = 0;
-                ++qid;
-                if (qid >= qid_end) {
-                    unsigned long long w = atomicAdd(&P.counters[CT_NEXT_QUERY], static_cast<unsigned long long>(kQueryBatch));
-                    if (w >= P.n_queries) { done = true; break; }
-                    qid = static_cast<uint32_t>(w);
-                    qid_end = qid + kQueryBatch < P.n_queries ? qid + kQueryBatch : P.n_queries;
-                }
-                bool delim = stage_query(P, qid, W, s_query, qstride);
-                toText = P.sa32 != nullptr && !delim;  // a query with the delimiter stays on the FM path
-            }
-            tbl = s_steps + next_search * qlen;
-            ++next_search;
-            uint4 root;
-            const int rc = fm_root(P, tbl, qsym, root);
-            if (rc == 2) emit(root.x, root.z, 0);
-            if (rc == 1) push(root.x, root.y, root.z, root.w);
-        }
-        if (done) break;
-        maxsp = sp > maxsp ? sp : maxsp;
-        const uint4 f = stack[--sp];
-        fm_node<SIGMA, EDIT>(P, tbl, f, nodes, qsym, push, emit);
-    }
-    outW.finish(P.out, P.out_cap);
-    seedW.finish(P.seeds, P.seed_cap);
-    if (nodes) atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(nodes));
-    if (overflow) atomicExch(&P.counters[CT_OVERFLOW], 1ull);
-    atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxsp));
-    if (emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(emitted));
-    if (seeded) atomicAdd(&P.counters[CT_SEEDS], static_cast<unsigned long long>(seeded));
 }
 
 // ================================================================================================
@@ -929,7 +908,7 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
             if (dead) continue;
         }
         if (step == qlen) {  // the end of the query: report (edit distance: not behind a substitution or deletion at either end)
-            if (!EDIT || (((Linfo | Rinfo) & 1u) == 0)) {
+            if (!EDIT || sb200_pol_end(&P.pol, Linfo, Rinfo)) {
                 const uint32_t n = len < max_hits - taken ? len : max_hits - taken;
                 taken += n;
                 uint4 cu = make_uint4(qid, lb, n, e);
@@ -955,8 +934,22 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
         const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift) | tlenNext;
         const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift) | tlenNext;
         const uint32_t mI = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_I << sideShift) | tlenSame;
-        const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
-        const bool insOK = EDIT && (T == INFO_M || T == INFO_I);
+        const bool delOK = EDIT && sb200_pol_del(&P.pol, T);
+        const bool insOK = EDIT && sb200_pol_ins(&P.pol, T);
+        // order of the children (policy; children are pushed in REVERSE visiting order): the match child first, then by
+        // default per symbol the deletion before the substitution, the insertion last
+        const bool subFirst = (P.pol.child_order & SB200_CHILD_SUB_BEFORE_DEL) != 0;
+        const bool insEarly = (P.pol.child_order & SB200_CHILD_INS_BEFORE_SYMBOLS) != 0;
+        // the deletion / substitution children of one symbol (the same cursor)
+        auto push_symbol = [&](uint32_t nlb, uint32_t nlbRev, uint32_t nlen, uint32_t flag) {
+            if (subFirst) {
+                if (delOK) push(nlb, nlbRev, nlen, mD | flag);
+                push(nlb, nlbRev, nlen, mS | flag);
+            } else {
+                push(nlb, nlbRev, nlen, mS | flag);
+                if (delOK) push(nlb, nlbRev, nlen, mD | flag);
+            }
+        };
         if (inText) {
             // the occurrence is T[a, a + tlen): the only non-empty child is the one of the text symbol next to it
             const uint32_t a = lb;
@@ -965,11 +958,9 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
             else if (a != 0) t = (ldg32(P.text4 + ((a - 1) >> 3)) >> (((a - 1) & 7u) * 4u)) & 0xfu;
             const uint32_t na = right ? a : a - 1;
             if (mmOK) {
-                if (insOK) push(a, 0, 1, mI);  // popped last
-                if (t != c && t != 0) {
-                    push(na, 0, 1, mS);
-                    if (delOK) push(na, 0, 1, mD);  // the deletion is tried before the substitution
-                }
+                if (insOK && !insEarly) push(a, 0, 1, mI);
+                if (t != c && t != 0) push_symbol(na, 0, 1, 0u);
+                if (insOK && insEarly) push(a, 0, 1, mI);
             }
             if (matchOK && t == c) push(na, 0, 1, mM);  // popped first
             continue;
@@ -977,19 +968,14 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
         uint32_t klb[SIGMA], klbRev[SIGMA], cnt[SIGMA];
         probe_children<SIGMA>(P, right, lb, lbRev, len, klb, klbRev, cnt);
         if (mmOK) {
-            if (insOK) push(lb, lbRev, len, mI);  // popped last
+            if (insOK && !insEarly) push(lb, lbRev, len, mI);
 #pragma unroll
             for (int s = SIGMA - 1; s >= 1; --s) {
                 if (static_cast<uint32_t>(s) == c || cnt[s] == 0) continue;
-                if (toText && cnt[s] == 1) {  // (one load of the text position for both frames)
-                    const uint32_t a = ldg32(P.sa32 + klb[s]);
-                    push(a, 0, 1, mS | META_OTEXT);
-                    if (delOK) push(a, 0, 1, mD | META_OTEXT);
-                } else {
-                    push(klb[s], klbRev[s], cnt[s], mS);
-                    if (delOK) push(klb[s], klbRev[s], cnt[s], mD);  // the deletion is tried before the substitution
-                }
+                if (toText && cnt[s] == 1) push_symbol(ldg32(P.sa32 + klb[s]), 0, 1, META_OTEXT);  // (one load of the text position for both frames)
+                else push_symbol(klb[s], klbRev[s], cnt[s], 0u);
             }
+            if (insOK && insEarly) push(lb, lbRev, len, mI);
         }
         if (matchOK) {  // popped first
             uint32_t mc = 0, nlb = 0, nlbRev = 0;
@@ -1001,208 +987,6 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
     }
     outW.finish(P.out, P.out_cap);
     if (nodes) atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(nodes));
-    if (overflow) atomicExch(&P.counters[CT_OVERFLOW], 1ull);
-    atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxsp));
-    if (emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(emitted));
-}
-
-constexpr uint32_t kSeedClaim = 1;  // seeds a thread takes per atomic (larger claims lose more to the tail than they save)
-
-// ================================================================================================
-// text_kernel body: in-text verification of the seeds.  A frame is (a, meta) with the same meta layout; the
-// occurrence is T[a, a + tlen).
-// ================================================================================================
-template <bool EDIT, int STACK>
-__device__ __forceinline__ void text_thread(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, uint32_t* s_query,
-                                            uint32_t qstride) {
-    uint2 stack[STACK];
-    int sp = 0;
-    const uint32_t* tbl = nullptr;
-    const uint8_t* runs = nullptr;
-    uint32_t qid = kInvalidQid;
-    uint32_t nodes = 0, emitted = 0;
-    ChunkWriter outW;
-    bool overflow = false;
-    int maxsp = 0;
-    const uint32_t qlen = P.len;
-    const uint32_t W = packed_words(qlen);
-    const unsigned long long slots = P.counters[CT_SEED_SLOTS];
-    const uint32_t n_slots = static_cast<uint32_t>(slots < P.seed_cap ? slots : P.seed_cap);
-
-    auto qsym = [&](uint32_t pos) -> uint32_t { return (s_query[(pos >> 3) * qstride] >> ((pos & 7u) * 4u)) & 0xfu; };
-    // the 8 query symbols that start at position pos; positions behind the query read as 0xF
-    auto query8 = [&](uint32_t pos) -> uint32_t {
-        const uint32_t w = pos >> 3;
-        const uint32_t lo = s_query[w * qstride];
-        const uint32_t hi = w + 1 < W ? s_query[(w + 1) * qstride] : 0xffffffffu;
-        return funnel_r(lo, hi, (pos & 7u) * 4u);
-    };
-    auto emit = [&](uint32_t a, uint32_t e) {
-        outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], P.textpos_out ? make_uint4(qid, a, 1, e | kCursorTextPosFlag) : make_uint4(qid, P.isa32[a], 1, e));
-        ++emitted;
-    };
-    auto push = [&](uint32_t a, uint32_t m) {
-        if (sp < STACK) stack[sp] = make_uint2(a, m);
-        else overflow = true;
-        ++sp;
-    };
-
-    uint32_t seed_i = 0, seed_end = 0;  // claimed range of seeds (consecutive seeds mostly share their query)
-    while (true) {
-        if (sp == 0) {
-            if (seed_i == seed_end) {
-                seed_i = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_SEED], static_cast<unsigned long long>(kSeedClaim)));
-                if (seed_i >= n_slots) break;
-                seed_end = seed_i + kSeedClaim < n_slots ? seed_i + kSeedClaim : n_slots;
-            }
-            uint4 seed = P.seeds[seed_i++];
-            if (seed.x == kInvalidQid) continue;
-            if (seed.x != qid) {
-                qid = seed.x;
-                stage_query(P, qid, W, s_query, qstride);
-            }
-            tbl = s_steps + seed.z * qlen;
-            runs = s_runs + seed.z * qlen * kRunE;
-            push(P.sa32[seed.y], seed.w);  // a = SA[lb]; the meta already carries tlen = b - a
-        }
-        maxsp = sp > maxsp ? sp : maxsp;
-        const uint2 f = stack[--sp];
-        uint32_t a = f.x;
-        const uint32_t meta = f.y;
-        uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
-        uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
-        const bool pair = (meta & META_PAIR) != 0;
-        uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
-
-        // ---- match-only run: compare query and text symbol by symbol, no stack traffic ---------------
-        bool dead = false;
-        if (!pair) {
-            uint32_t R = runs[step * kRunE + e];
-            while (R != 0) {
-                const uint32_t st = tbl[step];
-                const bool right = (st >> 24) & 1u;
-                const uint32_t p0 = st & 0xffffu;
-                // compare up to 8 symbols per round on the packed words (4 bits per symbol)
-                uint32_t r = 0;
-                if (right) {
-                    while (r < R) {
-                        const uint32_t n = R - r < 8u ? R - r : 8u;
-                        const uint32_t x = (text8(P.text4, a + tlen + r) ^ query8(p0 + r)) & nib_mask(n);
-                        if (x != 0) { r += (ctz32(x) >> 2); break; }
-                        r += n;
-                    }
-                } else {
-                    while (r < R) {
-                        if (a < r + 1) break;  // the delimiter before position 0
-                        const uint32_t endT = a - 1 - r, endQ = p0 - r;  // compare the symbols ending here, downwards
-                        uint32_t n = R - r < 8u ? R - r : 8u;
-                        if (n > endT + 1) n = endT + 1;
-                        const uint32_t x = (text8(P.text4, endT + 1 - n) ^ query8(endQ + 1 - n)) & nib_mask(n);
-                        if (x != 0) { r += n - 1 - ((31u - clz32(x)) >> 2); break; }
-                        r += n;
-                    }
-                }
-                if (r < R) {  // a symbol differs: the state at step + r has no child
-                    nodes += r + 1;
-                    dead = true;
-                    break;
-                }
-                nodes += R;
-                step += R;
-                tlen += R;
-                if (right) Rinfo = INFO_M;
-                else { Linfo = INFO_M; a -= R; }
-                if (step == qlen) {  // the last step matched
-                    const uint32_t O = right ? Linfo : Rinfo;
-                    if (!EDIT || (O & 1u) == 0) emit(a, e);
-                    dead = true;
-                    break;
-                }
-                if (((tbl[step] >> 16) & 0xfu) > e + 1) { dead = true; break; }  // dead at the next step
-                R = runs[step * kRunE + e];
-            }
-        }
-        if (dead) continue;
-        const uint32_t b = a + tlen;
-        const bool rightFrame = (tbl[step] >> 24) & 1u;  // the end the frame's own error (D / S) sits on
-        // the text symbols left and right of the occurrence (the delimiter before position 0)
-        uint32_t tL = 0;
-        if (a != 0) tL = (P.text4[(a - 1) >> 3] >> (((a - 1) & 7u) * 4u)) & 0xfu;
-        const uint32_t tR = (P.text4[b >> 3] >> ((b & 7u) * 4u)) & 0xfu;
-
-        bool second = false;
-        while (true) {
-            ++nodes;
-#if defined(SB200_TRACE)
-            if (P.debug_flags & 4u)
-                printf("TSTATE q=%u a=%u tlen=%u step=%u e=%u L=%u R=%u pair=%d second=%d\n", qid, a, tlen, step, e, Linfo, Rinfo, (int)pair,
-                       (int)second);
-#endif
-            const uint32_t st = tbl[step];
-            const uint32_t l = (st >> 16) & 0xfu, u = (st >> 20) & 0xfu;
-            const bool right = (st >> 24) & 1u;
-            const uint32_t c = qsym(st & 0xffffu);
-            const bool last = step + 1 == qlen;
-            const uint32_t stn = last ? 0u : tbl[step + 1];
-            const uint32_t lnext = (stn >> 16) & 0xfu;
-            const bool sameDirNext = !last && ((((stn >> 24) & 1u) != 0) == right);
-            const bool matchOK = l <= e && e <= u;
-            const bool mmOK = l <= e + 1 && e + 1 <= u;
-            const uint32_t T = right ? Rinfo : Linfo;
-            const uint32_t O = right ? Linfo : Rinfo;
-            const bool otherEndOK = !EDIT || (O & 1u) == 0;
-            const uint32_t t = right ? tR : tL;    // the only symbol whose child cursor is not empty
-            const uint32_t na = right ? a : a - 1;  // child occurrence T[na, na + tlen + 1)
-            const uint32_t keepL = right ? Linfo : 0u, keepR = right ? 0u : Rinfo;
-            const uint32_t sideShift = right ? 16u : 14u;
-            const uint32_t metaBase = (keepL << 14) | (keepR << 16) | ((tlen + 1) << META_TLEN_SHIFT);
-            if (t != 0) {
-                if (t == c) {
-                    if (matchOK) {
-                        if (last) {
-                            if (otherEndOK) emit(na, e);
-                        } else if (lnext <= e + 1) {
-                            push(na, metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift));
-                        }
-                    }
-                } else if (mmOK) {
-                    const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
-                    const bool subAlive = !last && lnext <= e + 2;
-                    const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift);
-                    const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift);
-                    // a pair only when both halves extend the same end: then the substitution half has T = S and
-                    // no insertion chain of its own (as in fm_kernel)
-                    if (delOK && subAlive && sameDirNext) push(na, mD | META_PAIR);
-                    else {
-                        if (delOK) push(na, mD);
-                        if (subAlive) push(na, mS);
-                    }
-                    if (!EDIT && last) emit(na, e + 1);
-                }
-            }
-            // next state on the same cursor
-            if (pair) {
-                if (second) break;
-                second = true;
-                step += 1;  // the substitution half: (step + 1, e), S at the end both halves extend
-                if (rightFrame) Rinfo = INFO_S; else Linfo = INFO_S;
-                continue;
-            }
-            const bool insOK = EDIT && mmOK && (T == INFO_M || T == INFO_I);
-            if (!insOK) break;
-            if (last) {
-                if (otherEndOK) emit(a, e + 1);
-                break;
-            }
-            if (lnext > e + 2) break;
-            step += 1;
-            e += 1;
-            if (right) Rinfo = INFO_I; else Linfo = INFO_I;
-        }
-    }
-    outW.finish(P.out, P.out_cap);
-    if (nodes) atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(nodes));
-    if (nodes) atomicAdd(&P.counters[CT_NODES_TEXT], static_cast<unsigned long long>(nodes));
     if (overflow) atomicExch(&P.counters[CT_OVERFLOW], 1ull);
     atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxsp));
     if (emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(emitted));
@@ -1381,7 +1165,7 @@ __device__ __forceinline__ void pool_emit(const SearchParams& P, PoolLane& ls, u
     ++ls.emitted;
 }
 
-// RUN frame: the match-only run(s) that start at its step, exactly like the run loop of text_thread; returns the
+// RUN frame: the match-only run(s) that start at its step, comparing packed words of query and text; returns the
 // number of frames pushed (0 or 1)
 template <bool EDIT>
 __device__ __forceinline__ uint32_t text_run(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, const TextPool& pool,
@@ -1438,8 +1222,7 @@ __device__ __forceinline__ uint32_t text_run(const SearchParams& P, const uint32
             return 1;
         }
         if (step == qlen) {  // the last step matched
-            const uint32_t O = right ? Linfo : Rinfo;
-            if (!EDIT || (O & 1u) == 0) pool_emit(P, ls, cx.qid, a, e);
+            if (!EDIT || sb200_pol_end(&P.pol, Linfo, Rinfo)) pool_emit(P, ls, cx.qid, a, e);  // (the end that moved carries M)
             ls.nodes += nodes;
             return 0;
         }
@@ -1451,7 +1234,7 @@ __device__ __forceinline__ uint32_t text_run(const SearchParams& P, const uint32
     return 1;
 }
 
-// STATE frame: the states on its cursor (pair halves, insertion chain), exactly like text_thread (the conditions
+// STATE frame: the states on its cursor (pair halves, insertion chain), expanded like fm_node does (the conditions
 // that depend on the scheme tables only come from the state flags); returns the number of frames pushed
 template <bool EDIT>
 __device__ __forceinline__ uint32_t text_states(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, const TextPool& pool,
@@ -1491,7 +1274,7 @@ __device__ __forceinline__ uint32_t text_states(const SearchParams& P, const uin
         const bool mmOK = (fl & SF_MISMATCH) != 0;
         const uint32_t T = right ? Rinfo : Linfo;
         const uint32_t O = right ? Linfo : Rinfo;
-        const bool otherEndOK = !EDIT || (O & 1u) == 0;
+        const bool otherEndOK = !EDIT || sb200_pol_end1(&P.pol, O);  // end filter of the policy, other end
         const uint32_t t = right ? tR : tL;    // the only symbol whose child cursor is not empty
         const uint32_t na = right ? a : a - 1;  // child occurrence T[na, na + tlen + 1)
         const uint32_t sideShift = right ? 16u : 14u;
@@ -1500,22 +1283,24 @@ __device__ __forceinline__ uint32_t text_states(const SearchParams& P, const uin
             if (t == c) {
                 if (fl & SF_MATCH) {
                     if (last) {
-                        if (otherEndOK) pool_emit(P, ls, cx.qid, na, e);
+                        if (otherEndOK && (!EDIT || sb200_pol_end1(&P.pol, INFO_M))) pool_emit(P, ls, cx.qid, na, e);
                     } else if (fl & SF_M_ALIVE) {
                         push(na, metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift), (fl & SF_RUN_M) != 0);
                     }
                 }
             } else if (mmOK) {
-                const bool delOK = EDIT && (T == INFO_M || T == INFO_D);
+                const bool delOK = EDIT && sb200_pol_del(&P.pol, T);
                 const uint32_t mD = metaBase | step | ((e + 1) << 10) | (INFO_D << sideShift);
                 const uint32_t mS = metaBase | (step + 1) | ((e + 1) << 10) | (INFO_S << sideShift);
-                // a pair only when both halves extend the same end (as in fm_kernel)
+                // a pair only when both halves extend the same end (as in fm_node) and the policy allows pairs (SF_PAIR)
                 if (delOK && (fl & SF_PAIR)) push(na, mD | META_PAIR, false);
                 else {
                     if (delOK) push(na, mD, (fl & SF_RUN_D) != 0);
                     if (fl & SF_SUB_ALIVE) push(na, mS, (fl & SF_RUN_S) != 0);
                 }
-                if (!EDIT && last) pool_emit(P, ls, cx.qid, na, e + 1);
+                // a substitution at the last step is reported under Hamming distance; under edit distance only when the
+                // policy reports an S at an end
+                if (last && (!EDIT || (otherEndOK && sb200_pol_end1(&P.pol, INFO_S)))) pool_emit(P, ls, cx.qid, na, e + 1);
             }
         }
         // next state on the same cursor
@@ -1526,10 +1311,10 @@ __device__ __forceinline__ uint32_t text_states(const SearchParams& P, const uin
             if (rightFrame) Rinfo = INFO_S; else Linfo = INFO_S;
             continue;
         }
-        const bool insOK = EDIT && mmOK && (T == INFO_M || T == INFO_I);
+        const bool insOK = EDIT && mmOK && sb200_pol_ins(&P.pol, T);
         if (!insOK) break;
         if (last) {
-            if (otherEndOK) pool_emit(P, ls, cx.qid, a, e + 1);
+            if (otherEndOK && sb200_pol_end1(&P.pol, INFO_I)) pool_emit(P, ls, cx.qid, a, e + 1);
             break;
         }
         if (!(fl & SF_SUB_ALIVE)) break;  // dead at the next step
@@ -1583,16 +1368,6 @@ __device__ __forceinline__ void pool_finish(const SearchParams& P, PoolLane& ls,
 }
 
 #if !defined(SB200_HOST_EMU)
-template <int SIGMA, bool EDIT, int STACK>
-__global__ void __launch_bounds__(256, 4) fm_kernel(const SearchParams P) {
-    extern __shared__ uint32_t s_steps[];
-    const uint32_t n_steps = P.n_searches * P.len;
-    for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) s_steps[i] = P.steps[i];
-    __syncthreads();
-    // word w of this thread's query lives at s_query[w * blockDim.x]: every lane stays in its own bank
-    fm_thread<SIGMA, EDIT, STACK>(P, s_steps, s_steps + n_steps + threadIdx.x, blockDim.x);
-}
-
 // ---- search_n, selection of the queries that exceed the limit -----------------------------------------
 // rows[q] += rows of every cursor of query q (cursors: the output slots of the first pass)
 __global__ void __launch_bounds__(256) cursor_rows_kernel(const uint4* cursors, uint64_t n, unsigned long long* rows) {
@@ -1651,18 +1426,6 @@ __global__ void __launch_bounds__(256, SB200_FM_ITEMS_BLOCKS) fm_items_kernel(co
     for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) s_steps[i] = P.steps[i];
     __syncthreads();
     fm_items_thread<SIGMA, EDIT, STACK>(P, s_steps);
-}
-
-template <bool EDIT, int STACK>
-__global__ void __launch_bounds__(256) text_kernel(const SearchParams P) {
-    extern __shared__ uint32_t s_steps[];
-    const uint32_t n_steps = P.n_searches * P.len;
-    const uint32_t n_run_words = (n_steps * kRunE + 3) / 4;
-    uint32_t* s_runs = s_steps + n_steps;
-    for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) s_steps[i] = P.steps[i];
-    for (uint32_t i = threadIdx.x; i < n_run_words; i += blockDim.x) s_runs[i] = reinterpret_cast<const uint32_t*>(P.runs)[i];
-    __syncthreads();
-    text_thread<EDIT, STACK>(P, s_steps, reinterpret_cast<const uint8_t*>(s_runs), s_runs + n_run_words + threadIdx.x, blockDim.x);
 }
 
 template <bool EDIT, int STACK>

@@ -4,6 +4,7 @@
 // /root/reference/src/sahara/index.cpp:53 (IVio 1.2.1 is not vendored): a record is a '>' header line
 // (id = the line without '>') followed by sequence lines that are concatenated without line breaks.
 #pragma once
+#include <cstring>
 #include <algorithm>
 #include <array>
 #include <cstdint>
@@ -208,5 +209,42 @@ struct Writer {
         }
     }
 };
+
+// ranks (one byte per base) -> 4 bits per base, 8 bases per little-endian word, (len + 7) / 8 words per read; unused
+// nibbles of the last word of a read are 0xF.  The format sb200_submit_reads takes as SB200_READS_PACKED4: half the
+// bytes on the way to the GPU.  `threads` host threads, each a contiguous range of reads.
+inline void packReads4(const uint8_t* ranks, uint64_t n_reads, uint32_t len, unsigned threads, uint32_t* out) {
+    const uint32_t W = (len + 7) / 8;
+    auto work = [&](uint64_t r0, uint64_t r1) {
+        for (uint64_t r = r0; r < r1; ++r) {
+            const uint8_t* src = ranks + r * len;
+            uint32_t* dst = out + r * W;
+            uint32_t i = 0;
+            for (uint32_t w = 0; w + 1 < W || (w < W && len % 8 == 0); ++w, i += 8) {
+                uint64_t x;
+                std::memcpy(&x, src + i, 8);
+                // low nibbles of 8 bytes -> 32 bits
+                x &= 0x0f0f0f0f0f0f0f0full;
+                x = (x | (x >> 4)) & 0x00ff00ff00ff00ffull;
+                x = (x | (x >> 8)) & 0x0000ffff0000ffffull;
+                x = (x | (x >> 16)) & 0x00000000ffffffffull;
+                dst[w] = static_cast<uint32_t>(x);
+            }
+            if (len % 8) {
+                uint32_t v = 0xffffffffu;
+                for (uint32_t j = 0; i + j < len; ++j) v = (v & ~(0xfu << (4 * j))) | (uint32_t(src[i + j] & 0xf) << (4 * j));
+                dst[W - 1] = v;
+            }
+        }
+    };
+    if (threads <= 1 || n_reads < 4096) {
+        work(0, n_reads);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const uint64_t per = (n_reads + threads - 1) / threads;
+    for (unsigned t = 0; t < threads; ++t) pool.emplace_back(work, std::min<uint64_t>(n_reads, per * t), std::min<uint64_t>(n_reads, per * (t + 1)));
+    for (auto& th : pool) th.join();
+}
 
 }  // namespace sahara::fasta

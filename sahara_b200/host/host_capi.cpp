@@ -191,6 +191,17 @@ int sbh_revcomp_ranks(const uint8_t* in, uint64_t n, uint8_t* out) {
 
 void sbh_free(void* p) { std::free(p); }
 
+int sbh_set_expand_rule(uint32_t rule) {
+    return guard([&] {
+        if (rule > 1) throw std::runtime_error("unknown expand rule");
+        sahara::scheme::expandLowerRule() = rule;
+    });
+}
+
+int sbh_pack_reads4(const uint8_t* ranks, uint64_t n_reads, uint32_t len, uint32_t threads, uint32_t* out) {
+    return guard([&] { sahara::fasta::packReads4(ranks, n_reads, len, threads, out); });
+}
+
 int sbh_fasta_load_reads(const char* path, uint64_t sigma, uint32_t threads, uint8_t** ranks, uint64_t* n_reads, uint64_t* len) {
     return guard([&] {
         if (sigma != 5 && sigma != 6) throw std::runtime_error("unknown index with " + std::to_string(sigma) + " letters");

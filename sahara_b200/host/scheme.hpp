@@ -24,6 +24,8 @@
 #include <string>
 #include <vector>
 
+#include "../../include/sahara_policy.h"
+
 namespace sahara::scheme {
 
 struct Search {
@@ -122,6 +124,14 @@ inline std::vector<size_t> expandCount(size_t parts, size_t len) {
 
 inline bool isExpandable(Search const& s, size_t len) { return s.pi.size() <= len; }
 
+// Rule `expand_lower` of the policy table (include/sahara_policy.h): the lower bound of the characters of a part that
+// are not its last one.  0 (the reconstruction in force): the previous part's lower bound — a part's own bound is only
+// demanded once its last character is consumed; 1: the part's own bound at every character.
+inline uint32_t& expandLowerRule() {
+    static uint32_t rule = [] { sb200_policy p = SB200_POLICY_DEFAULT; return p.expand_lower; }();
+    return rule;
+}
+
 inline Search expand(Search const& s, std::vector<size_t> const& counts) {
     size_t P = s.pi.size();
     std::vector<size_t> start(P + 1, 0);
@@ -132,9 +142,9 @@ inline Search expand(Search const& s, std::vector<size_t> const& counts) {
         bool right = (i == 0) ? (P < 2 || s.pi[0] < s.pi[1]) : (s.pi[i - 1] < s.pi[i]);
         for (size_t j = 0; j < counts[part]; ++j) {
             r.pi.push_back(right ? start[part] + j : start[part + 1] - 1 - j);
-            // lower bound: previous part's value until the last character of the part
+            // lower bound: previous part's value until the last character of the part (policy rule expand_lower)
             bool last = j + 1 == counts[part];
-            r.l.push_back(last ? s.l[i] : (i > 0 ? s.l[i - 1] : 0));
+            r.l.push_back((last || expandLowerRule() == 1u) ? s.l[i] : (i > 0 ? s.l[i - 1] : 0));
             r.u.push_back(s.u[i]);
         }
     }

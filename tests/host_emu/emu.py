@@ -12,6 +12,7 @@ SRC = os.path.join(HERE, "search_emu.cpp")
 def _load(name, flags):
     so = os.path.join(HERE, name)
     deps = [SRC] + [os.path.join(HERE, "..", "..", "sahara_b200", "csrc", f) for f in ("search.cuh", "layout.cuh")]
+    deps.append(os.path.join(HERE, "..", "..", "include", "sahara_policy.h"))
     if not (os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps)):
         subprocess.check_call(["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=undefined",
                                "-fno-sanitize-recover=undefined", *flags, SRC, "-o", so])
@@ -21,6 +22,7 @@ def _load(name, flags):
                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.emu_free.argtypes = [C.c_void_p]
     lib.emu_set_max_hits.argtypes = [C.c_uint32]
+    lib.emu_set_policy.argtypes = [C.c_void_p]
     lib.emu_ordered_max_depth.restype = C.c_uint32
     return lib
 
@@ -30,8 +32,12 @@ _lib = _load("libsearch_emu.so", [])
 # pops narrowly / depth first most of the time (head room = the private-stack bound of 96 frames)
 _lib_small_pool = _load("libsearch_emu_smallpool.so", ["-DSB200_POOL_CAP=24", "-DSB200_SPILL_CAP=120"])
 
-POOL = 8  # debug flag: run the in-text verification with the pooled kernel body (text_pool_kernel)
-ITEMS = 16  # debug flag: item-based walk (fm_roots_kernel + fm_items_kernel) instead of fm_kernel
+def set_policy(policy=None):
+    """the table of reconstructed rules the emulated kernels get (ctypes structure laid out like sb200_policy);
+    None = the default"""
+    for lib in (_lib, _lib_small_pool):
+        lib.emu_set_policy(C.byref(policy) if policy is not None else None)
+
 
 
 def QGRAM(q):

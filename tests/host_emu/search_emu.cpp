@@ -99,8 +99,14 @@ void run_text_pool(const SearchParams& P, const uint32_t* steps, const uint8_t* 
 
 uint32_t g_max_hits = 0;  // > 0: emu_search runs the ordered walk with a hit limit (fm_ordered_kernel)
 uint32_t g_ordered_maxsp = 0;
+sb200_policy g_policy = SB200_POLICY_DEFAULT;  // the table of reconstructed rules the kernels get (emu_set_policy)
 
 extern "C" {
+
+void emu_set_policy(const sb200_policy* p) {
+    sb200_policy def = SB200_POLICY_DEFAULT;
+    g_policy = p ? *p : def;
+}
 
 void emu_set_max_hits(uint32_t n) { g_max_hits = n; }
 uint32_t emu_ordered_max_depth() { return g_ordered_maxsp; }
@@ -125,7 +131,7 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
     if (kmax > 4) return 2;
     std::vector<uint8_t> runs(run_table_bytes(static_cast<uint32_t>(steps.size())) + 4, 0);
     build_runs(n_searches, len, steps.data(), runs.data());
-    build_state_flags(n_searches, len, steps.data(), runs.data());
+    build_state_flags(n_searches, len, steps.data(), runs.data(), g_policy);
     // optional in-text verification tables
     std::vector<uint32_t> isa, text4;
     if (sa32 && text) {
@@ -135,7 +141,7 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
         for (uint64_t i = 0; i < n_rows; ++i) text4[i / 8] |= uint32_t(text[i] & 0xf) << (4 * (i % 8));
     }
     uint32_t W = packed_words(len);
-    std::vector<uint32_t> packed(size_t(n_queries) * W, 0xffffffffu), stage(W + 1, 0);
+    std::vector<uint32_t> packed(size_t(n_queries) * W, 0xffffffffu);
     for (uint64_t qi = 0; qi < n_queries; ++qi)
         for (uint32_t i = 0; i < len; ++i) {
             uint32_t& w = packed[qi * W + i / 8];
@@ -164,12 +170,8 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
             qgram[code] = uint4{lb, lbRev, ln, 0};
         }
     }
-    std::vector<uint4> items;
-    std::vector<uint2> item_tags;
-    if (debug_flags & 16u) {
-        items.resize(size_t(n_queries) * n_searches + 1);
-        item_tags.resize(size_t(n_queries) * n_searches + 1);
-    }
+    std::vector<uint4> items(size_t(n_queries) * n_searches + 1);
+    std::vector<uint2> item_tags(size_t(n_queries) * n_searches + 1);
     uint64_t cap = 1 << 16, seed_cap = 1 << 16;
     std::vector<uint4> buf, seeds;
     unsigned long long counters[CT_COUNT];
@@ -196,6 +198,7 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
         P.qgram = qgram_q ? qgram.data() : nullptr;
         P.qgram_q = qgram_q;
         P.debug_flags = debug_flags & 0xffu;
+        P.pol = g_policy;
         P.sa32 = isa.empty() ? nullptr : sa32;
         P.isa32 = isa.empty() ? nullptr : isa.data();
         P.text4 = isa.empty() ? nullptr : text4.data();
@@ -214,7 +217,7 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
             } else return 3;
             g_ordered_maxsp = static_cast<uint32_t>(counters[CT_MAX_SP]);
             P.sa32 = nullptr;  // (no second kernel)
-        } else if (debug_flags & 16u) {  // item-based walk: fm_roots_kernel as a host loop, then fm_items_kernel as a one-lane warp
+        } else {  // fm_roots_kernel as a host loop, then fm_items_kernel as a one-lane warp
             if (P.qgram_q >= len) P.qgram = nullptr, P.qgram_q = 0;
             P.items = items.data();
             P.item_tags = item_tags.data();
@@ -226,23 +229,14 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
                 if (edit) fm_items_thread<5, true, 96>(P, steps.data());
                 else fm_items_thread<5, false, 96>(P, steps.data());
             } else return 3;
-        } else if (sigma == 6) {
-            if (edit) fm_thread<6, true, 96>(P, steps.data(), stage.data(), 1);
-            else fm_thread<6, false, 96>(P, steps.data(), stage.data(), 1);
-        } else if (sigma == 5) {
-            if (edit) fm_thread<5, true, 96>(P, steps.data(), stage.data(), 1);
-            else fm_thread<5, false, 96>(P, steps.data(), stage.data(), 1);
-        } else return 3;
+        }
         if (counters[CT_SEED_SLOTS] > seed_cap) {
             seed_cap = counters[CT_SEED_SLOTS];
             continue;
         }
-        if (P.sa32 && (debug_flags & 8u)) {  // second kernel, pooled version: one warp of 32 lanes in lockstep
+        if (P.sa32) {  // second kernel (text_pool_kernel): one warp of 32 lanes in lockstep
             if (edit) run_text_pool<true>(P, steps.data(), runs.data(), kmax);
             else run_text_pool<false>(P, steps.data(), runs.data(), kmax);
-        } else if (P.sa32) {  // second kernel: in-text verification of the seeds
-            if (edit) text_thread<true, 96>(P, steps.data(), runs.data(), stage.data(), 1);
-            else text_thread<false, 96>(P, steps.data(), runs.data(), stage.data(), 1);
         }
         if (counters[CT_OVERFLOW]) return 4;  // stack overflow
         if (counters[CT_OUT_SLOTS] <= cap) break;

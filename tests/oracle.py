@@ -27,6 +27,7 @@ _lib.orc_search_n.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.
                               C.c_int, C.c_uint64, C.POINTER(C.c_void_p), u64p, C.c_void_p]
 _lib.orc_locate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), u64p, C.c_void_p]
 _lib.orc_free.argtypes = [C.c_void_p]
+_lib.orc_set_policy.argtypes = [C.c_void_p]
 _lib.orc_bf_hamming.restype = C.c_uint64
 _lib.orc_bf_hamming.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
 _lib.orc_bf_edit_starts.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
@@ -43,6 +44,12 @@ def _check(rc):
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def set_policy(policy=None):
+    """replaces the oracle's table of reconstructed rules (include/sahara_policy.h; a ctypes structure with the layout of
+    sb200_policy); None restores the default"""
+    _check(_lib.orc_set_policy(C.byref(policy) if policy is not None else None))
 
 
 def max_threads():

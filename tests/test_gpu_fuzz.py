@@ -56,7 +56,13 @@ def test_random_configuration(seed):
             assert got_cur.shape == want_cur.shape and np.array_equal(got_cur, want_cur), (seed, gen, k, m, edit)
             if ctx.info()["device_bytes"] and not ctx.counters()["nodes"] > nodes:  # the q-gram table only removes nodes
                 assert ctx.counters()["nodes"] <= nodes
-            assert np.array_equal(ctx.search(q), O.sort_rows(ix.locate(want_cur))), (seed, gen, k, m, edit)
+            want_hits = O.sort_rows(ix.locate(want_cur))
+            assert np.array_equal(ctx.search(q), want_hits), (seed, gen, k, m, edit)
+            # the asynchronous pair (sb200_submit_reads / sb200_wait_batch): reads as ranks or 4-bit packed, batches of a
+            # few reads submitted two deep, CSR records back
+            reads = np.ascontiguousarray(q[0::2])
+            got_async = ctx.search_reads_async(reads, packed4=bool((seed + it) & 1), batch=(7, 40, 1000)[(seed + it) % 3])
+            assert got_async.shape == want_hits.shape and np.array_equal(got_async, want_hits), (seed, gen, k, m, edit, "async")
             # search_n with a random limit: the first rows of every query in the reference's recursion order
             n = (1, 2, 3, 7, 50)[(seed + it) % 5]  # (not drawn from rng: the configurations stay what they were)
             ctx.set_max_hits(n)

@@ -280,7 +280,7 @@ def test_text_mode_keeps_results(sb, ctx, cases, key):
     ctx.enable_text(False)
 
 
-def test_pipelined_host_search_with_small_chunks(sb, ctx, cases, monkeypatch):
+def test_pipelined_host_search_with_small_chunks(sb, ctx, cases):
     """sb200_search cuts the batch into chunks that overlap copies and kernels; tiny chunks exercise the
     double buffering, the growth of the pinned result buffer and the global query ids."""
     rng, seqs, ix, path = cases[("repeats", 6)]
@@ -293,8 +293,9 @@ def test_pipelined_host_search_with_small_chunks(sb, ctx, cases, monkeypatch):
     ctx.set_scheme(sch, True)
     want = O.sort_rows(ix.locate(ix.search(q, sch, True)))
     for chunk in ("7", "64", "100000"):
-        monkeypatch.setenv("SB200_CHUNK", chunk)
+        ctx.set_option("chunk", int(chunk))
         assert np.array_equal(ctx.search(q), want)
+    ctx.set_option("chunk", 0)  # (0 = default)
     ctx.build_qgram(0)
     ctx.enable_text(False)
 
@@ -353,7 +354,7 @@ def test_cli_besthits_follows_search_best(sb, cases, tmp_path):
 
 @pytest.mark.parametrize("key", [("random", 6), ("multi", 6), ("repeats", 6), ("random", 5)])
 @pytest.mark.parametrize("edit,k", [(False, 0), (False, 2), (True, 1), (True, 2), (True, 3)])
-def test_max_hits_matches_search_n(sb, ctx, cases, key, edit, k, monkeypatch):
+def test_max_hits_matches_search_n(sb, ctx, cases, key, edit, k):
     """sb200_set_max_hits (fm_ordered_kernel) against the oracle's search_n (search_ng24::search_n as called at
     /root/reference/src/sahara/search.cpp:228,231): the first n rows of every query in recursion order, the same number
     of cursor extensions; with and without the in-text verification tables / q-gram table loaded (not used here)."""
@@ -378,7 +379,7 @@ def test_max_hits_matches_search_n(sb, ctx, cases, key, edit, k, monkeypatch):
                 got_cur = ctx.search_cursors(q)
                 assert got_cur.shape == want_cur.shape and np.array_equal(got_cur, want_cur)
                 # the ordered walk over every query: the extensions of the reference's search_n, one by one
-                monkeypatch.setenv("SB200_ORDERED_ONLY", "1")
+                ctx.set_option("ordered_only", 1)
                 ctx.reset_counters()
                 got_cur = ctx.search_cursors(q)
                 assert got_cur.shape == want_cur.shape and np.array_equal(got_cur, want_cur)
@@ -386,7 +387,7 @@ def test_max_hits_matches_search_n(sb, ctx, cases, key, edit, k, monkeypatch):
                     assert ctx.counters()["nodes"] <= nodes_oracle
                 else:
                     assert ctx.counters()["nodes"] == nodes_oracle
-                monkeypatch.delenv("SB200_ORDERED_ONLY")
+                ctx.set_option("ordered_only", 0)
                 want_hits = O.sort_rows(ix.locate(want_cur))
                 assert np.array_equal(ctx.search(q), want_hits)
                 per_query = np.bincount(want_hits[:, 0].astype(np.int64), minlength=q.shape[0])
@@ -432,7 +433,7 @@ def test_cli_max_hits(sb, cases, tmp_path):
             assert got == sorted((int(a), int(b), int(c)) for a, b, c, d in hits)
 
 
-def test_search_reads_compact_matches_full_call(sb, ctx, cases, monkeypatch):
+def test_search_reads_compact_matches_full_call(sb, ctx, cases):
     """sb200_search_reads: reads only, reverse complements made on the device, 16-byte hits."""
     rng, seqs, ix, path = cases[("multi", 6)]
     ctx.load_index(path)
@@ -444,16 +445,17 @@ def test_search_reads_compact_matches_full_call(sb, ctx, cases, monkeypatch):
     ctx.set_scheme(sch, True)
     want = O.sort_rows(ix.locate(ix.search(q, sch, True)))
     for chunk in ("10", "500000"):
-        monkeypatch.setenv("SB200_CHUNK", chunk)
+        ctx.set_option("chunk", int(chunk))
         got = ctx.search_reads(reads)
         assert got.dtype == np.uint32 and np.array_equal(got.astype(np.uint64), want)
         fwd_only = ctx.search_reads(reads, with_reverse=False)
         want_fwd = O.sort_rows(ix.locate(ix.search(reads, sch, True)))
         assert np.array_equal(fwd_only.astype(np.uint64), want_fwd)
+    ctx.set_option("chunk", 0)
     ctx.enable_text(False)
 
 
-def test_host_buffer_call_edge_and_middle_chunks(sb, ctx, cases, monkeypatch):
+def test_host_buffer_call_edge_and_middle_chunks(sb, ctx, cases):
     """Large batches are cut into a short first chunk, middle pieces and a short last chunk
     (search_host_pipelined in csrc/capi.cu); the concatenated hit lists must equal the oracle's."""
     rng, seqs, ix, path = cases[("repeats", 6)]
@@ -466,13 +468,14 @@ def test_host_buffer_call_edge_and_middle_chunks(sb, ctx, cases, monkeypatch):
     ctx.set_scheme(sch, False)
     want = O.sort_rows(ix.locate(ix.search(q, sch, False, 4), 4))
     for chunk in ("40000", "2000000"):
-        monkeypatch.setenv("SB200_CHUNK", chunk)
+        ctx.set_option("chunk", int(chunk))
         assert np.array_equal(ctx.search_reads(reads).astype(np.uint64), want)
         assert np.array_equal(ctx.search(q), want)
+    ctx.set_option("chunk", 0)
     ctx.enable_text(False)
 
 
-def test_hit_sort_fused_and_pair_paths_agree(sb, ctx, cases, monkeypatch):
+def test_hit_sort_fused_and_pair_paths_agree(sb, ctx, cases):
     """Hits are sorted by one 64-bit key (query id above position and errors) when the bits fit, else by two
     stable pair sorts (locate_only in csrc/capi.cu): both orders must be the oracle's."""
     rng, seqs, ix, path = cases[("multi", 6)]
@@ -483,16 +486,19 @@ def test_hit_sort_fused_and_pair_paths_agree(sb, ctx, cases, monkeypatch):
     ctx.set_scheme(sch, True)
     want = O.sort_rows(ix.locate(ix.search(q, sch, True)))
     for fused in ("1", "0"):
-        monkeypatch.setenv("SB200_FUSED_SORT", fused)
+        ctx.set_option("fused_sort", int(fused))
+        ctx.set_option("bucket_sort", 0)  # (the global sort is the path that has the two key layouts)
         assert np.array_equal(ctx.search(q), want)
         assert np.array_equal(ctx.search_reads(np.ascontiguousarray(q[0::2])).astype(np.uint64), want)
+    ctx.set_option("fused_sort", -1)
+    ctx.set_option("bucket_sort", 1)
 
 
 @pytest.mark.parametrize("key", [("multi", 6), ("repeats", 6)])
-def test_kernel_variants_agree(sb, ctx, cases, key, monkeypatch):
-    """The walk has two formulations (fm_roots_kernel + fm_items_kernel, or the query-owning fm_kernel:
-    SB200_FM_ITEMS=0) and so has the in-text verification (text_pool_kernel, or text_kernel: SB200_TEXT_POOL=0);
-    every combination, with and without the q-gram table, reports the oracle's cursors and hits."""
+def test_launch_geometry_does_not_change_results(sb, ctx, cases, key):
+    """The options that tune launch geometry (blocks per SM of the walk, warps and blocks of the frame pools, run rounds
+    per pop) select between equivalent executions: every combination, with and without the q-gram table, reports the
+    oracle's cursors and hits."""
     rng, seqs, ix, path = cases[key]
     ctx.load_index(path)
     ctx.enable_text(True)
@@ -506,18 +512,23 @@ def test_kernel_variants_agree(sb, ctx, cases, key, monkeypatch):
     try:
         for qlen in (0, 4, 9):
             ctx.build_qgram(qlen)
-            for items in ("1", "0"):
-                for pool in ("1", "0"):
-                    monkeypatch.setenv("SB200_FM_ITEMS", items)
-                    monkeypatch.setenv("SB200_TEXT_POOL", pool)
-                    assert np.array_equal(ctx.search_cursors(q), want_cur), (qlen, items, pool)
-                    assert np.array_equal(ctx.search(q), want), (qlen, items, pool)
+            for items_blocks, pool_threads, pool_blocks, rounds in ((0, 0, 0, 0), (1, 64, 1, 1), (4, 128, 2, 3), (3, 384, 1, 6)):
+                ctx.set_option("items_blocks_per_sm", items_blocks)
+                ctx.set_option("pool_threads", pool_threads)
+                ctx.set_option("pool_blocks_per_sm", pool_blocks)
+                ctx.set_option("run_rounds", rounds)
+                assert np.array_equal(ctx.search_cursors(q), want_cur), (qlen, items_blocks, pool_threads)
+                assert np.array_equal(ctx.search(q), want), (qlen, items_blocks, pool_threads)
+        with pytest.raises(sb.SaharaError, match="unknown option"):
+            ctx.set_option("no_such_knob", 1)
     finally:
+        for name in ("items_blocks_per_sm", "pool_threads", "pool_blocks_per_sm", "run_rounds"):
+            ctx.set_option(name, 0)
         ctx.build_qgram(0)
         ctx.enable_text(False)
 
 
-def test_bucketed_locate_sort_all_segment_sizes(sb, ctx, monkeypatch):
+def test_bucketed_locate_sort_all_segment_sizes(sb, ctx):
     """Hits are located into per-query buckets and sorted per query (locate.cuh): a thread sorts <= 32 hits, a block
     <= 2048, a query with more falls back to the global radix sort; cursors with more than 8 rows are located by
     warp tasks.  Repeats of 40 / 300 / 3000 copies reach every one of these paths, with the sampled and the complete
@@ -541,13 +552,15 @@ def test_bucketed_locate_sort_all_segment_sizes(sb, ctx, monkeypatch):
                 ctx.enable_text(text)
                 for bucket in ("1", "0"):
                     for textpos in ("1", "0"):
-                        monkeypatch.setenv("SB200_BUCKET_SORT", bucket)
-                        monkeypatch.setenv("SB200_TEXTPOS", textpos)
+                        ctx.set_option("bucket_sort", int(bucket))
+                        ctx.set_option("textpos", int(textpos))
                         got = ctx.search(q)
                         assert got.shape == want.shape and np.array_equal(got, want), (text, bucket, textpos)
                         got32 = ctx.search_reads(np.ascontiguousarray(q[0::2])).astype(np.uint64)
                         assert np.array_equal(got32, want), (text, bucket, textpos)
     finally:
+        ctx.set_option("bucket_sort", 1)
+        ctx.set_option("textpos", 1)
         ctx.enable_text(False)
 
 

@@ -41,15 +41,13 @@ def test_kernel_source_matches_oracle(indexes, key, edit, k):
         before = int(ix.counters[0])
         want = O.sort_rows(ix.search(q, sch, edit))
         nodes_oracle = int(ix.counters[0]) - before
-        # fm_kernel alone, fm_kernel + text_kernel, fm_kernel + text_pool_kernel (full and tiny pool)
-        # the same with the item-based walk (fm_roots_kernel + fm_items_kernel)
-        for text, flags, small in ((None, 0, False), (tt, 0, False), (tt, emu.POOL, False), (tt, emu.POOL, True),
-                                   (None, emu.ITEMS, False), (tt, emu.ITEMS | emu.POOL, False)):
+        # the walk alone (fm_roots_kernel + fm_items_kernel), the walk + text_pool_kernel (full and tiny pool)
+        for text, flags, small in ((None, 0, False), (tt, 0, False), (tt, 0, True)):
             got, nodes = emu.search(ix, q, sch, edit, flags, text, small)
             assert got.shape == want.shape and np.array_equal(got, want)
             assert nodes == nodes_oracle  # every state the kernels expand is one extension of the reference recursion
         # with a q-gram jump table the leading error-free steps are skipped: same cursors, fewer nodes
-        for text, flags in ((None, emu.QGRAM(3)), (None, emu.ITEMS | emu.QGRAM(4)), (tt, emu.ITEMS | emu.POOL | emu.QGRAM(5))):
+        for text, flags in ((None, emu.QGRAM(3)), (None, emu.QGRAM(4)), (tt, emu.QGRAM(5))):
             got, nodes = emu.search(ix, q, sch, edit, flags, text)
             assert got.shape == want.shape and np.array_equal(got, want)
             assert nodes <= nodes_oracle
@@ -66,12 +64,12 @@ def test_debug_variants_agree(indexes):
 
 
 def test_qgram_covers_whole_query(indexes):
-    """q-gram as long as the query: fm_kernel reports the table entry, the item-based walk ignores the table"""
+    """q-gram as long as the query: the walk ignores the table"""
     rng, seqs, ix, tt = indexes["dna4"]
     q = W.sample_reads(rng, seqs, 50, 5, 0, False)
     sch = sb.SearchScheme.generate("h2-k2", 0, 0, 5, limit_to_hamming=True)
     want = O.sort_rows(ix.search(q, sch, False))
-    for flags in (emu.QGRAM(5), emu.ITEMS | emu.QGRAM(5), emu.QGRAM(6), emu.ITEMS | emu.QGRAM(6)):
+    for flags in (emu.QGRAM(5), emu.QGRAM(6)):
         got, _ = emu.search(ix, q, sch, False, flags)
         assert np.array_equal(got, want)
 
