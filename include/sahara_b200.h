@@ -134,7 +134,8 @@ int sb200_get_policy(sb200_ctx* ctx, sb200_policy* out);
 /* knobs of the host orchestration; none of them changes results (they select between equivalent kernels / sort paths
  * or tune launch geometry and chunking; tests use them to reach every path).  Names: bucket_sort, fused_sort, textpos,
  * ordered_only, debug, chunk, edge_div, pool_blocks_per_sm, pool_threads, run_rounds, items_blocks_per_sm,
- * ordered_blocks_per_sm.  The library reads no environment variables. */
+ * ordered_blocks_per_sm, overlap (how the batches in flight share the GPU: 0 one after the other, 1 unconstrained streams,
+ * 2 = default: own streams, the persistent verification kernel of a batch starts when its predecessor batch is complete).  The library reads no environment variables. */
 int sb200_set_option(sb200_ctx* ctx, const char* name, int64_t value);
 
 /* replaces the maxHits argument of fmc::search_ng24::search_n<Edit>(index, queries, scheme, maxHits, res_cb)

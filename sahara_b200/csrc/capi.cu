@@ -185,6 +185,11 @@ struct Options {
     uint64_t edge_div{5};      // ... first and last chunk = 1 / edge_div of the batch
     int pool_blocks_per_sm{0}, pool_threads{0}, run_rounds{0};  // text_pool_kernel geometry (0 = default)
     int items_blocks_per_sm{0}, ordered_blocks_per_sm{0};       // fm_items_kernel / fm_ordered_kernel blocks per SM (0 = default)
+    // how the batches of the pipelined calls share the GPU: 0 = one after the other on one stream; 1 = every slot on its own
+    // stream, unconstrained (two batches then run in lockstep and their copies are exposed); 2 = own streams, but the in-text
+    // verification kernel of a batch (a persistent kernel that fills every SM) starts only when its predecessor batch is
+    // complete: packing and the walk over the occurrence tables of batch i+1 fill the tail of batch i, nothing else waits
+    int overlap{2};
 };
 
 enum : int { IN_QUERIES_RANKS = 0, IN_READS_RANKS = 1, IN_READS_PACKED4 = 2 };
@@ -197,6 +202,7 @@ struct Work {
     bool busy{};              // handed out by submit, not yet released
     uint64_t ticket{};
     cudaStream_t own_stream{}, stream{};
+    bool pipelined{};         // the batch runs on the slot's own streams (asynchronous calls, chunks of the host-buffer calls)
     cudaEvent_t ev[12]{};     // timing: 0 start, 11 search end, 8..10 fm / text, 1..3 locate / sort
     cudaEvent_t ev_in{}, ev_done{}, ev_ready{}, ev_out{}, ev_fork{};
     DevBuf d_in, d_packed, d_items, d_item_tags, d_seeds, d_spill, d_cursors, d_counters, d_qpos, d_lc, d_tasks, d_bigsegs, d_keys[2], d_qids[2],
@@ -246,6 +252,7 @@ struct sb200_ctx {
     Work work[kSlots];
     Work* last{};          // slot that holds the result of the last synchronous search (sb200_fetch_hits, sb200_search_cursors)
     uint64_t next_ticket{1};
+    Work* prev_slot{};        // slot of the batch submitted last (overlap mode 2 chains on its ev_done)
     DevBuf d_tmp, d_scratch, d_counters;  // index construction, rank benchmark
     uint64_t nodes_text{};
     float ms_fm{}, ms_text{};
@@ -807,6 +814,8 @@ void enqueue_search_kernels(sb200_ctx* c, Work& w) {
         const unsigned tgrid = static_cast<unsigned>(c->sms) * g.per_sm;
         w.d_spill.reserve(size_t(tgrid) * (g.threads / 32) * 2 * kSpillCap * sizeof(uint4));
         const uint32_t run_rounds = c->opt.run_rounds > 0 ? static_cast<uint32_t>(c->opt.run_rounds) : kRunRounds;
+        // overlap mode 2: not before the batch submitted before this one is complete
+        if (w.pipelined && c->opt.overlap == 2 && c->prev_slot && c->prev_slot != &w) CUDA_TRY(cudaStreamWaitEvent(w.stream, c->prev_slot->ev_done, 0));
         with_stack(stack_k, [&](auto STACK) {
             auto go = [&](auto kern) {
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem)));
@@ -967,6 +976,7 @@ void enqueue_compute(sb200_ctx* c, Work& w) {
         enqueue_output(c, w, w.hit_cap, w.d_scratch.get<uint32_t>());
     }
     enqueue_publish(c, w, w.located);
+    if (w.pipelined) c->prev_slot = &w;
 }
 
 // search_n after the plain search: a query with at most max_hits rows is complete; the others (they end early by
@@ -1201,8 +1211,7 @@ void finish_batch(sb200_ctx* c, Work& w) {
     const unsigned long long* st = w.h_status;
     w.n_real_cursors = st[ST_COUNTERS + CT_CURSORS];
     if (!w.do_locate) w.n_hits = 0;
-    // accounting
-    CUDA_TRY(cudaStreamSynchronize(w.stream));
+    // accounting (everything of this batch is behind ev_done or a synchronous read-back)
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, w.ev[0], w.ev[11]));
     w.ms_search = ms;
@@ -1239,7 +1248,9 @@ void setup_batch(sb200_ctx* c, Work& w, const void* src, bool src_on_device, int
     if (!src || n_queries == 0) throw Error("query file was empty - abort");
     if (n_queries * uint64_t(c->n_searches) >= (1ull << 32)) throw Error("too many (query, search) pairs for one call; split the batch");
     if (c->n_searches > 255) throw Error("search schemes with more than 255 searches are not supported");
-    w.stream = stream;
+    w.pipelined = stream == w.own_stream;
+    // overlap mode 0: the batches of all slots run one after the other on the stream of slot 0
+    w.stream = (w.pipelined && c->opt.overlap == 0) ? c->work[0].own_stream : stream;
     w.n_queries = n_queries;
     w.len = len;
     w.in_fmt = in_fmt;
@@ -1269,8 +1280,8 @@ void setup_batch(sb200_ctx* c, Work& w, const void* src, bool src_on_device, int
 // stream; returns without waiting (w.ev_out marks the end)
 void enqueue_copy_out(sb200_ctx* c, Work& w, void* dst_records, uint32_t* dst_ends) {
     const size_t rec = out_record_bytes(c, w.out_fmt);
-    CUDA_TRY(cudaEventRecord(w.ev_ready, w.stream));
-    CUDA_TRY(cudaStreamWaitEvent(c->s_out, w.ev_ready, 0));
+    // (finish_batch has waited for everything of this batch: no event needed; in overlap mode 0 the slot's stream also
+    // carries the successors' kernels, which the copy must not wait for)
     if (w.n_hits) CUDA_TRY(cudaMemcpyAsync(dst_records, w.d_out.p, w.n_hits * rec, cudaMemcpyDeviceToHost, c->s_out));
     if (dst_ends) CUDA_TRY(cudaMemcpyAsync(dst_ends, w.d_qpos.p, w.n_queries * 4, cudaMemcpyDeviceToHost, c->s_out));
     CUDA_TRY(cudaEventRecord(w.ev_out, c->s_out));
@@ -1479,7 +1490,8 @@ int sb200_create(int device, sb200_ctx** out) {
             w.id = i;
             CUDA_TRY(cudaStreamCreateWithFlags(&w.own_stream, cudaStreamNonBlocking));
             for (auto& ev : w.ev) CUDA_TRY(cudaEventCreate(&ev));
-            for (cudaEvent_t* ev : {&w.ev_in, &w.ev_done, &w.ev_ready, &w.ev_out, &w.ev_fork}) CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+            for (cudaEvent_t* ev : {&w.ev_in, &w.ev_done, &w.ev_ready, &w.ev_out, &w.ev_fork})
+                CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
             CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&w.h_status), ST_COUNT * sizeof(unsigned long long), cudaHostAllocMapped));
             CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&w.h_status_dev), w.h_status, 0));
         }
@@ -1946,6 +1958,13 @@ int sb200_set_option(sb200_ctx* c, const char* name, int64_t value) {
         else if (n == "run_rounds") o.run_rounds = static_cast<int>(std::max<int64_t>(0, value));
         else if (n == "items_blocks_per_sm") o.items_blocks_per_sm = static_cast<int>(std::max<int64_t>(0, value));
         else if (n == "ordered_blocks_per_sm") o.ordered_blocks_per_sm = static_cast<int>(std::max<int64_t>(0, value));
+        else if (n == "overlap") {
+            if (value < 0 || value > 2) throw Error("option overlap takes 0, 1 or 2");
+            for (auto& w : c->work)
+                if (w.busy) throw Error("submitted batches are still in flight");
+            o.overlap = static_cast<int>(value);
+            c->prev_slot = nullptr;
+        }
         else throw Error("unknown option '" + n + "'");
     });
 }
@@ -2013,6 +2032,7 @@ static uint64_t submit_batch(sb200_ctx* c, const void* src, bool on_device, uint
     // fork from the caller's stream: work queued there before this call happens before the batch
     CUDA_TRY(cudaEventRecord(w.ev_fork, c->stream));
     CUDA_TRY(cudaStreamWaitEvent(w.own_stream, w.ev_fork, 0));
+    if (c->opt.overlap == 0) CUDA_TRY(cudaStreamWaitEvent(c->work[0].own_stream, w.ev_fork, 0));
     if (!on_device) CUDA_TRY(cudaStreamWaitEvent(c->s_in, w.ev_fork, 0));
     setup_batch(c, w, src, on_device, in_fmt, with_reverse, n_queries, len, true, out_fmt, 0, w.own_stream);
     enqueue_compute(c, w);
