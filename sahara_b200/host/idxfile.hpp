@@ -16,6 +16,7 @@
 // The loader checks every size relation it can and refuses files it does not understand; the deep
 // consistency checks (bitplanes disjoint, counters, histograms) run on the GPU in sb200_index_upload.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -52,7 +53,26 @@ struct IndexImage {
     }
 };
 
+// ---- the layout assumptions, one constant each (none of them has been checked against a file written by
+// upstream sahara — tools/pin_against_sahara.sh does that where a real binary exists) ---------------------------------
+namespace layout {
+constexpr uint64_t kRowsPerBlock = 64;          // InterleavedBitvector16: one block per 64 rows
+constexpr uint64_t kBlocksPerSuperblock = 1024; // u16 block counters: a superblock every 65536 rows
+constexpr uint64_t kBlockAlign = 64;            // upstream declares the block alignas(64): the padded stride the loader also accepts
+// bytes of one block as written: u16 counters + u64 one-hot bit words per symbol, packed
+constexpr uint64_t blockBytesPacked(uint64_t sigma) { return (2 + 8) * sigma; }
+constexpr uint64_t blockBytesPadded(uint64_t sigma) { return (blockBytesPacked(sigma) + kBlockAlign - 1) / kBlockAlign * kBlockAlign; }
+constexpr uint64_t blocksForRows(uint64_t rows) { return rows / kRowsPerBlock + 1; }
+constexpr uint64_t superblocksForBlocks(uint64_t blocks) { return (blocks + kBlocksPerSuperblock - 1) / kBlocksPerSuperblock; }
+constexpr uint64_t markerWordsForRows(uint64_t rows) { return rows / 64 + 1; }
+}  // namespace layout
+
 namespace detail {
+[[noreturn]] inline void layoutError(std::string const& what) {
+    throw std::runtime_error("index layout not understood: " + what +
+                             " (the field order of X.idx is reconstructed, see sahara_b200/host/idxfile.hpp; an index written by "
+                             "this repo's `sahara index` always loads)");
+}
 struct File {
     FILE* f{};
     File(std::string const& path, char const* mode) : f(fopen(path.c_str(), mode)) {}
@@ -60,7 +80,7 @@ struct File {
     File(File const&) = delete;
 };
 inline void readRaw(FILE* f, void* p, size_t n) {
-    if (n && fread(p, 1, n, f) != n) throw std::runtime_error("index layout not understood: unexpected end of file");
+    if (n && fread(p, 1, n, f) != n) layoutError("unexpected end of file");
 }
 inline uint64_t readU64(FILE* f) {
     uint64_t v;
@@ -90,35 +110,58 @@ inline IndexImage loadIndexFile(std::string const& path) {
     if (im.sigma != 5 && im.sigma != 6) throw std::runtime_error("unknown index with " + std::to_string(im.sigma) + " letters");
     auto readOcc = [&](std::vector<uint8_t>& blocks, std::vector<uint64_t>& super, uint64_t& rows, uint64_t& nBlocks) {
         nBlocks = readU64(f);
-        if (nBlocks == 0 || nBlocks > (uint64_t{1} << 40)) throw std::runtime_error("index layout not understood: block count");
-        blocks.resize(nBlocks * 10 * im.sigma);
-        readRaw(f, blocks.data(), blocks.size());
+        if (nBlocks == 0 || nBlocks > (uint64_t{1} << 40)) layoutError("block count " + std::to_string(nBlocks) + " where a u64 vector size was expected");
+        const uint64_t packed = layout::blockBytesPacked(im.sigma), padded = layout::blockBytesPadded(im.sigma);
+        const uint64_t wantSuper = layout::superblocksForBlocks(nBlocks);
+        // which stride were the blocks written with?  The u64 behind them must be the superblock count.
+        const long at = ftell(f);
+        uint64_t stride = 0;
+        for (uint64_t cand : {packed, padded}) {
+            uint64_t v = 0;
+            if (fseek(f, at + static_cast<long>(nBlocks * cand), SEEK_SET) == 0 && fread(&v, 8, 1, f) == 1 && v == wantSuper) {
+                stride = cand;
+                break;
+            }
+        }
+        if (stride == 0)
+            layoutError("no superblock count of " + std::to_string(wantSuper) + " (one per " + std::to_string(layout::kBlocksPerSuperblock) + " blocks) behind " +
+                        std::to_string(nBlocks) + " blocks of " + std::to_string(packed) + " (packed) or " + std::to_string(padded) + " (64-byte aligned) bytes");
+        fseek(f, at, SEEK_SET);
+        blocks.resize(nBlocks * packed);
+        if (stride == packed) readRaw(f, blocks.data(), blocks.size());
+        else {  // padded blocks: keep the leading counters + bit words
+            std::vector<uint8_t> buf(stride);
+            for (uint64_t b = 0; b < nBlocks; ++b) {
+                readRaw(f, buf.data(), stride);
+                std::copy(buf.begin(), buf.begin() + static_cast<long>(packed), blocks.begin() + static_cast<long>(b * packed));
+            }
+        }
         uint64_t nSuper = readU64(f);
-        if (nSuper != (nBlocks + 1023) / 1024) throw std::runtime_error("index layout not understood: superblock count");
         super.resize(nSuper * im.sigma);
         readRaw(f, super.data(), super.size() * 8);
         rows = readU64(f);
-        if (rows / 64 + 1 != nBlocks) throw std::runtime_error("index layout not understood: row count vs block count");
+        if (layout::blocksForRows(rows) != nBlocks)
+            layoutError("row count " + std::to_string(rows) + " does not give " + std::to_string(nBlocks) + " blocks of " + std::to_string(layout::kRowsPerBlock) + " rows");
     };
     uint64_t rowsRev = 0, blocksRev = 0;
     readOcc(im.bwt_blocks, im.bwt_super, im.n_rows, im.n_blocks);
     readOcc(im.bwtrev_blocks, im.bwtrev_super, rowsRev, blocksRev);
-    if (rowsRev != im.n_rows) throw std::runtime_error("index layout not understood: bwt and bwtRev differ in size");
+    if (rowsRev != im.n_rows) layoutError("bwt and bwtRev differ in size (expected: bwt, bwtRev, C, csa in this order)");
     im.C.resize(im.sigma + 1);
     readRaw(f, im.C.data(), im.C.size() * 8);
     uint64_t nSamples = readU64(f);
-    if (nSamples > im.n_rows) throw std::runtime_error("index layout not understood: sample count");
+    if (nSamples > im.n_rows) layoutError("sample count " + std::to_string(nSamples) + " exceeds the row count (expected the csa's sample vector behind C[sigma + 1])");
     im.ssa.resize(nSamples);
     readRaw(f, im.ssa.data(), nSamples * 8);
     uint64_t nWords = readU64(f);
-    if (nWords != im.n_rows / 64 + 1) throw std::runtime_error("index layout not understood: marker words");
+    if (nWords != layout::markerWordsForRows(im.n_rows)) layoutError("marker bitvector of " + std::to_string(nWords) + " words, expected rows / 64 + 1 behind the samples");
     im.mark_bits.resize(nWords);
     readRaw(f, im.mark_bits.data(), nWords * 8);
-    if (readU64(f) != im.n_rows) throw std::runtime_error("index layout not understood: marker length");
+    if (readU64(f) != im.n_rows) layoutError("marker bitvector length differs from the row count");
     im.sampling_rate = readU64(f);
     im.bits_for_position = readU64(f);
     uint8_t extra;
-    if (fread(&extra, 1, 1, f) != 0) throw std::runtime_error("index layout not understood: trailing bytes");
+    if (fread(&extra, 1, 1, f) != 0) layoutError("trailing bytes behind samplingRate / bitsForPosition");
     return im;
 }
 
@@ -128,10 +171,10 @@ inline void saveIndexFile(std::string const& path, sb200_index_view const& v) {
     if (!file.f) throw std::runtime_error("cannot open " + path + " for writing");
     FILE* f = file.f;
     writeU64(f, v.sigma);
-    uint64_t nSuper = (v.n_blocks + 1023) / 1024;
+    uint64_t nSuper = layout::superblocksForBlocks(v.n_blocks);
     auto writeOcc = [&](void const* blocks, uint64_t const* super) {
         writeU64(f, v.n_blocks);
-        writeRaw(f, blocks, v.n_blocks * 10 * v.sigma);
+        writeRaw(f, blocks, v.n_blocks * layout::blockBytesPacked(v.sigma));
         writeU64(f, nSuper);
         writeRaw(f, super, nSuper * v.sigma * 8);
         writeU64(f, v.n_rows);
@@ -141,7 +184,7 @@ inline void saveIndexFile(std::string const& path, sb200_index_view const& v) {
     writeRaw(f, v.C, (v.sigma + 1) * 8);
     writeU64(f, v.n_ssa);
     writeRaw(f, v.ssa, v.n_ssa * 8);
-    uint64_t nWords = v.n_rows / 64 + 1;
+    uint64_t nWords = layout::markerWordsForRows(v.n_rows);
     writeU64(f, nWords);
     writeRaw(f, v.mark_bits, nWords * 8);
     writeU64(f, v.n_rows);

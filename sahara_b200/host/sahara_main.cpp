@@ -108,6 +108,25 @@ Args parse(int argc, char** argv, int first) {
     return a;
 }
 
+// numeric option value; a malformed one names the option instead of surfacing a bare "stoul"
+long long numOpt(Args const& a, std::string const& key, std::string const& def) {
+    std::string v = a.get(key, def);
+    try {
+        size_t used = 0;
+        long long x = std::stoll(v, &used);
+        if (used != v.size()) throw std::invalid_argument(v);
+        return x;
+    } catch (std::exception const&) {
+        fail("option " + key + " expects a number, got \"" + v + "\"");
+    }
+    return 0;
+}
+size_t sizeOpt(Args const& a, std::string const& key, std::string const& def) {
+    long long x = numOpt(a, key, def);
+    if (x < 0) fail("option " + key + " must not be negative");
+    return static_cast<size_t>(x);
+}
+
 void printTiming(std::vector<std::pair<std::string, double>> const& timing, double* total) {
     printf("stats:\n");
     *total = 0;
@@ -188,10 +207,10 @@ void runSearch(Args const& a) {
     constexpr size_t Sigma = Alphabet::size();
     std::string queryPath = a.get("--query"), indexPath = a.get("--index"), outPath = a.get("--output", "sahara-output.txt");
     std::string generator = a.get("--generator", "h2-k2"), mode = a.get("--search_mode", "all"), metric = a.get("--distance-metric", "lev");
-    size_t k = std::stoul(a.get("--errors", "0"));
+    size_t k = sizeOpt(a, "--errors", "0");
     bool noReverse = a.has("--no-reverse");
-    long maxHits = std::stol(a.get("--max_hits", "0"));
-    size_t limitQueries = std::stoul(a.get("--limit_queries", "0"));
+    long maxHits = static_cast<long>(numOpt(a, "--max_hits", "0"));
+    size_t limitQueries = sizeOpt(a, "--limit_queries", "0");
     if (mode != "all" && mode != "besthits") fail("unknown search mode \"" + mode + "\"");
     if (metric != "ham" && metric != "lev") fail("unknown distance metric \"" + metric + "\"");
     const bool bestHits = mode == "besthits";
@@ -236,7 +255,7 @@ void runSearch(Args const& a) {
     if (!std::filesystem::exists(indexPath)) fail("no valid index path at " + indexPath);
 
     int nGpus = gpuCount();
-    if (a.has("--gpus")) nGpus = std::min(nGpus, std::max(1, std::stoi(a.get("--gpus"))));
+    if (a.has("--gpus")) nGpus = std::min(nGpus, std::max(1, static_cast<int>(numOpt(a, "--gpus", "1"))));
     nGpus = static_cast<int>(std::min<size_t>(nGpus, (nQueries + 1) / 2));
     auto image = sahara::loadIndexFile(indexPath);
     auto view = image.view();
@@ -245,13 +264,13 @@ void runSearch(Args const& a) {
         check(sb200_create(g, &ctxs[g]));
         check(sb200_index_upload(ctxs[g], &view));
         check(sb200_set_max_hits(ctxs[g], static_cast<uint64_t>(maxHits)));  // search_n / search_best_n (search.cpp:228,231,240)
-        if (a.has("--device-sa-rate")) check(sb200_index_densify(ctxs[g], std::stoul(a.get("--device-sa-rate"))));
+        if (a.has("--device-sa-rate")) check(sb200_index_densify(ctxs[g], static_cast<uint32_t>(sizeOpt(a, "--device-sa-rate", "16"))));
         // in-text verification (17 more bytes per row on the device) and the q-gram jump table are on by default
         if (!a.has("--no-text")) check(sb200_index_enable_text(ctxs[g], 1));
         unsigned q = 0;
         for (uint64_t n = image.n_rows; n >= 4 && q < 15; n /= 4) ++q;  // floor(log4(rows))
         q = std::min(15u, q);  // the depth at which cursors become unique; 4^15 x 16 B = 17 GB at most (3.1 Gbp genomes)
-        if (a.has("--qgram")) q = static_cast<unsigned>(std::stoul(a.get("--qgram")));
+        if (a.has("--qgram")) q = static_cast<unsigned>(sizeOpt(a, "--qgram", "0"));
         check(sb200_index_build_qgram(ctxs[g], q));
     }
     timing.emplace_back("ld index", sw.reset());
@@ -319,7 +338,7 @@ void runSearch(Args const& a) {
         uint64_t firstQuery;  // added to the query ids of the block
         bool owned;           // allocated here (besthits), not by the library
     };
-    size_t batch = std::stoul(a.get("--batch", "2000000"));
+    size_t batch = sizeOpt(a, "--batch", "2000000");
     batch += batch & 1;  // keep both strands of a read together
     const size_t batchReads = std::max<size_t>(1, batch / per);
     std::vector<std::vector<HitBlock>> results(nGpus);

@@ -478,6 +478,99 @@ inline Scheme kucherov_k1(size_t minK, size_t K) {
     return zeroRunSeeded(K + 1, minK, K);
 }
 
+// Lam et al. 2009 (2BWT): K+1 parts; the published cases are K = 1 (forward + backward search) and K = 2 (forward,
+// backward and one bidirectional search that starts in the middle part).  Beyond K = 2 the paper gives no scheme:
+// constructive fallback with K+1 parts.
+inline Scheme lam(size_t minK, size_t K) {
+    if (minK == 0 && K == 0) return backtracking(0, 0);
+    if (minK == 0 && K == 1) return {table({1, 2}, {0, 0}, {0, 1}), table({2, 1}, {0, 0}, {0, 1})};
+    if (minK == 0 && K == 2)
+        return {table({1, 2, 3}, {0, 0, 0}, {0, 2, 2}), table({3, 2, 1}, {0, 0, 0}, {0, 1, 2}),
+                table({2, 1, 3}, {0, 0, 1}, {0, 1, 2})};
+    return zeroRunSeeded(K + 1, minK, K);
+}
+
+// PEX (Navarro & Baeza-Yates, hierarchical verification) written as a search scheme.  The pattern is cut into K+1
+// leaves; an inner node with children of budgets kl and kr has the budget kl + kr + 1, so a node that matches within
+// its budget has a child that matches within the child's.  One search per leaf: it starts with the leaf (0 errors) and
+// climbs the tree, at every ancestor covering the sibling subtree (rightwards when the sibling is on the right, leftwards
+// otherwise) under the ancestor's budget.  `lower`: a search that arrives from a right child only has to find what the
+// left child's searches cannot, i.e. occurrences whose left sibling exceeds its budget (cumulated lower bound kl + 1).
+struct PexNode {
+    size_t lo, hi;     // leaves [lo, hi)
+    size_t budget;
+    int left{-1}, right{-1}, parent{-1};
+};
+inline std::vector<PexNode> pexTreeTopDown(size_t K) {
+    std::vector<PexNode> t;
+    std::function<int(size_t, size_t, size_t, int)> make = [&](size_t lo, size_t hi, size_t k, int parent) {
+        int id = static_cast<int>(t.size());
+        t.push_back(PexNode{lo, hi, k, -1, -1, parent});
+        if (hi - lo > 1) {  // k + 1 leaves below a node of budget k
+            size_t kl = k / 2;  // the left child gets ceil((k + 1) / 2) leaves
+            size_t kr = k - 1 - kl;
+            int l = make(lo, lo + kl + 1, kl, id);
+            int r = make(lo + kl + 1, hi, kr, id);
+            t[id].left = l;
+            t[id].right = r;
+        }
+        return id;
+    };
+    make(0, K + 1, K, -1);
+    return t;
+}
+inline std::vector<PexNode> pexTreeBottomUp(size_t K) {
+    std::vector<PexNode> t;
+    std::vector<int> level;
+    for (size_t i = 0; i <= K; ++i) {
+        level.push_back(static_cast<int>(t.size()));
+        t.push_back(PexNode{i, i + 1, 0, -1, -1, -1});
+    }
+    while (level.size() > 1) {  // pair neighbours; an odd node at the end moves up unchanged
+        std::vector<int> next;
+        for (size_t i = 0; i + 1 < level.size(); i += 2) {
+            int l = level[i], r = level[i + 1];
+            int id = static_cast<int>(t.size());
+            t.push_back(PexNode{t[l].lo, t[r].hi, t[l].budget + t[r].budget + 1, l, r, -1});
+            t[l].parent = id;
+            t[r].parent = id;
+            next.push_back(id);
+        }
+        if (level.size() % 2) next.push_back(level.back());
+        level = next;
+    }
+    return t;
+}
+inline Scheme pexScheme(std::vector<PexNode> const& t, size_t minK, size_t K, bool lower) {
+    size_t P = K + 1;
+    Scheme ss;
+    for (size_t leaf = 0; leaf < P; ++leaf) {
+        int node = -1;
+        for (size_t i = 0; i < t.size(); ++i)
+            if (t[i].left < 0 && t[i].lo == leaf) node = static_cast<int>(i);
+        Search s{{leaf}, {0}, {0}};
+        size_t lb = 0;
+        while (t[node].parent >= 0) {
+            int par = t[node].parent;
+            bool fromRight = t[par].right == node;
+            int sib = fromRight ? t[par].left : t[par].right;
+            std::vector<size_t> parts;
+            if (fromRight) for (size_t j = t[sib].hi; j-- > t[sib].lo;) parts.push_back(j);
+            else for (size_t j = t[sib].lo; j < t[sib].hi; ++j) parts.push_back(j);
+            for (size_t j = 0; j < parts.size(); ++j) {
+                s.pi.push_back(parts[j]);
+                s.u.push_back(t[par].budget);
+                if (lower && fromRight && j + 1 == parts.size()) lb = std::max(lb, t[sib].budget + 1);
+                s.l.push_back(lb);
+            }
+            node = par;
+        }
+        ss.push_back(s);
+    }
+    applyMinK(ss, minK);
+    return ss;
+}
+
 inline Scheme h2(size_t P, size_t minK, size_t K) {
     // Reconstruction: with the part counts for which an optimum table is known use it, otherwise the
     // constructive zero-run seeded scheme (the upstream h2 tables are not available).
@@ -517,6 +610,19 @@ inline std::map<std::string, Entry> const& all() {
         add("kucherov-k1", "Kucherov et al. schemes with K+1 parts", kucherov_k1);
         add("kucherov-k2", "Kucherov et al. schemes with K+2 parts (constructive)",
             [](size_t a, size_t b) { return zeroRunSeeded(b + 2, a, b); });
+        add("lam", "Lam et al. 2009, K+1 parts (published for K <= 2, constructive beyond)", lam);
+        // upstream ships tables computed by the Hato tool (Renders et al. 2024, ILP + greedy search); they are not
+        // available offline: constructive scheme with K+2 parts; real tables come in through --scheme-file
+        add("hato", "Hato-designed schemes (tables not available: constructive K+2 parts, reconstructed)",
+            [](size_t a, size_t b) { return b == 0 ? backtracking(a, 0) : zeroRunSeeded(b + 2, a, b); });
+        add("pex-td", "PEX tree built top down, one search per leaf (reconstructed)",
+            [](size_t a, size_t b) { return pexScheme(pexTreeTopDown(b), a, b, false); });
+        add("pex-td-l", "PEX tree built top down, with lower bounds (reconstructed)",
+            [](size_t a, size_t b) { return pexScheme(pexTreeTopDown(b), a, b, true); });
+        add("pex-bu", "PEX tree built bottom up, one search per leaf (reconstructed)",
+            [](size_t a, size_t b) { return pexScheme(pexTreeBottomUp(b), a, b, false); });
+        add("pex-bu-l", "PEX tree built bottom up, with lower bounds (reconstructed)",
+            [](size_t a, size_t b) { return pexScheme(pexTreeBottomUp(b), a, b, true); });
         return r;
     }();
     return m;

@@ -160,6 +160,41 @@ def test_index_file_reader_agrees_with_oracle_and_rejects_garbage(tmp_path):
     assert "no valid index path" in N.host.sbh_last_error().decode()
 
 
+def test_index_file_reader_accepts_64_byte_aligned_blocks(tmp_path):
+    """upstream declares the occurrence block alignas(64); should it be serialized with its padding, the loader finds the
+    stride from the position of the superblock count (layout::blockBytesPadded)"""
+    rng = np.random.default_rng(4)
+    ix = O.OracleIndex.build([W.random_genome(rng, 3000)], 6, 16)
+    path = os.path.join(tmp_path, "a.idx")
+    ix.save(path)
+    data = open(path, "rb").read()
+    view, handle = N.IndexView(), C.c_void_p()
+    N.check_host(N.host.sbh_idx_load(path.encode(), C.byref(view), C.byref(handle)))
+    nb, sigma = view.n_blocks, 6
+    N.host.sbh_idx_free(handle)
+    packed = 10 * sigma
+
+    def pad_occ(buf, at):  # one occurrence table at offset `at`: u64 count, blocks, ... -> (bytes with 64-byte blocks, end of the blocks)
+        assert int.from_bytes(buf[at:at + 8], "little") == nb
+        blocks = np.frombuffer(buf[at + 8:at + 8 + nb * packed], np.uint8).reshape(nb, packed)
+        wide = np.zeros((nb, 64), np.uint8)
+        wide[:, :packed] = blocks
+        return buf[at:at + 8] + wide.tobytes(), at + 8 + nb * packed
+
+    first, end1 = pad_occ(data, 8)
+    n_super = (nb + 1023) // 1024
+    tail1 = 8 + n_super * sigma * 8 + 8   # superblock vector + rows
+    second, end2 = pad_occ(data, end1 + tail1)
+    padded = data[:8] + first + data[end1:end1 + tail1] + second + data[end2:]
+    p2 = os.path.join(tmp_path, "padded.idx")
+    open(p2, "wb").write(padded)
+    view2, handle2 = N.IndexView(), C.c_void_p()
+    N.check_host(N.host.sbh_idx_load(p2.encode(), C.byref(view2), C.byref(handle2)))
+    again = O.OracleIndex.from_view(view2)
+    N.host.sbh_idx_free(handle2)
+    assert np.array_equal(again.bwt(0), ix.bwt(0)) and np.array_equal(again.bwt(1), ix.bwt(1))
+
+
 def test_synth_mirror_is_deterministic():
     from sahara_b200 import synth
     g = synth.genome(5000, 42)

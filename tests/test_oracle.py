@@ -75,7 +75,7 @@ def test_index_matches_naive_suffix_array():
 
 
 @pytest.mark.parametrize("k", [0, 1, 2, 3])
-@pytest.mark.parametrize("gen", ["h2-k2", "pigeon", "01*0", "suffix", "optimum", "kianfar", "backtracking"])
+@pytest.mark.parametrize("gen", ["h2-k2", "pigeon", "01*0", "suffix", "optimum", "kianfar", "backtracking", "lam", "hato", "pex-td", "pex-td-l", "pex-bu", "pex-bu-l"])
 def test_hamming_equals_brute_force_for_every_scheme(k, gen):
     if gen == "backtracking" and k > 2:
         pytest.skip("too slow")

@@ -5,11 +5,11 @@ import pytest
 import sahara_b200 as sb
 
 ALL = ["backtracking", "optimum", "01*0", "01*0_opt", "pigeon", "pigeon_opt", "suffix", "h2-k1", "h2-k2", "h2-k3", "kianfar",
-       "kucherov-k1", "kucherov-k2"]
+       "kucherov-k1", "kucherov-k2", "lam", "hato", "pex-td", "pex-td-l", "pex-bu", "pex-bu-l"]
 
 
 def test_names_match_reference_list():
-    # the subset of /root/reference/src/sahara/search_scheme.cpp:192 implemented so far
+    # every name of /root/reference/src/sahara/search_scheme.cpp:192
     assert sorted(sb.SearchScheme.names()) == sorted(ALL)
 
 

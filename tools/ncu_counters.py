@@ -47,7 +47,7 @@ for row in rows[2:]:
            "dram_bytes": dram * mult,
            "l2_miss_sectors": num(row, "lts__t_sectors_srcunit_tex_lookup_miss.sum"),
            "l2_miss_requests": num(row, "lts__t_requests_srcunit_tex_lookup_miss.sum"),
-           "duration_under_ncu_ns": num(row, "gpu__time_duration.sum"),
+           "duration_under_ncu_ms": round((num(row, "gpu__time_duration.sum") or 0) / 1e6, 4),
            "registers_per_thread": num(row, "launch__registers_per_thread"),
            "warps_active_pct": num(row, "sm__warps_active.avg.pct_of_peak_sustained_active"),
            "nodes_per_launch": step["nodes_text"] if short == "text_pool_kernel" else step["nodes_fm"],
