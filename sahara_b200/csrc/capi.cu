@@ -1439,9 +1439,10 @@ void upload_scheme_tables(sb200_ctx* c) {
     const std::vector<uint32_t>& steps = c->h_steps;
     c->d_steps.reserve(steps.size() * 4);
     CUDA_TRY(cudaMemcpyAsync(c->d_steps.p, steps.data(), steps.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    std::vector<uint8_t> runs(run_table_bytes(static_cast<uint32_t>(steps.size())) + 4, 0);  // run lengths, then state flags
+    std::vector<uint8_t> runs(run_table_bytes(static_cast<uint32_t>(steps.size())) + 4, 0);  // run lengths, state flags, path windows
     build_runs(c->n_searches, c->qlen, steps.data(), runs.data());
     build_state_flags(c->n_searches, c->qlen, steps.data(), runs.data(), c->policy);
+    build_path_windows(c->n_searches, c->qlen, steps.data(), runs.data());
     c->d_runs.reserve(runs.size());
     CUDA_TRY(cudaMemcpyAsync(c->d_runs.p, runs.data(), runs.size(), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));

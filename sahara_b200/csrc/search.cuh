@@ -51,6 +51,7 @@ __host__ __device__ inline uint32_t pack_meta(uint32_t step, uint32_t e, uint32_
     return step | (e << 10) | (L << 14) | (R << 16);
 }
 constexpr uint32_t META_PAIR = 1u << 18;
+constexpr uint32_t META_STREAK = 1u << 19;  // (text_pool_kernel) the state was reached by a match that followed a match
 constexpr uint32_t META_TLEN_SHIFT = 20;
 constexpr uint32_t kEmitChunk = 16;   // output slots a thread reserves per atomic
 constexpr uint32_t kInvalidQid = 0xffffffffu;
@@ -96,7 +97,42 @@ enum : uint32_t {
     SF_RUN_S = 128    // the substitution child (step + 1, e + 1) starts a match-only run
 };
 __host__ __device__ inline uint32_t state_flags_offset(uint32_t n_steps) { return (n_steps * kRunE + 3u) & ~3u; }
-__host__ __device__ inline uint32_t run_table_bytes(uint32_t n_steps) { return 2u * state_flags_offset(n_steps); }
+__host__ __device__ inline uint32_t run_table_bytes(uint32_t n_steps) { return 3u * state_flags_offset(n_steps); }
+// Path windows.  window(step, e) = w > 0: the states (step + j, e), j < w, of a search whose extended end carries M can be
+// expanded together by text_path — they extend the same end over consecutive query positions, none of them or of the states
+// of their insertion chains is the last step, and the state flags of every error level from e on are the same over the
+// window, the chains and the children's first steps.  The table sits behind the state flags:
+// window(step, e) = runs[2 * state_flags_offset(n_steps) + step * kRunE + e].
+constexpr uint32_t kPathWindow = 8;   // steps per window: the symbols of one packed word
+inline void build_path_windows(uint32_t n_searches, uint32_t len, const uint32_t* steps, uint8_t* runs) {
+    const uint32_t off = state_flags_offset(n_searches * len);
+    const uint8_t* flags = runs + off;
+    uint8_t* win = runs + 2u * off;
+    uint32_t kmax = 0;
+    for (uint32_t i = 0; i < n_searches * len; ++i) kmax = ((steps[i] >> 20) & 0xfu) > kmax ? (steps[i] >> 20) & 0xfu : kmax;
+    if (kmax >= kRunE) kmax = kRunE - 1;
+    for (uint32_t j = 0; j < n_searches; ++j)
+        for (uint32_t e = 0; e < kRunE; ++e) {
+            uint32_t same = 0;  // steps behind i that look like step i (directions, positions, flags of the levels e ..)
+            for (uint32_t i = len; i-- > 0;) {
+                const uint32_t idx = (j * len + i) * kRunE;
+                bool like_next = false;
+                if (i + 1 < len) {
+                    const uint32_t st = steps[j * len + i], sn = steps[j * len + i + 1];
+                    const uint32_t right = (st >> 24) & 1u, pi = st & 0xffffu, pn = sn & 0xffffu;
+                    like_next = ((sn >> 24) & 1u) == right && (right ? pn == pi + 1 : pn + 1 == pi);
+                    for (uint32_t ee = e; ee < kRunE && like_next; ++ee) like_next = flags[idx + ee] == flags[idx + kRunE + ee];
+                }
+                same = like_next ? same + 1 : 0;
+                const uint32_t f = flags[idx + e];
+                const bool walk = e <= kmax && runs[idx + e] == 0 && (f & SF_MATCH) && (f & SF_M_ALIVE) && !(f & SF_RUN_M);
+                // behind the window: the insertion chains (kmax - e steps) and the first step of their children
+                const uint32_t margin = kmax - (e <= kmax ? e : kmax) + 1u;
+                uint32_t w = walk && same > margin ? same - margin : 0u;
+                win[idx + e] = static_cast<uint8_t>(w > kPathWindow ? kPathWindow : w);
+            }
+        }
+}
 inline void build_state_flags(uint32_t n_searches, uint32_t len, const uint32_t* steps, uint8_t* runs, const sb200_policy& pol) {
     const bool pairs = sb200_pol_pairs(&pol) != 0;  // (a PAIR frame expands no insertion child of either half)
     uint8_t* flags = runs + state_flags_offset(n_searches * len);
@@ -716,6 +752,19 @@ __device__ __forceinline__ uint32_t text8(const uint32_t* text4, uint32_t pos) {
     return funnel_r(text4[w], text4[w + 1], (pos & 7u) * 4u);
 }
 
+// nibble j of the result = nibble 7 - j of x
+__device__ __forceinline__ uint32_t rev8(uint32_t x) {
+    x = ((x & 0x0f0f0f0fu) << 4) | ((x >> 4) & 0x0f0f0f0fu);
+    x = ((x & 0x00ff00ffu) << 8) | ((x >> 8) & 0x00ff00ffu);
+    return (x << 16) | (x >> 16);
+}
+// bit 4j of the result is set when nibble j of x is not zero
+__device__ __forceinline__ uint32_t nz_nibbles(uint32_t x) {
+    x |= x >> 1;
+    x |= x >> 2;
+    return x & 0x11111111u;
+}
+
 // ================================================================================================
 // Ordered walk with a hit limit (fm_ordered_kernel): fmc::search_ng24::search_n<Edit>(index, queries, scheme, maxHits, cb)
 // as called at /root/reference/src/sahara/search.cpp:228,231.  A query ends as soon as maxHits suffix-array rows were
@@ -1012,15 +1061,18 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
 #if defined(SB200_POOL_CAP)
 constexpr uint32_t kPoolCapS = SB200_POOL_CAP;     // (tests: tiny pools exercise the spill area and the narrow pops)
 constexpr uint32_t kPoolCapR = SB200_POOL_CAP;
+constexpr uint32_t kPoolCapP = SB200_POOL_CAP / 2;
 constexpr uint32_t kSpillCap = SB200_SPILL_CAP;
 #else
 #if !defined(SB200_CAP_S)
-#define SB200_CAP_S 64
-#define SB200_CAP_R 48
+#define SB200_CAP_S 40
+#define SB200_CAP_R 44
+#define SB200_CAP_P 34
 #endif
 constexpr uint32_t kPoolCapS = SB200_CAP_S;    // state frames per warp held in shared memory
 constexpr uint32_t kPoolCapR = SB200_CAP_R;    // run frames per warp held in shared memory
-constexpr uint32_t kSpillCap = 512;   // frames per warp and stack that spill to global memory behind them (rare)
+constexpr uint32_t kPoolCapP = SB200_CAP_P;    // path frames per warp (shared memory only: one that does not fit is an ordinary state frame)
+constexpr uint32_t kSpillCap = 2048;  // frames per warp and stack that spill to global memory behind them (rare)
 #endif
 #if defined(SB200_POOL_SLOTS)
 constexpr uint32_t kPoolSlots = SB200_POOL_SLOTS;
@@ -1040,6 +1092,7 @@ struct FrameStack {
 };
 struct TextPool {
     FrameStack S, R;       // state frames, run frames
+    FrameStack Pth;        // path frames: state frames at the start of a path window (text_path); no spill area
     uint32_t* live;        // [kPoolSlots] frames of the slot's seed that are still in the pool or being expanded
     uint32_t* ctx_qid;     // [kPoolSlots] query id of the seed in the slot
     uint32_t* ctx_search;  // [kPoolSlots] its search
@@ -1054,22 +1107,23 @@ struct PoolLane {
 __host__ __device__ inline uint32_t pool_query_stride(uint32_t len) { return packed_words(len) | 1u; }
 // bytes of shared memory one warp's pool takes
 __host__ __device__ inline uint32_t pool_bytes(uint32_t len) {
-    const uint32_t frames = kPoolCapS + kPoolCapR;
-    return frames * 8u + ((frames + 7u) & ~7u) + 8u + 3u * kPoolSlots * 4u + kPoolSlots * pool_query_stride(len) * 4u;
+    const uint32_t frames = kPoolCapS + kPoolCapR + kPoolCapP;
+    return frames * 8u + ((frames + 7u) & ~7u) + 16u + 3u * kPoolSlots * 4u + kPoolSlots * pool_query_stride(len) * 4u;
 }
 // carves one warp's pool out of `base` (8-byte aligned, pool_bytes(len) bytes); spill: 2 * kSpillCap entries
 __host__ __device__ inline TextPool pool_carve(uint8_t* base, uint4* spill, uint32_t len) {
     TextPool pool;
-    const uint32_t frames = kPoolCapS + kPoolCapR;
+    const uint32_t frames = kPoolCapS + kPoolCapR + kPoolCapP;
     uint2* fr = reinterpret_cast<uint2*>(base);
     uint8_t* sl = base + frames * 8u;
     uint32_t* words = reinterpret_cast<uint32_t*>(base + frames * 8u + ((frames + 7u) & ~7u));
     pool.S = FrameStack{fr, sl, spill, words, kPoolCapS};
     pool.R = FrameStack{fr + kPoolCapS, sl + kPoolCapS, spill + kSpillCap, words + 1, kPoolCapR};
-    pool.live = words + 2;
-    pool.ctx_qid = words + 2 + kPoolSlots;
-    pool.ctx_search = words + 2 + 2 * kPoolSlots;
-    pool.query = words + 2 + 3 * kPoolSlots;
+    pool.Pth = FrameStack{fr + kPoolCapS + kPoolCapR, sl + kPoolCapS + kPoolCapR, nullptr, words + 2, kPoolCapP};
+    pool.live = words + 4;
+    pool.ctx_qid = words + 4 + kPoolSlots;
+    pool.ctx_search = words + 4 + 2 * kPoolSlots;
+    pool.query = words + 4 + 3 * kPoolSlots;
     pool.Wp = pool_query_stride(len);
     return pool;
 }
@@ -1120,6 +1174,25 @@ __device__ __forceinline__ void pool_push_to(const TextPool& pool, bool run, uin
         ls.overflow = true;
     }
 }
+// a PATH frame (the path stack is small: a frame that does not fit is pushed as an ordinary state frame, which is always right)
+__device__ __forceinline__ void path_push(const TextPool& pool, uint32_t a, uint32_t meta, uint32_t slot, PoolLane& ls) {
+#if defined(SB200_HOST_EMU)
+    const uint32_t idx = (*pool.Pth.top)++;
+#else
+    const uint32_t idx = atomicAdd(pool.Pth.top, 1u);
+#endif
+    if (idx < kPoolCapP) {
+        pool.Pth.frames[idx] = make_uint2(a, meta);
+        pool.Pth.slots[idx] = static_cast<uint8_t>(slot);
+        return;
+    }
+#if defined(SB200_HOST_EMU)
+    (*pool.Pth.top)--;
+#else
+    atomicSub(pool.Pth.top, 1u);
+#endif
+    pool_push_to(pool, false, a, meta, slot, ls);
+}
 // frame idx of the stack -> (a, meta), slot
 __device__ __forceinline__ uint2 stack_get(const FrameStack& st, uint32_t idx, uint32_t& slot) {
     if (idx < st.cap) {
@@ -1143,6 +1216,7 @@ struct SeedCtx {
     const uint32_t* tbl;
     const uint8_t* runs;
     const uint8_t* flags;  // state flags of the search (build_state_flags)
+    const uint8_t* win;    // path windows of the search (build_path_windows)
     uint32_t qid, W;
     __device__ __forceinline__ uint32_t qsym(uint32_t pos) const { return (q[pos >> 3] >> ((pos & 7u) * 4u)) & 0xfu; }
     // the 8 query symbols that start at position pos; positions behind the query read as 0xF
@@ -1152,17 +1226,33 @@ struct SeedCtx {
         const uint32_t hi = w + 1 < W ? q[w + 1] : 0xffffffffu;
         return funnel_r(lo, hi, (pos & 7u) * 4u);
     }
+    // the 8 query symbols at the positions pos, pos - 1, .., pos - 7 (nibble j = position pos - j); positions before the
+    // query read as 0xF
+    __device__ __forceinline__ uint32_t query8_down(uint32_t pos) const {
+        if (pos >= 7u) return rev8(query8(pos - 7u));
+        const uint32_t sh = (7u - pos) * 4u;
+        return rev8((query8(0) << sh) | ((1u << sh) - 1u));
+    }
 };
 __device__ __forceinline__ SeedCtx seed_ctx(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, const TextPool& pool,
                                             uint32_t slot) {
     const uint32_t sid = pool.ctx_search[slot];
     const uint8_t* runs = s_runs + sid * P.len * kRunE;
-    return SeedCtx{pool.query + slot * pool.Wp, s_steps + sid * P.len, runs, runs + state_flags_offset(P.n_searches * P.len), pool.ctx_qid[slot],
-                   packed_words(P.len)};
+    const uint32_t off = state_flags_offset(P.n_searches * P.len);
+    return SeedCtx{pool.query + slot * pool.Wp, s_steps + sid * P.len, runs, runs + off, runs + 2u * off, pool.ctx_qid[slot], packed_words(P.len)};
 }
 __device__ __forceinline__ void pool_emit(const SearchParams& P, PoolLane& ls, uint32_t qid, uint32_t a, uint32_t e) {
     ls.outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], P.textpos_out ? make_uint4(qid, a, 1, e | kCursorTextPosFlag) : make_uint4(qid, P.isa32[a], 1, e));
     ++ls.emitted;
+}
+
+// where a frame whose extended end carries M goes: the run stack when its step starts a match-only run, the path stack
+// when a path window starts there, else the state stack
+__device__ __forceinline__ void route_push(const TextPool& pool, const SeedCtx& cx, uint32_t a, uint32_t meta, uint32_t slot, PoolLane& ls) {
+    const uint32_t at = (meta & 0x3ffu) * kRunE + ((meta >> 10) & 0xfu);
+    if (cx.runs[at] != 0) stack_push(pool.R, a, meta, slot, ls);
+    else if (cx.win[at] >= 2u) path_push(pool, a, meta | META_STREAK, slot, ls);
+    else stack_push(pool.S, a, meta, slot, ls);
 }
 
 // RUN frame: the match-only run(s) that start at its step, comparing packed words of query and text; returns the
@@ -1230,7 +1320,11 @@ __device__ __forceinline__ uint32_t text_run(const SearchParams& P, const uint32
         R = cx.runs[step * kRunE + e];
     }
     ls.nodes += nodes;
-    stack_push(pool.S, a, pack_meta(step, e, Linfo, Rinfo) | (tlen << META_TLEN_SHIFT), slot, ls);  // states follow
+    // states follow; behind a run the extended end carries M: a path window may start here
+    const uint32_t m2 = pack_meta(step, e, Linfo, Rinfo) | (tlen << META_TLEN_SHIFT);
+    const bool right = (cx.tbl[step] >> 24) & 1u;
+    if (nodes != 0 && (right ? Rinfo : Linfo) == INFO_M && cx.win[step * kRunE + e] >= 2u) path_push(pool, a, m2 | META_STREAK, slot, ls);
+    else stack_push(pool.S, a, m2, slot, ls);
     return 1;
 }
 
@@ -1264,6 +1358,7 @@ __device__ __forceinline__ uint32_t text_states(const SearchParams& P, const uin
     const uint32_t tlenNext = (tlen + 1) << META_TLEN_SHIFT;
 
     bool second = false;
+    bool first = !pair;  // the first state of a frame that is not a pair: where a matching path runs through
     while (true) {
         ++nodes;
         const uint32_t st = tbl[step];
@@ -1285,7 +1380,14 @@ __device__ __forceinline__ uint32_t text_states(const SearchParams& P, const uin
                     if (last) {
                         if (otherEndOK && (!EDIT || sb200_pol_end1(&P.pol, INFO_M))) pool_emit(P, ls, cx.qid, na, e);
                     } else if (fl & SF_M_ALIVE) {
-                        push(na, metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift), (fl & SF_RUN_M) != 0);
+                        const uint32_t mM = metaBase | (step + 1) | (e << 10) | (INFO_M << sideShift);
+                        if (fl & SF_RUN_M) push(na, mM, true);
+                        else if (first && T == INFO_M && cx.win[(step + 1) * kRunE + e] >= 2u &&
+                                 ((tbl[step + 1] >> 24) & 1u) == static_cast<uint32_t>(right)) {
+                            // the second match in a row at this end: most likely an alignment, and a path window starts at the child
+                            path_push(pool, na, mM | META_STREAK, slot, ls);
+                            ++pushed;
+                        } else push(na, mM, false);
                     }
                 }
             } else if (mmOK) {
@@ -1304,6 +1406,7 @@ __device__ __forceinline__ uint32_t text_states(const SearchParams& P, const uin
             }
         }
         // next state on the same cursor
+        first = false;
         if (pair) {
             if (second) break;
             second = true;
@@ -1326,6 +1429,91 @@ __device__ __forceinline__ uint32_t text_states(const SearchParams& P, const uin
     return pushed;
 }
 
+// PATH frame: a state (step, e) whose extended end carries M at the start of a path window (build_path_windows).  The lane
+// expands up to 8 consecutive states (step + j, e) along the matching symbols at once — what text_states does with them one
+// frame at a time — from packed-word compares of the text window with the query on the diagonals 0 .. k - e:
+//   diagonal 0   how far the path matches (m states);
+//   diagonal i   the i-th state of the insertion chain of every path state j < m compares the text symbol t_j with the
+//                query symbol of step + j + i: the match child, or the deletion / substitution children, per path state.
+// The flags of the window are those of its first step (that is what makes it a window), so the only data-dependent part
+// is which nibbles are equal.  A child that starts a match-only run is compared with its first symbol right here (the
+// next nibble of its diagonal): a run that ends there costs its one node and no frame.  Children and node counts are
+// exactly those of text_states + text_run on the same states.  wlim: states a lane may take this trip (stack room).
+template <bool EDIT>
+__device__ __forceinline__ uint32_t text_path(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, const TextPool& pool,
+                                              const uint2 f, const uint32_t slot, PoolLane& ls, const uint32_t wlim) {
+    const SeedCtx cx = seed_ctx(P, s_steps, s_runs, pool, slot);
+    const uint32_t a = f.x, meta = f.y & ~META_STREAK;
+    const uint32_t step = meta & 0x3ffu, e = (meta >> 10) & 0xfu;
+    const uint32_t Linfo = (meta >> 14) & 3u, Rinfo = (meta >> 16) & 3u;
+    const uint32_t tlen = (meta >> META_TLEN_SHIFT) & 0x3ffu;
+    const uint32_t st = cx.tbl[step];
+    const bool right = (st >> 24) & 1u;
+    const uint32_t p0 = st & 0xffffu;
+    uint32_t w = cx.win[step * kRunE + e];
+    if (w > wlim) w = wlim;
+    // no window after all (pair frame, another operation at the end, too close to the text start): an ordinary state frame
+    if (w == 0 || (meta & META_PAIR) || (right ? Rinfo : Linfo) != INFO_M || (!right && a < 8u)) {
+        stack_push(pool.S, a, meta, slot, ls);
+        return 1;
+    }
+    const uint32_t tw = right ? text8(P.text4, a + tlen) : rev8(text8(P.text4, a - 8u));  // nibble j = the symbol path state j consumes
+    const uint32_t nz0 = nz_nibbles(tw ^ (right ? cx.query8(p0) : cx.query8_down(p0)));
+    uint32_t m = nz0 ? ctz32(nz0) >> 2 : 8u;  // path states whose symbol matches
+    if (m > w) m = w;
+    if (m == 0) {
+        stack_push(pool.S, a, meta, slot, ls);
+        return 1;
+    }
+    uint32_t pushed = 0, nodes = m;
+    const uint32_t sideShift = right ? 16u : 14u;
+    const uint32_t keep = ((right ? Linfo : 0u) << 14) | ((right ? 0u : Rinfo) << 16);  // the other end
+    // child of path state j: look = the diagonal its first step compares on (nz_nibbles)
+    auto child = [&](uint32_t j, uint32_t cstep, uint32_t ce, uint32_t info, uint32_t extra, bool run, uint32_t look) {
+        if (run && j < 7u && ((look >> (4u * (j + 1u))) & 1u)) {  // a run that ends at its first symbol
+            ++nodes;
+            return;
+        }
+        pool_push_to(pool, run, right ? a : a - j - 1u,
+                     keep | ((tlen + j + 1u) << META_TLEN_SHIFT) | cstep | (ce << 10) | (info << sideShift) | extra, slot, ls);
+        ++pushed;
+    };
+    if (EDIT) {
+        const uint32_t valid = nib_mask(m) & 0x11111111u;
+        const bool delOK = sb200_pol_del(&P.pol, INFO_I) != 0;  // (the chain states carry I at the extended end)
+        uint32_t flp = cx.flags[step * kRunE + e], Tp = INFO_M, nzp = nz0;
+        for (uint32_t i = 1; (flp & SF_MISMATCH) && sb200_pol_ins(&P.pol, Tp) && (flp & SF_SUB_ALIVE); ++i) {
+            const uint32_t fl = cx.flags[(step + i) * kRunE + e + i];
+            nodes += m;
+            const uint32_t nzi = nz_nibbles(tw ^ (right ? cx.query8(p0 + i) : cx.query8_down(p0 - i)));
+            if ((fl & SF_MATCH) && (fl & SF_M_ALIVE))
+                for (uint32_t mk = ~nzi & valid; mk; mk &= mk - 1u) {
+                    const uint32_t j = ctz32(mk) >> 2;
+                    child(j, step + j + i + 1u, e + i, INFO_M, 0u, (fl & SF_RUN_M) != 0, nzi);
+                }
+            if (fl & SF_MISMATCH)
+                for (uint32_t mk = nzi & valid; mk; mk &= mk - 1u) {
+                    const uint32_t j = ctz32(mk) >> 2;
+                    if (delOK && (fl & SF_PAIR)) child(j, step + j + i, e + i + 1u, INFO_D, META_PAIR, false, 0u);
+                    else {
+                        if (delOK) child(j, step + j + i, e + i + 1u, INFO_D, 0u, (fl & SF_RUN_D) != 0, nzp);
+                        if (fl & SF_SUB_ALIVE) child(j, step + j + i + 1u, e + i + 1u, INFO_S, 0u, (fl & SF_RUN_S) != 0, nzi);
+                    }
+                }
+            flp = fl;
+            Tp = INFO_I;
+            nzp = nzi;
+        }
+    }
+    // the state behind the last matching one: unseen when the window (or the trip's limit) ended, else a state whose
+    // symbol differs — the ordinary expansion
+    const uint32_t cm = keep | ((tlen + m) << META_TLEN_SHIFT) | (step + m) | (e << 10) | (static_cast<uint32_t>(INFO_M) << sideShift);
+    if (m == w) route_push(pool, cx, right ? a : a - m, cm, slot, ls);
+    else stack_push(pool.S, right ? a : a - m, cm, slot, ls);
+    ls.nodes += nodes;
+    return pushed + 1u;
+}
+
 // one seed into slot `slot`: stage its query, remember its context, push its root frame
 __device__ __forceinline__ void pool_load_seed(const SearchParams& P, const uint8_t* s_runs, const TextPool& pool, uint32_t slot,
                                                const uint4 seed, PoolLane& ls) {
@@ -1336,7 +1524,51 @@ __device__ __forceinline__ void pool_load_seed(const SearchParams& P, const uint
     pool.ctx_qid[slot] = seed.x;
     pool.ctx_search[slot] = seed.z;
     pool.live[slot] = 1;
-    pool_push(pool, s_runs + seed.z * P.len * kRunE, P.sa32[seed.y], seed.w, slot, ls);
+    // the root frame: run stack, path stack (the extended end carries M and a path window starts) or state stack
+    const uint32_t step = seed.w & 0x3ffu, e = (seed.w >> 10) & 0xfu;
+    const uint32_t at = (seed.z * P.len + step) * kRunE + e;
+    const bool right = (P.steps[seed.z * P.len + step] >> 24) & 1u;
+    const uint32_t a = P.sa32[seed.y];
+    if (seed.w & META_PAIR) stack_push(pool.S, a, seed.w, slot, ls);
+    else if (s_runs[at] != 0) stack_push(pool.R, a, seed.w, slot, ls);
+    else if (((seed.w >> (right ? 16u : 14u)) & 3u) == INFO_M && s_runs[2u * state_flags_offset(P.n_searches * P.len) + at] >= 2u)
+        path_push(pool, a, seed.w | META_STREAK, slot, ls);
+    else stack_push(pool.S, a, seed.w, slot, ls);
+}
+
+// The next trip of a warp: which stack it pops, how many lanes, and for a path trip how many states a lane may take.
+// Run frames first when there is a full trip of them or the run stack leaves no room for the children of a state trip;
+// then full trips of path and state frames; else the fullest stack.  A path lane pushes up to
+// 1 + w * (maxpush - 2) frames (w states, per state and chain level a match child or a deletion + substitution).
+struct PoolTrip { uint32_t kind, n, w; };  // kind: 0 state, 1 run, 2 path
+__host__ __device__ inline PoolTrip pool_pick(uint32_t topS, uint32_t topR, uint32_t topP, uint32_t maxpush, uint32_t stack) {
+    const uint32_t capS = kPoolCapS + kSpillCap - stack, capR = kPoolCapR + kSpillCap;
+    const uint32_t nR = topR < 32u ? topR : 32u;
+    if (topR != 0 && (topS + topP == 0 || topR >= 32u || topR + 32u * maxpush > capR)) return PoolTrip{1u, nR, 0u};
+    uint32_t nP = 0, w = 0;
+    if (topP != 0) {
+        const uint32_t roomS = topS < capS ? capS - topS : 0u, roomR = capR - topR;
+        const uint32_t room = roomS < roomR ? roomS : roomR;
+        const uint32_t per = maxpush > 2u ? maxpush - 2u : 1u;
+        nP = topP < 32u ? topP : 32u;
+        if (room >= nP * (1u + kPathWindow * per)) w = kPathWindow;  // (no division on the common path)
+        else {
+            w = room / nP > 1u ? (room / nP - 1u) / per : 0u;
+            if (w > kPathWindow) w = kPathWindow;
+            if (w == 0) {  // one state per lane, fewer lanes
+                nP = room / (1u + per) < nP ? room / (1u + per) : nP;
+                w = nP ? 1u : 0u;
+            }
+        }
+    }
+    if (w != 0 && (topP >= 32u || (topS < 32u && topP >= topS && topP >= topR))) return PoolTrip{2u, nP, w};
+    if (topS != 0 && (topS >= topR || topR == 0)) {
+        const uint32_t n = pool_pop_width(topS, topR, maxpush, 32u, stack);
+        if (n != 0) return PoolTrip{0u, n, 0u};
+    }
+    if (topR != 0) return PoolTrip{1u, nR, 0u};
+    if (topS != 0) return PoolTrip{0u, pool_pop_width(topS, topR, maxpush, 32u, stack), 0u};
+    return PoolTrip{2u, nP, w};  // only path frames are left (w > 0: both other stacks are empty)
 }
 
 // the expanded frame is gone, `pushed` frames of the same seed were added
@@ -1347,15 +1579,6 @@ __device__ __forceinline__ void pool_retire(const TextPool& pool, uint32_t slot,
 #else
     atomicAdd(&pool.live[slot], pushed - 1u);
 #endif
-}
-
-// which stack the next trip pops: run frames first when there is a full trip of them or the state stack could not
-// push into the run stack; else the fuller stack
-__host__ __device__ inline bool pool_pick_run(uint32_t topS, uint32_t topR, uint32_t maxpush) {
-    if (topR == 0) return false;
-    if (topS == 0 || topR >= 32u) return true;
-    if (topR + 32u * maxpush > kPoolCapR + kSpillCap) return true;
-    return topR > topS;
 }
 
 __device__ __forceinline__ void pool_finish(const SearchParams& P, PoolLane& ls, uint32_t maxtop) {
@@ -1440,7 +1663,7 @@ __global__ void __launch_bounds__(kPoolThreads, 3) text_pool_kernel(const Search
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint8_t* base = reinterpret_cast<uint8_t*>(s_steps) + (((n_steps + n_run_words) * 4u + 7u) & ~7u) + warp * pool_bytes(P.len);
     const TextPool pool = pool_carve(base, spill + (static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * 2u * kSpillCap, P.len);
-    if (lane == 0) { *pool.S.top = 0; *pool.R.top = 0; }
+    if (lane == 0) { *pool.S.top = 0; *pool.R.top = 0; *pool.Pth.top = 0; }
     for (uint32_t i = lane; i < kPoolSlots; i += 32u) pool.live[i] = 0;
     __syncthreads();
 
@@ -1451,8 +1674,8 @@ __global__ void __launch_bounds__(kPoolThreads, 3) text_pool_kernel(const Search
     uint32_t maxtop = 0;
     bool exhausted = false;  // (warp uniform) the seed list has been handed out
     while (true) {
-        uint32_t topS = *pool.S.top, topR = *pool.R.top;
-        if (topS < 32u && topR < 32u && !exhausted) {  // the warp starves: new seeds into every free slot
+        uint32_t topS = *pool.S.top, topR = *pool.R.top, topP = *pool.Pth.top;
+        if (topS < 32u && topR < 32u && topP < 32u && !exhausted) {  // the warp starves: new seeds into every free slot
             constexpr uint32_t kRounds = (kPoolSlots + 31u) / 32u;
             uint32_t my_free[kRounds];
             uint32_t n_free = 0, my_rank[kRounds];
@@ -1464,43 +1687,54 @@ __global__ void __launch_bounds__(kPoolThreads, 3) text_pool_kernel(const Search
                 my_rank[j] = n_free + __popc(m & ((1u << lane) - 1u));
                 n_free += __popc(m);
             }
-            uint32_t first = 0;
-            if (lane == 0) first = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_SEED], static_cast<unsigned long long>(n_free)));
-            first = __shfl_sync(0xffffffffu, first, 0);
-            exhausted = first + n_free >= n_slots;
+            if (n_free != 0) {
+                uint32_t first = 0;
+                if (lane == 0) first = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_SEED], static_cast<unsigned long long>(n_free)));
+                first = __shfl_sync(0xffffffffu, first, 0);
+                exhausted = first + n_free >= n_slots;
 #pragma unroll
-            for (uint32_t j = 0; j < kRounds; ++j) {
-                const uint32_t i = first + my_rank[j];
-                if (my_free[j] && i < n_slots) {
-                    const uint4 seed = P.seeds[i];
-                    if (seed.x != kInvalidQid) pool_load_seed(P, runs8, pool, j * 32u + lane, seed, ls);
+                for (uint32_t j = 0; j < kRounds; ++j) {
+                    const uint32_t i = first + my_rank[j];
+                    if (my_free[j] && i < n_slots) {
+                        const uint4 seed = P.seeds[i];
+                        if (seed.x != kInvalidQid) pool_load_seed(P, runs8, pool, j * 32u + lane, seed, ls);
+                    }
                 }
+                __syncwarp();
+                topS = *pool.S.top;
+                topR = *pool.R.top;
+                topP = *pool.Pth.top;
             }
-            __syncwarp();
-            topS = *pool.S.top;
-            topR = *pool.R.top;
         }
-        if (topS + topR == 0) {
+        if (topS + topR + topP == 0) {
             if (exhausted) break;
             continue;  // only padding entries were fetched
         }
-        maxtop = topS + topR > maxtop ? topS + topR : maxtop;
+        maxtop = topS + topR + topP > maxtop ? topS + topR + topP : maxtop;
         uint2 f = make_uint2(0, 0);
         uint32_t slot = 0;
-        if (pool_pick_run(topS, topR, maxpush)) {
-            const uint32_t n = topR < 32u ? topR : 32u;
-            if (lane < n) f = stack_get(pool.R, topR - 1 - lane, slot);
+        const PoolTrip trip = pool_pick(topS, topR, topP, maxpush, STACK);
+        if (trip.kind == 2u) {
+            if (lane < trip.n) {
+                slot = pool.Pth.slots[topP - 1 - lane];
+                f = pool.Pth.frames[topP - 1 - lane];
+            }
             __syncwarp();
-            if (lane == 0) *pool.R.top = topR - n;
+            if (lane == 0) *pool.Pth.top = topP - trip.n;
             __syncwarp();
-            if (lane < n) pool_retire(pool, slot, text_run<EDIT>(P, s_steps, runs8, pool, f, slot, ls, run_rounds));
+            if (lane < trip.n) pool_retire(pool, slot, text_path<EDIT>(P, s_steps, runs8, pool, f, slot, ls, trip.w));
+        } else if (trip.kind == 1u) {
+            if (lane < trip.n) f = stack_get(pool.R, topR - 1 - lane, slot);
+            __syncwarp();
+            if (lane == 0) *pool.R.top = topR - trip.n;
+            __syncwarp();
+            if (lane < trip.n) pool_retire(pool, slot, text_run<EDIT>(P, s_steps, runs8, pool, f, slot, ls, run_rounds));
         } else {
-            const uint32_t n = pool_pop_width(topS, topR, maxpush, 32u, STACK);
-            if (lane < n) f = stack_get(pool.S, topS - 1 - lane, slot);
+            if (lane < trip.n) f = stack_get(pool.S, topS - 1 - lane, slot);
             __syncwarp();
-            if (lane == 0) *pool.S.top = topS - n;
+            if (lane == 0) *pool.S.top = topS - trip.n;
             __syncwarp();
-            if (lane < n) pool_retire(pool, slot, text_states<EDIT>(P, s_steps, runs8, pool, f, slot, ls));
+            if (lane < trip.n) pool_retire(pool, slot, text_states<EDIT>(P, s_steps, runs8, pool, f, slot, ls));
         }
         __syncwarp();
     }

@@ -27,7 +27,9 @@ def _load(name, flags):
     return lib
 
 
-_lib = _load("libsearch_emu.so", [])
+# EMU_FLAGS (analysis runs only): extra -D flags for the kernel source, compiled into a library of its own
+_extra = os.environ.get("EMU_FLAGS", "").split()
+_lib = _load("libsearch_emu_%08x.so" % (hash(tuple(_extra)) & 0xffffffff), _extra) if _extra else _load("libsearch_emu.so", [])
 # the same source with a 24-frame pool and 120 spill frames: the pooled text kernel then spills all the time and
 # pops narrowly / depth first most of the time (head room = the private-stack bound of 96 frames)
 _lib_small_pool = _load("libsearch_emu_smallpool.so", ["-DSB200_POOL_CAP=24", "-DSB200_SPILL_CAP=120"])

@@ -4,6 +4,7 @@
 // compare the real kernel source with the oracle.
 #define SB200_HOST_EMU 1
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
@@ -39,6 +40,12 @@ struct HostOcc {
     }
 };
 
+// trip statistics of the emulated warp (EMU_STATS=1 in the environment prints them): how full the trips of each kind are
+struct TripStats {
+    uint64_t trips[3]{}, lanes[3]{}, iters[3]{}, pushed[3]{};
+    uint64_t max_lane_iters[3]{};  // sum over trips of the longest lane (what the warp waits for)
+} g_stats;
+
 // text_pool_kernel as one warp of 32 lanes in lockstep: the pops of a trip all read the pool before any lane
 // expands (what the __syncwarp()s of the kernel guarantee), then the lanes expand one after the other.
 template <bool EDIT>
@@ -53,47 +60,65 @@ void run_text_pool(const SearchParams& P, const uint32_t* steps, const uint8_t* 
     const uint32_t n_slots = static_cast<uint32_t>(slots_total < P.seed_cap ? slots_total : P.seed_cap);
     uint32_t maxtop = 0;
     bool exhausted = false;
-    uint32_t &topS = *pool.S.top, &topR = *pool.R.top;
+    uint32_t &topS = *pool.S.top, &topR = *pool.R.top, &topP = *pool.Pth.top;
     while (true) {
-        if (topS < LANES && topR < LANES && !exhausted) {
+        if (topS < LANES && topR < LANES && topP < LANES && !exhausted) {
             std::vector<uint32_t> free_slots;
             for (uint32_t sl = 0; sl < kPoolSlots; ++sl)
                 if (pool.live[sl] == 0) free_slots.push_back(sl);
-            const uint32_t first = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_SEED], static_cast<unsigned long long>(free_slots.size())));
-            exhausted = first + free_slots.size() >= n_slots;
+            const uint32_t first = free_slots.empty() ? 0u : static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_SEED], static_cast<unsigned long long>(free_slots.size())));
+            if (!free_slots.empty()) exhausted = first + free_slots.size() >= n_slots;
             for (uint32_t r = 0; r < free_slots.size(); ++r) {
                 const uint32_t i = first + r;
                 if (i < n_slots && P.seeds[i].x != kInvalidQid)
                     pool_load_seed(P, runs, pool, free_slots[r], P.seeds[i], lanes[free_slots[r] % LANES]);
             }
         }
-        if (topS + topR == 0) {
+        if (topS + topR + topP == 0) {
             if (exhausted) break;
             continue;
         }
-        maxtop = std::max(maxtop, topS + topR);
+        maxtop = std::max(maxtop, topS + topR + topP);
         uint2 f[LANES];
         uint32_t sl[LANES];
-        if (pool_pick_run(topS, topR, maxpush)) {
-            const uint32_t n = std::min(topR, LANES);
-            for (uint32_t lane = 0; lane < n; ++lane) f[lane] = stack_get(pool.R, topR - 1 - lane, sl[lane]);
-            topR -= n;
-            for (uint32_t lane = 0; lane < n; ++lane)
-                pool_retire(pool, sl[lane], text_run<EDIT>(P, steps, runs, pool, f[lane], sl[lane], lanes[lane], kRunRounds));
-        } else {
-            const uint32_t n = pool_pop_width(topS, topR, maxpush, LANES, STACK);
-            if (n == 0) {  // cannot happen: pool_pick_run pops run frames first when the run stack is that full
-                atomicExch(&P.counters[CT_OVERFLOW], 1ull);
-                break;
-            }
-            for (uint32_t lane = 0; lane < n; ++lane) f[lane] = stack_get(pool.S, topS - 1 - lane, sl[lane]);
-            topS -= n;
-            for (uint32_t lane = 0; lane < n; ++lane) pool_retire(pool, sl[lane], text_states<EDIT>(P, steps, runs, pool, f[lane], sl[lane], lanes[lane]));
+        const PoolTrip trip = pool_pick(topS, topR, topP, maxpush, STACK);
+        if (trip.n == 0) {  // cannot happen: pool_pick always finds a stack to pop
+            atomicExch(&P.counters[CT_OVERFLOW], 1ull);
+            break;
         }
+        const uint32_t n = trip.n;
+        FrameStack const& st = trip.kind == 2u ? pool.Pth : trip.kind == 1u ? pool.R : pool.S;
+        uint32_t& top = *st.top;
+        for (uint32_t lane = 0; lane < n; ++lane) f[lane] = stack_get(st, top - 1 - lane, sl[lane]);
+        top -= n;
+        g_stats.trips[trip.kind]++;
+        g_stats.lanes[trip.kind] += n;
+        uint32_t longest = 0;
+        for (uint32_t lane = 0; lane < n; ++lane) {
+            const uint32_t n0 = lanes[lane].nodes;
+            uint32_t pushed;
+            if (trip.kind == 2u) pushed = text_path<EDIT>(P, steps, runs, pool, f[lane], sl[lane], lanes[lane], trip.w);
+            else if (trip.kind == 1u) pushed = text_run<EDIT>(P, steps, runs, pool, f[lane], sl[lane], lanes[lane], kRunRounds);
+            else pushed = text_states<EDIT>(P, steps, runs, pool, f[lane], sl[lane], lanes[lane]);
+            pool_retire(pool, sl[lane], pushed);
+            g_stats.iters[trip.kind] += lanes[lane].nodes - n0;
+            g_stats.pushed[trip.kind] += pushed;
+            longest = std::max(longest, lanes[lane].nodes - n0);
+        }
+        g_stats.max_lane_iters[trip.kind] += longest;
     }
     for (uint32_t sl2 = 0; sl2 < kPoolSlots; ++sl2)
         if (pool.live[sl2] != 0) atomicExch(&P.counters[CT_OVERFLOW], 1ull);  // a seed was lost: report as failure
     for (auto& ls : lanes) pool_finish(P, ls, maxtop);
+    if (std::getenv("EMU_STATS")) {
+        const char* names[3] = {"state", "run", "path"};
+        for (int t = 0; t < 3; ++t)
+            if (g_stats.trips[t])
+                std::fprintf(stderr, "%-5s trips %9llu  lanes/trip %5.1f  nodes/trip %6.1f  longest-lane nodes/trip %5.2f  pushed/frame %4.2f\n", names[t],
+                             (unsigned long long)g_stats.trips[t], double(g_stats.lanes[t]) / g_stats.trips[t], double(g_stats.iters[t]) / g_stats.trips[t],
+                             double(g_stats.max_lane_iters[t]) / g_stats.trips[t], double(g_stats.pushed[t]) / g_stats.lanes[t]);
+        g_stats = TripStats{};
+    }
 }
 }  // namespace
 
@@ -132,6 +157,7 @@ int emu_search(const uint8_t* bwt, const uint8_t* bwtRev, uint64_t n_rows, int s
     std::vector<uint8_t> runs(run_table_bytes(static_cast<uint32_t>(steps.size())) + 4, 0);
     build_runs(n_searches, len, steps.data(), runs.data());
     build_state_flags(n_searches, len, steps.data(), runs.data(), g_policy);
+    build_path_windows(n_searches, len, steps.data(), runs.data());
     // optional in-text verification tables
     std::vector<uint32_t> isa, text4;
     if (sa32 && text) {
