@@ -57,6 +57,13 @@ constexpr uint32_t kEmitChunk = 16;   // output slots a thread reserves per atom
 constexpr uint32_t kInvalidQid = 0xffffffffu;
 constexpr uint32_t kRunE = 5;         // error levels 0..4 in the run table
 constexpr uint32_t kCursorTextPosFlag = 0x10u;  // == kCursorTextPos of locate.cuh
+// rare paths are kept out of line: text_pool_kernel is as sensitive to the size of its code (instruction fetch) as to the
+// instructions it executes
+#if defined(SB200_HOST_EMU) || !defined(__CUDACC__)
+#define SB200_COLD inline
+#else
+#define SB200_COLD __noinline__
+#endif
 
 // Match-only runs.  At (step, e) with u[step] == e and l[step] <= e only a match is possible (no error may be
 // added) — in the text kernel such steps are compared symbol by symbol without touching the stack.  run(step, e)
@@ -364,6 +371,7 @@ struct ChunkWriter {
     }
     // unused slots of the last chunk become empty entries
     __device__ __forceinline__ void finish(uint4* buf, uint32_t cap) {
+#pragma unroll 1
         for (; pos < end; ++pos)
             if (pos < cap) buf[pos] = make_uint4(kInvalidQid, 0, 0, 0);
     }
@@ -1140,6 +1148,11 @@ __host__ __device__ inline uint32_t pool_pop_width(uint32_t top, uint32_t topR, 
     if (n > roomR) n = roomR;
     return n;
 }
+#if defined(SB200_HOST_EMU)
+static inline uint32_t top_fetch_add(uint32_t* p, uint32_t n) { const uint32_t v = *p; *p = v + n; return v; }
+#else
+__device__ __forceinline__ uint32_t top_fetch_add(uint32_t* p, uint32_t n) { return atomicAdd(p, n); }
+#endif
 __device__ __forceinline__ void stack_push(const FrameStack& st, uint32_t a, uint32_t meta, uint32_t slot, PoolLane& ls) {
 #if defined(SB200_HOST_EMU)
     const uint32_t idx = (*st.top)++;
@@ -1468,16 +1481,6 @@ __device__ __forceinline__ uint32_t text_path(const SearchParams& P, const uint3
     uint32_t pushed = 0, nodes = m;
     const uint32_t sideShift = right ? 16u : 14u;
     const uint32_t keep = ((right ? Linfo : 0u) << 14) | ((right ? 0u : Rinfo) << 16);  // the other end
-    // child of path state j: look = the diagonal its first step compares on (nz_nibbles)
-    auto child = [&](uint32_t j, uint32_t cstep, uint32_t ce, uint32_t info, uint32_t extra, bool run, uint32_t look) {
-        if (run && j < 7u && ((look >> (4u * (j + 1u))) & 1u)) {  // a run that ends at its first symbol
-            ++nodes;
-            return;
-        }
-        pool_push_to(pool, run, right ? a : a - j - 1u,
-                     keep | ((tlen + j + 1u) << META_TLEN_SHIFT) | cstep | (ce << 10) | (info << sideShift) | extra, slot, ls);
-        ++pushed;
-    };
     if (EDIT) {
         const uint32_t valid = nib_mask(m) & 0x11111111u;
         const bool delOK = sb200_pol_del(&P.pol, INFO_I) != 0;  // (the chain states carry I at the extended end)
@@ -1486,20 +1489,59 @@ __device__ __forceinline__ uint32_t text_path(const SearchParams& P, const uint3
             const uint32_t fl = cx.flags[(step + i) * kRunE + e + i];
             nodes += m;
             const uint32_t nzi = nz_nibbles(tw ^ (right ? cx.query8(p0 + i) : cx.query8_down(p0 - i)));
-            if ((fl & SF_MATCH) && (fl & SF_M_ALIVE))
-                for (uint32_t mk = ~nzi & valid; mk; mk &= mk - 1u) {
-                    const uint32_t j = ctz32(mk) >> 2;
-                    child(j, step + j + i + 1u, e + i, INFO_M, 0u, (fl & SF_RUN_M) != 0, nzi);
-                }
-            if (fl & SF_MISMATCH)
-                for (uint32_t mk = nzi & valid; mk; mk &= mk - 1u) {
-                    const uint32_t j = ctz32(mk) >> 2;
-                    if (delOK && (fl & SF_PAIR)) child(j, step + j + i, e + i + 1u, INFO_D, META_PAIR, false, 0u);
-                    else {
-                        if (delOK) child(j, step + j + i, e + i + 1u, INFO_D, 0u, (fl & SF_RUN_D) != 0, nzp);
-                        if (fl & SF_SUB_ALIVE) child(j, step + j + i + 1u, e + i + 1u, INFO_S, 0u, (fl & SF_RUN_S) != 0, nzi);
+            const bool pairF = delOK && (fl & SF_PAIR);
+            // the children of this chain level, one kind after the other (one copy of the push loop: code size):
+            // match children of the path states whose symbol equals, deletion (or pair) and substitution children of the others
+#pragma unroll 1
+            for (uint32_t q = 0; q < 3u; ++q) {
+                uint32_t mk = 0, look = nzi, info = INFO_M, rbit = SF_RUN_M, dstep = 1, de = 0, extra = 0;
+                if (q == 0) {
+                    if ((fl & SF_MATCH) && (fl & SF_M_ALIVE)) mk = ~nzi & valid;
+                } else if (fl & SF_MISMATCH) {
+                    if (q == 1) {
+                        if (delOK) {
+                            mk = nzi & valid;
+                            info = INFO_D;
+                            rbit = pairF ? 0u : static_cast<uint32_t>(SF_RUN_D);
+                            dstep = 0;
+                            de = 1;
+                            look = nzp;  // a deletion consumes no query symbol: its first step compares on the previous diagonal
+                            extra = pairF ? META_PAIR : 0u;
+                        }
+                    } else if (!pairF && (fl & SF_SUB_ALIVE)) {
+                        mk = nzi & valid;
+                        info = INFO_S;
+                        rbit = SF_RUN_S;
+                        de = 1;
                     }
                 }
+                if (mk == 0) continue;
+                const bool run = (fl & rbit) != 0;
+                if (run) {  // runs that end at their first symbol (the next nibble of their diagonal): one node each, no frame
+                    const uint32_t dead = mk & (look >> 4);
+                    nodes += popc32(dead);
+                    mk &= ~dead;
+                    if (mk == 0) continue;
+                }
+                const uint32_t n = popc32(mk);
+                uint32_t idx = top_fetch_add(pool.S.top + (run ? 1 : 0), n);  // one reservation for all of them
+                const uint32_t cap = run ? kPoolCapR : kPoolCapS, base = run ? kPoolCapS : 0u;
+                const uint32_t m0 = keep | ((tlen + 1u) << META_TLEN_SHIFT) | (step + i + dstep) | ((e + i + de) << 10) | (info << sideShift) | extra;
+                for (; mk; mk &= mk - 1u, ++idx) {
+                    const uint32_t jj = ctz32(mk) >> 2;
+                    const uint32_t ca = right ? a : a - jj - 1u;
+                    const uint32_t cmeta = m0 + jj * ((1u << META_TLEN_SHIFT) + 1u);  // step + j, tlen + j
+                    if (idx < cap) {
+                        pool.S.frames[base + idx] = make_uint2(ca, cmeta);
+                        pool.S.slots[base + idx] = static_cast<uint8_t>(slot);
+                    } else if (idx - cap < kSpillCap) {
+                        pool.S.spill[idx - cap + (run ? kSpillCap : 0u)] = make_uint4(ca, cmeta, slot, 0);
+                    } else {
+                        ls.overflow = true;
+                    }
+                }
+                pushed += n;
+            }
             flp = fl;
             Tp = INFO_I;
             nzp = nzi;
@@ -1514,13 +1556,17 @@ __device__ __forceinline__ uint32_t text_path(const SearchParams& P, const uint3
     return pushed + 1u;
 }
 
-// one seed into slot `slot`: stage its query, remember its context, push its root frame
+// one seed into slot `slot`: stage its query (COPY; the kernel stages the queries of a refill with all lanes instead),
+// remember its context, push its root frame
+template <bool COPY>
 __device__ __forceinline__ void pool_load_seed(const SearchParams& P, const uint8_t* s_runs, const TextPool& pool, uint32_t slot,
                                                const uint4 seed, PoolLane& ls) {
-    const uint32_t W = packed_words(P.len);
-    const uint32_t* src = P.packed + static_cast<uint64_t>(seed.x) * W;
-    uint32_t* dst = pool.query + slot * pool.Wp;
-    for (uint32_t w = 0; w < W; ++w) dst[w] = src[w];
+    if (COPY) {
+        const uint32_t W = packed_words(P.len);
+        const uint32_t* src = P.packed + static_cast<uint64_t>(seed.x) * W;
+        uint32_t* dst = pool.query + slot * pool.Wp;
+        for (uint32_t w = 0; w < W; ++w) dst[w] = src[w];
+    }
     pool.ctx_qid[slot] = seed.x;
     pool.ctx_search[slot] = seed.z;
     pool.live[slot] = 1;
@@ -1541,7 +1587,8 @@ __device__ __forceinline__ void pool_load_seed(const SearchParams& P, const uint
 // then full trips of path and state frames; else the fullest stack.  A path lane pushes up to
 // 1 + w * (maxpush - 2) frames (w states, per state and chain level a match child or a deletion + substitution).
 struct PoolTrip { uint32_t kind, n, w; };  // kind: 0 state, 1 run, 2 path
-__host__ __device__ inline PoolTrip pool_pick(uint32_t topS, uint32_t topR, uint32_t topP, uint32_t maxpush, uint32_t stack) {
+// (the stacks are nearly full: lanes and states per lane from the room that is left; rare, not inlined)
+__host__ __device__ SB200_COLD PoolTrip pool_pick_tight(uint32_t topS, uint32_t topR, uint32_t topP, uint32_t maxpush, uint32_t stack) {
     const uint32_t capS = kPoolCapS + kSpillCap - stack, capR = kPoolCapR + kSpillCap;
     const uint32_t nR = topR < 32u ? topR : 32u;
     if (topR != 0 && (topS + topP == 0 || topR >= 32u || topR + 32u * maxpush > capR)) return PoolTrip{1u, nR, 0u};
@@ -1551,14 +1598,11 @@ __host__ __device__ inline PoolTrip pool_pick(uint32_t topS, uint32_t topR, uint
         const uint32_t room = roomS < roomR ? roomS : roomR;
         const uint32_t per = maxpush > 2u ? maxpush - 2u : 1u;
         nP = topP < 32u ? topP : 32u;
-        if (room >= nP * (1u + kPathWindow * per)) w = kPathWindow;  // (no division on the common path)
-        else {
-            w = room / nP > 1u ? (room / nP - 1u) / per : 0u;
-            if (w > kPathWindow) w = kPathWindow;
-            if (w == 0) {  // one state per lane, fewer lanes
-                nP = room / (1u + per) < nP ? room / (1u + per) : nP;
-                w = nP ? 1u : 0u;
-            }
+        w = room / nP > 1u ? (room / nP - 1u) / per : 0u;
+        if (w > kPathWindow) w = kPathWindow;
+        if (w == 0) {  // one state per lane, fewer lanes
+            nP = room / (1u + per) < nP ? room / (1u + per) : nP;
+            w = nP ? 1u : 0u;
         }
     }
     if (w != 0 && (topP >= 32u || (topS < 32u && topP >= topS && topP >= topR))) return PoolTrip{2u, nP, w};
@@ -1569,6 +1613,19 @@ __host__ __device__ inline PoolTrip pool_pick(uint32_t topS, uint32_t topR, uint
     if (topR != 0) return PoolTrip{1u, nR, 0u};
     if (topS != 0) return PoolTrip{0u, pool_pop_width(topS, topR, maxpush, 32u, stack), 0u};
     return PoolTrip{2u, nP, w};  // only path frames are left (w > 0: both other stacks are empty)
+}
+__host__ __device__ inline PoolTrip pool_pick(uint32_t topS, uint32_t topR, uint32_t topP, uint32_t maxpush, uint32_t stack) {
+    const uint32_t capS = kPoolCapS + kSpillCap - stack, capR = kPoolCapR + kSpillCap;
+    const uint32_t per = maxpush > 2u ? maxpush - 2u : 1u;
+    const uint32_t wfull = per <= 6u ? kPathWindow : kPathWindow / 2u;  // (k = 4: half windows, so that a full trip always has room)
+    const uint32_t worst = 32u * (1u + wfull * per);  // frames a trip can push (a state trip: 32 * maxpush, less)
+    if (topS + worst > capS || topR + worst > capR) return pool_pick_tight(topS, topR, topP, maxpush, stack);
+    const uint32_t nS = topS < 32u ? topS : 32u, nR = topR < 32u ? topR : 32u, nP = topP < 32u ? topP : 32u;
+    if (topR != 0 && (topS + topP == 0 || topR >= 32u)) return PoolTrip{1u, nR, 0u};
+    if (topP != 0 && (topP >= 32u || (topS < 32u && topP >= topS && topP >= topR))) return PoolTrip{2u, nP, wfull};
+    if (topS != 0 && topS >= topR) return PoolTrip{0u, nS, 0u};
+    if (topR != 0) return PoolTrip{1u, nR, 0u};
+    return PoolTrip{2u, nP, wfull};
 }
 
 // the expanded frame is gone, `pushed` frames of the same seed were added
@@ -1677,28 +1734,34 @@ __global__ void __launch_bounds__(kPoolThreads, 3) text_pool_kernel(const Search
         uint32_t topS = *pool.S.top, topR = *pool.R.top, topP = *pool.Pth.top;
         if (topS < 32u && topR < 32u && topP < 32u && !exhausted) {  // the warp starves: new seeds into every free slot
             constexpr uint32_t kRounds = (kPoolSlots + 31u) / 32u;
-            uint32_t my_free[kRounds];
-            uint32_t n_free = 0, my_rank[kRounds];
+            uint32_t n_free = 0;
 #pragma unroll
-            for (uint32_t j = 0; j < kRounds; ++j) {
-                const bool fr = j * 32u + lane < kPoolSlots && pool.live[j * 32u + lane] == 0;
-                const uint32_t m = __ballot_sync(0xffffffffu, fr);
-                my_free[j] = fr;
-                my_rank[j] = n_free + __popc(m & ((1u << lane) - 1u));
-                n_free += __popc(m);
-            }
+            for (uint32_t j = 0; j < kRounds; ++j)
+                n_free += __popc(__ballot_sync(0xffffffffu, j * 32u + lane < kPoolSlots && pool.live[j * 32u + lane] == 0));
             if (n_free != 0) {
                 uint32_t first = 0;
                 if (lane == 0) first = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_SEED], static_cast<unsigned long long>(n_free)));
                 first = __shfl_sync(0xffffffffu, first, 0);
                 exhausted = first + n_free >= n_slots;
-#pragma unroll
-                for (uint32_t j = 0; j < kRounds; ++j) {
-                    const uint32_t i = first + my_rank[j];
-                    if (my_free[j] && i < n_slots) {
-                        const uint4 seed = P.seeds[i];
-                        if (seed.x != kInvalidQid) pool_load_seed(P, runs8, pool, j * 32u + lane, seed, ls);
+                const uint32_t W = packed_words(P.len);
+#pragma unroll 1
+                for (uint32_t j = 0; j < kRounds; ++j) {  // (one copy of pool_load_seed: code size)
+                    const bool fr = j * 32u + lane < kPoolSlots && pool.live[j * 32u + lane] == 0;
+                    const uint32_t m = __ballot_sync(0xffffffffu, fr);
+                    const uint32_t i = first + __popc(m & ((1u << lane) - 1u));
+                    first += __popc(m);
+                    uint4 seed = make_uint4(kInvalidQid, 0, 0, 0);
+                    if (fr && i < n_slots) seed = P.seeds[i];
+                    const bool has = seed.x != kInvalidQid;
+                    // the queries of this round's seeds, staged by all lanes: word w of a query by lane w
+                    for (uint32_t mm = __ballot_sync(0xffffffffu, has); mm; mm &= mm - 1u) {
+                        const uint32_t src = static_cast<uint32_t>(__ffs(static_cast<int>(mm)) - 1);
+                        const uint32_t qx = __shfl_sync(0xffffffffu, seed.x, src);
+                        const uint32_t* from = P.packed + static_cast<uint64_t>(qx) * W;
+                        uint32_t* to = pool.query + (j * 32u + src) * pool.Wp;
+                        for (uint32_t w = lane; w < W; w += 32u) to[w] = from[w];
                     }
+                    if (has) pool_load_seed<false>(P, runs8, pool, j * 32u + lane, seed, ls);
                 }
                 __syncwarp();
                 topS = *pool.S.top;

@@ -71,7 +71,7 @@ void run_text_pool(const SearchParams& P, const uint32_t* steps, const uint8_t* 
             for (uint32_t r = 0; r < free_slots.size(); ++r) {
                 const uint32_t i = first + r;
                 if (i < n_slots && P.seeds[i].x != kInvalidQid)
-                    pool_load_seed(P, runs, pool, free_slots[r], P.seeds[i], lanes[free_slots[r] % LANES]);
+                    pool_load_seed<true>(P, runs, pool, free_slots[r], P.seeds[i], lanes[free_slots[r] % LANES]);
             }
         }
         if (topS + topR + topP == 0) {

@@ -1,9 +1,17 @@
-"""Prints the metrics we care about from an .ncu-rep (first launch): python tools/ncu_summary.py file.ncu-rep"""
+"""Prints the metrics we care about from an .ncu-rep: python tools/ncu_summary.py file.ncu-rep [kernel substring]
+(the first launch whose name contains the substring; default: the first launch)"""
 import csv, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 h = rows[0]
+if len(sys.argv) > 2:
+    ki = h.index("Kernel Name")
+    sel = [r for r in rows[2:] if len(r) > ki and sys.argv[2] in r[ki]]
+    if not sel:
+        sys.exit("no launch of " + sys.argv[2])
+    rows = [rows[0], rows[1], sel[0]]
+    print("kernel:", sel[0][ki][:100])
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__sectors_read.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'smsp__thread_inst_executed_per_inst_executed.ratio',
