@@ -55,7 +55,9 @@ def parse_args():
 
 
 class ClockSampler(threading.Thread):
-    """samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs"""
+    """samples SM clock / throttle reasons of one GPU while the timed region runs: NVML in this process every few
+    milliseconds (a timed region of some 60 ms is over before an nvidia-smi child has printed its first line), one sample
+    taken synchronously when the region starts; nvidia-smi -lms only when NVML cannot be loaded"""
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
@@ -63,8 +65,38 @@ class ClockSampler(threading.Thread):
         self.rows = []
         self.stop_flag = threading.Event()
         self.proc = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            try:
+                import torch
+                pr = torch.cuda.get_device_properties(gpu)
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                idx = int(vis.split(",")[gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        except Exception:
+            self.nvml = None
+
+    def sample(self):
+        n = self.nvml
+        try:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            flags = ["Active" if r & b else "Not Active" for b in (0x8, 0x40, 0x20, 0x4)]  # hw, hw thermal, sw thermal, sw power cap
+            self.rows.append([str(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)), str(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)),
+                              "0"] + flags)
+        except Exception:
+            pass
 
     def run(self):
+        if self.nvml is not None:
+            while not self.stop_flag.is_set():
+                self.sample()
+                time.sleep(0.004)
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -78,6 +110,8 @@ class ClockSampler(threading.Thread):
             pass
 
     def finish(self):
+        if self.nvml is not None:
+            self.sample()  # (the GPU is still busy with the last step's tail when the region's closing synchronize returns)
         self.stop_flag.set()
         if self.proc:
             try:

@@ -1089,7 +1089,13 @@ constexpr uint32_t kPoolThreads = SB200_POOL_THREADS;
 constexpr uint32_t kPoolSlots = 52;   // seeds a warp works on at a time (52: 36 warps per SM still fit next to the tables of a 4-search scheme at 150 bp)
 constexpr uint32_t kPoolThreads = 384;  // at most 12 warps per block: three blocks (36 warps) fit the shared memory of an SM at 150 bp
 #endif
-constexpr uint32_t kRunRounds = 2;    // rounds of 8 symbols per pop (measured: 1 -> 6.47 ms, 2 -> 6.39, 3 -> 6.42, 6 -> 6.73)
+#if !defined(SB200_REFILL_MIN)
+#define SB200_REFILL_MIN 16
+#define SB200_REFILL_DRY 48
+#endif
+constexpr uint32_t kRefillMin = SB200_REFILL_MIN;  // free seed slots that trigger a refill ...
+constexpr uint32_t kRefillDry = SB200_REFILL_DRY;  // ... or fewer frames than this in the pool
+constexpr uint32_t kRunRounds = 3;    // rounds of 8 symbols per pop (measured with path frames: 1 -> 4.32 ms, 2 -> 4.10, 3 -> 4.04, 4 -> 4.05, 8 -> 4.13)
 
 struct FrameStack {
     uint2* frames;   // [cap] (a, meta): frames 0 .. cap-1 of the stack, shared memory
@@ -1732,13 +1738,14 @@ __global__ void __launch_bounds__(kPoolThreads, 3) text_pool_kernel(const Search
     bool exhausted = false;  // (warp uniform) the seed list has been handed out
     while (true) {
         uint32_t topS = *pool.S.top, topR = *pool.R.top, topP = *pool.Pth.top;
-        if (topS < 32u && topR < 32u && topP < 32u && !exhausted) {  // the warp starves: new seeds into every free slot
+        if (topS < 32u && topR < 32u && topP < 32u && !exhausted) {  // no full trip: new seeds into the free slots
             constexpr uint32_t kRounds = (kPoolSlots + 31u) / 32u;
             uint32_t n_free = 0;
 #pragma unroll
             for (uint32_t j = 0; j < kRounds; ++j)
                 n_free += __popc(__ballot_sync(0xffffffffu, j * 32u + lane < kPoolSlots && pool.live[j * 32u + lane] == 0));
-            if (n_free != 0) {
+            // a refill costs the same instructions for one seed as for 32: wait for kRefillMin free slots unless the pool runs dry
+            if (n_free >= kRefillMin || (n_free != 0 && topS + topR + topP < kRefillDry)) {
                 uint32_t first = 0;
                 if (lane == 0) first = static_cast<uint32_t>(atomicAdd(&P.counters[CT_NEXT_SEED], static_cast<unsigned long long>(n_free)));
                 first = __shfl_sync(0xffffffffu, first, 0);

@@ -23,9 +23,13 @@ ap.add_argument("--warm", type=int, default=1)
 ap.add_argument("--text", type=int, default=1)
 ap.add_argument("--qgram", type=int, default=-1)
 ap.add_argument("--out", default="")
+ap.add_argument("--opt", action="append", default=[], help="name=value for sb200_set_option (repeatable)")
 a = ap.parse_args()
 edit = a.metric == "lev"
 ctx = sb.Context(0)
+for o in a.opt:
+    k, v = o.split("=")
+    ctx.set_option(k, int(v))
 dg = ctx.synth_genome(a.genome, 42)
 ctx.build_index_device(dg, [a.genome], 6, 16)
 q = a.qgram if a.qgram >= 0 else max(0, min(15, int(math.log(max(4, ctx.info()["n_rows"]), 4))))
