@@ -437,6 +437,9 @@ def main():
         ms1 = ms / a.steps
         n1 = n_nodes / a.steps
         p = prof.get(name, {})
+        # the committed capture belongs to one workload shape; its per-node instruction and sector counts do not carry over
+        if p and f" x {a.len} bp, k={a.errors} {a.metric}" not in p.get("workload", ""):
+            p = {}
         out = {"kernel": "sb200::" + name, "ms_per_launch": round(ms1, 3), "nodes_per_launch": int(n1), "does": what}
         # scaled from the committed ncu capture by the node count (the workload is seeded: same launches, same counts)
         scale = n1 / p["nodes_per_launch"] if p.get("nodes_per_launch") else None

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SB200_ABI_VERSION 2
+#define SB200_ABI_VERSION 3
 
 typedef struct sb200_ctx sb200_ctx;
 
@@ -115,6 +115,13 @@ int sb200_index_enable_text(sb200_ctx* ctx, int enable);
 /* builds the q-gram jump table: the cursor of every string of `q` symbols over A,C,G,T, used to skip
  * the first error-free steps of a search (q = 0 removes it; q <= 15, 16 bytes x 4^q of device memory). */
 int sb200_index_build_qgram(sb200_ctx* ctx, uint32_t q);
+
+/* copies the index of `src` — occurrence tables, samples, and whatever derived tables it holds (verification tables,
+ * q-gram table, densified samples) — into `dst`, GPU to GPU (cudaMemcpyPeerAsync: NVLink where the GPUs are peers).
+ * One process driving several GPUs loads / derives the index once and replicates it; the reference loads its index once
+ * per process too (/root/reference/src/sahara/search.cpp:162-169).  `src` must not change during the call; several
+ * destinations may clone from the same source at the same time. */
+int sb200_index_clone(sb200_ctx* dst, sb200_ctx* src);
 
 /* ---- search scheme ---------------------------------------------------------------------------------
  * expanded scheme, one entry per query character: pi/l/u are [n_searches][len] row-major — the

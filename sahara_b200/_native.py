@@ -97,6 +97,7 @@ SB200_SYMBOLS = {
     "sb200_set_policy": (C.c_int, [C.c_void_p, C.POINTER(Policy)]),
     "sb200_get_policy": (C.c_int, [C.c_void_p, C.POINTER(Policy)]),
     "sb200_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "sb200_index_clone": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sb200_submit_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, u64p]),
     "sb200_submit_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, u64p]),
     "sb200_wait_batch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(BatchResult)]),

@@ -138,6 +138,13 @@ def pack_reads4(reads, threads=4, out=None):
     return out
 
 
+def device_count():
+    """CUDA devices the library sees (sb200_device_count)"""
+    n = C.c_int()
+    check(cuda.sb200_device_count(C.byref(n)))
+    return n.value
+
+
 def default_policy():
     """SB200_POLICY_DEFAULT of include/sahara_policy.h"""
     return N.Policy(del_after=0b1001, ins_after=0b0101, end_ok=0b0101, child_order=0, expand_lower=0)
@@ -266,6 +273,10 @@ class Context:
         p = N.Policy()
         check(cuda.sb200_get_policy(self._h, C.byref(p)))
         return p
+
+    def clone_index_from(self, other):
+        """replicates the index of `other` (a Context on another GPU, or the same one) with GPU-to-GPU copies (sb200_index_clone)"""
+        check(cuda.sb200_index_clone(self._h, other._h))
 
     def set_option(self, name, value):
         """knobs of the host orchestration (sb200_set_option); results never depend on them"""

@@ -1889,6 +1889,43 @@ int sb200_index_build_qgram(sb200_ctx* c, uint32_t q) {
     });
 }
 
+int sb200_index_clone(sb200_ctx* dst, sb200_ctx* src) {
+    return guard([&] {
+        if (!src || !dst || src == dst) throw Error("sb200_index_clone needs two different contexts");
+        if (!src->idx.loaded) throw Error("no index loaded in the source context");
+        use(dst);
+        if (dst->device != src->device) {  // direct GPU-to-GPU copies where the devices are peers (else the runtime stages them)
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, dst->device, src->device));
+            if (can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_TRY(e);
+                cudaGetLastError();
+            }
+        }
+        DeviceIndex& d = dst->idx;
+        const DeviceIndex& s = src->idx;
+        d.release();
+        auto copy = [&](DevBuf& to, const DevBuf& from) {
+            if (!from.p) return;
+            CUDA_TRY(cudaMalloc(&to.p, from.cap));
+            to.cap = from.cap;
+            CUDA_TRY(cudaMemcpyPeerAsync(to.p, dst->device, from.p, src->device, from.cap, dst->stream));
+        };
+        copy(d.bwt_blk, s.bwt_blk); copy(d.bwt_sup, s.bwt_sup); copy(d.rev_blk, s.rev_blk); copy(d.rev_sup, s.rev_sup);
+        copy(d.d_C, s.d_C); copy(d.marks, s.marks); copy(d.ssa, s.ssa); copy(d.ref_mark_words, s.ref_mark_words);
+        copy(d.ref_ssa, s.ref_ssa); copy(d.qgram, s.qgram); copy(d.sa32, s.sa32); copy(d.isa32, s.isa32); copy(d.text4, s.text4);
+        copy(d.seq_start, s.seq_start);
+        d.sigma = s.sigma; d.n_rows = s.n_rows; d.n_blocks = s.n_blocks; d.n_sup = s.n_sup;
+        for (int i = 0; i < 8; ++i) { d.C[i] = s.C[i]; d.C64[i] = s.C64[i]; }
+        d.n_mark = s.n_mark; d.full_sa = s.full_sa; d.n_ssa = s.n_ssa; d.sampling_rate = s.sampling_rate;
+        d.bits_for_position = s.bits_for_position; d.device_rate = s.device_rate; d.key_bits = s.key_bits; d.n_ref_ssa = s.n_ref_ssa;
+        d.qgram_q = s.qgram_q; d.n_seqs = s.n_seqs; d.text_mode = s.text_mode;
+        CUDA_TRY(cudaStreamSynchronize(dst->stream));
+        d.loaded = true;
+    });
+}
+
 int sb200_set_scheme(sb200_ctx* c, uint32_t n_searches, uint32_t len, const uint16_t* pi, const uint8_t* l, const uint8_t* u, int edit) {
     return guard([&] {
         use(c);

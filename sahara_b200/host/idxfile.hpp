@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -27,11 +28,26 @@
 
 namespace sahara {
 
+// storage the file is read into: uninitialised (a std::vector would write 8 GB of zeros first for a human-sized index)
+template <typename T>
+struct RawBuf {
+    std::unique_ptr<T[]> p;
+    size_t n{0};
+    void resize(size_t count) {
+        p.reset(count ? new T[count] : nullptr);
+        n = count;
+    }
+    T* data() { return p.get(); }
+    T const* data() const { return p.get(); }
+    size_t size() const { return n; }
+    T* begin() { return p.get(); }
+};
+
 struct IndexImage {
     uint64_t sigma{}, n_rows{}, n_blocks{};
-    std::vector<uint8_t> bwt_blocks, bwtrev_blocks;
-    std::vector<uint64_t> bwt_super, bwtrev_super;
-    std::vector<uint64_t> C, ssa, mark_bits;
+    RawBuf<uint8_t> bwt_blocks, bwtrev_blocks;
+    RawBuf<uint64_t> bwt_super, bwtrev_super;
+    RawBuf<uint64_t> C, ssa, mark_bits;
     uint64_t sampling_rate{}, bits_for_position{};
 
     sb200_index_view view() const {
@@ -108,7 +124,7 @@ inline IndexImage loadIndexFile(std::string const& path) {
     IndexImage im;
     im.sigma = readU64(f);
     if (im.sigma != 5 && im.sigma != 6) throw std::runtime_error("unknown index with " + std::to_string(im.sigma) + " letters");
-    auto readOcc = [&](std::vector<uint8_t>& blocks, std::vector<uint64_t>& super, uint64_t& rows, uint64_t& nBlocks) {
+    auto readOcc = [&](RawBuf<uint8_t>& blocks, RawBuf<uint64_t>& super, uint64_t& rows, uint64_t& nBlocks) {
         nBlocks = readU64(f);
         if (nBlocks == 0 || nBlocks > (uint64_t{1} << 40)) layoutError("block count " + std::to_string(nBlocks) + " where a u64 vector size was expected");
         const uint64_t packed = layout::blockBytesPacked(im.sigma), padded = layout::blockBytesPadded(im.sigma);
@@ -133,7 +149,7 @@ inline IndexImage loadIndexFile(std::string const& path) {
             std::vector<uint8_t> buf(stride);
             for (uint64_t b = 0; b < nBlocks; ++b) {
                 readRaw(f, buf.data(), stride);
-                std::copy(buf.begin(), buf.begin() + static_cast<long>(packed), blocks.begin() + static_cast<long>(b * packed));
+                std::copy(buf.begin(), buf.begin() + static_cast<long>(packed), blocks.data() + b * packed);
             }
         }
         uint64_t nSuper = readU64(f);

@@ -27,6 +27,7 @@
 #include <iterator>
 #include <stdexcept>
 #include <string>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -260,19 +261,37 @@ void runSearch(Args const& a) {
     auto image = sahara::loadIndexFile(indexPath);
     auto view = image.view();
     std::vector<sb200_ctx*> ctxs(nGpus, nullptr);
-    for (int g = 0; g < nGpus; ++g) {
-        check(sb200_create(g, &ctxs[g]));
-        check(sb200_index_upload(ctxs[g], &view));
-        check(sb200_set_max_hits(ctxs[g], static_cast<uint64_t>(maxHits)));  // search_n / search_best_n (search.cpp:228,231,240)
-        if (a.has("--device-sa-rate")) check(sb200_index_densify(ctxs[g], static_cast<uint32_t>(sizeOpt(a, "--device-sa-rate", "16"))));
+    // GPU 0 gets the index from the file and derives its tables; the other GPUs copy everything from a GPU that already
+    // has it — round r: GPUs 2^r .. 2^(r+1)-1 from GPU g - 2^r, all copies of a round at once (NVLink, sb200_index_clone)
+    {
+        check(sb200_create(0, &ctxs[0]));
+        check(sb200_index_upload(ctxs[0], &view));
+        if (a.has("--device-sa-rate")) check(sb200_index_densify(ctxs[0], static_cast<uint32_t>(sizeOpt(a, "--device-sa-rate", "16"))));
         // in-text verification (17 more bytes per row on the device) and the q-gram jump table are on by default
-        if (!a.has("--no-text")) check(sb200_index_enable_text(ctxs[g], 1));
+        if (!a.has("--no-text")) check(sb200_index_enable_text(ctxs[0], 1));
         unsigned q = 0;
         for (uint64_t n = image.n_rows; n >= 4 && q < 15; n /= 4) ++q;  // floor(log4(rows))
         q = std::min(15u, q);  // the depth at which cursors become unique; 4^15 x 16 B = 17 GB at most (3.1 Gbp genomes)
         if (a.has("--qgram")) q = static_cast<unsigned>(sizeOpt(a, "--qgram", "0"));
-        check(sb200_index_build_qgram(ctxs[g], q));
+        check(sb200_index_build_qgram(ctxs[0], q));
     }
+    for (int have = 1; have < nGpus; have *= 2) {
+        std::vector<std::thread> setup;
+        std::vector<std::string> setupErrors(nGpus);
+        for (int g = have; g < std::min(2 * have, nGpus); ++g)
+            setup.emplace_back([&, g, have] {
+                try {
+                    check(sb200_create(g, &ctxs[g]));
+                    check(sb200_index_clone(ctxs[g], ctxs[g - have]));
+                } catch (std::exception const& e) {
+                    setupErrors[g] = e.what();
+                }
+            });
+        for (auto& t : setup) t.join();
+        for (auto const& e : setupErrors)
+            if (!e.empty()) fail(e);
+    }
+    for (int g = 0; g < nGpus; ++g) check(sb200_set_max_hits(ctxs[g], static_cast<uint64_t>(maxHits)));  // search_n / search_best_n (search.cpp:228,231,240)
     timing.emplace_back("ld index", sw.reset());
 
     // search scheme (search.cpp:174-212, 226); besthits: one scheme per stratum of exactly j errors (search.cpp:234-237)
@@ -342,6 +361,14 @@ void runSearch(Args const& a) {
     batch += batch & 1;  // keep both strands of a read together
     const size_t batchReads = std::max<size_t>(1, batch / per);
     std::vector<std::vector<HitBlock>> results(nGpus);
+    // the plain search formats the hit lines of a batch while the next batches run: text per GPU, in batch order
+    struct TextBuf {  // (uninitialised storage: a std::vector would zero 33 bytes per hit first)
+        std::unique_ptr<char[]> p;
+        size_t n{0};
+    };
+    std::vector<std::vector<TextBuf>> text(nGpus);
+    std::vector<size_t> textHits(nGpus, 0);
+    const unsigned fmtThreads = std::max(1u, hostThreads / static_cast<unsigned>(nGpus));
     std::vector<std::string> errors(nGpus);
     std::vector<double> msSearch(nGpus, 0), msLocate(nGpus, 0);
     const size_t readsPerGpu = (nReads + nGpus - 1) / nGpus;
@@ -370,7 +397,8 @@ void runSearch(Args const& a) {
                     msSearch[g] += ct.ms_search;
                     msLocate[g] += ct.ms_locate + ct.ms_sort;
                 };
-                if (!bestHits) {
+                if (!bestHits && maxHits > 0) {
+                    // search_n stops queries at a row limit and walks them again in recursion order: the synchronous call
                     setScheme(ctxs[g], schemes[0]);
                     for (size_t b = r0; b < r1; b += batchReads) {
                         const size_t n = std::min(batchReads, r1 - b);
@@ -381,6 +409,75 @@ void runSearch(Args const& a) {
                         results[g].push_back(HitBlock{hits, nHits, b * per, false});
                         account();
                     }
+                } else if (!bestHits) {
+                    // sb200_submit_reads / sb200_wait_batch: up to two batches in flight, so that the reads of the next batch
+                    // travel to the GPU and the hits of the previous one come back (5-byte CSR records) while a batch computes;
+                    // the hit lines "{queryId} {seqId} {pos}\n" (search.cpp:257-259) of a finished batch are formatted right
+                    // here, by this GPU's share of the host threads, while the GPU works on the following batches
+                    setScheme(ctxs[g], schemes[0]);
+                    struct InFlight { uint64_t ticket, firstQuery; };
+                    std::vector<InFlight> flight;
+                    auto putNum = [](char*& out, uint64_t v, char sep) {
+                        char tmp[24];
+                        int n = 0;
+                        do { tmp[n++] = static_cast<char>('0' + v % 10); v /= 10; } while (v);
+                        while (n) *out++ = tmp[--n];
+                        *out++ = sep;
+                    };
+                    auto collect = [&](InFlight const& fl) {
+                        sb200_batch_result res{};
+                        check(sb200_wait_batch(ctxs[g], fl.ticket, 1, &res));
+                        msSearch[g] += res.ms_search;
+                        msLocate[g] += res.ms_locate + res.ms_sort;
+                        // slices of queries with about the same number of hits, one per formatting thread
+                        std::vector<uint64_t> cut(fmtThreads + 1, res.n_queries);
+                        cut[0] = 0;
+                        for (unsigned t = 1; t < fmtThreads; ++t)
+                            cut[t] = static_cast<uint64_t>(std::lower_bound(res.hit_end, res.hit_end + res.n_queries,
+                                                                             static_cast<uint32_t>(res.n_hits * t / fmtThreads)) - res.hit_end);
+                        const size_t firstBuf = text[g].size();
+                        text[g].resize(firstBuf + fmtThreads);
+                        std::vector<size_t> kept(fmtThreads, 0);
+                        auto format = [&](unsigned t) {
+                            const uint64_t qa = cut[t], qb = std::max(cut[t], cut[t + 1]);
+                            const uint64_t h0 = qa ? res.hit_end[qa - 1] : 0, h1 = qb ? res.hit_end[qb - 1] : 0;
+                            auto& buf = text[g][firstBuf + t];
+                            buf.p.reset(new char[(h1 - h0) * 33 + 1]);  // 3 numbers of at most 10 digits + separators
+                            char* out = buf.p.get();
+                            const uint64_t posMask = (uint64_t{1} << res.bits_for_position) - 1;
+                            uint64_t h = h0;
+                            for (uint64_t q = qa; q < qb; ++q) {
+                                const uint64_t end = res.hit_end[q], query = fl.firstQuery + q;
+                                if (query >= nQueries) { h = end; continue; }  // (the reverse strand of the last read when --limit_queries is odd)
+                                for (; h < end; ++h) {
+                                    uint64_t v = 0;
+                                    std::memcpy(&v, res.records + h * res.record_bytes, res.record_bytes);
+                                    v >>= 4;  // (the low 4 bits are the errors)
+                                    putNum(out, query, ' ');
+                                    putNum(out, v >> res.bits_for_position, ' ');
+                                    putNum(out, v & posMask, '\n');
+                                    ++kept[t];
+                                }
+                            }
+                            buf.n = static_cast<size_t>(out - buf.p.get());
+                        };
+                        std::vector<std::thread> pool;
+                        for (unsigned t = 1; t < fmtThreads; ++t) pool.emplace_back(format, t);
+                        format(0);
+                        for (auto& th : pool) th.join();
+                        for (size_t kk : kept) textHits[g] += kk;
+                        check(sb200_release_batch(ctxs[g], fl.ticket));
+                    };
+                    size_t done = 0;
+                    for (size_t b = r0; b < r1; b += batchReads) {
+                        const size_t n = std::min(batchReads, r1 - b);
+                        uint64_t ticket = 0;
+                        check(sb200_submit_reads(ctxs[g], reads.data() + b * qlen, n, static_cast<uint32_t>(qlen), SB200_READS_RANKS, noReverse ? 0 : 1,
+                                                 &ticket));
+                        flight.push_back(InFlight{ticket, b * per});
+                        if (flight.size() - done >= 2) collect(flight[done++]);
+                    }
+                    while (done < flight.size()) collect(flight[done++]);
                 } else {
                     // strata of exactly j errors; queries that found a hit leave the pool
                     const size_t q0 = std::min(nQueries, r0 * per), q1 = std::min(nQueries, r1 * per);
@@ -474,6 +571,10 @@ void runSearch(Args const& a) {
             }
             buf.resize(static_cast<size_t>(out - buf.data()));
         };
+        for (int g = 0; g < nGpus; ++g) {
+            for (auto const& buf : text[g]) fwrite(buf.p.get(), 1, buf.n, ofs);
+            nHitsTotal += textHits[g];
+        }
         for (int g = 0; g < nGpus; ++g)
             for (auto const& hb : results[g]) {
                 for (size_t base = 0; base < hb.n; base += kSlice * hostThreads) {

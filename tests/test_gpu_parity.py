@@ -111,6 +111,35 @@ def test_densified_locate_is_unchanged(sb, ctx, cases, rate):
     assert np.array_equal(ctx.search(q), want)
 
 
+@pytest.mark.parametrize("variant", ["plain", "text+qgram", "densified"])
+def test_cloned_index_answers_like_its_source(sb, cases, variant):
+    """sb200_index_clone: a second context (the next GPU when the box has one, else the same device) gets the index and
+    its derived tables GPU to GPU and must give the oracle's hits"""
+    rng, seqs, ix, path = cases[("multi", 6)]
+    src = sb.Context(0)
+    dst = sb.Context(1 if sb.device_count() > 1 else 0)
+    try:
+        src.load_index(path)
+        if variant == "text+qgram":
+            src.enable_text(True)
+            src.build_qgram(6)
+        elif variant == "densified":
+            src.densify(4)
+        dst.clone_index_from(src)
+        assert dst.info()["n_rows"] == src.info()["n_rows"] and dst.info()["device_bytes"] > 0
+        src.close()  # the copy stands alone
+        src = None
+        m, k = 48, 2
+        q = W.sample_reads(rng, seqs, 300, m, k, True)
+        sch = sb.SearchScheme.generate("h2-k2", 0, k, m)
+        dst.set_scheme(sch, True)
+        assert np.array_equal(dst.search(q), O.sort_rows(ix.locate(ix.search(q, sch, True))))
+    finally:
+        if src is not None:
+            src.close()
+        dst.close()
+
+
 @pytest.mark.parametrize("qlen", [4, 7, 9])
 def test_qgram_jump_table_keeps_results(sb, ctx, cases, qlen):
     rng, seqs, ix, path = cases[("random", 6)]

@@ -32,7 +32,7 @@ def test_cuda_library_exports_every_declared_symbol():
     exp = exported("libsahara_b200.so")
     assert [n for n in names if n not in exp] == []
     assert sorted(N.SB200_SYMBOLS) == names  # the ctypes table binds exactly the header
-    assert N.cuda.sb200_abi_version() == 2
+    assert N.cuda.sb200_abi_version() == 3
 
 
 def test_host_library_exports_every_declared_symbol():
