@@ -141,6 +141,11 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def metric_name(a):
+    """BASELINE.json's metric for the default shape; another shape (--len / --errors / --metric) is named as what it is"""
+    return f"queries/s ({a.len}bp, k={a.errors} {'edit' if a.metric == 'lev' else 'Hamming'})"
+
+
 def kernel_profile():
     """per-launch counters of the search kernels from the committed ncu captures (profiles/r02_kernel_counters.json,
     written by tools/ncu_counters.py): warp instructions, lanes per instruction, DRAM bytes, L2-miss requests and the node
@@ -254,7 +259,7 @@ def main():
         res = cpu_baseline(sample, a.steps, a.warmup)
         total_t = sum(res["times"])
         value = sample * a.steps / total_t
-        line = {"impl": "reference", "metric": "queries/s (150bp, k=2 edit)", "value": round(value, 1), "unit": "reads/s",
+        line = {"impl": "reference", "metric": metric_name(a), "value": round(value, 1), "unit": "reads/s",
                 "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1e3 * total_t / a.steps, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": dict(config, reads_per_step_per_gpu=sample),
@@ -493,7 +498,7 @@ def main():
         return {"ms_per_step": round(1e3 * secs / a.steps, 3), "kernel_ms_per_step": round(sum(r["ms_search"] + r["ms_locate"] + r["ms_sort"] for r in res) / n, 3),
                 "h2d_ms_at_55GBs": round(res[0]["h2d"] / 55e9 * 1e3, 3), "d2h_ms_at_55GBs": round(sum(r["d2h"] for r in res) / n / 55e9 * 1e3, 3)}
 
-    line = {"metric": "queries/s (150bp, k=2 edit)", "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": a.steps,
+    line = {"metric": metric_name(a), "value": round(value, 1), "unit": "reads/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": round(dev_ms / a.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": dict({"value": round(world * R * a.steps / e2e_s, 1), "unit": "reads/s", "h2d_bytes_per_step": int(res_e2e[0]["h2d"]),

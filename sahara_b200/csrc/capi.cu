@@ -253,6 +253,7 @@ struct sb200_ctx {
     Work* last{};          // slot that holds the result of the last synchronous search (sb200_fetch_hits, sb200_search_cursors)
     uint64_t next_ticket{1};
     Work* prev_slot{};        // slot of the batch submitted last (overlap mode 2 chains on its ev_done)
+    uint64_t cap_cursor{}, cap_seed{}, cap_hit{};  // buffer capacities the work slots have learned (shared: a slot starts with them)
     DevBuf d_tmp, d_scratch, d_counters;  // index construction, rank benchmark
     uint64_t nodes_text{};
     float ms_fm{}, ms_text{};
@@ -945,6 +946,9 @@ void enqueue_compute(sb200_ctx* c, Work& w) {
     auto& ix = c->idx;
     const uint64_t n_queries = w.n_queries;
     const uint32_t len = w.len, W = packed_words(len);
+    w.cursor_cap = std::max(w.cursor_cap, c->cap_cursor);  // (capacities other slots needed for this workload)
+    w.seed_cap = std::max(w.seed_cap, c->cap_seed);
+    w.hit_cap = std::max(w.hit_cap, c->cap_hit);
     if (w.cursor_cap < n_queries * 16) w.cursor_cap = std::max<uint64_t>(1 << 20, n_queries * 16);
     if (w.seed_cap < n_queries * 4) w.seed_cap = std::max<uint64_t>(1 << 20, n_queries * 4);
     if (w.hit_cap < n_queries * 12) w.hit_cap = std::max<uint64_t>(1 << 20, n_queries * 12);
@@ -1132,11 +1136,17 @@ void finish_batch(sb200_ctx* c, Work& w) {
         if (n_slots >= 0xfffffffeull || n_seed_slots >= 0xfffffffeull) throw Error("more than 2^32 cursors in one call; split the batch");
         bool fits = true;
         if (n_seed_slots > w.seed_cap) {  // the text kernel saw a truncated seed list
+            // (the cursors counted so far come from the part of the list it saw: scale them, and the hits they will give,
+            // so that one restart is enough instead of one per buffer)
+            const uint64_t est = n_slots / std::max<uint64_t>(1, w.seed_cap) * n_seed_slots + n_slots % std::max<uint64_t>(1, w.seed_cap) * n_seed_slots / std::max<uint64_t>(1, w.seed_cap);
             w.seed_cap = n_seed_slots + n_seed_slots / 4;
+            w.cursor_cap = std::max(w.cursor_cap, est + est / 4);
+            w.hit_cap = std::max(w.hit_cap, est + est / 4);
             fits = false;
         }
         if (n_slots > w.cursor_cap) {
             w.cursor_cap = n_slots + n_slots / 4;
+            w.hit_cap = std::max(w.hit_cap, w.cursor_cap);  // (every cursor gives at least one hit)
             fits = false;
         }
         bool radix = false;
@@ -1160,6 +1170,10 @@ void finish_batch(sb200_ctx* c, Work& w) {
             enqueue_compute(c, w);
             continue;
         }
+        // what this slot learned about the workload holds for the other slots too
+        c->cap_cursor = std::max(c->cap_cursor, w.cursor_cap);
+        c->cap_seed = std::max(c->cap_seed, w.seed_cap);
+        c->cap_hit = std::max(c->cap_hit, w.hit_cap);
         w.n_cursor_slots = n_slots;
         if (c->max_hits && !c->opt.ordered_only) {
             if (!refine_max_hits(c, w, n_slots)) {
