@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--text", type=int, default=1, help="in-text verification of unique cursors (1 = on)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="name=value for sb200_set_option (experiments; results never depend on it)")
     ap.add_argument("--total-reads", type=int, default=10_000_000, help="configs[3] as stated: reads sharded over the GPUs (strong scaling leg)")
     return ap.parse_args()
 
@@ -196,6 +197,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     ctx = sb.Context(local)
+    for o in a.opt:
+        ctx.set_option(o.split("=")[0], int(o.split("=")[1]))
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
 
@@ -314,7 +317,7 @@ def main():
                 touched = 0
                 if copy and res.n_hits:  # touch the result on the host: first and last record, last end
                     rec = C.cast(res.records, C.POINTER(C.c_uint8))
-                    touched = rec[0] + rec[res.n_hits * res.record_bytes - 1] + C.cast(res.hit_end, C.POINTER(C.c_uint32))[res.n_queries - 1]
+                    touched = rec[0] + rec[res.n_record_bytes - 1] + C.cast(res.hit_end, C.POINTER(C.c_uint32))[res.n_queries - 1]
                 out.append(dict(n_hits=res.n_hits, n_cursors=res.n_cursors, ms_search=res.ms_search, ms_locate=res.ms_locate,
                                 ms_sort=res.ms_sort, h2d=res.h2d_bytes, d2h=res.d2h_bytes, touched=touched))
                 ctx.release_batch(tickets[j - first])
@@ -333,9 +336,16 @@ def main():
     res_dev = pipelined(lambda b: ctx.submit_device(d_batches[b], 2 * R, m), a.warmup, n_batches, False)
     e1.record(stream)
     barrier()
-    dev_ms = allmax(e0.elapsed_time(e1))
+    my_ms = e0.elapsed_time(e1)
+    dev_ms = allmax(my_ms)
     clocks = sampler.finish()
     ct = ctx.counters()
+    # what every rank saw in the timed region: its own time and the batches it had to run again (buffer estimates)
+    rank_info = [{"ms_per_step": round(my_ms / a.steps, 3), "batch_restarts": int(ct["batch_restarts"])}]
+    if use_dist:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, rank_info[0])
+        rank_info = gathered
     launches = int(ct["kernel_launches"])
     value = world * R * a.steps / (dev_ms * 1e-3)
     hits_total = sum(r["n_hits"] for r in res_dev)
@@ -505,7 +515,7 @@ def main():
                          "d2h_bytes_per_step": int(sum(r["d2h"] for r in res_e2e) / len(res_e2e)),
                          "device_event_ms_per_step": round(1e3 * e2e_dev_s / a.steps, 3),
                          "call": "sb200_submit_reads(SB200_READS_PACKED4) / sb200_wait_batch, 2 batches in flight: 4-bit packed reads in "
-                                 "(reverse complements on the device), hits out as CSR records of 5 bytes + 4 bytes per query",
+                                 "(reverse complements on the device), hits out as delta-coded CSR records (5 bytes for the first hit of a query, a varint difference for the others) + 4 bytes per query",
                          "hits_match_device_run": bool(sum(r["n_hits"] for r in res_e2e) == hits_total)}, **brk(res_e2e, e2e_s)),
             "e2e_rank_bytes_in": dict({"value": round(world * R * a.steps / e2e_ranks_s, 1), "unit": "reads/s", "h2d_bytes_per_step": int(res_ranks[0]["h2d"]),
                                        "d2h_bytes_per_step": int(sum(r["d2h"] for r in res_ranks) / len(res_ranks)),
@@ -519,7 +529,7 @@ def main():
                                                "end to end through sb200_submit_reads with host buffers (wall clock, max over ranks)"},
             "gpu_launches": launches, "roofline": roofline,
             "hits_per_step": int(hits_total / a.steps), "cursors_per_step": int(cursors_total / a.steps),
-            "batch_restarts": int(ctx.counters()["batch_restarts"])}
+            "batch_restarts": sum(r["batch_restarts"] for r in rank_info), "ranks": rank_info}
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:  # (the contract: on rank 0 at N = 1 only)
         sample = a.cpu_sample or 20_000

@@ -205,6 +205,11 @@ int sb200_search_reads(sb200_ctx* ctx, const uint8_t* reads, uint64_t n_reads, u
  *           record_bytes little-endian bytes holding ((seq_id << bits_for_position | pos) << 4) | errors, sorted by that
  *           value within a query.  query ids count as in the reference (2i = read i, 2i+1 = its reverse complement when
  *           with_reverse != 0).  5 bytes per hit for a human-sized genome instead of the reference's 32-byte tuple.
+ *           Delta coding (the default; sb200_set_option(ctx, "delta_records", 0) turns it off): the hits of a query lie close
+ *           together, so only the first record of a query is stored as above; every further one is the difference of its
+ *           value to its predecessor's as a variable-length integer (7 bits per byte, low bits first, top bit = another
+ *           byte follows) — about 1.3 bytes per hit.  hit_end[q] is then the end of query q's BYTES in `records`, and the
+ *           number of its hits follows from decoding.  sbh_decode_records (libsahara_host) turns either form into tuples.
  *           The arrays belong to the batch and stay valid until sb200_release_batch(ticket). */
 #define SB200_MAX_IN_FLIGHT 3
 #define SB200_READS_RANKS 0
@@ -216,6 +221,8 @@ typedef struct sb200_batch_result {
     uint32_t record_bytes, bits_for_position;
     uint64_t h2d_bytes, d2h_bytes;          /* bytes this batch moved over PCIe */
     float ms_search, ms_locate, ms_sort;    /* CUDA-event times of the batch's kernels */
+    uint32_t delta_coded;                   /* 1: `records` is delta coded and hit_end[] holds BYTE offsets (see above) */
+    uint64_t n_record_bytes;                /* size of `records` */
 } sb200_batch_result;
 int sb200_submit_reads(sb200_ctx* ctx, const void* reads, uint64_t n_reads, uint32_t len, int format, int with_reverse,
                        uint64_t* ticket);

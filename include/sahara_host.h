@@ -64,6 +64,11 @@ int sbh_revcomp_ranks(const uint8_t* in, uint64_t n, uint8_t* out);
  * little-endian 32-bit word, (len + 7) / 8 words per read, unused nibbles of a read's last word 0xF.  out: n_reads *
  * ((len + 7) / 8) words (page-locked memory from sb200_host_alloc makes the copy to the GPU a single DMA). */
 int sbh_pack_reads4(const uint8_t* ranks, uint64_t n_reads, uint32_t len, uint32_t threads, uint32_t* out);
+/* CSR result of sb200_wait_batch (include/sahara_b200.h: hit_end, records, record_bytes, bits_for_position, delta_coded) ->
+ * tuples: out[4 * i + 0..3] = queryId (first_query + q), seqId, pos, errors of hit i, in the order of the records; out holds
+ * 4 * n_hits values.  Fails when the records do not decode to exactly n_hits hits. */
+int sbh_decode_records(const uint32_t* hit_end, const uint8_t* records, uint64_t n_queries, uint64_t n_hits, uint32_t record_bytes,
+                       uint32_t bits_for_position, int delta_coded, uint64_t first_query, uint64_t* out);
 /* rule `expand_lower` of the policy table (include/sahara_policy.h) used by every expansion that follows (default 0) */
 int sbh_set_expand_rule(uint32_t rule);
 

@@ -71,6 +71,7 @@ class BatchResult(C.Structure):
         ("record_bytes", C.c_uint32), ("bits_for_position", C.c_uint32),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
         ("ms_search", C.c_float), ("ms_locate", C.c_float), ("ms_sort", C.c_float),
+        ("delta_coded", C.c_uint32), ("n_record_bytes", C.c_uint64),
     ]
 
 
@@ -146,6 +147,7 @@ SBH_SYMBOLS = {
     "sbh_revcomp_ranks": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "sbh_pack_reads4": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),
     "sbh_set_expand_rule": (C.c_int, [C.c_uint32]),
+    "sbh_decode_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.c_void_p]),
     "sbh_free": (None, [C.c_void_p]),
 }
 

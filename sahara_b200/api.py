@@ -156,22 +156,13 @@ def set_expand_rule(rule):
 
 
 def decode_batch(res, first_query=0):
-    """sb200_batch_result -> uint64 [n_hits, 4] = (queryId, seqId, pos, errors) in the order of the records"""
-    nq, nh, rb, bits = res.n_queries, res.n_hits, res.record_bytes, res.bits_for_position
-    if nh == 0:
-        return np.zeros((0, 4), dtype=np.uint64)
-    ends = np.ctypeslib.as_array(C.cast(res.hit_end, N.u32p), shape=(nq,)).astype(np.int64)
-    raw = np.ctypeslib.as_array(C.cast(res.records, N.u8p), shape=(nh * rb,)).reshape(nh, rb)
-    key = np.zeros(nh, dtype=np.uint64)
-    for b in range(rb):
-        key |= raw[:, b].astype(np.uint64) << np.uint64(8 * b)
-    counts = np.diff(np.concatenate([[0], ends]))
-    out = np.empty((nh, 4), dtype=np.uint64)
-    out[:, 0] = np.repeat(np.arange(nq, dtype=np.uint64) + np.uint64(first_query), counts)
-    v = key >> np.uint64(4)
-    out[:, 1] = v >> np.uint64(bits)
-    out[:, 2] = v & np.uint64((1 << bits) - 1)
-    out[:, 3] = key & np.uint64(15)
+    """sb200_batch_result -> uint64 [n_hits, 4] = (queryId, seqId, pos, errors) in the order of the records
+    (fixed or delta-coded records: sbh_decode_records of the host library)"""
+    out = np.empty((res.n_hits, 4), dtype=np.uint64)
+    if res.n_hits == 0:
+        return out
+    check_host(host.sbh_decode_records(res.hit_end, res.records, res.n_queries, res.n_hits, res.record_bytes, res.bits_for_position,
+                                       int(res.delta_coded), int(first_query), _ptr(out)))
     return out
 
 

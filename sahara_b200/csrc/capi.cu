@@ -190,6 +190,7 @@ struct Options {
     // verification kernel of a batch (a persistent kernel that fills every SM) starts only when its predecessor batch is
     // complete: packing and the walk over the occurrence tables of batch i+1 fill the tail of batch i, nothing else waits
     int overlap{2};
+    int delta_records{1};      // CSR results of the asynchronous calls: records behind the first of a query as differences (varint)
 };
 
 enum : int { IN_QUERIES_RANKS = 0, IN_READS_RANKS = 1, IN_READS_PACKED4 = 2 };
@@ -225,11 +226,14 @@ struct Work {
     uint32_t fused_shift{0};  // hit keys of a global sort carry the query id above this bit (0: separate array)
     int sorted_keys{0};       // d_keys[] buffer that holds the sorted hits
     uint64_t n_cursor_slots{}, n_real_cursors{}, n_hits{};
+    DevBuf d_bsize, d_bpos, d_btmp;   // delta-coded records: bytes per query, their inclusive scan, scan scratch
+    bool delta{};             // the records in d_out are delta coded
+    uint64_t n_rec_bytes{};   // their total size
     uint64_t h2d_bytes{}, d2h_bytes{};
     float ms_search{}, ms_locate{}, ms_sort{}, ms_fm{}, ms_text{};
     void release_buffers() {
         for (DevBuf* b : {&d_in, &d_packed, &d_items, &d_item_tags, &d_seeds, &d_spill, &d_cursors, &d_counters, &d_qpos, &d_lc, &d_tasks, &d_bigsegs,
-                          &d_keys[0], &d_keys[1], &d_qids[0], &d_qids[1], &d_offsets, &d_tmp, &d_scratch, &d_rows, &d_redo, &d_ostack, &d_out})
+                          &d_keys[0], &d_keys[1], &d_qids[0], &d_qids[1], &d_offsets, &d_tmp, &d_scratch, &d_rows, &d_redo, &d_ostack, &d_out, &d_bsize, &d_bpos, &d_btmp})
             b->release();
     }
 };
@@ -682,13 +686,14 @@ void read_back_words(sb200_ctx* c, cudaStream_t s, const void* d_src, int n, int
 }
 
 // status block a batch publishes into mapped host memory (one kernel at its end)
-enum : int { ST_COUNTERS = 0, ST_LC = CT_COUNT, ST_HITS = CT_COUNT + LC_COUNT, ST_COUNT = CT_COUNT + LC_COUNT + 2 };
+enum : int { ST_COUNTERS = 0, ST_LC = CT_COUNT, ST_HITS = CT_COUNT + LC_COUNT, ST_BYTES = ST_HITS + 1, ST_COUNT = CT_COUNT + LC_COUNT + 2 };
 __global__ void publish_status_kernel(const unsigned long long* counters, const unsigned int* lc, const uint32_t* total_hits,
-                                      unsigned long long* dst) {
+                                      const uint32_t* total_bytes, unsigned long long* dst) {
     const int t = threadIdx.x;
     if (t < CT_COUNT) dst[ST_COUNTERS + t] = counters[t];
     else if (t < CT_COUNT + LC_COUNT) dst[t] = lc ? lc[t - CT_COUNT] : 0u;
     else if (t == ST_HITS) dst[t] = total_hits ? *total_hits : 0u;
+    else if (t == ST_BYTES) dst[t] = total_bytes ? *total_bytes : 0u;
 }
 
 SearchParams search_params(sb200_ctx* c, Work& w) {
@@ -770,7 +775,6 @@ PoolGeometry pool_geometry(sb200_ctx* c, uint32_t n_searches, uint32_t len) {
 void enqueue_search_kernels(sb200_ctx* c, Work& w) {
     auto& ix = c->idx;
     const uint64_t n_queries = w.n_queries;
-    const uint32_t len = w.len;
     w.d_cursors.reserve((w.cursor_cap + 1) * sizeof(uint4));
     if (ix.text_mode) w.d_seeds.reserve((w.seed_cap + 1) * sizeof(uint4));
     unsigned long long* ctr = w.d_counters.get<unsigned long long>();
@@ -929,14 +933,32 @@ void enqueue_output(sb200_ctx* c, Work& w, uint64_t n, const uint32_t* n_dev) {
     else if (w.out_fmt == OUT_HIT64)
         expand_hits_kernel<<<grid, 256, 0, w.stream>>>(keys, w.d_qids[0].get<uint32_t>(), n, n_dev, static_cast<uint32_t>(ix.bits_for_position),
                                                       w.first_query, w.fused_shift, w.d_out.get<uint64_t>());
-    else
+    else if (!w.delta)
         pack_records_kernel<<<grid, 256, 0, w.stream>>>(keys, n, n_dev, w.fused_shift, static_cast<uint32_t>(rec), w.d_out.get<uint8_t>());
+    else {
+        // delta-coded records (locate.cuh): bytes per query, their scan, the bytes; the per-query ends are in w.d_qpos
+        const uint32_t nq = static_cast<uint32_t>(w.n_queries);
+        w.d_out.reserve((std::max<uint64_t>(1, n) + 4) * (rec + 1) + 64);  // (a difference takes at most rec + 1 bytes)
+        w.d_bsize.reserve((size_t(nq) + 1) * 4);
+        w.d_bpos.reserve((size_t(nq) + 1) * 4);
+        delta_size_kernel<<<std::max(1u, grid_for(nq)), 256, 0, w.stream>>>(keys, static_cast<uint32_t>(std::min<uint64_t>(n, 0xfffffff0ull)), w.d_qpos.get<uint32_t>(), nq, w.fused_shift, static_cast<uint32_t>(rec),
+                                                                             w.d_bsize.get<uint32_t>());
+        launch_check(c);
+        size_t tmp = 0;
+        CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, tmp, w.d_bsize.get<uint32_t>(), w.d_bpos.get<uint32_t>(), nq, w.stream));
+        w.d_btmp.reserve(tmp);
+        CUDA_TRY(cub::DeviceScan::InclusiveSum(w.d_btmp.p, tmp, w.d_bsize.get<uint32_t>(), w.d_bpos.get<uint32_t>(), nq, w.stream));
+        c->ct.kernel_launches += 2;
+        delta_write_kernel<<<std::max(1u, grid_for(nq)), 256, 0, w.stream>>>(keys, static_cast<uint32_t>(std::min<uint64_t>(n, 0xfffffff0ull)), w.d_qpos.get<uint32_t>(), w.d_bpos.get<uint32_t>(), nq, w.fused_shift,
+                                                                              static_cast<uint32_t>(rec), w.d_out.get<uint8_t>());
+    }
     launch_check(c);
 }
 
 void enqueue_publish(sb200_ctx* c, Work& w, bool located) {
     publish_status_kernel<<<1, 64, 0, w.stream>>>(w.d_counters.get<unsigned long long>(), located ? w.d_lc.get<unsigned int>() : nullptr,
-                                                  located ? w.d_scratch.get<uint32_t>() : nullptr, w.h_status_dev);
+                                                  located ? w.d_scratch.get<uint32_t>() : nullptr,
+                                                  located && w.delta && w.n_queries ? w.d_bpos.get<uint32_t>() + (w.n_queries - 1) : nullptr, w.h_status_dev);
     launch_check(c);
     CUDA_TRY(cudaEventRecord(w.ev_done, w.stream));
 }
@@ -1114,6 +1136,12 @@ void locate_radix(sb200_ctx* c, Work& w, uint64_t n_cursors, uint64_t n_queries_
     read_back_words(c, w.stream, ctr, CT_COUNT);
     w.h_status[ST_COUNTERS + CT_LF_STEPS] = c->h_counters[CT_LF_STEPS];
     w.n_hits = total_rows;
+    if (w.delta && w.out_fmt == OUT_CSR && w.n_queries) {
+        uint32_t bytes = 0;
+        CUDA_TRY(cudaMemcpyAsync(&bytes, w.d_bpos.get<uint32_t>() + (w.n_queries - 1), 4, cudaMemcpyDeviceToHost, w.stream));
+        CUDA_TRY(cudaStreamSynchronize(w.stream));
+        w.n_rec_bytes = bytes;
+    }
 }
 
 // waits for the batch, grows buffers and starts over when something did not fit, finishes the parts that need the host
@@ -1163,6 +1191,7 @@ void finish_batch(sb200_ctx* c, Work& w) {
             } else {
                 radix = st[ST_LC + LC_HUGE] != 0;  // a query with more hits than a block sorts
                 w.n_hits = total;
+                w.n_rec_bytes = st[ST_BYTES];
             }
         }
         if (!fits) {
@@ -1271,6 +1300,8 @@ void setup_batch(sb200_ctx* c, Work& w, const void* src, bool src_on_device, int
     w.with_reverse = with_reverse;
     w.do_locate = do_locate;
     w.out_fmt = do_locate ? out_fmt : OUT_NONE;
+    w.delta = w.out_fmt == OUT_CSR && c->opt.delta_records != 0;
+    w.n_rec_bytes = 0;
     w.first_query = first_query;
     w.packed_ready = false;
     w.located = false;
@@ -1296,10 +1327,12 @@ void enqueue_copy_out(sb200_ctx* c, Work& w, void* dst_records, uint32_t* dst_en
     const size_t rec = out_record_bytes(c, w.out_fmt);
     // (finish_batch has waited for everything of this batch: no event needed; in overlap mode 0 the slot's stream also
     // carries the successors' kernels, which the copy must not wait for)
-    if (w.n_hits) CUDA_TRY(cudaMemcpyAsync(dst_records, w.d_out.p, w.n_hits * rec, cudaMemcpyDeviceToHost, c->s_out));
-    if (dst_ends) CUDA_TRY(cudaMemcpyAsync(dst_ends, w.d_qpos.p, w.n_queries * 4, cudaMemcpyDeviceToHost, c->s_out));
+    const size_t rec_bytes_total = w.delta ? w.n_rec_bytes : w.n_hits * rec;
+    if (w.n_hits) CUDA_TRY(cudaMemcpyAsync(dst_records, w.d_out.p, rec_bytes_total, cudaMemcpyDeviceToHost, c->s_out));
+    // (delta-coded records: the ends are byte offsets)
+    if (dst_ends) CUDA_TRY(cudaMemcpyAsync(dst_ends, w.delta ? w.d_bpos.p : w.d_qpos.p, w.n_queries * 4, cudaMemcpyDeviceToHost, c->s_out));
     CUDA_TRY(cudaEventRecord(w.ev_out, c->s_out));
-    w.d2h_bytes = w.n_hits * rec + (dst_ends ? w.n_queries * 4 : 0);
+    w.d2h_bytes = rec_bytes_total + (dst_ends ? w.n_queries * 4 : 0);
 }
 
 // the synchronous entry points run on slot 0 and the caller's stream
@@ -2010,6 +2043,7 @@ int sb200_set_option(sb200_ctx* c, const char* name, int64_t value) {
         else if (n == "run_rounds") o.run_rounds = static_cast<int>(std::max<int64_t>(0, value));
         else if (n == "items_blocks_per_sm") o.items_blocks_per_sm = static_cast<int>(std::max<int64_t>(0, value));
         else if (n == "ordered_blocks_per_sm") o.ordered_blocks_per_sm = static_cast<int>(std::max<int64_t>(0, value));
+        else if (n == "delta_records") o.delta_records = value != 0;
         else if (n == "overlap") {
             if (value < 0 || value > 2) throw Error("option overlap takes 0, 1 or 2");
             for (auto& w : c->work)
@@ -2131,8 +2165,10 @@ int sb200_wait_batch(sb200_ctx* c, uint64_t ticket, int copy_to_host, sb200_batc
         out->n_cursors = w.n_real_cursors;
         out->record_bytes = static_cast<uint32_t>(rec);
         out->bits_for_position = static_cast<uint32_t>(c->idx.bits_for_position);
+        out->delta_coded = w.delta ? 1u : 0u;
+        out->n_record_bytes = w.delta ? w.n_rec_bytes : w.n_hits * rec;
         if (copy_to_host) {
-            const size_t need = (w.n_hits + 4) * rec + 64, need_ends = (w.n_queries + 1) * 4;
+            const size_t need = (w.delta ? w.n_rec_bytes : (w.n_hits + 4) * rec) + 64, need_ends = (w.n_queries + 1) * 4;
             if (need > w.h_out_cap) {
                 if (w.h_out) cudaFreeHost(w.h_out);
                 w.h_out = nullptr;

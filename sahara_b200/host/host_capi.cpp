@@ -202,6 +202,55 @@ int sbh_pack_reads4(const uint8_t* ranks, uint64_t n_reads, uint32_t len, uint32
     return guard([&] { sahara::fasta::packReads4(ranks, n_reads, len, threads, out); });
 }
 
+int sbh_decode_records(const uint32_t* hit_end, const uint8_t* records, uint64_t n_queries, uint64_t n_hits, uint32_t record_bytes,
+                       uint32_t bits_for_position, int delta_coded, uint64_t first_query, uint64_t* out) {
+    return guard([&] {
+        if (record_bytes == 0 || record_bytes > 8 || bits_for_position == 0 || bits_for_position > 56) throw std::runtime_error("records: bad format");
+        const uint64_t posMask = (uint64_t{1} << bits_for_position) - 1;
+        uint64_t h = 0;
+        auto put = [&](uint64_t q, uint64_t v) {
+            if (h >= n_hits) throw std::runtime_error("records decode to more hits than announced");
+            uint64_t* o = out + 4 * h++;
+            o[0] = first_query + q;
+            o[1] = (v >> 4) >> bits_for_position;
+            o[2] = (v >> 4) & posMask;
+            o[3] = v & 15;
+        };
+        for (uint64_t q = 0; q < n_queries; ++q) {
+            const uint64_t b = q ? hit_end[q - 1] : 0, e = hit_end[q];
+            if (!delta_coded) {
+                for (uint64_t i = b; i < e; ++i) {
+                    uint64_t v = 0;
+                    std::memcpy(&v, records + i * record_bytes, record_bytes);
+                    put(q, v);
+                }
+                continue;
+            }
+            uint64_t at = b, v = 0;
+            while (at < e) {
+                if (at == b) {
+                    if (at + record_bytes > e) throw std::runtime_error("records: truncated first record of a query");
+                    std::memcpy(&v, records + at, record_bytes);
+                    at += record_bytes;
+                } else {
+                    uint64_t d = 0;
+                    unsigned shift = 0;
+                    while (true) {
+                        if (at >= e || shift > 56) throw std::runtime_error("records: truncated difference");
+                        const uint8_t byte = records[at++];
+                        d |= uint64_t(byte & 0x7f) << shift;
+                        shift += 7;
+                        if (!(byte & 0x80)) break;
+                    }
+                    v += d;
+                }
+                put(q, v);
+            }
+        }
+        if (h != n_hits) throw std::runtime_error("records decode to fewer hits than announced");
+    });
+}
+
 int sbh_fasta_load_reads(const char* path, uint64_t sigma, uint32_t threads, uint8_t** ranks, uint64_t* n_reads, uint64_t* len) {
     return guard([&] {
         if (sigma != 5 && sigma != 6) throw std::runtime_error("unknown index with " + std::to_string(sigma) + " letters");

@@ -429,34 +429,59 @@ void runSearch(Args const& a) {
                         check(sb200_wait_batch(ctxs[g], fl.ticket, 1, &res));
                         msSearch[g] += res.ms_search;
                         msLocate[g] += res.ms_locate + res.ms_sort;
-                        // slices of queries with about the same number of hits, one per formatting thread
+                        // slices of queries with about the same amount of records (hits, or bytes when delta coded), one per
+                        // formatting thread
+                        const uint64_t units = res.n_queries ? res.hit_end[res.n_queries - 1] : 0;
                         std::vector<uint64_t> cut(fmtThreads + 1, res.n_queries);
                         cut[0] = 0;
                         for (unsigned t = 1; t < fmtThreads; ++t)
                             cut[t] = static_cast<uint64_t>(std::lower_bound(res.hit_end, res.hit_end + res.n_queries,
-                                                                             static_cast<uint32_t>(res.n_hits * t / fmtThreads)) - res.hit_end);
+                                                                             static_cast<uint32_t>(units * t / fmtThreads)) - res.hit_end);
                         const size_t firstBuf = text[g].size();
                         text[g].resize(firstBuf + fmtThreads);
                         std::vector<size_t> kept(fmtThreads, 0);
                         auto format = [&](unsigned t) {
                             const uint64_t qa = cut[t], qb = std::max(cut[t], cut[t + 1]);
-                            const uint64_t h0 = qa ? res.hit_end[qa - 1] : 0, h1 = qb ? res.hit_end[qb - 1] : 0;
+                            const uint64_t u0 = qa ? res.hit_end[qa - 1] : 0, u1 = qb ? res.hit_end[qb - 1] : 0;
                             auto& buf = text[g][firstBuf + t];
-                            buf.p.reset(new char[(h1 - h0) * 33 + 1]);  // 3 numbers of at most 10 digits + separators
+                            // 3 numbers of at most 10 digits + separators per hit; a delta-coded hit takes at least one byte
+                            buf.p.reset(new char[(u1 - u0) * 33 + 1]);
                             char* out = buf.p.get();
                             const uint64_t posMask = (uint64_t{1} << res.bits_for_position) - 1;
-                            uint64_t h = h0;
+                            auto line = [&](uint64_t query, uint64_t v) {
+                                v >>= 4;  // (the low 4 bits are the errors)
+                                putNum(out, query, ' ');
+                                putNum(out, v >> res.bits_for_position, ' ');
+                                putNum(out, v & posMask, '\n');
+                                ++kept[t];
+                            };
+                            uint64_t at = u0;
                             for (uint64_t q = qa; q < qb; ++q) {
                                 const uint64_t end = res.hit_end[q], query = fl.firstQuery + q;
-                                if (query >= nQueries) { h = end; continue; }  // (the reverse strand of the last read when --limit_queries is odd)
-                                for (; h < end; ++h) {
-                                    uint64_t v = 0;
-                                    std::memcpy(&v, res.records + h * res.record_bytes, res.record_bytes);
-                                    v >>= 4;  // (the low 4 bits are the errors)
-                                    putNum(out, query, ' ');
-                                    putNum(out, v >> res.bits_for_position, ' ');
-                                    putNum(out, v & posMask, '\n');
-                                    ++kept[t];
+                                const bool skip = query >= nQueries;  // (the reverse strand of the last read when --limit_queries is odd)
+                                if (!res.delta_coded) {
+                                    for (; at < end; ++at) {
+                                        uint64_t v = 0;
+                                        std::memcpy(&v, res.records + at * res.record_bytes, res.record_bytes);
+                                        if (!skip) line(query, v);
+                                    }
+                                    continue;
+                                }
+                                uint64_t v = 0;
+                                for (bool first = true; at < end; first = false) {
+                                    if (first) {
+                                        std::memcpy(&v, res.records + at, res.record_bytes);
+                                        at += res.record_bytes;
+                                    } else {  // difference to the previous record: 7 bits per byte, low bits first
+                                        uint64_t d = 0;
+                                        for (unsigned shift = 0;; shift += 7) {
+                                            const uint8_t byte = res.records[at++];
+                                            d |= uint64_t(byte & 0x7f) << shift;
+                                            if (!(byte & 0x80)) break;
+                                        }
+                                        v += d;
+                                    }
+                                    if (!skip) line(query, v);
                                 }
                             }
                             buf.n = static_cast<size_t>(out - buf.p.get());

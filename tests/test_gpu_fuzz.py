@@ -65,7 +65,14 @@ def test_random_configuration(seed):
             both[0::2] = reads
             both[1::2] = np.stack([W.revcomp(r) for r in reads])
             want_async = want_hits if np.array_equal(both, q) else O.sort_rows(ix.locate(ix.search(both, sch, edit)))
-            got_async = ctx.search_reads_async(reads, packed4=bool((seed + it) & 1), batch=(7, 40, 1000)[(seed + it) % 3])
+            # records delta coded or fixed, sorted through the per-query buckets or the global radix sort
+            ctx.set_option("delta_records", ((seed + it) >> 1) & 1)
+            ctx.set_option("bucket_sort", 0 if (seed + it) % 5 == 4 else 1)
+            try:
+                got_async = ctx.search_reads_async(reads, packed4=bool((seed + it) & 1), batch=(7, 40, 1000)[(seed + it) % 3])
+            finally:
+                ctx.set_option("delta_records", 1)
+                ctx.set_option("bucket_sort", 1)
             assert got_async.shape == want_async.shape and np.array_equal(got_async, want_async), (seed, gen, k, m, edit, "async")
             # search_n with a random limit: the first rows of every query in the reference's recursion order
             n = (1, 2, 3, 7, 50)[(seed + it) % 5]  # (not drawn from rng: the configurations stay what they were)

@@ -195,6 +195,45 @@ def test_index_file_reader_accepts_64_byte_aligned_blocks(tmp_path):
     assert np.array_equal(again.bwt(0), ix.bwt(0)) and np.array_equal(again.bwt(1), ix.bwt(1))
 
 
+def test_record_decoder_reads_fixed_and_delta_coded_results():
+    """sbh_decode_records against a Python encoder of both CSR forms of sb200_wait_batch (include/sahara_b200.h)"""
+    rng = np.random.default_rng(9)
+    bits, rec = 32, 5
+    nq = 300
+    hits, ends_fixed, fixed, ends_delta, delta = [], [], bytearray(), [], bytearray()
+    for q in range(nq):
+        n = int(rng.integers(0, 12)) if q % 7 else 0
+        base = int(rng.integers(0, 1 << 31))
+        vals = sorted(((int(rng.integers(0, 3)) << bits | (base + int(rng.integers(0, 40)) if rng.random() < 0.8 else int(rng.integers(0, 1 << 32)))) << 4)
+                      | int(rng.integers(0, 3)) for _ in range(n))
+        prev = None
+        for v in vals:
+            hits.append((q + 10, (v >> 4) >> bits, (v >> 4) & ((1 << bits) - 1), v & 15))
+            fixed += v.to_bytes(rec, "little")
+            if prev is None:
+                delta += v.to_bytes(rec, "little")
+            else:
+                d = v - prev
+                while d >= 128:
+                    delta.append((d & 0x7f) | 0x80)
+                    d >>= 7
+                delta.append(d)
+            prev = v
+        ends_fixed.append(len(fixed) // rec)
+        ends_delta.append(len(delta))
+    want = np.array(hits, dtype=np.uint64).reshape(-1, 4)
+    for ends, blob, coded in ((ends_fixed, fixed, 0), (ends_delta, delta, 1)):
+        e = np.array(ends, dtype=np.uint32)
+        b = np.frombuffer(bytes(blob) + b"\0" * 8, dtype=np.uint8)
+        out = np.zeros((want.shape[0], 4), dtype=np.uint64)
+        N.check_host(N.host.sbh_decode_records(e.ctypes.data, b.ctypes.data, nq, want.shape[0], rec, bits, coded, 10, out.ctypes.data))
+        assert np.array_equal(out, want)
+        # a wrong hit count is refused
+        assert N.host.sbh_decode_records(e.ctypes.data, b.ctypes.data, nq, want.shape[0] + 1, rec, bits, coded, 10,
+                                         np.zeros((want.shape[0] + 1, 4), np.uint64).ctypes.data) != 0
+    assert len(delta) < len(fixed)
+
+
 def test_synth_mirror_is_deterministic():
     from sahara_b200 import synth
     g = synth.genome(5000, 42)
