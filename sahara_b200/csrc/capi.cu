@@ -228,6 +228,7 @@ struct Work {
     uint64_t n_cursor_slots{}, n_real_cursors{}, n_hits{};
     DevBuf d_bsize, d_bpos, d_btmp;   // delta-coded records: bytes per query, their inclusive scan, scan scratch
     bool delta{};             // the records in d_out are delta coded
+    bool counted{};           // the search kernels counted the rows per query into d_qpos (no hit_count_kernel pass)
     uint64_t n_rec_bytes{};   // their total size
     uint64_t h2d_bytes{}, d2h_bytes{};
     float ms_search{}, ms_locate{}, ms_sort{}, ms_fm{}, ms_text{};
@@ -781,6 +782,14 @@ void enqueue_search_kernels(sb200_ctx* c, Work& w) {
     CUDA_TRY(cudaMemsetAsync(ctr, 0, CT_BAD_QUERY * sizeof(unsigned long long), w.stream));  // keeps CT_BAD_QUERY
     CUDA_TRY(cudaMemsetAsync(ctr + CT_NODES_TEXT, 0, (CT_COUNT - CT_NODES_TEXT) * sizeof(unsigned long long), w.stream));
     SearchParams P = search_params(c, w);
+    // the rows per query are counted while the cursors are written when the bucketed locate follows right behind
+    // (no row limit, no foreign cursors): saves its counting pass over the cursor list
+    w.counted = w.do_locate && c->max_hits == 0 && c->opt.bucket_sort;
+    if (w.counted) {
+        w.d_qpos.reserve((n_queries + 1) * 4);
+        CUDA_TRY(cudaMemsetAsync(w.d_qpos.p, 0, (n_queries + 1) * 4, w.stream));
+        P.qcount = w.d_qpos.get<uint32_t>();
+    }
     CUDA_TRY(cudaEventRecord(w.ev[8], w.stream));
     // search_n by the ordered walk alone (option ordered_only); the default is the plain search first, then the queries
     // above the limit again in recursion order (refine_max_hits)
@@ -857,12 +866,15 @@ void enqueue_locate_bucketed(sb200_ctx* c, Work& w) {
     CUDA_TRY(cudaEventRecord(w.ev[1], w.stream));
     w.d_qpos.reserve((n_queries + 1) * 4);
     w.d_lc.reserve(LC_COUNT * 4);
-    CUDA_TRY(cudaMemsetAsync(w.d_qpos.p, 0, (n_queries + 1) * 4, w.stream));
     CUDA_TRY(cudaMemsetAsync(w.d_lc.p, 0, LC_COUNT * 4, w.stream));
     const uint32_t cur_cap = static_cast<uint32_t>(std::min<uint64_t>(w.cursor_cap, 0xfffffffeull));
     const unsigned wide = static_cast<unsigned>(c->sms) * 8;
-    hit_count_kernel<<<wide, 256, 0, w.stream>>>(w.d_cursors.get<uint4>(), cur_cap, ctr + CT_OUT_SLOTS, w.d_qpos.get<uint32_t>(), ctr + CT_TOTAL_ROWS);
-    launch_check(c);
+    if (!w.counted) {  // (else the search kernels have counted the rows per query as they wrote the cursors)
+        CUDA_TRY(cudaMemsetAsync(w.d_qpos.p, 0, (n_queries + 1) * 4, w.stream));
+        hit_count_kernel<<<wide, 256, 0, w.stream>>>(w.d_cursors.get<uint4>(), cur_cap, ctr + CT_OUT_SLOTS, w.d_qpos.get<uint32_t>(), ctr + CT_TOTAL_ROWS);
+        launch_check(c);
+    }
+    w.counted = false;  // (a later bucketed pass over this batch — search_n — counts for itself)
     size_t tmp_bytes = 0;
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, w.d_qpos.get<uint32_t>(), w.d_qpos.get<uint32_t>(), n_queries + 1, w.stream));
     w.d_tmp.reserve(tmp_bytes);

@@ -215,6 +215,8 @@ struct SearchParams {
     uint4* ostack;
     uint32_t ostack_frames;  // frames per thread
     const uint32_t* redo;    // optional: the queries to walk (n_queries = their number); nullptr = all queries
+    uint32_t* qcount;        // optional: rows reported per query, counted as the cursors are written (what hit_count_kernel of
+                             // locate.cuh would count in a pass of its own); rows beyond the first of a cursor also go to CT_TOTAL_ROWS
 };
 
 __host__ __device__ inline uint32_t packed_words(uint32_t len) { return (len + 7) / 8; }
@@ -661,6 +663,10 @@ __device__ __forceinline__ void fm_items_thread(const SearchParams& P, const uin
     auto qsym = [&](uint32_t pos) -> uint32_t { return (ldg32(qwords + (pos >> 3)) >> ((pos & 7u) * 4u)) & 0xfu; };
     auto emit = [&](uint32_t lb, uint32_t len, uint32_t e) {
         outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], make_uint4(qid, lb, len, e));
+        if (P.qcount != nullptr && len != 0) {
+            atomicAdd(&P.qcount[qid], len);
+            if (len > 1) atomicAdd(&P.counters[CT_TOTAL_ROWS], static_cast<unsigned long long>(len - 1));
+        }
         ++emitted;
     };
     auto push = [&](uint32_t nlb, uint32_t nlbRev, uint32_t nlen, uint32_t m) {
@@ -1109,7 +1115,7 @@ struct TextPool {
     FrameStack Pth;        // path frames: state frames at the start of a path window (text_path); no spill area
     uint32_t* live;        // [kPoolSlots] frames of the slot's seed that are still in the pool or being expanded
     uint32_t* ctx_qid;     // [kPoolSlots] query id of the seed in the slot
-    uint32_t* ctx_search;  // [kPoolSlots] its search
+    uint32_t* ctx_search;  // [kPoolSlots] its search, as the index of the search's first step in the tables (search * len)
     uint32_t* query;       // [kPoolSlots][Wp] staged packed queries
     uint32_t Wp;           // odd stride (words) between the queries: spreads the slots over the banks
 };
@@ -1255,13 +1261,14 @@ struct SeedCtx {
 };
 __device__ __forceinline__ SeedCtx seed_ctx(const SearchParams& P, const uint32_t* s_steps, const uint8_t* s_runs, const TextPool& pool,
                                             uint32_t slot) {
-    const uint32_t sid = pool.ctx_search[slot];
-    const uint8_t* runs = s_runs + sid * P.len * kRunE;
+    const uint32_t first_step = pool.ctx_search[slot];  // search * len: the first step of the seed's search in the tables
+    const uint8_t* runs = s_runs + first_step * kRunE;
     const uint32_t off = state_flags_offset(P.n_searches * P.len);
-    return SeedCtx{pool.query + slot * pool.Wp, s_steps + sid * P.len, runs, runs + off, runs + 2u * off, pool.ctx_qid[slot], packed_words(P.len)};
+    return SeedCtx{pool.query + slot * pool.Wp, s_steps + first_step, runs, runs + off, runs + 2u * off, pool.ctx_qid[slot], packed_words(P.len)};
 }
 __device__ __forceinline__ void pool_emit(const SearchParams& P, PoolLane& ls, uint32_t qid, uint32_t a, uint32_t e) {
     ls.outW.put(P.out, P.out_cap, &P.counters[CT_OUT_SLOTS], P.textpos_out ? make_uint4(qid, a, 1, e | kCursorTextPosFlag) : make_uint4(qid, P.isa32[a], 1, e));
+    if (P.qcount != nullptr) atomicAdd(&P.qcount[qid], 1u);
     ++ls.emitted;
 }
 
@@ -1574,7 +1581,7 @@ __device__ __forceinline__ void pool_load_seed(const SearchParams& P, const uint
         for (uint32_t w = 0; w < W; ++w) dst[w] = src[w];
     }
     pool.ctx_qid[slot] = seed.x;
-    pool.ctx_search[slot] = seed.z;
+    pool.ctx_search[slot] = seed.z * P.len;
     pool.live[slot] = 1;
     // the root frame: run stack, path stack (the extended end carries M and a path window starts) or state stack
     const uint32_t step = seed.w & 0x3ffu, e = (seed.w >> 10) & 0xfu;
@@ -1734,7 +1741,6 @@ __global__ void __launch_bounds__(kPoolThreads, 3) text_pool_kernel(const Search
     const unsigned long long slots = P.counters[CT_SEED_SLOTS];
     const uint32_t n_slots = static_cast<uint32_t>(slots < P.seed_cap ? slots : P.seed_cap);
     const uint8_t* runs8 = reinterpret_cast<const uint8_t*>(s_runs);
-    uint32_t maxtop = 0;
     bool exhausted = false;  // (warp uniform) the seed list has been handed out
     while (true) {
         uint32_t topS = *pool.S.top, topR = *pool.R.top, topP = *pool.Pth.top;
@@ -1780,7 +1786,6 @@ __global__ void __launch_bounds__(kPoolThreads, 3) text_pool_kernel(const Search
             if (exhausted) break;
             continue;  // only padding entries were fetched
         }
-        maxtop = topS + topR + topP > maxtop ? topS + topR + topP : maxtop;
         uint2 f = make_uint2(0, 0);
         uint32_t slot = 0;
         const PoolTrip trip = pool_pick(topS, topR, topP, maxpush, STACK);
@@ -1808,7 +1813,7 @@ __global__ void __launch_bounds__(kPoolThreads, 3) text_pool_kernel(const Search
         }
         __syncwarp();
     }
-    pool_finish(P, ls, maxtop);
+    pool_finish(P, ls, 0);  // (the deepest pool is not tracked: it would be five instructions in every trip for a diagnostic)
 }
 #endif
 
