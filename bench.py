@@ -570,6 +570,51 @@ def main():
                                           f"{res['threads']} OpenMP threads",
                                 "one_thread_value": round(res["one_thread_reads_s"], 1)}
     if rank == 0:
+        # ---- the two other kernels of the path, timed alone on rank 0 (BASELINE.json: "occ-rank ops/s vs HBM roofline";
+        # north_star kernel 3, the locate that walks LF to sampled suffix-array rows — the search above never needs it,
+        # its verified occurrences carry text positions) ----
+        try:
+            chains, iters = 1 << 22, 64
+            ms_r, _ = ctx.rank_bench(0, chains, iters, 7)
+            ops = chains * iters
+            line["rank_ops"] = {"value": round(ops / (ms_r * 1e-3), 1), "unit": "all-symbol rank ops/s", "ms": round(ms_r, 3),
+                                "what": f"{chains} independent chains of {iters} dependent all_ranks probes at pseudo-random rows of the "
+                                        "occurrence table (one 32-byte block per probe, the superblock from L2)",
+                                "booked_gbs_at_64B_per_op": round(ops * 64 / (ms_r * 1e-3) / 1e9, 1), "hbm_peak_gbs": peak,
+                                "frac_of_hbm_at_64B_per_op": round(ops * 64 / (ms_r * 1e-3) / 1e9 / peak, 3),
+                                "frac_of_random_access_ceiling": round(ops / (ms_r * 1e-3) / 1e9 / 38.4, 3),
+                                "random_access_ceiling": "38.4 G requests/s (profiles/r01_gather_microbench.txt)"}
+            # LF-walking locate: without the verification tables every row is walked to a sampled row (rate 16)
+            n_loc = 4_000_000
+            rng = np.random.default_rng(11)
+            cur = np.zeros((n_loc, 4), dtype=np.uint64)
+            cur[:, 0] = np.arange(n_loc) // 8
+            cur[:, 1] = rng.integers(0, info["n_rows"] - 1, size=n_loc)
+            cur[:, 2] = 1
+            ctx.build_qgram(0)
+            ctx.enable_text(False)
+            # (an index built on the device keeps its complete suffix array; the file image has the reference's samples:
+            # download it and upload it again, as `sahara search` does with X.idx)
+            view = ctx.download_view()
+            try:
+                ctx.upload_view(view)
+            finally:
+                ctx.free_view(view)
+            ctx.locate(cur)  # (untimed: sizes the work buffers)
+            ctx.reset_counters()
+            t_l = time.perf_counter()
+            located = ctx.locate(cur)
+            wall_l = time.perf_counter() - t_l
+            cl = ctx.counters()
+            ms_l = cl["ms_locate"]
+            line["lf_locate"] = {"rows": n_loc, "hits": int(located.shape[0]), "lf_steps": int(cl["lf_steps"]), "ms_kernel": round(ms_l, 3),
+                                 "rows_per_s": round(n_loc / (ms_l * 1e-3), 1), "lf_steps_per_s": round(cl["lf_steps"] / (ms_l * 1e-3), 1),
+                                 "requests_per_step": 2, "frac_of_random_access_ceiling": round(2 * cl["lf_steps"] / (ms_l * 1e-3) / 1e9 / 38.4, 3),
+                                 "wall_s_with_copies": round(wall_l, 3),
+                                 "what": "sb200_locate of random single rows of the 3.1 Gbp index with the sampled suffix array only (rate 16): "
+                                         "one marker record + one occurrence block per LF step, issued together"}
+        except Exception as ex:  # (never fails the bench line)
+            line["extra_legs_error"] = str(ex)[:200]
         emit_json(line)
     if use_dist:
         dist.barrier()
