@@ -341,7 +341,8 @@ def main():
     clocks = sampler.finish()
     ct = ctx.counters()
     # what every rank saw in the timed region: its own time and the batches it had to run again (buffer estimates)
-    rank_info = [{"ms_per_step": round(my_ms / a.steps, 3), "batch_restarts": int(ct["batch_restarts"])}]
+    rank_info = [{"ms_per_step": round(my_ms / a.steps, 3), "batch_restarts": int(ct["batch_restarts"]), "sm_mhz": clocks.get("sm_mhz"),
+                  "reasons": clocks.get("reasons")}]
     if use_dist:
         gathered = [None] * world
         dist.all_gather_object(gathered, rank_info[0])
