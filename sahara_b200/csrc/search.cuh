@@ -1722,7 +1722,10 @@ __global__ void __launch_bounds__(256, SB200_FM_ITEMS_BLOCKS) fm_items_kernel(co
 }
 
 template <bool EDIT, int STACK>
-__global__ void __launch_bounds__(kPoolThreads, 3) text_pool_kernel(const SearchParams P, const uint32_t maxpush, const uint32_t run_rounds, uint4* spill) {
+#if !defined(SB200_POOL_MINBLOCKS)
+#define SB200_POOL_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(kPoolThreads, SB200_POOL_MINBLOCKS) text_pool_kernel(const SearchParams P, const uint32_t maxpush, const uint32_t run_rounds, uint4* spill) {
     extern __shared__ uint32_t s_steps[];
     const uint32_t n_steps = P.n_searches * P.len;
     const uint32_t n_run_words = run_table_bytes(n_steps) / 4;  // run lengths + state flags
