@@ -587,9 +587,16 @@ def test_bucketed_locate_sort_all_segment_sizes(sb, ctx):
                         assert got.shape == want.shape and np.array_equal(got, want), (text, bucket, textpos)
                         got32 = ctx.search_reads(np.ascontiguousarray(q[0::2])).astype(np.uint64)
                         assert np.array_equal(got32, want), (text, bucket, textpos)
+                        # the asynchronous batches over the same segment sizes, records fixed and delta coded (a query
+                        # with thousands of hits: long runs of small differences, and the radix fallback inside a batch)
+                        for delta in (0, 1):
+                            ctx.set_option("delta_records", delta)
+                            got_async = ctx.search_reads_async(np.ascontiguousarray(q[0::2]), packed4=bool(delta), batch=40)
+                            assert np.array_equal(got_async, want), (text, bucket, textpos, delta)
     finally:
         ctx.set_option("bucket_sort", 1)
         ctx.set_option("textpos", 1)
+        ctx.set_option("delta_records", 1)
         ctx.enable_text(False)
 
 
