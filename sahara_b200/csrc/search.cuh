@@ -53,7 +53,10 @@ __host__ __device__ inline uint32_t pack_meta(uint32_t step, uint32_t e, uint32_
 constexpr uint32_t META_PAIR = 1u << 18;
 constexpr uint32_t META_STREAK = 1u << 19;  // (text_pool_kernel) the state was reached by a match that followed a match
 constexpr uint32_t META_TLEN_SHIFT = 20;
-constexpr uint32_t kEmitChunk = 16;   // output slots a thread reserves per atomic
+#if !defined(SB200_EMIT_CHUNK)
+#define SB200_EMIT_CHUNK 16
+#endif
+constexpr uint32_t kEmitChunk = SB200_EMIT_CHUNK;   // output slots a thread reserves per atomic
 constexpr uint32_t kInvalidQid = 0xffffffffu;
 constexpr uint32_t kRunE = 5;         // error levels 0..4 in the run table
 constexpr uint32_t kCursorTextPosFlag = 0x10u;  // == kCursorTextPos of locate.cuh
@@ -360,13 +363,14 @@ __global__ void pack_packed4_kernel(const uint32_t* reads, uint64_t n_queries, u
 }
 #endif
 
-// chunked append to a global array: one atomic per kEmitChunk entries
-struct ChunkWriter {
+// chunked append to a global array: one atomic per CHUNK entries
+template <uint32_t CHUNK>
+struct ChunkWriterT {
     uint32_t pos{0}, end{0};
     __device__ __forceinline__ void put(uint4* buf, uint32_t cap, unsigned long long* counter, uint4 v) {
         if (pos == end) {
-            pos = static_cast<uint32_t>(atomicAdd(counter, static_cast<unsigned long long>(kEmitChunk)));
-            end = pos + kEmitChunk;
+            pos = static_cast<uint32_t>(atomicAdd(counter, static_cast<unsigned long long>(CHUNK)));
+            end = pos + CHUNK;
         }
         if (pos < cap) buf[pos] = v;
         ++pos;
@@ -378,6 +382,15 @@ struct ChunkWriter {
             if (pos < cap) buf[pos] = make_uint4(kInvalidQid, 0, 0, 0);
     }
 };
+using ChunkWriter = ChunkWriterT<kEmitChunk>;
+#if !defined(SB200_SEED_CHUNK)
+#define SB200_SEED_CHUNK 64
+#endif
+// seed slots a thread of the walk reserves per atomic.  All threads add to ONE counter, and same-address atomics are served one
+// after the other: with 16 slots per atomic the reservations of fm_items_kernel took as long as its probes (45 % of its stall
+// samples; 16 / 32 / 64 / 128 slots: 0.96 / 0.77 / 0.73 / 0.75 ms for the walk of the headline workload); the unused slots of a
+// thread's last chunk are empty entries that text_pool_kernel skips
+constexpr uint32_t kSeedChunk = SB200_SEED_CHUNK;
 
 // ================================================================================================
 // Shared pieces of the FM-index walk.
@@ -637,7 +650,8 @@ __device__ __forceinline__ void fm_items_thread(const SearchParams& P, const uin
     uint4 stack[STACK];
     int sp = 0;
     uint32_t nodes = 0, emitted = 0, seeded = 0;
-    ChunkWriter outW, seedW;
+    ChunkWriter outW;
+    ChunkWriterT<kSeedChunk> seedW;
     bool overflow = false;
     int maxsp = 0;
     const uint32_t qlen = P.len;
