@@ -401,6 +401,8 @@ static inline uint32_t warp_ballot(bool p) { return p ? 1u : 0u; }
 static inline uint32_t warp_bcast0(uint32_t v) { return v; }
 static inline uint32_t warp_lane() { return 0u; }
 static inline uint32_t popc32(uint32_t v) { return static_cast<uint32_t>(__builtin_popcount(v)); }
+static inline void warp_counter_add(unsigned long long* counter, uint32_t v) { *counter += v; }
+static inline void warp_counter_max(unsigned long long* counter, uint32_t v) { if (v > *counter) *counter = v; }
 static inline uint32_t ldg32(const uint32_t* p) { return *p; }
 static inline uint4 ldg128(const uint4* p) { return *p; }
 static inline uint2 ldg64(const uint2* p) { return *p; }
@@ -409,6 +411,16 @@ __device__ __forceinline__ uint32_t warp_ballot(bool p) { return __ballot_sync(0
 __device__ __forceinline__ uint32_t warp_bcast0(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ uint32_t warp_lane() { return threadIdx.x & 31u; }
 __device__ __forceinline__ uint32_t popc32(uint32_t v) { return static_cast<uint32_t>(__popc(v)); }
+// the lanes of a converged warp add their values to one counter: reduced over the warp first, one atomic per warp (all
+// warps of a kernel end at about the same time, and same-address atomics are served one after the other)
+__device__ __forceinline__ void warp_counter_add(unsigned long long* counter, uint32_t v) {
+    const uint32_t sum = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31u) == 0 && sum != 0) atomicAdd(counter, static_cast<unsigned long long>(sum));
+}
+__device__ __forceinline__ void warp_counter_max(unsigned long long* counter, uint32_t v) {
+    const uint32_t mx = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31u) == 0 && mx != 0) atomicMax(counter, static_cast<unsigned long long>(mx));
+}
 __device__ __forceinline__ uint32_t ldg32(const uint32_t* p) { return __ldg(p); }
 __device__ __forceinline__ uint4 ldg128(const uint4* p) { return __ldg(p); }
 __device__ __forceinline__ uint2 ldg64(const uint2* p) { return __ldg(p); }
@@ -757,11 +769,12 @@ __device__ __forceinline__ void fm_items_thread(const SearchParams& P, const uin
     }
     outW.finish(P.out, P.out_cap);
     seedW.finish(P.seeds, P.seed_cap);
-    if (nodes) atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(nodes));
+    // (the warp is converged here: its loop ends on a vote)
+    warp_counter_add(&P.counters[CT_NODES], nodes);
     if (overflow) atomicExch(&P.counters[CT_OVERFLOW], 1ull);
-    atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxsp));
-    if (emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(emitted));
-    if (seeded) atomicAdd(&P.counters[CT_SEEDS], static_cast<unsigned long long>(seeded));
+    warp_counter_max(&P.counters[CT_MAX_SP], maxsp);
+    warp_counter_add(&P.counters[CT_CURSORS], emitted);
+    warp_counter_add(&P.counters[CT_SEEDS], seeded);
 }
 
 __device__ __forceinline__ uint32_t nib_mask(uint32_t n) { return n >= 8u ? 0xffffffffu : ((1u << (4u * n)) - 1u); }
@@ -1667,11 +1680,23 @@ __device__ __forceinline__ void pool_retire(const TextPool& pool, uint32_t slot,
 
 __device__ __forceinline__ void pool_finish(const SearchParams& P, PoolLane& ls, uint32_t maxtop) {
     ls.outW.finish(P.out, P.out_cap);
-    if (ls.nodes) atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(ls.nodes));
-    if (ls.nodes) atomicAdd(&P.counters[CT_NODES_TEXT], static_cast<unsigned long long>(ls.nodes));
     if (ls.overflow) atomicExch(&P.counters[CT_OVERFLOW], 1ull);
-    atomicMax(&P.counters[CT_MAX_SP], static_cast<unsigned long long>(maxtop));
-    if (ls.emitted) atomicAdd(&P.counters[CT_CURSORS], static_cast<unsigned long long>(ls.emitted));
+#if defined(SB200_HOST_EMU)
+    // (the emulation calls this once per lane, one after the other)
+    P.counters[CT_NODES] += ls.nodes;
+    P.counters[CT_NODES_TEXT] += ls.nodes;
+    P.counters[CT_CURSORS] += ls.emitted;
+    if (maxtop > P.counters[CT_MAX_SP]) P.counters[CT_MAX_SP] = maxtop;
+#else
+    // (the warp is converged: its loop ends on warp-uniform conditions)
+    const uint32_t nodes = __reduce_add_sync(0xffffffffu, ls.nodes);
+    if ((threadIdx.x & 31u) == 0 && nodes != 0) {
+        atomicAdd(&P.counters[CT_NODES], static_cast<unsigned long long>(nodes));
+        atomicAdd(&P.counters[CT_NODES_TEXT], static_cast<unsigned long long>(nodes));
+    }
+    warp_counter_add(&P.counters[CT_CURSORS], ls.emitted);
+    warp_counter_max(&P.counters[CT_MAX_SP], maxtop);
+#endif
 }
 
 #if !defined(SB200_HOST_EMU)
