@@ -902,6 +902,8 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
         top = make_uint4(nlb, nlbRev, nlen, m);
         haveTop = true;
     };
+    constexpr unsigned long long kOrderedClaim = 4;
+    unsigned long long wnext = 0, wend = 0;
     while (true) {
         if (taken >= max_hits) {  // the limit is reached: the query ends
             sp = 0;
@@ -910,7 +912,12 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
         }
         if (!haveTop && sp == 0) {  // next search of the query, or the next query
             if (j == P.n_searches) {
-                const unsigned long long w = atomicAdd(&P.counters[CT_NEXT_QUERY], 1ull);
+                // (queries are claimed kOrderedClaim at a time: every thread of the launch adds to this one counter)
+                if (wnext == wend) {
+                    wnext = atomicAdd(&P.counters[CT_NEXT_QUERY], static_cast<unsigned long long>(kOrderedClaim));
+                    wend = wnext + kOrderedClaim;
+                }
+                const unsigned long long w = wnext++;
                 if (w >= P.n_queries) break;
                 qid = P.redo ? ldg32(P.redo + w) : static_cast<uint32_t>(w);
                 q = P.packed + static_cast<uint64_t>(qid) * W;
@@ -1708,23 +1715,36 @@ __global__ void __launch_bounds__(256) cursor_rows_kernel(const uint4* cursors, 
     const uint4 cu = cursors[i];
     if (cu.x != kInvalidQid && cu.z != 0) atomicAdd(&rows[cu.x], static_cast<unsigned long long>(cu.z));
 }
-// queries with more rows than the limit -> redo[0 .. tally[0]); tally[1] = cursors the ordered walk can report for them
+// queries with more rows than the limit -> redo[0 .. tally[0]); tally[1] = cursors the ordered walk can report for them.
+// (One reservation per warp: with a low limit nearly every query is on the list, and a million atomics on one counter
+// are served one after the other.)  The order of the list does not matter.
 __global__ void __launch_bounds__(256) redo_list_kernel(const unsigned long long* rows, uint32_t n_queries, uint32_t max_hits, uint32_t* redo,
                                                         unsigned long long* tally) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_queries || rows[q] <= max_hits) return;
-    redo[atomicAdd(&tally[0], 1ull)] = q;
-    atomicAdd(&tally[1], static_cast<unsigned long long>(max_hits));
+    const bool over = q < n_queries && rows[q] > max_hits;
+    const uint32_t m = __ballot_sync(0xffffffffu, over);
+    if (m == 0) return;
+    const uint32_t lane = threadIdx.x & 31u, n = static_cast<uint32_t>(__popc(m));
+    unsigned long long base = 0;
+    if (lane == 0) {
+        base = atomicAdd(&tally[0], static_cast<unsigned long long>(n));
+        atomicAdd(&tally[1], static_cast<unsigned long long>(n) * max_hits);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (over) redo[base + __popc(m & ((1u << lane) - 1u))] = q;
 }
 // cursors of those queries become empty entries; tally[2] = how many were dropped
 __global__ void __launch_bounds__(256) drop_cursors_kernel(uint4* cursors, uint64_t n, const unsigned long long* rows, uint32_t max_hits,
                                                            unsigned long long* tally) {
     const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (i >= n) return;
-    const uint4 cu = cursors[i];
-    if (cu.x == kInvalidQid || rows[cu.x] <= max_hits) return;
-    cursors[i] = make_uint4(kInvalidQid, 0, 0, 0);
-    atomicAdd(&tally[2], 1ull);
+    bool drop = false;
+    if (i < n) {
+        const uint4 cu = cursors[i];
+        drop = cu.x != kInvalidQid && rows[cu.x] > max_hits;
+        if (drop) cursors[i] = make_uint4(kInvalidQid, 0, 0, 0);
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, drop);
+    if (m != 0 && (threadIdx.x & 31u) == 0) atomicAdd(&tally[2], static_cast<unsigned long long>(__popc(m)));
 }
 
 // search_n: one thread per query, children visited in the order of the reference recursion (fm_ordered_thread)
