@@ -50,8 +50,9 @@ for row in rows[2:]:
            "issue_active_pct": num(row, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
            "dram_bytes": dram,
            "l2_miss_sectors": miss,
-           # (random 32-byte gathers: one request per missed sector when the report has no request counter)
-           "l2_miss_requests": num(row, "lts__t_requests_srcunit_tex_lookup_miss.sum") or miss,
+           # (only when the report has a request counter: missed SECTORS also count streamed traffic — items, seed records —
+           # and must not be held against the dependent-gather ceiling)
+           "l2_miss_requests": num(row, "lts__t_requests_srcunit_tex_lookup_miss.sum"),
            "duration_under_ncu_ms": round(num(row, "gpu__time_duration.sum", True) or 0, 4),
            "registers_per_thread": num(row, "launch__registers_per_thread"),
            "warps_active_pct": num(row, "sm__warps_active.avg.pct_of_peak_sustained_active"),
