@@ -372,8 +372,8 @@ def main():
     ct = ctx.counters()
 
     # ---- end to end through the host-buffer calls: pinned host buffers, H2D and D2H inside the timed region ----
-    W4 = (m + 7) // 8
-    host_reads, host_packed = [], []
+    W4, W2 = (m + 7) // 8, (m + 15) // 16
+    host_reads, host_packed, host_packed2 = [], [], []
     for b in range(n_batches):  # queries go device -> pinned host once, outside the timed region
         tq = torch.empty(2 * R * m, dtype=torch.uint8, pin_memory=True)
         check(cuda.sb200_copy_to_host(ctx._h, C.c_void_p(tq.data_ptr()), C.c_void_p(d_batches[b]), 2 * R * m))
@@ -383,6 +383,9 @@ def main():
         tp = torch.empty(R * W4, dtype=torch.int32, pin_memory=True)  # what the host-side reader hands over: 4 bits per base
         sb.pack_reads4(tr.view(R, m).numpy(), threads=8, out=tp.view(R, W4).numpy().view(np.uint32))
         host_packed.append(tp)
+        tp2 = torch.empty(R * W2, dtype=torch.int32, pin_memory=True)  # 2 bits per base (the synthetic reads hold A, C, G, T only)
+        sb.pack_reads2(tr.view(R, m).numpy(), threads=8, out=tp2.view(R, W2).numpy().view(np.uint32))
+        host_packed2.append(tp2)
         del tq
 
     def e2e_run(submit):
@@ -397,8 +400,10 @@ def main():
         barrier()
         return allmax(wall), allmax(ea.elapsed_time(eb) * 1e-3), res
 
-    # the call a user of this library makes: reads 4-bit packed by the host reader, hits back as CSR records
-    e2e_s, e2e_dev_s, res_e2e = e2e_run(lambda b: ctx.submit_reads((host_packed[b].data_ptr(), R, m), packed4=True))
+    # the call a user of this library makes: reads 2-bit packed by the host reader, hits back as delta-coded CSR records
+    e2e_s, e2e_dev_s, res_e2e = e2e_run(lambda b: ctx.submit_reads((host_packed2[b].data_ptr(), R, m), packed2=True))
+    # the same with 4 bits per base in (reads that hold N)
+    e2e_p4_s, _, res_p4 = e2e_run(lambda b: ctx.submit_reads((host_packed[b].data_ptr(), R, m), packed4=True))
     # the same with one byte per base in (the reference's std::vector<uint8_t> per read)
     e2e_ranks_s, _, res_ranks = e2e_run(lambda b: ctx.submit_reads((host_reads[b].data_ptr(), R, m), packed4=False))
 
@@ -436,7 +441,7 @@ def main():
             hits10 += res.n_hits
             ctx.release_batch(tickets[i - 2])
         if i < n10:  # (the reads of the timed batches, reused round robin: the index is far larger than L2)
-            tickets.append(ctx.submit_reads((host_packed[i % n_batches].data_ptr(), sizes10[i], m), packed4=True))
+            tickets.append(ctx.submit_reads((host_packed2[i % n_batches].data_ptr(), sizes10[i], m), packed2=True))
     barrier()
     strong_s = allmax(time.perf_counter() - t_start)
 
@@ -515,9 +520,13 @@ def main():
             "e2e": dict({"value": round(world * R * a.steps / e2e_s, 1), "unit": "reads/s", "h2d_bytes_per_step": int(res_e2e[0]["h2d"]),
                          "d2h_bytes_per_step": int(sum(r["d2h"] for r in res_e2e) / len(res_e2e)),
                          "device_event_ms_per_step": round(1e3 * e2e_dev_s / a.steps, 3),
-                         "call": "sb200_submit_reads(SB200_READS_PACKED4) / sb200_wait_batch, 2 batches in flight: 4-bit packed reads in "
+                         "call": "sb200_submit_reads(SB200_READS_PACKED2) / sb200_wait_batch, 2 batches in flight: 2-bit packed reads in "
                                  "(reverse complements on the device), hits out as delta-coded CSR records (5 bytes for the first hit of a query, a varint difference for the others) + 4 bytes per query",
                          "hits_match_device_run": bool(sum(r["n_hits"] for r in res_e2e) == hits_total)}, **brk(res_e2e, e2e_s)),
+            "e2e_packed4_in": dict({"value": round(world * R * a.steps / e2e_p4_s, 1), "unit": "reads/s", "h2d_bytes_per_step": int(res_p4[0]["h2d"]),
+                                    "d2h_bytes_per_step": int(sum(r["d2h"] for r in res_p4) / len(res_p4)),
+                                    "call": "sb200_submit_reads(SB200_READS_PACKED4): 4 bits per base in (what reads with N need), delta-coded CSR records out"},
+                                   **brk(res_p4, e2e_p4_s)),
             "e2e_rank_bytes_in": dict({"value": round(world * R * a.steps / e2e_ranks_s, 1), "unit": "reads/s", "h2d_bytes_per_step": int(res_ranks[0]["h2d"]),
                                        "d2h_bytes_per_step": int(sum(r["d2h"] for r in res_ranks) / len(res_ranks)),
                                        "call": "sb200_submit_reads(SB200_READS_RANKS): one byte per base in, CSR records out"}, **brk(res_ranks, e2e_ranks_s)),
@@ -548,7 +557,7 @@ def main():
             want = O.sort_rows(oix.locate(cur, res["threads"]))
             got = ctx.search(qs)
             reads = np.ascontiguousarray(qs[0::2])
-            got_async = ctx.search_reads_async(reads, packed4=True, batch=reads.shape[0] // 2 + 1)
+            got_async = ctx.search_reads_async(reads, packed2=True, batch=reads.shape[0] // 2 + 1)
             return bool(np.array_equal(got, want) and np.array_equal(got_async, want)), oracle_nodes, int(want.shape[0])
 
         ok_first, oracle_nodes, n_first = parity(res["first_batch"])
@@ -557,7 +566,7 @@ def main():
         line["parity_sample_ok"] = bool(ok_first and ok_last)
         line["parity_samples"] = {"first_batch_first_reads": {"reads": sample, "hits": n_first, "ok": ok_first},
                                   "last_batch_last_reads": {"reads": sample, "hits": n_last, "ok": ok_last},
-                                  "checked": "sb200_search and sb200_submit_reads(packed4) hit lists == oracle search + locate, bit-exact"}
+                                  "checked": "sb200_search and sb200_submit_reads(2-bit packed reads, delta-coded records) hit lists == oracle search + locate, bit-exact"}
         # the roofline numerator: with the q-gram table off the kernels expand exactly the oracle's extensions
         ctx.build_qgram(0)
         ctx.reset_counters()

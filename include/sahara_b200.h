@@ -200,7 +200,9 @@ int sb200_search_reads(sb200_ctx* ctx, const uint8_t* reads, uint64_t n_reads, u
  *           sb200_wait_batch returned.  format SB200_READS_RANKS: n_reads * len ranks, one byte each (the reference's
  *           std::vector<uint8_t> per read, src/sahara/search.cpp:115-124).  SB200_READS_PACKED4: 4 bits per base, 8 bases
  *           per little-endian 32-bit word, (len + 7) / 8 words per read (what sbh_pack_reads4 of the host library and the
- *           CLI's FASTA reader produce): half the PCIe bytes.
+ *           CLI's FASTA reader produce): half the PCIe bytes.  SB200_READS_PACKED2: 2 bits per base (A, C, G, T = 0 .. 3), 16
+ *           bases per little-endian 32-bit word, (len + 15) / 16 words per read (sbh_pack_reads2, which refuses reads with
+ *           any other symbol — send those batches in one of the other formats): a quarter of the bytes.
  *   result  hits in CSR form: the hits of query q are records [q ? hit_end[q-1] : 0, hit_end[q]); a record is
  *           record_bytes little-endian bytes holding ((seq_id << bits_for_position | pos) << 4) | errors, sorted by that
  *           value within a query.  query ids count as in the reference (2i = read i, 2i+1 = its reverse complement when
@@ -214,6 +216,7 @@ int sb200_search_reads(sb200_ctx* ctx, const uint8_t* reads, uint64_t n_reads, u
 #define SB200_MAX_IN_FLIGHT 3
 #define SB200_READS_RANKS 0
 #define SB200_READS_PACKED4 1
+#define SB200_READS_PACKED2 2
 typedef struct sb200_batch_result {
     uint64_t n_queries, n_hits, n_cursors;
     const uint32_t* hit_end;   /* [n_queries] */

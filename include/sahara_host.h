@@ -64,6 +64,9 @@ int sbh_revcomp_ranks(const uint8_t* in, uint64_t n, uint8_t* out);
  * little-endian 32-bit word, (len + 7) / 8 words per read, unused nibbles of a read's last word 0xF.  out: n_reads *
  * ((len + 7) / 8) words (page-locked memory from sb200_host_alloc makes the copy to the GPU a single DMA). */
 int sbh_pack_reads4(const uint8_t* ranks, uint64_t n_reads, uint32_t len, uint32_t threads, uint32_t* out);
+/* ranks -> SB200_READS_PACKED2: 2 bits per base (ranks 1 .. 4 = A, C, G, T -> 0 .. 3), 16 bases per little-endian 32-bit word,
+ * (len + 15) / 16 words per read.  Fails (and names the read) when a read holds any other symbol. */
+int sbh_pack_reads2(const uint8_t* ranks, uint64_t n_reads, uint32_t len, uint32_t threads, uint32_t* out);
 /* CSR result of sb200_wait_batch (include/sahara_b200.h: hit_end, records, record_bytes, bits_for_position, delta_coded) ->
  * tuples: out[4 * i + 0..3] = queryId (first_query + q), seqId, pos, errors of hit i, in the order of the records; out holds
  * 4 * n_hits values.  Fails when the records do not decode to exactly n_hits hits. */

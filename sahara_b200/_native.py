@@ -146,6 +146,7 @@ SBH_SYMBOLS = {
     "sbh_fasta_load_reads": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p), u64p, u64p]),
     "sbh_revcomp_ranks": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "sbh_pack_reads4": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "sbh_pack_reads2": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),
     "sbh_set_expand_rule": (C.c_int, [C.c_uint32]),
     "sbh_decode_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.c_void_p]),
     "sbh_free": (None, [C.c_void_p]),

@@ -138,6 +138,19 @@ def pack_reads4(reads, threads=4, out=None):
     return out
 
 
+def pack_reads2(reads, threads=4, out=None):
+    """ranks [n_reads, len] of A, C, G, T only -> SB200_READS_PACKED2 words [n_reads, (len + 15) // 16] (uint32); raises
+    SaharaError when a read holds another symbol"""
+    r = np.ascontiguousarray(reads, dtype=np.uint8)
+    if r.ndim != 2:
+        raise ValueError("reads must be a dense [n_reads, length] array of ranks")
+    W = (r.shape[1] + 15) // 16
+    if out is None:
+        out = np.empty((r.shape[0], W), dtype=np.uint32)
+    check_host(host.sbh_pack_reads2(_ptr(r), r.shape[0], r.shape[1], threads, C.c_void_p(out.ctypes.data)))
+    return out
+
+
 def device_count():
     """CUDA devices the library sees (sb200_device_count)"""
     n = C.c_int()
@@ -316,8 +329,8 @@ class Context:
             cuda.sb200_free(p)
 
     # ---- asynchronous batches (sb200_submit_reads / sb200_wait_batch / sb200_release_batch) ----
-    def submit_reads(self, reads, length=None, packed4=False, with_reverse=True):
-        """reads: ranks [n, len] (uint8), or with packed4 the words of pack_reads4 [n, (len + 7) // 8] (uint32) — or an
+    def submit_reads(self, reads, length=None, packed4=False, with_reverse=True, packed2=False):
+        """reads: ranks [n, len] (uint8), or with packed4 / packed2 the words of pack_reads4 / pack_reads2 (uint32) — or an
         int address of such a (page-locked) buffer together with (n_reads, length) in `length`.  Returns a ticket; the
         buffer must stay alive until wait_batch."""
         if isinstance(reads, tuple):
@@ -329,7 +342,7 @@ class Context:
             addr = a.ctypes.data
             self._keep = getattr(self, "_keep", {})
         t = C.c_uint64()
-        check(cuda.sb200_submit_reads(self._h, C.c_void_p(addr), n_reads, ln, 1 if packed4 else 0, int(with_reverse), C.byref(t)))
+        check(cuda.sb200_submit_reads(self._h, C.c_void_p(addr), n_reads, ln, 2 if packed2 else 1 if packed4 else 0, int(with_reverse), C.byref(t)))
         if not isinstance(reads, tuple):
             self._keep[t.value] = a
         return t.value
@@ -348,14 +361,14 @@ class Context:
         check(cuda.sb200_release_batch(self._h, ticket))
         getattr(self, "_keep", {}).pop(ticket, None)
 
-    def search_reads_async(self, reads, packed4=False, with_reverse=True, batch=None, depth=2):
+    def search_reads_async(self, reads, packed4=False, with_reverse=True, batch=None, depth=2, packed2=False):
         """the reads cut into batches that are submitted `depth` deep -> uint64 [n_hits, 4] like search()"""
         r = self._queries(reads)
         n, m = r.shape
         batch = batch or n
         per = 2 if with_reverse else 1
         pieces = [(o, min(n, o + batch)) for o in range(0, n, batch)]
-        bufs = [pack_reads4(r[a:b]) if packed4 else np.ascontiguousarray(r[a:b]) for a, b in pieces]
+        bufs = [pack_reads2(r[a:b]) if packed2 else pack_reads4(r[a:b]) if packed4 else np.ascontiguousarray(r[a:b]) for a, b in pieces]
         out, tickets = [], []
         for i in range(len(pieces) + depth):
             if i >= depth:
@@ -364,7 +377,7 @@ class Context:
                 out.append(decode_batch(res, first_query=pieces[j][0] * per))
                 self.release_batch(tickets[j])
             if i < len(pieces):
-                tickets.append(self.submit_reads(bufs[i], length=m, packed4=packed4, with_reverse=with_reverse))
+                tickets.append(self.submit_reads(bufs[i], length=m, packed4=packed4, with_reverse=with_reverse, packed2=packed2))
         return np.concatenate(out) if out else np.zeros((0, 4), dtype=np.uint64)
 
     def search_cursors(self, queries):

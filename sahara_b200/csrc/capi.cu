@@ -193,7 +193,11 @@ struct Options {
     int delta_records{1};      // CSR results of the asynchronous calls: records behind the first of a query as differences (varint)
 };
 
-enum : int { IN_QUERIES_RANKS = 0, IN_READS_RANKS = 1, IN_READS_PACKED4 = 2 };
+enum : int { IN_QUERIES_RANKS = 0, IN_READS_RANKS = 1, IN_READS_PACKED4 = 2, IN_READS_PACKED2 = 3 };
+// bytes of one read (or query) of the batch as the caller hands it over
+inline size_t input_item_bytes(int in_fmt, uint32_t len) {
+    return in_fmt == IN_READS_PACKED4 ? size_t((len + 7) / 8) * 4 : in_fmt == IN_READS_PACKED2 ? size_t((len + 15) / 16) * 4 : len;
+}
 enum : int { OUT_NONE = 0, OUT_HIT64 = 1, OUT_HIT32 = 2, OUT_CSR = 3 };
 constexpr int kSlots = 3;
 
@@ -994,7 +998,10 @@ void enqueue_compute(sb200_ctx* c, Work& w) {
         CUDA_TRY(cudaMemsetAsync(ctr, 0, CT_COUNT * sizeof(unsigned long long), w.stream));
         const uint8_t* in = w.d_src;
         const unsigned grid = grid_for(n_queries * W);
-        if (w.in_fmt == IN_READS_PACKED4)
+        if (w.in_fmt == IN_READS_PACKED2)
+            pack_packed2_kernel<<<grid, 256, 0, w.stream>>>(reinterpret_cast<const uint32_t*>(in), n_queries, len, w.with_reverse ? 1u : 0u,
+                                                           w.d_packed.get<uint32_t>());
+        else if (w.in_fmt == IN_READS_PACKED4)
             pack_packed4_kernel<<<grid, 256, 0, w.stream>>>(reinterpret_cast<const uint32_t*>(in), n_queries, len, ix.sigma, w.with_reverse ? 1u : 0u,
                                                            w.d_packed.get<uint32_t>(), ctr);
         else if (w.in_fmt == IN_READS_RANKS && w.with_reverse)
@@ -1319,7 +1326,7 @@ void setup_batch(sb200_ctx* c, Work& w, const void* src, bool src_on_device, int
     w.located = false;
     w.n_hits = w.n_cursor_slots = w.n_real_cursors = 0;
     const uint64_t n_items = (with_reverse && in_fmt != IN_QUERIES_RANKS) ? n_queries / 2 : n_queries;
-    const uint64_t bytes = in_fmt == IN_READS_PACKED4 ? n_items * packed_words(len) * 4 : n_items * len;
+    const uint64_t bytes = n_items * input_item_bytes(in_fmt, len);
     if (src_on_device) {
         w.d_src = static_cast<const uint8_t*>(src);
     } else {
@@ -1397,7 +1404,7 @@ void search_host_pipelined(sb200_ctx* c, const uint8_t* src, uint64_t n_items, u
     const uint64_t per_item = (with_reverse && in_fmt != IN_QUERIES_RANKS) ? 2 : 1;  // queries per host item
     const uint64_t n_queries = n_items * per_item;
     const size_t hit_bytes = out_record_bytes(c, out_fmt);
-    const size_t item_bytes = in_fmt == IN_READS_PACKED4 ? size_t(packed_words(len)) * 4 : len;
+    const size_t item_bytes = input_item_bytes(in_fmt, len);
     // Chunk boundaries (in queries).  Every chunk costs a kernel drain (the longest single seed), so few chunks: a short
     // first one (its copy-in cannot be hidden), a short last one (its copy-out cannot be hidden), and the rest in pieces
     // of at most `chunk` queries whose copies hide behind the neighbours' kernels.
@@ -2143,9 +2150,9 @@ int sb200_submit_reads(sb200_ctx* c, const void* reads, uint64_t n_reads, uint32
     return guard([&] {
         use(c);
         if (!ticket) throw Error("null argument");
-        if (format != SB200_READS_RANKS && format != SB200_READS_PACKED4) throw Error("unknown read format");
+        if (format != SB200_READS_RANKS && format != SB200_READS_PACKED4 && format != SB200_READS_PACKED2) throw Error("unknown read format");
         if (c->max_hits) throw Error("sb200_submit_reads does not support --max_hits: use sb200_search_reads");
-        *ticket = submit_batch(c, reads, false, n_reads, len, format == SB200_READS_PACKED4 ? IN_READS_PACKED4 : IN_READS_RANKS,
+        *ticket = submit_batch(c, reads, false, n_reads, len, format == SB200_READS_PACKED4 ? IN_READS_PACKED4 : format == SB200_READS_PACKED2 ? IN_READS_PACKED2 : IN_READS_RANKS,
                                with_reverse != 0, OUT_CSR);
     });
 }

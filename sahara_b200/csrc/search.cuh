@@ -363,6 +363,39 @@ __global__ void pack_packed4_kernel(const uint32_t* reads, uint64_t n_queries, u
 }
 #endif
 
+#if !defined(SB200_HOST_EMU)
+// the same from reads of 2 bits per base (A, C, G, T = 0 .. 3; 16 bases per little-endian word, (len + 15) / 16 words per
+// read): half the bytes of the 4-bit form over PCIe.  Nothing to verify — every code is a symbol of the alphabet.
+__global__ void pack_packed2_kernel(const uint32_t* reads, uint64_t n_queries, uint32_t len, uint32_t with_reverse, uint32_t* out) {
+    const uint32_t W = packed_words(len), W2 = (len + 15u) / 16u;
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n_queries * W) return;
+    const uint64_t qi = i / W;
+    const uint32_t w = static_cast<uint32_t>(i % W);
+    const bool rc = with_reverse && (qi & 1u);
+    const uint32_t* src = reads + (with_reverse ? (qi >> 1) : qi) * W2;
+    const uint32_t n = len - w * 8 < 8u ? len - w * 8 : 8u;
+    // the 8 codes that start at symbol p of the read (forward: w * 8; reverse strand: the n symbols that end at len - 1 - w * 8)
+    const uint32_t p = rc ? len - w * 8 - n : w * 8;
+    const uint32_t w0 = p >> 4;
+    const uint32_t lo = src[w0], hi = w0 + 1 < W2 ? src[w0 + 1] : 0u;
+    uint32_t x = __funnelshift_r(lo, hi, (p & 15u) * 2u) & 0xffffu;
+    if (rc) x ^= 0xffffu;  // complement: A <-> T, C <-> G = 3 - code
+    // 8 codes of 2 bits -> 8 nibbles
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    if (rc) {  // reverse the nibbles, then move the n valid ones (now at the top) down
+        x = ((x & 0x0f0f0f0fu) << 4) | ((x >> 4) & 0x0f0f0f0fu);
+        x = __byte_perm(x, 0, 0x0123);
+        x >>= 4u * (8u - n);
+    }
+    uint32_t v = x + 0x11111111u;  // ranks 1 .. 4
+    if (n < 8) v |= ~((1u << (4 * n)) - 1u);
+    out[i] = v;
+}
+#endif
+
 // chunked append to a global array: one atomic per CHUNK entries
 template <uint32_t CHUNK>
 struct ChunkWriterT {

@@ -213,6 +213,41 @@ struct Writer {
 // ranks (one byte per base) -> 4 bits per base, 8 bases per little-endian word, (len + 7) / 8 words per read; unused
 // nibbles of the last word of a read are 0xF.  The format sb200_submit_reads takes as SB200_READS_PACKED4: half the
 // bytes on the way to the GPU.  `threads` host threads, each a contiguous range of reads.
+// ranks -> 2 bits per base (A, C, G, T = ranks 1 .. 4 -> 0 .. 3), 16 bases per little-endian 32-bit word, (len + 15) / 16 words
+// per read (SB200_READS_PACKED2).  Returns the index of the first read that holds another symbol (it cannot be packed),
+// or n_reads when all reads were packed.
+inline uint64_t packReads2(const uint8_t* ranks, uint64_t n_reads, uint32_t len, unsigned threads, uint32_t* out) {
+    const uint32_t W = (len + 15) / 16;
+    std::vector<uint64_t> firstBad(std::max(1u, threads), n_reads);
+    auto work = [&](unsigned t, uint64_t r0, uint64_t r1) {
+        for (uint64_t r = r0; r < r1; ++r) {
+            const uint8_t* src = ranks + r * len;
+            uint32_t* dst = out + r * W;
+            bool bad = false;
+            for (uint32_t w = 0; w < W; ++w) {
+                uint32_t v = 0;
+                const uint32_t n = std::min<uint32_t>(16, len - w * 16);
+                for (uint32_t j = 0; j < n; ++j) {
+                    const uint32_t c = src[w * 16 + j];
+                    bad = bad || c < 1 || c > 4;
+                    v |= ((c - 1u) & 3u) << (2 * j);
+                }
+                dst[w] = v;
+            }
+            if (bad && firstBad[t] == n_reads) firstBad[t] = r;
+        }
+    };
+    if (threads <= 1 || n_reads < 4096) {
+        work(0, 0, n_reads);
+    } else {
+        std::vector<std::thread> pool;
+        const uint64_t per = (n_reads + threads - 1) / threads;
+        for (unsigned t = 0; t < threads; ++t) pool.emplace_back(work, t, std::min<uint64_t>(n_reads, per * t), std::min<uint64_t>(n_reads, per * (t + 1)));
+        for (auto& th : pool) th.join();
+    }
+    return *std::min_element(firstBad.begin(), firstBad.end());
+}
+
 inline void packReads4(const uint8_t* ranks, uint64_t n_reads, uint32_t len, unsigned threads, uint32_t* out) {
     const uint32_t W = (len + 7) / 8;
     auto work = [&](uint64_t r0, uint64_t r1) {

@@ -198,6 +198,15 @@ int sbh_set_expand_rule(uint32_t rule) {
     });
 }
 
+int sbh_pack_reads2(const uint8_t* ranks, uint64_t n_reads, uint32_t len, uint32_t threads, uint32_t* out) {
+    return guard([&] {
+        const uint64_t bad = sahara::fasta::packReads2(ranks, n_reads, len, threads, out);
+        if (bad != n_reads)
+            throw std::runtime_error("read " + std::to_string(bad) + " holds a symbol other than A, C, G, T: 2 bits per base cannot carry it, "
+                                     "send this batch as SB200_READS_PACKED4 or SB200_READS_RANKS");
+    });
+}
+
 int sbh_pack_reads4(const uint8_t* ranks, uint64_t n_reads, uint32_t len, uint32_t threads, uint32_t* out) {
     return guard([&] { sahara::fasta::packReads4(ranks, n_reads, len, threads, out); });
 }

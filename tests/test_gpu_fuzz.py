@@ -69,7 +69,9 @@ def test_random_configuration(seed):
             ctx.set_option("delta_records", ((seed + it) >> 1) & 1)
             ctx.set_option("bucket_sort", 0 if (seed + it) % 5 == 4 else 1)
             try:
-                got_async = ctx.search_reads_async(reads, packed4=bool((seed + it) & 1), batch=(7, 40, 1000)[(seed + it) % 3])
+                # reads in as ranks, 4-bit words or — when they hold A, C, G, T only — 2-bit words
+                two_bit = (seed + it) % 3 == 2 and bool(np.all((reads >= 1) & (reads <= 4)))
+                got_async = ctx.search_reads_async(reads, packed4=bool((seed + it) & 1), packed2=two_bit, batch=(7, 40, 1000)[(seed + it) % 3])
             finally:
                 ctx.set_option("delta_records", 1)
                 ctx.set_option("bucket_sort", 1)

@@ -234,6 +234,23 @@ def test_record_decoder_reads_fixed_and_delta_coded_results():
     assert len(delta) < len(fixed)
 
 
+def test_two_bit_packer():
+    """sbh_pack_reads2: A, C, G, T at 2 bits per base, 16 per word; any other symbol is refused with the read's index"""
+    rng = np.random.default_rng(12)
+    for m in (1, 15, 16, 17, 150, 250):
+        r = rng.integers(1, 5, size=(37, m), dtype=np.uint8)
+        p = sb.pack_reads2(r, threads=3)
+        assert p.shape == (37, (m + 15) // 16)
+        codes = np.zeros((37, p.shape[1] * 16), dtype=np.uint8)
+        for j in range(16):
+            codes[:, j::16] = (p >> np.uint32(2 * j)) & np.uint32(3)
+        assert np.array_equal(codes[:, :m] + 1, r) and not codes[:, m:].any()
+    bad = rng.integers(1, 5, size=(9000, 40), dtype=np.uint8)
+    bad[7123, 5] = 5
+    with pytest.raises(sb.SaharaError, match="read 7123 holds a symbol other than A, C, G, T"):
+        sb.pack_reads2(bad, threads=4)
+
+
 def test_synth_mirror_is_deterministic():
     from sahara_b200 import synth
     g = synth.genome(5000, 42)
