@@ -66,6 +66,7 @@ class ClockSampler(threading.Thread):
         self.rows = []
         self.stop_flag = threading.Event()
         self.proc = None
+        self.interval = float(os.environ.get("SB200_BENCH_SAMPLE_MS", "4")) * 1e-3  # NVML polling period
         self.nvml = None
         try:
             import pynvml
@@ -96,7 +97,7 @@ class ClockSampler(threading.Thread):
         if self.nvml is not None:
             while not self.stop_flag.is_set():
                 self.sample()
-                time.sleep(0.004)
+                time.sleep(self.interval)
             return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -342,7 +343,8 @@ def main():
     ct = ctx.counters()
     # what every rank saw in the timed region: its own time and the batches it had to run again (buffer estimates)
     rank_info = [{"ms_per_step": round(my_ms / a.steps, 3), "batch_restarts": int(ct["batch_restarts"]), "sm_mhz": clocks.get("sm_mhz"),
-                  "reasons": clocks.get("reasons")}]
+                  "reasons": clocks.get("reasons"), "hits_per_step": int(sum(r["n_hits"] for r in res_dev) / a.steps),
+                  "nodes_per_step": int(ct["nodes"] / a.steps)}]
     if use_dist:
         gathered = [None] * world
         dist.all_gather_object(gathered, rank_info[0])
