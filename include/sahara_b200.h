@@ -19,7 +19,8 @@
  * clear error, none is silently truncated:
  *   - the index has fewer than 2^32 - 8192 rows (text + delimiters; a 3.1 Gbp genome has 3.1e9) — rows are u32 on the GPU;
  *   - at most 4 errors (search schemes with u <= 4), queries of at most 1000 characters, at most 255 searches per scheme;
- *   - fewer than 2^32 (query, search) pairs, cursors and hits per call (split the batch);
+ *   - fewer than 2^32 (query, search) pairs, cursors and hits per call, and fewer than 2^32 bytes of delta-coded hit records
+ *     per batch (about 700 M hits; split the batch);
  *   - the 16-byte and packed hit formats (sb200_search_reads, sb200_submit_reads) need bits_for_position <= 32;
  *     sb200_search returns the reference's full 64-bit tuples.
  */

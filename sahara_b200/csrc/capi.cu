@@ -1211,6 +1211,9 @@ void finish_batch(sb200_ctx* c, Work& w) {
                 radix = st[ST_LC + LC_HUGE] != 0;  // a query with more hits than a block sorts
                 w.n_hits = total;
                 w.n_rec_bytes = st[ST_BYTES];
+                // (the byte offsets of delta-coded records are u32 like the hit offsets: a record takes at most rec + 1 bytes)
+                if (w.delta && total * (out_record_bytes(c, OUT_CSR) + 1) >= (1ull << 32))
+                    throw Error("more than 2^32 bytes of hit records in one batch; split the batch");
             }
         }
         if (!fits) {
