@@ -1129,15 +1129,18 @@ __device__ __forceinline__ void fm_ordered_thread(const SearchParams& P, const u
 // therefore stay busy as long as the warp has frames at all — the private-stack version (text_thread) keeps 6.6 of
 // 32 lanes active because the lanes drift into different phases — and a heavy seed is expanded by many lanes at
 // once, which also shortens the drain at the end of the kernel.
-//   * The pool is two stacks: RUN frames (next step is a match-only run: compare packed words) and STATE frames
-//     (expand search states).  A trip pops from one of them, so all lanes of a trip execute the same code.
-//   * kPoolSlots seeds are in flight per warp; a slot is refilled when the last frame of its seed is gone
-//     (live[] counts them).
+//   * The pool is three stacks: RUN frames (next step is a match-only run: compare packed words), STATE frames (expand
+//     search states, text_states) and PATH frames (a state at the start of a path window: up to 8 states along a matching
+//     stretch expanded at once, text_path).  A trip pops from one of them (pool_pick), so all lanes of a trip execute
+//     the same code.
+//   * kPoolSlots seeds are in flight per warp; slots whose seed has no frame left (live[] counts them) are refilled
+//     kRefillMin at a time, the queries of the new seeds staged by all lanes.
 //   * A run frame compares at most kRunRounds x 8 symbols per pop, then is pushed back.
 //   * The first kPoolCapS / kPoolCapR frames of a stack live in shared memory, the rest spills to global memory
 //     (rare).  Pops of the state stack only narrow down when even the spill area is nearly full; with one frame per
 //     trip the order is depth first and the stack cannot grow by more than the private-stack bound (STACK), which
-//     is kept as head room.  Run frames never multiply (a pop pushes at most one frame).
+//     is kept as head room.  Run frames never multiply (a pop pushes at most one frame); the path stack has no spill
+//     area (a path frame that does not fit is an ordinary state frame).
 // ================================================================================================
 #if defined(SB200_POOL_CAP)
 constexpr uint32_t kPoolCapS = SB200_POOL_CAP;     // (tests: tiny pools exercise the spill area and the narrow pops)
